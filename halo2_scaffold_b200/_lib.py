@@ -1,0 +1,248 @@
+"""
+ctypes binding of libh2b200.so -- the C ABI declared in include/h2b200.h.
+
+The product library is CUDA-only (sm_100a).  There is no CPU fallback: if the shared library is
+missing, or no Blackwell GPU is usable, loading / initialisation raises.  The CPU "kernel-logic
+emulator" build (tools/emu, used by unit tests of the kernel sources) is refused here unless a test
+asks for it explicitly with `allow_emulator=True`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "lib", "libh2b200.so")
+
+H2B_OK = 0
+
+
+class H2BError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("h2b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_EXPORTS = [
+    "h2b_init", "h2b_init_device", "h2b_shutdown", "h2b_device_count", "h2b_last_error", "h2b_version",
+    "h2b_is_emulator", "h2b_msm_bn254_g1", "h2b_ntt_bn254_fr", "h2b_register_bases", "h2b_unregister_bases",
+    "h2b_msm_bn254_g1_registered", "h2b_ntt_bn254_fr_dev", "h2b_msm_bn254_g1_dev",
+    "h2b_msm_bn254_g1_dev_partial", "h2b_msm_fold_partials", "h2b_fr_scale_dev",
+    "h2b_dev_alloc", "h2b_dev_free", "h2b_memcpy_h2d", "h2b_memcpy_d2h", "h2b_dev_sync", "h2b_gen_points_dev",
+    "h2b_gen_scalars_dev", "h2b_field_op", "h2b_ec_op", "h2b_imad_bench", "h2b_set_msm_window",
+]
+
+
+def exported_symbols():
+    """Every symbol include/h2b200.h declares (checked by the CPU test-suite against the built .so)."""
+    return list(_EXPORTS)
+
+
+def _u64(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a
+
+
+class Lib:
+    def __init__(self, path: str | None = None, allow_emulator: bool = False):
+        path = path or os.environ.get("H2B200_LIB", DEFAULT_LIB)
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "libh2b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % path)
+        self.path = path
+        L = ctypes.CDLL(path)
+        vp, sz, u64, u32, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+        L.h2b_init.argtypes = [i32]
+        L.h2b_init_device.argtypes = [i32]
+        L.h2b_shutdown.restype = None
+        L.h2b_last_error.restype = ctypes.c_char_p
+        L.h2b_version.restype = ctypes.c_char_p
+        L.h2b_msm_bn254_g1.argtypes = [vp, vp, sz, vp]
+        L.h2b_ntt_bn254_fr.argtypes = [vp, vp, u32]
+        L.h2b_register_bases.argtypes = [vp, sz, ctypes.POINTER(u64)]
+        L.h2b_unregister_bases.argtypes = [u64]
+        L.h2b_msm_bn254_g1_registered.argtypes = [vp, u64, sz, sz, vp]
+        L.h2b_ntt_bn254_fr_dev.argtypes = [i32, vp, vp, u32, vp]
+        L.h2b_msm_bn254_g1_dev.argtypes = [i32, vp, vp, sz, vp, vp]
+        L.h2b_msm_bn254_g1_dev_partial.argtypes = [i32, vp, vp, sz, vp, vp]
+        L.h2b_msm_fold_partials.argtypes = [i32, vp, sz, vp]
+        L.h2b_fr_scale_dev.argtypes = [i32, vp, sz, vp, i32, vp]
+        L.h2b_dev_alloc.argtypes = [i32, sz, ctypes.POINTER(vp)]
+        L.h2b_dev_free.argtypes = [i32, vp]
+        L.h2b_memcpy_h2d.argtypes = [i32, vp, vp, sz]
+        L.h2b_memcpy_d2h.argtypes = [i32, vp, vp, sz]
+        L.h2b_dev_sync.argtypes = [i32]
+        L.h2b_gen_points_dev.argtypes = [i32, u64, sz, vp, vp]
+        L.h2b_gen_scalars_dev.argtypes = [i32, u64, sz, i32, vp, vp]
+        L.h2b_field_op.argtypes = [i32, i32, vp, vp, sz, vp]
+        L.h2b_ec_op.argtypes = [i32, vp, vp, sz, vp]
+        L.h2b_imad_bench.argtypes = [i32, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
+        L.h2b_set_msm_window.argtypes = [i32]
+        self.L = L
+        self.is_emulator = bool(L.h2b_is_emulator())
+        if self.is_emulator and not allow_emulator:
+            raise RuntimeError("%s is the CPU kernel-logic emulator build; the product path only runs the CUDA library" % path)
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def check(self, rc: int):
+        if rc != H2B_OK:
+            raise H2BError(rc, (self.L.h2b_last_error() or b"").decode())
+
+    def version(self) -> str:
+        return self.L.h2b_version().decode()
+
+    # ---- lifecycle ------------------------------------------------------------------------------
+    def init(self, n_devices: int = 0):
+        self.check(self.L.h2b_init(n_devices))
+
+    def init_device(self, device: int):
+        self.check(self.L.h2b_init_device(device))
+
+    def shutdown(self):
+        self.L.h2b_shutdown()
+
+    def device_count(self) -> int:
+        return self.L.h2b_device_count()
+
+    # ---- host-pointer drop-ins ------------------------------------------------------------------
+    def msm(self, scalars: np.ndarray, bases: np.ndarray) -> np.ndarray:
+        scalars, bases = _u64(scalars), _u64(bases)
+        n = scalars.shape[0] if scalars.ndim > 1 else scalars.size // 4
+        nb = bases.shape[0] if bases.ndim > 1 else bases.size // 8
+        if n != nb:
+            raise AssertionError("best_multiexp: coeffs.len() != bases.len() (%d vs %d)" % (n, nb))
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.L.h2b_msm_bn254_g1(scalars.ctypes.data, bases.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def ntt(self, a: np.ndarray, omega: np.ndarray, log_n: int) -> np.ndarray:
+        """In place on a C-contiguous uint64 (2^log_n, 4) array; returns it."""
+        assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+        assert a.size == 4 << log_n, "best_fft: a.len() != 1 << log_n"
+        omega = _u64(omega)
+        self.check(self.L.h2b_ntt_bn254_fr(a.ctypes.data, omega.ctypes.data, log_n))
+        return a
+
+    def register_bases(self, bases: np.ndarray) -> int:
+        bases = _u64(bases)
+        h = ctypes.c_uint64(0)
+        self.check(self.L.h2b_register_bases(bases.ctypes.data, bases.size // 8, ctypes.byref(h)))
+        return h.value
+
+    def unregister_bases(self, handle: int):
+        self.check(self.L.h2b_unregister_bases(handle))
+
+    def msm_registered(self, scalars: np.ndarray, handle: int, offset: int = 0) -> np.ndarray:
+        scalars = _u64(scalars)
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.L.h2b_msm_bn254_g1_registered(scalars.ctypes.data, handle, offset, scalars.size // 4, out.ctypes.data))
+        return out
+
+    # ---- device-pointer entry points ------------------------------------------------------------
+    def ntt_dev(self, device: int, d_a: int, omega: np.ndarray, log_n: int, stream: int = 0):
+        omega = _u64(omega)
+        self.check(self.L.h2b_ntt_bn254_fr_dev(device, d_a, omega.ctypes.data, log_n, stream))
+
+    def msm_dev(self, device: int, d_scalars: int, d_bases: int, n: int, d_out: int, stream: int = 0):
+        self.check(self.L.h2b_msm_bn254_g1_dev(device, d_scalars, d_bases, n, d_out, stream))
+
+    def msm_dev_partial(self, device: int, d_scalars: int, d_bases: int, n: int, d_out_block: int, stream: int = 0):
+        self.check(self.L.h2b_msm_bn254_g1_dev_partial(device, d_scalars, d_bases, n, d_out_block, stream))
+
+    def msm_fold_partials(self, blocks: np.ndarray, device: int = 0) -> np.ndarray:
+        blocks = _u64(blocks).reshape(-1, 28)
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.L.h2b_msm_fold_partials(device, blocks.ctypes.data, blocks.shape[0], out.ctypes.data))
+        return out
+
+    def fr_scale_dev(self, device: int, d_a: int, n: int, factors: np.ndarray, stream: int = 0):
+        factors = _u64(factors).reshape(-1, 4)
+        self.check(self.L.h2b_fr_scale_dev(device, d_a, n, factors.ctypes.data, factors.shape[0], stream))
+
+    def dev_alloc(self, device: int, nbytes: int) -> int:
+        p = ctypes.c_void_p(0)
+        self.check(self.L.h2b_dev_alloc(device, nbytes, ctypes.byref(p)))
+        return p.value or 0
+
+    def dev_free(self, device: int, p: int):
+        self.check(self.L.h2b_dev_free(device, p))
+
+    def h2d(self, device: int, d_dst: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self.check(self.L.h2b_memcpy_h2d(device, d_dst, src.ctypes.data, src.nbytes))
+
+    def d2h(self, device: int, dst: np.ndarray, d_src: int):
+        assert dst.flags["C_CONTIGUOUS"]
+        self.check(self.L.h2b_memcpy_d2h(device, dst.ctypes.data, d_src, dst.nbytes))
+
+    def dev_sync(self, device: int = 0):
+        self.check(self.L.h2b_dev_sync(device))
+
+    # ---- synthetic workload + diagnostics -----------------------------------------------------------
+    def gen_points_dev(self, device: int, seed: int, n: int, d_out: int, stream: int = 0):
+        self.check(self.L.h2b_gen_points_dev(device, seed, n, d_out, stream))
+
+    def gen_scalars_dev(self, device: int, seed: int, n: int, kind: int, d_out: int, stream: int = 0):
+        self.check(self.L.h2b_gen_scalars_dev(device, seed, n, kind, d_out, stream))
+
+    def gen_points(self, seed: int, n: int, device: int = 0) -> np.ndarray:
+        out = np.empty((n, 8), dtype=np.uint64)
+        d = self.dev_alloc(device, max(n, 1) * 64)
+        try:
+            self.gen_points_dev(device, seed, n, d)
+            self.dev_sync(device)
+            if n:
+                self.d2h(device, out, d)
+        finally:
+            self.dev_free(device, d)
+        return out
+
+    def gen_scalars(self, seed: int, n: int, kind: int = 0, device: int = 0) -> np.ndarray:
+        out = np.empty((n, 4), dtype=np.uint64)
+        d = self.dev_alloc(device, max(n, 1) * 32)
+        try:
+            self.gen_scalars_dev(device, seed, n, kind, d)
+            self.dev_sync(device)
+            if n:
+                self.d2h(device, out, d)
+        finally:
+            self.dev_free(device, d)
+        return out
+
+    def field_op(self, field: str, op: str, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+        a = _u64(a)
+        b = a if b is None else _u64(b)
+        out = np.empty_like(a)
+        ops = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "from_mont": 5, "to_mont": 6}
+        self.check(self.L.h2b_field_op({"fr": 0, "fq": 1}[field], ops[op], a.ctypes.data, b.ctypes.data, a.size // 4, out.ctypes.data))
+        return out
+
+    def ec_op(self, op: int, p: np.ndarray, q: np.ndarray) -> np.ndarray:
+        p, q = _u64(p), _u64(q)
+        out = np.empty_like(p)
+        self.check(self.L.h2b_ec_op(op, p.ctypes.data, q.ctypes.data, p.size // 8, out.ctypes.data))
+        return out
+
+    def imad_bench(self, kind: int, iters: int, device: int = 0):
+        ms, ops = ctypes.c_float(0), ctypes.c_double(0)
+        self.check(self.L.h2b_imad_bench(device, kind, iters, ctypes.byref(ms), ctypes.byref(ops)))
+        return ms.value, ops.value
+
+    def set_msm_window(self, c: int):
+        self.check(self.L.h2b_set_msm_window(c))
+
+
+_default: Lib | None = None
+
+
+def load(path: str | None = None, allow_emulator: bool = False) -> Lib:
+    """Load (once) and return the product library. Raises if it is missing -- there is no fallback."""
+    global _default
+    if path is not None or allow_emulator:
+        return Lib(path, allow_emulator)
+    if _default is None:
+        _default = Lib()
+    return _default

@@ -1,0 +1,489 @@
+// C ABI of libh2b200 (declared in include/h2b200.h): lifecycle, host-pointer drop-ins for
+// best_multiexp / best_fft with device-resident SRS caching and point-range sharding across the
+// GPUs of one box, device-pointer entry points, diagnostics.
+#include <atomic>
+#include <memory>
+#include <thread>
+
+#include "../../include/h2b200.h"
+#include "common.h"
+
+namespace h2b {
+
+static thread_local std::string t_error;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+const char* get_error() { return t_error.c_str(); }
+
+// A base array resident on every initialised device (full copy per device: any point range can be
+// handed to any device; 2^26 points are 4 GiB of a B200's 180 GB).
+struct BaseSet {
+    uint64_t handle = 0;
+    const void* host_ptr = nullptr;   // only for implicitly cached sets
+    size_t n = 0;
+    uint64_t samples[16][8];          // sampled points, validates pointer reuse
+    uint64_t last_use = 0;
+    std::vector<void*> dev;           // per device
+};
+
+struct Global {
+    std::mutex mu;
+    std::vector<std::unique_ptr<DeviceCtx>> devs;
+    std::vector<std::unique_ptr<BaseSet>> sets;
+    uint64_t next_handle = 1;
+    uint64_t use_counter = 0;
+    std::atomic<unsigned> rr{0};
+};
+static Global G;
+
+static const size_t IMPLICIT_CACHE_MAX_SETS = 4;
+static const size_t MULTI_DEVICE_MIN_POINTS = (size_t)1 << 18;
+
+static int require_init() {
+    if (G.devs.empty()) { set_error("h2b200 is not initialised (call h2b_init)"); return H2B_ERR_NOT_INITIALIZED; }
+    return H2B_OK;
+}
+static int get_ctx(int device, DeviceCtx** out) {
+    H2B_TRY(require_init());
+    if (device < 0 || (size_t)device >= G.devs.size()) { set_error("device index %d out of range (have %zu)", device, G.devs.size()); return H2B_ERR_BAD_ARGUMENT; }
+    *out = G.devs[device].get();
+    H2B_CUDA(cudaSetDevice((*out)->device));
+    return H2B_OK;
+}
+
+static int init_devices(const std::vector<int>& ordinals) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    if (!G.devs.empty()) return H2B_OK;
+    for (int ord : ordinals) {
+        std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+        c->device = ord;
+        H2B_CUDA(cudaSetDevice(ord));
+        cudaDeviceProp prop;
+        H2B_CUDA(cudaGetDeviceProperties(&prop, ord));
+#ifndef H2B_EMU
+        if (prop.major < 10) { set_error("device %d (%s, sm_%d%d) is not a Blackwell-class GPU; this library only ships sm_100a code", ord, prop.name, prop.major, prop.minor); G.devs.clear(); return H2B_ERR_NO_DEVICE; }
+#endif
+        c->sm_count = prop.multiProcessorCount;
+        H2B_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        G.devs.push_back(std::move(c));
+    }
+    return H2B_OK;
+}
+
+// pick a device for a single-device call: round robin, preferring one that is idle
+static DeviceCtx* pick_device(std::unique_lock<std::mutex>& lock_out) {
+    size_t nd = G.devs.size();
+    unsigned start = G.rr.fetch_add(1);
+    for (size_t k = 0; k < nd; ++k) {
+        DeviceCtx* c = G.devs[(start + k) % nd].get();
+        std::unique_lock<std::mutex> lk(c->mu, std::try_to_lock);
+        if (lk.owns_lock()) { lock_out = std::move(lk); return c; }
+    }
+    DeviceCtx* c = G.devs[start % nd].get();
+    lock_out = std::unique_lock<std::mutex>(c->mu);
+    return c;
+}
+
+static void sample_points(const uint64_t* bases, size_t n, uint64_t out[16][8]) {
+    for (int k = 0; k < 16; ++k) {
+        size_t idx = n <= 1 ? 0 : (size_t)(((unsigned __int128)k * (n - 1)) / 15);
+        memcpy(out[k], bases + 8 * idx, 64);
+    }
+}
+
+static int upload_set(BaseSet& bs, const uint64_t* bases, size_t n) {
+    bs.n = n;
+    bs.dev.assign(G.devs.size(), nullptr);
+    for (size_t d = 0; d < G.devs.size(); ++d) {
+        H2B_CUDA(cudaSetDevice(G.devs[d]->device));
+        cudaError_t e = cudaMalloc(&bs.dev[d], n * 64 + 64);
+        if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes for SRS bases failed: %s", n * 64, cudaGetErrorString(e)); return H2B_ERR_OOM; }
+        H2B_CUDA(cudaMemcpy(bs.dev[d], bases, n * 64, cudaMemcpyHostToDevice));
+    }
+    return H2B_OK;
+}
+static void free_set(BaseSet& bs) {
+    for (size_t d = 0; d < bs.dev.size(); ++d) {
+        if (bs.dev[d]) { cudaSetDevice(G.devs[d]->device); cudaFree(bs.dev[d]); }
+    }
+    bs.dev.clear();
+}
+
+// find or create the implicit cache entry for (bases, n). Caller holds G.mu.
+static int implicit_set(const uint64_t* bases, size_t n, BaseSet** out) {
+    for (auto& up : G.sets) {
+        BaseSet& bs = *up;
+        if (bs.host_ptr != bases || bs.n < n) continue;
+        // validate against pointer reuse: every sampled point that lies inside the requested prefix must still
+        // match what was uploaded (only [0, n) of the caller's array may be read)
+        bool same = true;
+        for (int k = 0; k < 16 && same; ++k) {
+            size_t idx = bs.n <= 1 ? 0 : (size_t)(((unsigned __int128)k * (bs.n - 1)) / 15);
+            if (idx < n && memcmp(bases + 8 * idx, bs.samples[k], 64) != 0) same = false;
+        }
+        if (same) { bs.last_use = ++G.use_counter; *out = &bs; return H2B_OK; }
+    }
+    // miss: drop stale entries with the same pointer, evict LRU implicit entries beyond the budget
+    for (size_t i = 0; i < G.sets.size();) {
+        if (G.sets[i]->host_ptr == bases) { free_set(*G.sets[i]); G.sets.erase(G.sets.begin() + i); }
+        else ++i;
+    }
+    for (;;) {
+        size_t implicit = 0, victim = (size_t)-1;
+        for (size_t i = 0; i < G.sets.size(); ++i) {
+            if (!G.sets[i]->host_ptr) continue;
+            ++implicit;
+            if (victim == (size_t)-1 || G.sets[i]->last_use < G.sets[victim]->last_use) victim = i;
+        }
+        if (implicit < IMPLICIT_CACHE_MAX_SETS) break;
+        free_set(*G.sets[victim]);
+        G.sets.erase(G.sets.begin() + victim);
+    }
+    std::unique_ptr<BaseSet> bs(new BaseSet());
+    bs->handle = G.next_handle++;
+    bs->host_ptr = bases;
+    sample_points(bases, n, bs->samples);
+    bs->last_use = ++G.use_counter;
+    int rc = upload_set(*bs, bases, n);
+    if (rc != H2B_OK) { free_set(*bs); return rc; }
+    *out = bs.get();
+    G.sets.push_back(std::move(bs));
+    return H2B_OK;
+}
+
+// one device: scalars (host) x bases (device) -> 224-byte result block in host memory
+static int msm_on_device(DeviceCtx& c, const uint64_t* scalars, const void* d_bases, size_t n, uint64_t* out_block /*28 x u64*/) {
+    H2B_CUDA(cudaSetDevice(c.device));
+    H2B_TRY(c.msm_scalars.reserve(n * 32 + 32));
+    H2B_TRY(c.msm_out.reserve(256));
+    if (n) H2B_CUDA(cudaMemcpyAsync(c.msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
+    H2B_TRY(msm_run(c, c.msm_scalars.p, d_bases, n, c.msm_out.p, true, c.stream));
+    H2B_CUDA(cudaMemcpyAsync(out_block, c.msm_out.p, 224, cudaMemcpyDeviceToHost, c.stream));
+    H2B_CUDA(cudaStreamSynchronize(c.stream));
+    return H2B_OK;
+}
+
+static int msm_host(const uint64_t* scalars, BaseSet& bs, size_t offset, size_t n, uint64_t out_jac[12]) {
+    const size_t nd = G.devs.size();
+    if (nd == 1 || n < MULTI_DEVICE_MIN_POINTS) {
+        std::unique_lock<std::mutex> lk;
+        DeviceCtx* c = pick_device(lk);
+        size_t d = 0;
+        for (size_t k = 0; k < nd; ++k) if (G.devs[k].get() == c) d = k;
+        uint64_t block[28];
+        H2B_TRY(msm_on_device(*c, scalars, (const char*)bs.dev[d] + offset * 64, n, block));
+        memcpy(out_jac, block, 96);
+        return H2B_OK;
+    }
+    // point-range sharding: device d owns [lo_d, hi_d); partial sums are folded on device 0
+    std::vector<uint64_t> blocks(28 * nd);
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; ++d) {
+        th.emplace_back([&, d] {
+            size_t lo = n * d / nd, hi = n * (d + 1) / nd;
+            DeviceCtx& c = *G.devs[d];
+            std::lock_guard<std::mutex> lk(c.mu);
+            rcs[d] = msm_on_device(c, scalars + 4 * lo, (const char*)bs.dev[d] + (offset + lo) * 64, hi - lo, &blocks[28 * d]);
+            if (rcs[d]) errs[d] = get_error();
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t d = 0; d < nd; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
+    DeviceCtx& c0 = *G.devs[0];
+    std::lock_guard<std::mutex> lk(c0.mu);
+    H2B_CUDA(cudaSetDevice(c0.device));
+    H2B_TRY(c0.msm_scalars.reserve(224 * nd));
+    H2B_TRY(c0.msm_out.reserve(256));
+    H2B_CUDA(cudaMemcpyAsync(c0.msm_scalars.p, blocks.data(), 224 * nd, cudaMemcpyHostToDevice, c0.stream));
+    H2B_TRY(msm_sum_partials_run(c0, c0.msm_scalars.p, (uint32_t)nd, c0.msm_out.p, c0.stream));
+    H2B_CUDA(cudaMemcpyAsync(out_jac, c0.msm_out.p, 96, cudaMemcpyDeviceToHost, c0.stream));
+    H2B_CUDA(cudaStreamSynchronize(c0.stream));
+    return H2B_OK;
+}
+
+}  // namespace h2b
+
+using namespace h2b;
+
+extern "C" {
+
+int h2b_init(int n_devices) {
+    if (!G.devs.empty()) return H2B_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no usable CUDA device (%s); h2b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return H2B_ERR_NO_DEVICE;
+    }
+    if (n_devices < 0 || n_devices > count) { set_error("h2b_init(%d): only %d device(s) visible", n_devices, count); return H2B_ERR_BAD_ARGUMENT; }
+    if (n_devices == 0) n_devices = count;
+    std::vector<int> ords;
+    for (int i = 0; i < n_devices; ++i) ords.push_back(i);
+    return init_devices(ords);
+}
+
+int h2b_init_device(int device) {
+    if (!G.devs.empty()) return H2B_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no usable CUDA device (%s); h2b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return H2B_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { set_error("h2b_init_device(%d): only %d device(s) visible", device, count); return H2B_ERR_BAD_ARGUMENT; }
+    return init_devices(std::vector<int>{device});
+}
+
+void h2b_shutdown(void) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    for (auto& bs : G.sets) free_set(*bs);
+    G.sets.clear();
+    for (auto& c : G.devs) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        ntt_release(*c);
+        msm_release(*c);
+        c->msm_scalars.release();
+        c->msm_out.release();
+        cudaStreamDestroy(c->stream);
+    }
+    G.devs.clear();
+}
+
+int h2b_device_count(void) { return (int)G.devs.size(); }
+const char* h2b_last_error(void) { return get_error(); }
+const char* h2b_version(void) {
+#ifdef H2B_EMU
+    return "h2b200 0.1 (kernel-logic emulator build: NOT a product library)";
+#else
+    return "h2b200 0.1 (CUDA sm_100a)";
+#endif
+}
+int h2b_is_emulator(void) {
+#ifdef H2B_EMU
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+int h2b_msm_bn254_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]) {
+    H2B_TRY(require_init());
+    if (!out_jac || (n && (!scalars || !bases))) { set_error("h2b_msm_bn254_g1: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) {
+        memset(out_jac, 0, 96);
+        for (int i = 0; i < 4; ++i) out_jac[4 + i] = (uint64_t)FpParams<FQ>::ONE(2 * i) | ((uint64_t)FpParams<FQ>::ONE(2 * i + 1) << 32);
+        return H2B_OK;
+    }
+    BaseSet* bs = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        H2B_TRY(implicit_set(bases, n, &bs));
+    }
+    return msm_host(scalars, *bs, 0, n, out_jac);
+}
+
+int h2b_register_bases(const uint64_t* bases, size_t n, uint64_t* handle) {
+    H2B_TRY(require_init());
+    if (!bases || !handle || n == 0) { set_error("h2b_register_bases: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(G.mu);
+    std::unique_ptr<BaseSet> bs(new BaseSet());
+    bs->handle = G.next_handle++;
+    bs->host_ptr = nullptr;
+    bs->last_use = ++G.use_counter;
+    int rc = upload_set(*bs, bases, n);
+    if (rc != H2B_OK) { free_set(*bs); return rc; }
+    *handle = bs->handle;
+    G.sets.push_back(std::move(bs));
+    return H2B_OK;
+}
+
+int h2b_unregister_bases(uint64_t handle) {
+    H2B_TRY(require_init());
+    std::lock_guard<std::mutex> lk(G.mu);
+    for (size_t i = 0; i < G.sets.size(); ++i) {
+        if (G.sets[i]->handle == handle) {
+            free_set(*G.sets[i]);
+            G.sets.erase(G.sets.begin() + i);
+            return H2B_OK;
+        }
+    }
+    set_error("unknown base-set handle %llu", (unsigned long long)handle);
+    return H2B_ERR_BAD_HANDLE;
+}
+
+int h2b_msm_bn254_g1_registered(const uint64_t* scalars, uint64_t handle, size_t offset, size_t n, uint64_t out_jac[12]) {
+    H2B_TRY(require_init());
+    if (!out_jac || (n && !scalars)) { set_error("h2b_msm_bn254_g1_registered: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    BaseSet* bs = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        for (auto& up : G.sets) if (up->handle == handle) bs = up.get();
+    }
+    if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
+    if (offset > bs->n || n > bs->n - offset) { set_error("range [%zu, %zu) exceeds the registered set of %zu points", offset, offset + n, bs->n); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) {
+        memset(out_jac, 0, 96);
+        for (int i = 0; i < 4; ++i) out_jac[4 + i] = (uint64_t)FpParams<FQ>::ONE(2 * i) | ((uint64_t)FpParams<FQ>::ONE(2 * i + 1) << 32);
+        return H2B_OK;
+    }
+    return msm_host(scalars, *bs, offset, n, out_jac);
+}
+
+int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
+    H2B_TRY(require_init());
+    if (!a || !omega) { set_error("h2b_ntt_bn254_fr: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (log_n > 28) { set_error("h2b_ntt_bn254_fr: log_n = %u exceeds the two-adicity of Fr (28)", log_n); return H2B_ERR_BAD_ARGUMENT; }
+    if (log_n == 0) return H2B_OK;
+    std::unique_lock<std::mutex> lk;
+    DeviceCtx* c = pick_device(lk);
+    H2B_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)32 << log_n;
+    H2B_TRY(c->ntt_io.reserve(bytes));
+    H2B_CUDA(cudaMemcpyAsync(c->ntt_io.p, a, bytes, cudaMemcpyHostToDevice, c->stream));
+    H2B_TRY(ntt_run(*c, c->ntt_io.p, omega, log_n, c->stream));
+    H2B_CUDA(cudaMemcpyAsync(a, c->ntt_io.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    H2B_CUDA(cudaStreamSynchronize(c->stream));
+    return H2B_OK;
+}
+
+int h2b_ntt_bn254_fr_dev(int device, void* d_a, const uint64_t omega[4], uint32_t log_n, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!omega) { set_error("h2b_ntt_bn254_fr_dev: null omega"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return ntt_run(*c, d_a, omega, log_n, (cudaStream_t)stream);
+}
+
+int h2b_msm_bn254_g1_dev(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_jac, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_out_jac) { set_error("h2b_msm_bn254_g1_dev: null output"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return msm_run(*c, d_scalars, d_bases, n, d_out_jac, false, (cudaStream_t)stream);
+}
+
+int h2b_msm_bn254_g1_dev_partial(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_block, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_out_block) { set_error("h2b_msm_bn254_g1_dev_partial: null output"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return msm_run(*c, d_scalars, d_bases, n, d_out_block, true, (cudaStream_t)stream);
+}
+
+int h2b_msm_fold_partials(int device, const uint64_t* host_blocks, size_t count, uint64_t out_jac[12]) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!host_blocks || !out_jac || count == 0 || count > 4096) { set_error("h2b_msm_fold_partials: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    H2B_TRY(c->msm_scalars.reserve(224 * count));
+    H2B_TRY(c->msm_out.reserve(256));
+    H2B_CUDA(cudaMemcpyAsync(c->msm_scalars.p, host_blocks, 224 * count, cudaMemcpyHostToDevice, c->stream));
+    H2B_TRY(msm_sum_partials_run(*c, c->msm_scalars.p, (uint32_t)count, c->msm_out.p, c->stream));
+    H2B_CUDA(cudaMemcpyAsync(out_jac, c->msm_out.p, 96, cudaMemcpyDeviceToHost, c->stream));
+    H2B_CUDA(cudaStreamSynchronize(c->stream));
+    return H2B_OK;
+}
+
+int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, int count, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!factors || (n && !d_a)) { set_error("h2b_fr_scale_dev: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    return ntt_scale_run(*c, d_a, n, factors, count, (cudaStream_t)stream);
+}
+
+int h2b_dev_alloc(int device, size_t bytes, void** out) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!out) { set_error("h2b_dev_alloc: null out"); return H2B_ERR_BAD_ARGUMENT; }
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return H2B_ERR_OOM; }
+    return H2B_OK;
+}
+int h2b_dev_free(int device, void* p) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    H2B_CUDA(cudaFree(p));
+    return H2B_OK;
+}
+int h2b_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    H2B_CUDA(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return H2B_OK;
+}
+int h2b_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    H2B_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return H2B_OK;
+}
+int h2b_dev_sync(int device) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    H2B_CUDA(cudaDeviceSynchronize());
+    return H2B_OK;
+}
+
+int h2b_gen_points_dev(int device, uint64_t seed, size_t n, void* d_out_affine, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    return gen_points_run(*c, seed, n, d_out_affine, (cudaStream_t)stream);
+}
+int h2b_gen_scalars_dev(int device, uint64_t seed, size_t n, int kind, void* d_out, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    return gen_scalars_run(*c, seed, n, kind, d_out, (cudaStream_t)stream);
+}
+
+static int elementwise_host(int which, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out, size_t elem_bytes) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(0, &c));
+    if (!a || !b || !out) { set_error("elementwise op: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) return H2B_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DevBuf da, db, dout;
+    int rc = da.reserve(n * elem_bytes);
+    if (!rc) rc = db.reserve(n * elem_bytes);
+    if (!rc) rc = dout.reserve(n * elem_bytes);
+    if (!rc) {
+        cudaMemcpyAsync(da.p, a, n * elem_bytes, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(db.p, b, n * elem_bytes, cudaMemcpyHostToDevice, c->stream);
+        rc = which == 0 ? field_selftest_run(*c, field, op, da.p, db.p, n, dout.p, c->stream) : ec_selftest_run(*c, op, da.p, db.p, n, dout.p, c->stream);
+    }
+    if (!rc) {
+        cudaMemcpyAsync(out, dout.p, n * elem_bytes, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error("elementwise op: %s", cudaGetErrorString(e)); rc = H2B_ERR_CUDA; }
+    }
+    da.release(); db.release(); dout.release();
+    return rc;
+}
+int h2b_field_op(int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+    if (field < 0 || field > 1 || op < 0 || op > 6) { set_error("h2b_field_op: bad field/op"); return H2B_ERR_BAD_ARGUMENT; }
+    return elementwise_host(0, field, op, a, b, n, out, 32);
+}
+int h2b_ec_op(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) {
+    if (op < 0 || op > 3) { set_error("h2b_ec_op: bad op"); return H2B_ERR_BAD_ARGUMENT; }
+    return elementwise_host(1, 0, op, p, q, n, out, 64);
+}
+
+int h2b_imad_bench(int device, int kind, int iters, float* ms_out, double* ops_out) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!ms_out || !ops_out) { set_error("h2b_imad_bench: null output"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return imad_bench_run(*c, kind, iters, c->sm_count * 8, 256, ms_out, ops_out, c->stream);
+}
+
+int h2b_set_msm_window(int c) { return msm_set_window(c); }
+
+}  // extern "C"

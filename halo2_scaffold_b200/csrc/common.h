@@ -1,0 +1,99 @@
+// Shared host-side plumbing of libh2b200: per-device context, error reporting, scratch buffers.
+#pragma once
+#include <cstdarg>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/h2b200.h"   // H2B_OK / H2B_ERR_* codes
+#include "field.cuh"
+
+namespace h2b {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define H2B_CUDA(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            h2b::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? H2B_ERR_OOM : H2B_ERR_CUDA;     \
+        }                                                                                        \
+    } while (0)
+
+#define H2B_TRY(expr)             \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != 0) return _r;   \
+    } while (0)
+
+// A grow-only device buffer (scratch space reused across calls on one device).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return H2B_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            return H2B_ERR_OOM;
+        }
+        cap = want;
+        return H2B_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct NttTwiddles;   // ntt.cu
+struct MsmScratch;    // msm.cu
+struct BaseSet;       // api.cu
+
+struct DeviceCtx {
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;     // stream used by the host-pointer entry points
+    std::mutex mu;                     // serialises calls that share this context's scratch
+    DevBuf ntt_work;                   // ping-pong buffer of the multi-pass NTT
+    bool ntt_attr_set = false;
+    DevBuf ntt_io;                     // staging for the host-pointer NTT entry point
+    DevBuf msm_scalars;                // staging for host-pointer MSM scalars
+    DevBuf msm_out;                    // 96-byte result
+    std::vector<NttTwiddles*> twiddles;  // small LRU cache keyed by (omega, log_n)
+    MsmScratch* msm = nullptr;
+    void* pinned = nullptr;            // small pinned bounce buffer
+    size_t pinned_cap = 0;
+};
+
+// ---- ntt.cu ----
+int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
+int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);
+void ntt_release(DeviceCtx& ctx);
+// ---- msm.cu ----
+int msm_run(DeviceCtx& ctx, const void* d_scalars, const void* d_bases, size_t n, void* d_out, bool with_xyzz, cudaStream_t stream);
+int msm_sum_partials_run(DeviceCtx& ctx, const void* d_blocks, uint32_t count, void* d_out_jac, cudaStream_t stream);
+void msm_release(DeviceCtx& ctx);
+int msm_set_window(int c);   // 0 = automatic
+// ---- testgen.cu ----
+int gen_points_run(DeviceCtx& ctx, uint64_t seed, size_t n, void* d_out_affine, cudaStream_t stream);
+int gen_scalars_run(DeviceCtx& ctx, uint64_t seed, size_t n, int kind, void* d_out, cudaStream_t stream);
+int field_selftest_run(DeviceCtx& ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t stream);
+int ec_selftest_run(DeviceCtx& ctx, int op, const void* d_p, const void* d_q, size_t n, void* d_out, cudaStream_t stream);
+int imad_bench_run(DeviceCtx& ctx, int kind, int iters, int blocks, int threads, float* ms_out, double* ops_out, cudaStream_t stream);
+
+}  // namespace h2b

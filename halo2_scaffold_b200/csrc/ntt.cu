@@ -1,0 +1,353 @@
+// Radix-2 NTT over BN254 Fr for sm_100a -- the device side of `best_fft`
+// ([UP] halo2_proofs/src/arithmetic.rs::best_fft @ v2023_02_02; SURVEY.md section 8 rows a3/a4;
+// reached from src/scaffold.rs:135,149,287,301 (keygen_pk) and :191-214,322-346 (create_proof)).
+//
+// Contract (identical to the reference): a[0..2^log_n) in Montgomery form, natural order in,
+// natural order out, out[i] = sum_j a[j] * omega^(i*j), no scaling.
+//
+// Design (tools/ntt_model.py proves the index math against the O(n^2) DFT):
+//   n = N_1 * ... * N_P, N_p = 2^(b_p) <= 2^9.  Pass p works on segments of length
+//   L_p = n / (N_1..N_{p-1}); one CTA stages a tile of N_p x T elements in shared memory (T
+//   consecutive elements per stride so that global accesses are T*32-byte runs), runs the b_p DIF
+//   butterfly stages out of shared memory with an N_p/2-entry twiddle table that also lives in
+//   shared memory, leaves the digit bit-reversed in place and applies the inter-pass twiddle
+//   w^(S_p * jr * bitrev(q)) from a two-level table (w^e = hi[e >> h] * lo[e & mask], both tables
+//   L2-resident).  The bit-reversal permutation of the reference is never materialised: the last
+//   pass scatters straight to out[bitrev(pos)], tiling over the top index bits so that those
+//   writes are T*32-byte runs as well.  HBM traffic: P reads + P writes of the vector.
+#include "common.h"
+
+namespace h2b {
+
+static const int NTT_MAX_TILE_LOG = 11;      // 2048 elements = 64 KiB of shared memory per CTA
+static const int NTT_MAX_PASSES = 4;
+
+struct NttPassParams {
+    const uint4* in;
+    uint4* out;
+    const uint4* tw_small;   // Omega^t, t < N/2, Omega = w^(n/N)
+    const uint4* tw_lo;      // w^j,          j < 2^h
+    const uint4* tw_hi;      // w^(j * 2^h),  j < 2^(log_n - h)
+    uint32_t log_n;
+    uint32_t b;              // digit bits of this pass
+    uint32_t logT;           // tile width
+    uint32_t logL;           // segment length
+    uint32_t h;              // split of the two-level table
+    uint32_t last;
+};
+
+__device__ __forceinline__ Fr sm_get(const uint4* lo, const uint4* hi, uint32_t e) {
+    uint4 a = lo[e], b = hi[e];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, uint32_t e, const Fr& v) {
+    lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
+    H2B_DYN_SMEM(uint4, sm);
+    const uint32_t b = p.b, logT = p.logT;
+    const uint32_t N = 1u << b, T = 1u << logT, E = N << logT;
+    uint4* lo = sm;
+    uint4* hi = sm + E;
+    uint4* tlo = sm + 2 * E;              // small twiddles, split in the same two planes
+    uint4* thi = tlo + (N >> 1);
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    const uint32_t blk = blockIdx.x;
+
+    uint32_t base = 0, M = 0, tau = 0, nseg = 0;
+    if (!p.last) {
+        // tile (q, t), q < N, t < T  <->  global base + q*M + t ; shared e = q*T + t
+        const uint32_t logM = p.logL - b;
+        M = 1u << logM;
+        const uint32_t tiles_per_seg = M >> logT;
+        const uint32_t seg = blk / tiles_per_seg;
+        tau = blk - seg * tiles_per_seg;
+        base = (seg << p.logL) + (tau << logT);
+        for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
+            uint32_t half = idx & 1, t = (idx >> 1) & (T - 1), q = idx >> (1 + logT);
+            uint32_t g = base + q * M + t;
+            uint4 v = p.in[2 * (size_t)g + half];
+            uint32_t e = (q << logT) + t;
+            if (half) hi[e] = v; else lo[e] = v;
+        }
+    } else {
+        // last pass: T segments that differ in the TOP logT bits of the position;
+        // element (q, t) <-> global ((t*nseg + blk) << b) + q ; shared e = t*N + q
+        nseg = (1u << (p.log_n - b)) >> logT;
+        for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
+            uint32_t half = idx & 1, q = (idx >> 1) & (N - 1), t = idx >> (1 + b);
+            uint32_t g = ((t * nseg + blk) << b) + q;
+            uint4 v = p.in[2 * (size_t)g + half];
+            uint32_t e = (t << b) + q;
+            if (half) hi[e] = v; else lo[e] = v;
+        }
+    }
+    for (uint32_t idx = tid; idx < N; idx += nthr) {
+        uint32_t half = idx & 1, j = idx >> 1;
+        uint4 v = p.tw_small[2 * j + half];
+        if (half) thi[j] = v; else tlo[j] = v;
+    }
+    __syncthreads();
+
+    const uint32_t SQ = p.last ? 1u : T;
+    uint32_t logh = b - 1;
+    for (uint32_t h = N >> 1; h >= 1; h >>= 1, --logh) {
+        for (uint32_t i = tid; i < (E >> 1); i += nthr) {
+            uint32_t t, bq;
+            if (!p.last) { t = i & (T - 1); bq = i >> logT; }
+            else { bq = i & ((N >> 1) - 1); t = i >> (b - 1); }
+            uint32_t r = bq & (h - 1);
+            uint32_t q = ((bq - r) << 1) | r;
+            uint32_t e0 = p.last ? ((t << b) + q) : ((q << logT) + t);
+            uint32_t e1 = e0 + h * SQ;
+            Fr x = sm_get(lo, hi, e0), y = sm_get(lo, hi, e1);
+            Fr s = fp_add(x, y), d = fp_sub(x, y);
+            uint32_t twi = r << (b - 1 - logh);
+            if (twi != 0) d = fp_mul(d, sm_get(tlo, thi, twi));
+            sm_put(lo, hi, e0, s);
+            sm_put(lo, hi, e1, d);
+        }
+        __syncthreads();
+        if (h == 1) break;
+    }
+
+    if (!p.last) {
+        const uint32_t logS = p.log_n - p.logL;          // S_p = n / L_p
+        const uint32_t hmask = (1u << p.h) - 1;
+        for (uint32_t i = tid; i < E; i += nthr) {
+            uint32_t t = i & (T - 1), q = i >> logT;
+            Fr v = sm_get(lo, hi, i);
+            uint32_t ip = __brev(q) >> (32 - b);
+            uint32_t jr = (tau << logT) + t;
+            uint32_t ex = (jr * ip) << logS;
+            if (ex != 0) {
+                Fr w = fp_load<FR>(p.tw_lo + 2 * (size_t)(ex & hmask));
+                uint32_t eh = ex >> p.h;
+                if (eh != 0) w = fp_mul(w, fp_load<FR>(p.tw_hi + 2 * (size_t)eh));
+                v = fp_mul(v, w);
+            }
+            uint32_t g = base + q * M + t;
+            fp_store<FR>(p.out + 2 * (size_t)g, v);
+        }
+    } else {
+        for (uint32_t i = tid; i < E; i += nthr) {
+            uint32_t tr = i & (T - 1), q = i >> logT;
+            uint32_t t = logT ? (__brev(tr) >> (32 - logT)) : 0u;
+            Fr v = sm_get(lo, hi, (t << b) + q);
+            uint32_t pos = ((t * nseg + blk) << b) + q;
+            uint32_t oidx = __brev(pos) >> (32 - p.log_n);
+            fp_store<FR>(p.out + 2 * (size_t)oidx, v);
+        }
+    }
+}
+
+// ---- twiddle tables ---------------------------------------------------------------------------
+struct TwTableDesc {
+    uint32_t start;    // first flat thread index of this table
+    uint32_t count;    // entries
+    uint32_t shift;    // table base = w^(2^shift)
+    uint32_t offset;   // element offset of the table in the output buffer
+};
+struct TwGenParams {
+    uint32_t l[8];     // omega, Montgomery limbs
+    TwTableDesc tab[NTT_MAX_PASSES + 2];
+    uint32_t ntab;
+    uint32_t total;
+    uint4* out;
+};
+
+__global__ void __launch_bounds__(128) ntt_twiddle_kernel(TwGenParams g) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.total) return;
+    uint32_t k = 0;
+    for (uint32_t i = 1; i < g.ntab; ++i) if (idx >= g.tab[i].start) k = i;
+    uint32_t j = idx - g.tab[k].start;
+    Fr base;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) base.l[i] = g.l[i];
+    for (uint32_t s = 0; s < g.tab[k].shift; ++s) base = fp_sqr(base);
+    Fr r = fp_one<FR>();
+    for (uint32_t e = j; e != 0; e >>= 1) {
+        if (e & 1) r = fp_mul(r, base);
+        base = fp_sqr(base);
+    }
+    fp_store<FR>(g.out + 2 * (size_t)(g.tab[k].offset + j), r);
+}
+
+struct NttPass { uint32_t b, logT, logL; };
+struct NttTwiddles {
+    uint64_t omega[4];
+    uint32_t log_n;
+    uint64_t last_use;
+    DevBuf buf;
+    uint32_t npass;
+    NttPass pass[NTT_MAX_PASSES];
+    uint32_t small_off[NTT_MAX_PASSES];
+    uint32_t lo_off, hi_off, h;
+};
+
+static uint64_t g_use_counter = 0;
+
+static int ntt_bmax() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("H2B_NTT_BMAX");
+        v = e ? atoi(e) : 9;
+        if (v < 1 || v > NTT_MAX_TILE_LOG) v = 9;
+    }
+    return v;
+}
+
+static void ntt_plan(uint32_t log_n, NttTwiddles& tw) {
+    uint32_t P;
+    if (log_n <= (uint32_t)NTT_MAX_TILE_LOG) P = 1;
+    else P = (log_n + ntt_bmax() - 1) / ntt_bmax();
+    if (P > (uint32_t)NTT_MAX_PASSES) P = NTT_MAX_PASSES;   // log_n <= 28 < 4 * 9
+    tw.npass = P;
+    uint32_t logL = log_n;
+    for (uint32_t p = 0; p < P; ++p) {
+        uint32_t b = log_n / P + (p < log_n % P ? 1 : 0);
+        uint32_t logT = NTT_MAX_TILE_LOG - b;
+        uint32_t room = (p + 1 < P) ? (logL - b) : (log_n - b);   // tile cannot exceed the stride / segment count
+        if (logT > room) logT = room;
+        tw.pass[p].b = b;
+        tw.pass[p].logT = logT;
+        tw.pass[p].logL = logL;
+        logL -= b;
+    }
+}
+
+static int ntt_get_twiddles(DeviceCtx& ctx, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream, NttTwiddles** out) {
+    for (NttTwiddles* t : ctx.twiddles) {
+        if (t->log_n == log_n && memcmp(t->omega, omega, 32) == 0) {
+            t->last_use = ++g_use_counter;
+            *out = t;
+            return H2B_OK;
+        }
+    }
+    NttTwiddles* t;
+    if (ctx.twiddles.size() >= 16) {   // evict the least recently used entry
+        size_t victim = 0;
+        for (size_t i = 1; i < ctx.twiddles.size(); ++i)
+            if (ctx.twiddles[i]->last_use < ctx.twiddles[victim]->last_use) victim = i;
+        t = ctx.twiddles[victim];
+        ctx.twiddles.erase(ctx.twiddles.begin() + victim);
+        H2B_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        t = new NttTwiddles();
+    }
+    memcpy(t->omega, omega, 32);
+    t->log_n = log_n;
+    t->last_use = ++g_use_counter;
+    ntt_plan(log_n, *t);
+
+    TwGenParams g;
+    memset(&g, 0, sizeof(g));
+    memcpy(g.l, omega, 32);
+    uint32_t off = 0, start = 0, nt = 0;
+    for (uint32_t p = 0; p < t->npass; ++p) {
+        uint32_t b = t->pass[p].b, cnt = b ? (1u << (b - 1)) : 1u;
+        t->small_off[p] = off;
+        g.tab[nt++] = TwTableDesc{start, cnt, log_n - b, off};
+        off += cnt; start += cnt;
+    }
+    t->h = (log_n + 1) / 2;
+    t->lo_off = off;
+    g.tab[nt++] = TwTableDesc{start, 1u << t->h, 0, off};
+    off += 1u << t->h; start += 1u << t->h;
+    t->hi_off = off;
+    g.tab[nt++] = TwTableDesc{start, 1u << (log_n - t->h), t->h, off};
+    off += 1u << (log_n - t->h); start += 1u << (log_n - t->h);
+    g.ntab = nt;
+    g.total = start;
+    int rc = t->buf.reserve((size_t)off * 32);
+    if (rc != H2B_OK) { delete t; return rc; }
+    g.out = (uint4*)t->buf.p;
+    H2B_LAUNCH(ntt_twiddle_kernel, (g.total + 127) / 128, 128, 0, stream, g);
+    H2B_CUDA(cudaGetLastError());
+    ctx.twiddles.push_back(t);
+    *out = t;
+    return H2B_OK;
+}
+
+int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream) {
+    if (log_n > 28) { set_error("ntt: log_n = %u exceeds the two-adicity of Fr (28)", log_n); return H2B_ERR_BAD_ARGUMENT; }
+    if (log_n == 0) return H2B_OK;
+    if (!d_a) { set_error("ntt: null data pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    NttTwiddles* tw = nullptr;
+    H2B_TRY(ntt_get_twiddles(ctx, omega, log_n, stream, &tw));
+    const size_t n = (size_t)1 << log_n;
+    if (tw->npass > 1) H2B_TRY(ctx.ntt_work.reserve(n * 32));
+    auto kfn = ntt_pass_kernel;
+    if (!ctx.ntt_attr_set) {
+        H2B_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 << NTT_MAX_TILE_LOG) + 32 * (1 << (NTT_MAX_TILE_LOG - 1))));
+        ctx.ntt_attr_set = true;
+    }
+    const uint4* tbl = (const uint4*)tw->buf.p;
+    for (uint32_t p = 0; p < tw->npass; ++p) {
+        NttPassParams a;
+        const bool first = (p == 0), last = (p + 1 == tw->npass);
+        // pass 1: a -> work, middle passes in place in work, last pass: work -> a (scatter)
+        a.in = (const uint4*)(first ? d_a : ctx.ntt_work.p);
+        a.out = (uint4*)(last ? d_a : ctx.ntt_work.p);
+        a.tw_small = tbl + 2 * (size_t)tw->small_off[p];
+        a.tw_lo = tbl + 2 * (size_t)tw->lo_off;
+        a.tw_hi = tbl + 2 * (size_t)tw->hi_off;
+        a.log_n = log_n;
+        a.b = tw->pass[p].b;
+        a.logT = tw->pass[p].logT;
+        a.logL = tw->pass[p].logL;
+        a.h = tw->h;
+        a.last = last ? 1u : 0u;
+        const uint32_t logE = a.b + a.logT;
+        const uint32_t grid = 1u << (log_n - logE);
+        uint32_t threads = (1u << logE) / 2;
+        if (threads > 256) threads = 256;
+        if (threads < 32) threads = 32;
+        const size_t smem = ((size_t)32 << logE) + 32 * ((size_t)1 << (a.b - 1));
+        H2B_LAUNCH(kfn, grid, threads, smem, stream, a);
+        H2B_CUDA(cudaGetLastError());
+    }
+    return H2B_OK;
+}
+
+// a[i] *= factors[i % count]   (count in {1, 3}: the 1/n of lagrange_to_coeff / extended_to_coeff and the
+// zeta-coset pattern of coeff_to_extended, [UP] halo2_proofs/src/poly/domain.rs)
+struct ScaleParams { uint32_t f[3][8]; uint32_t count; };
+__global__ void __launch_bounds__(256) ntt_scale_kernel(uint4* a, size_t n, ScaleParams s) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = s.count == 1 ? 0u : (uint32_t)(i % 3);
+    Fr f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f.l[j] = k == 0 ? s.f[0][j] : (k == 1 ? s.f[1][j] : s.f[2][j]);
+    Fr v = fp_load<FR>(a + 2 * i);
+    fp_store<FR>(a + 2 * i, fp_mul(v, f));
+}
+
+int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors, int count, cudaStream_t stream) {
+    (void)ctx;
+    if (count != 1 && count != 3) { set_error("scale: count must be 1 or 3"); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) return H2B_OK;
+    ScaleParams s;
+    memset(&s, 0, sizeof(s));
+    s.count = (uint32_t)count;
+    memcpy(s.f, factors, (size_t)count * 32);
+    H2B_LAUNCH(ntt_scale_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, (uint4*)d_a, n, s);
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
+void ntt_release(DeviceCtx& ctx) {
+    for (NttTwiddles* t : ctx.twiddles) { t->buf.release(); delete t; }
+    ctx.twiddles.clear();
+    ctx.ntt_work.release();
+    ctx.ntt_io.release();
+}
+
+}  // namespace h2b

@@ -1,0 +1,125 @@
+/*
+ * h2b200 -- B200-native (sm_100a) replacement for the data-parallel hot path of the Halo2 KZG
+ * prover as DCMMC/halo2-scaffold exercises it: BN254 G1 multi-scalar multiplication and the
+ * radix-2 NTT over BN254 Fr.  Plain C ABI: pointers and sizes only, no C++ types, no exceptions.
+ *
+ * What each entry point replaces (the arithmetic lives in un-vendored git dependencies of the
+ * reference, marked [UP]; the reference's own call sites are given as file:line under
+ * /root/reference):
+ *
+ *   h2b_msm_bn254_g1   <- [UP] halo2_proofs::arithmetic::best_multiexp::<G1Affine>
+ *                         (halo2_proofs/src/arithmetic.rs, PSE tag v2023_02_02 -- Cargo.toml:13 --
+ *                          and the Axiom fork `axiom/dev` -- Cargo.toml:16), reached through
+ *                         ParamsKZG::commit / commit_lagrange from keygen_vk / keygen_pk
+ *                         (src/scaffold.rs:132,135,146,149,284,287,298,301), create_proof
+ *                         (src/scaffold.rs:191-199,207-214,322-330,338-346;
+ *                          examples/standard_plonk.rs:41-49) and verify_proof
+ *                         (src/scaffold.rs:223-230,354-361; examples/standard_plonk.rs:57-64).
+ *   h2b_ntt_bn254_fr   <- [UP] halo2_proofs::arithmetic::best_fft::<Fr>, reached through
+ *                         EvaluationDomain::{lagrange_to_coeff, coeff_to_extended,
+ *                         extended_to_coeff} from keygen_pk (src/scaffold.rs:135,149,287,301) and
+ *                         create_proof (same lines as above).
+ *
+ * Data layouts are exactly halo2curves 0.3.x's in-memory layouts, so Rust slices can be passed
+ * by pointer cast:
+ *   Fr / Fq   : 4 x u64 little-endian limbs, Montgomery form (R = 2^256), fully reduced.
+ *   G1Affine  : x | y (8 x u64); the identity is (0, 0).
+ *   G1        : x | y | z Jacobian (12 x u64); z == 0 is the identity.
+ *
+ * Errors: every function returns 0 on success and a negative H2B_ERR_* code otherwise;
+ * h2b_last_error() returns a thread-local description.  The upstream Rust functions are
+ * infallible (they assert/panic), so the Rust shim turns a non-zero return into a panic.
+ * Threading: all entry points may be called concurrently from several host threads; host-pointer
+ * calls are synchronous (they return after the result is in caller memory).
+ * There is no CPU fallback: without a usable CUDA device h2b_init fails.
+ */
+#ifndef H2B200_H
+#define H2B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2B_OK 0
+#define H2B_ERR_NOT_INITIALIZED (-1)
+#define H2B_ERR_BAD_ARGUMENT (-2)
+#define H2B_ERR_CUDA (-3)
+#define H2B_ERR_OOM (-4)
+#define H2B_ERR_NO_DEVICE (-5)
+#define H2B_ERR_BAD_HANDLE (-6)
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+/* Use CUDA devices 0..n_devices-1 (0 = every visible device).  Idempotent. */
+int h2b_init(int n_devices);
+/* Use exactly one device, by CUDA ordinal (one-process-per-GPU launches: pass LOCAL_RANK). */
+int h2b_init_device(int device);
+void h2b_shutdown(void);
+int h2b_device_count(void);
+const char* h2b_last_error(void);
+const char* h2b_version(void);
+/* 1 if this binary is the CPU kernel-logic emulator build used by unit tests, 0 for the CUDA build. */
+int h2b_is_emulator(void);
+
+/* ---- drop-in entry points (host pointers, synchronous) ------------------------------------------- */
+/* best_multiexp(coeffs, bases): out_jac = sum_i scalars[i] * bases[i].  n may be any value >= 0
+ * (n == 0 gives the identity).  The bases array is uploaded once and cached on the device(s),
+ * keyed by (pointer, sampled contents), because the only base arrays of the prover are the SRS
+ * vectors `g` and `g_lagrange`.  With more than one device the point range is
+ * split across devices and the partial sums are added on device 0. */
+int h2b_msm_bn254_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]);
+
+/* best_fft(a, omega, log_n) for G = Fr: in place, natural order in and out, no scaling;
+ * a has 2^log_n elements, log_n <= 28. */
+int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n);
+
+/* Explicit device residency for an SRS vector (copied; the host array may be freed afterwards). */
+int h2b_register_bases(const uint64_t* bases, size_t n, uint64_t* handle);
+int h2b_unregister_bases(uint64_t handle);
+/* MSM over bases[offset .. offset+n) of a registered set. */
+int h2b_msm_bn254_g1_registered(const uint64_t* scalars, uint64_t handle, size_t offset, size_t n, uint64_t out_jac[12]);
+
+/* ---- device-resident entry points (device pointers on `device`, caller's CUDA stream) ------------- */
+/* Asynchronous with respect to the host: work is enqueued on `stream` (a cudaStream_t; NULL = the
+ * legacy default stream).  `device` is an index into the devices given to h2b_init. */
+int h2b_ntt_bn254_fr_dev(int device, void* d_a, const uint64_t omega[4], uint32_t log_n, void* stream);
+int h2b_msm_bn254_g1_dev(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_jac /* 96 B */, void* stream);
+/* Point-range sharding across processes (one process per GPU): each rank computes a partial
+ * result block (224 B: Jacobian x|y|z followed by the XYZZ form) for its slice, the blocks are gathered by the
+ * caller (e.g. torch.distributed.all_gather) and folded on one device. */
+int h2b_msm_bn254_g1_dev_partial(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_block /* 224 B */, void* stream);
+int h2b_msm_fold_partials(int device, const uint64_t* host_blocks /* count x 28 u64 */, size_t count, uint64_t out_jac[12]);
+/* a[i] *= factors[i % count], count in {1, 3}: the 1/n scaling of lagrange_to_coeff / extended_to_coeff and
+ * the (1, zeta, zeta^2) coset pattern of coeff_to_extended ([UP] halo2_proofs/src/poly/domain.rs). */
+int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, int count, void* stream);
+
+/* ---- raw device memory helpers (so that non-CUDA hosts -- ctypes, Rust -- can hold device buffers) --- */
+int h2b_dev_alloc(int device, size_t bytes, void** out);
+int h2b_dev_free(int device, void* p);
+int h2b_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes);
+int h2b_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes);
+int h2b_dev_sync(int device);
+
+/* ---- synthetic workload + diagnostics ---------------------------------------------------------------- */
+/* P_i = [z_i] G with z_i the i-th SplitMix64 value of stream `seed` (valid, distinct G1 points). */
+int h2b_gen_points_dev(int device, uint64_t seed, size_t n, void* d_out_affine, void* stream);
+/* kind 0: uniform in [0, r);  kind 1: witness-like (50% 0, 20% 1, 20% < 2^19, 10% r - small). */
+int h2b_gen_scalars_dev(int device, uint64_t seed, size_t n, int kind, void* d_out, void* stream);
+/* element-wise field op on host arrays.  field: 0 Fr, 1 Fq.  op: 0 add, 1 sub, 2 mul, 3 sqr(a), 4 inv(a),
+ * 5 from_mont(a), 6 to_mont(a) */
+int h2b_field_op(int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
+/* element-wise group op on host arrays of affine points; op: 0 p+q, 1 p-q, 2 4(p+q) via the general
+ * XYZZ adder and doubling, 3 p+q through the Jacobian conversion.  out: affine. */
+int h2b_ec_op(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out);
+/* integer-pipe micro-benchmark; kind 0 IMAD, 1 IMAD.WIDE, 2 dependent Fq multiplications, 3 dependent
+ * XYZZ mixed additions.  Returns elapsed milliseconds and the number of operations executed. */
+int h2b_imad_bench(int device, int kind, int iters, float* ms_out, double* ops_out);
+/* force the MSM window size (0 = automatic) -- tuning / tests only */
+int h2b_set_msm_window(int c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2B200_H */

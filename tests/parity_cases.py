@@ -1,0 +1,101 @@
+"""Parity checks shared by the emulator tests (CPU, small sizes) and the GPU tests (C ABI on a B200)."""
+import numpy as np
+
+import bn254 as o
+
+
+def omega_words(oc, k, inverse=False):
+    w = o.omega_for(k)
+    if inverse:
+        w = pow(w, -1, o.R_MOD)
+    return oc.ints_to_words([o.to_mont(w, o.R_MOD)])[0]
+
+
+def affine_of(oc, jac):
+    return oc.g1_to_affine(np.ascontiguousarray(jac, dtype=np.uint64))
+
+
+def check_field(L, oc, n=2048):
+    a, b = oc.random_fr(1, n), oc.random_fr(2, n)
+    a[0] = 0
+    b[1] = 0
+    a[2] = b[2]
+    for f in ("fr", "fq"):
+        for op in ("add", "sub", "mul"):
+            assert (L.field_op(f, op, a, b) == oc.field_op(f, op, a, b)).all(), (f, op)
+        assert (L.field_op(f, "sqr", a) == oc.field_op(f, "mul", a, a)).all(), (f, "sqr")
+    assert (L.field_op("fr", "from_mont", a) == oc.fr_from_mont(a)).all()
+    assert (L.field_op("fr", "to_mont", a) == oc.fr_to_mont(a)).all()
+    m = min(n, 64)
+    inv = L.field_op("fq", "inv", a[3:m])
+    one = L.field_op("fq", "mul", inv, a[3:m])
+    R1 = oc.ints_to_words([(1 << 256) % o.P_MOD])[0]
+    assert (one == R1).all()
+
+
+def check_group(L, oc, n=64):
+    def aff(w):
+        v = oc.words_to_ints(np.ascontiguousarray(w).reshape(-1, 4))
+        return [None if (v[2 * i] == 0 and v[2 * i + 1] == 0) else (o.from_mont(v[2 * i], o.P_MOD), o.from_mont(v[2 * i + 1], o.P_MOD))
+                for i in range(len(v) // 2)]
+    P, Q = oc.gen_points(7, n), oc.gen_points(9, n)
+    Q[5] = P[5]          # doubling branch
+    Q[6] = 0             # identity operands
+    P[7] = 0
+    Q[8, :4] = P[8, :4]  # q = -p
+    Q[8, 4:] = oc.field_op("fq", "sub", np.zeros((1, 4), dtype=np.uint64), P[8:9, 4:])[0]
+    pa, qa = aff(P), aff(Q)
+    r = [aff(L.ec_op(op, P, Q)) for op in range(4)]
+    for i in range(n):
+        s = o.g1_add(pa[i], qa[i])
+        assert r[0][i] == s, (i, "add")
+        assert r[3][i] == s, (i, "jacobian")
+        assert r[1][i] == o.g1_add(pa[i], o.g1_neg(qa[i])), (i, "sub")
+        assert r[2][i] == (o.g1_mul(s, 4) if s else None), (i, "x4")
+
+
+def check_ntt(L, oc, k, seed=0):
+    a = oc.random_fr(0xA000 + 97 * k + seed, 1 << k)
+    for inverse in (False, True):
+        w = omega_words(oc, k, inverse)
+        got = L.ntt(a.copy(), w, k)
+        want = oc.best_fft(a, w, k)
+        assert (got == want).all(), "NTT mismatch at k=%d inverse=%s" % (k, inverse)
+
+
+def edge_msm_inputs(L, oc, n, kind, seed):
+    s = L.gen_scalars(seed, n, kind)
+    P = oc.gen_points(seed + 1, n) if n <= (1 << 16) else L.gen_points(seed + 1, n)
+    if n > 40:
+        s[1] = 0
+        P[3] = 0
+        P[5] = P[4]
+        s[5] = s[4]
+        P[9] = P[8]
+    return s, P
+
+
+def check_msm(L, oc, n, kind=0, windows=(0,), seed=1):
+    s, P = edge_msm_inputs(L, oc, n, kind, seed + n)
+    want = affine_of(oc, oc.best_multiexp(s, P))
+    for cw in windows:
+        L.set_msm_window(cw)
+        try:
+            got = affine_of(oc, L.msm(s, P))
+        finally:
+            L.set_msm_window(0)
+        assert (got == want).all(), "MSM mismatch n=%d kind=%d window=%d" % (n, kind, cw)
+
+
+def check_golden_ntt(L, g):
+    for k in (1, 2, 3, 5, 8):
+        for tag, wkey in (("fwd", "omega"), ("inv", "omega_inv")):
+            a = np.array(g["k%d_in" % k], dtype=np.uint64, order="C")
+            got = L.ntt(a, g["k%d_%s" % (k, wkey)], k)
+            assert (got == g["k%d_%s" % (k, tag)]).all(), (k, tag)
+
+
+def check_golden_msm(L, oc, g):
+    for tag in ("n1", "n2", "n8", "n64", "n200", "cancel", "anchor"):
+        got = affine_of(oc, L.msm(g[tag + "_scalars"], g[tag + "_bases"]))
+        assert (got == g[tag + "_result"]).all(), tag

@@ -1,0 +1,95 @@
+"""
+CPU: the shipped kernel sources (csrc/*.cu) compiled for the kernel-logic emulator (tools/emu) and checked
+against the oracle and the golden fixtures.  This exercises the real index math, sorting, bucket planning and
+reduction code of the CUDA kernels at sizes a CPU finishes in seconds; the GPU tests repeat the same checks through
+the C ABI on a B200 at full sizes.
+"""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+
+
+def test_field_arithmetic(emu, oc):
+    pc.check_field(emu, oc, 512)
+
+
+def test_group_law_edge_cases(emu, oc):
+    pc.check_group(emu, oc, 32)
+
+
+def test_generators_match_oracle_streams(emu, oc):
+    assert (emu.gen_points(7, 100) == oc.gen_points(7, 100)).all()
+    assert (emu.gen_scalars(11, 300, 0) == oc.random_fr(11, 300)).all()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 10, 11, 12, 13, 15])
+def test_ntt_matches_oracle(emu, oc, k):
+    pc.check_ntt(emu, oc, k)
+
+
+def test_ntt_golden(emu, golden):
+    pc.check_golden_ntt(emu, golden["ntt"])
+
+
+def test_ntt_three_and_four_pass_plans(emu, oc, monkeypatch):
+    # small B_MAX forces the 3- and 4-pass code paths at CPU-friendly sizes (fresh library instance: the
+    # plan is read once per process)
+    import os, subprocess, sys
+    code = (
+        "import sys; sys.path[:0]=[%r,%r,%r]\n"
+        "import oracle_c as oc, parity_cases as pc\n"
+        "from halo2_scaffold_b200._lib import Lib\n"
+        "L=Lib(%r, allow_emulator=True); L.init(1)\n"
+        "[pc.check_ntt(L, oc, k) for k in (12, 13, 14, 16)]\n"
+        "print('ok')\n") % (pc.__file__.rsplit('/tests/', 1)[0], pc.__file__.rsplit('/tests/', 1)[0] + '/oracle',
+                            pc.__file__.rsplit('/', 1)[0], emu.path)
+    env = dict(os.environ, H2B_NTT_BMAX="4")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 32, 33, 100, 1000])
+def test_msm_matches_oracle(emu, oc, n):
+    pc.check_msm(emu, oc, n, kind=0, windows=(0,) if n < 100 else (0, 3, 6))
+
+
+def test_msm_witness_like_scalars_split_buckets(emu, oc):
+    # 50% zero / 20% one / small / small negatives: exercises bucket splitting + warp combine
+    pc.check_msm(emu, oc, 3000, kind=1, windows=(0, 5, 10))
+
+
+def test_msm_golden(emu, oc, golden):
+    pc.check_golden_msm(emu, oc, golden["msm"])
+
+
+def test_msm_registered_prefix_and_offset(emu, oc):
+    n = 600
+    s, P = oc.random_fr(5, n), oc.gen_points(6, n)
+    h = emu.register_bases(P)
+    try:
+        for off, m in ((0, n), (0, 100), (37, 400)):
+            got = pc.affine_of(oc, emu.msm_registered(s[:m], h, off))
+            want = pc.affine_of(oc, oc.best_multiexp(s[:m], P[off:off + m]))
+            assert (got == want).all()
+    finally:
+        emu.unregister_bases(h)
+    with pytest.raises(Exception):
+        emu.msm_registered(s, h, 0)
+
+
+def test_msm_empty_and_identity(emu, oc):
+    out = emu.msm(np.zeros((0, 4), dtype=np.uint64), np.zeros((0, 8), dtype=np.uint64))
+    assert (pc.affine_of(oc, out) == 0).all()
+    s = oc.random_fr(1, 10)
+    out = emu.msm(s, np.zeros((10, 8), dtype=np.uint64))      # all bases are the identity
+    assert (pc.affine_of(oc, out) == 0).all()
+    out = emu.msm(np.zeros((10, 4), dtype=np.uint64), oc.gen_points(2, 10))   # all scalars zero
+    assert (pc.affine_of(oc, out) == 0).all()
+
+
+def test_length_mismatch_asserts_like_the_reference(emu, oc):
+    with pytest.raises(AssertionError):
+        emu.msm(oc.random_fr(1, 4), oc.gen_points(1, 5))
+    with pytest.raises(AssertionError):
+        emu.ntt(np.zeros((3, 4), dtype=np.uint64), np.zeros(4, dtype=np.uint64), 2)
