@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""
+bench.py -- headline benchmark of the hot path (BASELINE.json: "BN254 MSM points/s & NTT elems/s").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference's path (oracle)
+
+A *step* is one pass of the hot path over one batch of synthetic input: one BN254 G1 MSM over
+2^k points per GPU (k = 24 by default: BASELINE.json configs[3], the synthetic sweep; the other
+configs need the Rust prover and are parity-test cases).  With N > 1 the MSM is sharded by point
+range -- every rank owns 2^k points (weak scaling), computes its partial sum, the 224-byte partials
+are all-gathered over NCCL and folded on the device.  After the MSM region the same K/W protocol
+times the Fr NTT at 2^k per GPU; its numbers ride along in the "ntt" object of the same JSON line.
+
+`value`  : whole-job MSM throughput, inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : the same metric through the reference-facing call best_multiexp(coeffs, bases) with HOST buffers
+           (pinned): every step uploads the scalars, runs, downloads the 96-byte result.  Bases are the SRS:
+           registered once outside the timed region, exactly like ParamsKZG holds `g` / `g_lagrange`.
+`roofline`: dominant kernel (msm_accumulate_kernel) against the measured integer-pipe peak.
+`cpu_baseline`: the C++ restatement of halo2_proofs' best_multiexp/best_fft (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMADS_PER_POINT = 21760          # 16 windows x 10 Fq-muls x 136 MACs
+MACS_PER_FR_MUL = 136
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--k", type=int, default=24, help="log2 of the points / elements per GPU")
+    ap.add_argument("--scalars", default="uniform", choices=["uniform", "witness"])
+    ap.add_argument("--sweep", action="store_true", help="also print a k=16..26 sweep (extra JSON lines on stderr)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_for(args, n_gpus):
+    return {
+        "workload": "synthetic BN254 G1 MSM (+ Fr NTT) at k=%d per GPU (BASELINE.json configs[3])" % args.k,
+        "k": args.k,
+        "points_per_gpu": 1 << args.k,
+        "scalars": args.scalars,
+        "parallelism": "point-range shard x%d, partial sums all-gathered + folded" % n_gpus if n_gpus > 1 else "single GPU",
+        "l2": "inputs (%.1f GB per GPU) exceed the 126 MB L2; no flush needed" % ((96 << args.k) / 1e9),
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.25 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+def omega_words(k):
+    from halo2_scaffold_b200.domain import FR_MODULUS, FR_ROOT_OF_UNITY, FR_S, fr_to_words
+    w = FR_ROOT_OF_UNITY
+    for _ in range(k, FR_S):
+        w = w * w % FR_MODULUS
+    return fr_to_words(w)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own algorithm for this path on the host cores: oracle/h2_oracle.cpp, the C++ restatement of
+    halo2_proofs v2023_02_02 best_multiexp / best_fft (the Rust original is un-vendored and there is no cargo here,
+    so oracle/_ref cannot exist).  Each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c as oc
+    oc.build()
+    cores = oc.hardware_threads()
+    ks = min(args.k, 20)
+    n = 1 << ks
+    scal = oc.random_fr(0xB2000000 + ks, n)
+    pts = oc.gen_points(0xB2001000 + ks, n)
+    for _ in range(args.warmup):
+        oc.best_multiexp(scal, pts, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oc.best_multiexp(scal, pts, cores)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    w = omega_words(ks)
+    oc.best_fft(scal, w, ks, cores)
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        oc.best_fft(scal, w, ks, cores)
+    ntt_value = n * args.steps / (time.perf_counter() - t1)
+    sample = "best_multiexp over 2^%d of the 2^%d points per step (uniform scalars), %d threads" % (ks, args.k, cores)
+    line = {
+        "impl": "reference", "metric": "bn254_g1_msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": config_for(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
+                         "ntt_value": ntt_value, "ntt_unit": "elements/s", "ntt_sample": "best_fft at 2^%d" % ks},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "C++ restatement of halo2_proofs v2023_02_02 (oracle/h2_oracle.cpp); the Rust reference cannot be built here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import halo2_scaffold_b200 as h2
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = h2.load()
+    L.init_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    k, n = args.k, 1 << args.k
+    K, W = args.steps, args.warmup
+    st = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- synthetic inputs, generated on the device (each rank owns its own point range) ------------
+    d_scal = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    d_base = torch.empty(n * 8, dtype=torch.int64, device=dev)
+    d_block = torch.empty(28, dtype=torch.int64, device=dev)
+    d_blocks = torch.empty(28 * world, dtype=torch.int64, device=dev)
+    d_out = torch.empty(12, dtype=torch.int64, device=dev)
+    kind = 0 if args.scalars == "uniform" else 1
+    L.gen_scalars_dev(0, 0xB2000000 + k + 1000 * rank, n, kind, d_scal.data_ptr(), st)
+    L.gen_points_dev(0, 0xB2001000 + k + 1000 * rank, n, d_base.data_ptr(), st)
+    torch.cuda.synchronize()
+
+    def msm_step():
+        L.msm_dev_partial(0, d_scal.data_ptr(), d_base.data_ptr(), n, d_block.data_ptr(), st)
+        if world > 1:
+            dist.all_gather_into_tensor(d_blocks, d_block)
+            L.msm_fold_partials_dev(0, d_blocks.data_ptr(), world, d_out.data_ptr(), st)
+        else:
+            L.msm_fold_partials_dev(0, d_block.data_ptr(), 1, d_out.data_ptr(), st)
+
+    # integer-pipe peak, measured on this GPU right now (the MSM roofline denominator)
+    imad_ms, imad_ops = L.imad_bench(0, 4096)
+    imad_peak = imad_ops / imad_ms * 1e3          # IMAD/s
+    mul_ms, mul_ops = L.imad_bench(2, 4096)
+    fqmul_peak = mul_ops / mul_ms * 1e3
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- MSM, device resident ------------------------------------------------------------------------------
+    for _ in range(W):
+        msm_step()
+    barrier()
+    L.profile_enable(True)
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(K):
+        msm_step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    msm_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = L.launch_count() - launches0
+    prof = L.profile_read()
+    L.profile_enable(False)
+    acc_ms = [ms for (tag, ms) in prof if tag == 5]
+    phase_ms = {}
+    for tag, ms in prof:
+        phase_ms[tag] = phase_ms.get(tag, 0.0) + ms / K
+    msm_value = world * n * K / (msm_ms / 1e3)
+    result_host = d_out.cpu().numpy().astype(np.uint64)
+
+    # ---- MSM, end to end through the host-pointer drop-in ---------------------------------------------------
+    h_scal = torch.empty(n * 4, dtype=torch.int64).pin_memory()
+    h_scal.copy_(d_scal)
+    h_base = d_base.cpu()
+    handle = L.register_bases(h_base.numpy().view(np.uint64))           # SRS upload: once, outside the timed region
+    del h_base
+    scal_np = h_scal.numpy().view(np.uint64).reshape(n, 4)
+    for _ in range(max(1, W - 1)):
+        r = L.msm_registered(scal_np, handle)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        r = L.msm_registered(scal_np, handle)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n * K / e2e_s
+    L.unregister_bases(handle)
+
+    # ---- NTT, device resident + end to end --------------------------------------------------------------------
+    w_words = omega_words(k)
+    d_ntt = d_scal          # reuse: 2^k Fr elements
+    for _ in range(W):
+        L.ntt_dev(0, d_ntt.data_ptr(), w_words, k, st)
+    barrier()
+    L.profile_enable(True)
+    e0.record()
+    for _ in range(K):
+        L.ntt_dev(0, d_ntt.data_ptr(), w_words, k, st)
+    e1.record()
+    barrier()
+    ntt_ms = max_over_ranks(e0.elapsed_time(e1))
+    nprof = L.profile_read()
+    L.profile_enable(False)
+    pass_ms = [ms for (tag, ms) in nprof if tag >= 16]
+    ntt_value = world * n * K / (ntt_ms / 1e3)
+    a_np = h_scal.numpy().view(np.uint64).reshape(n, 4)
+    L.ntt(a_np, w_words, k)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        L.ntt(a_np, w_words, k)
+    barrier()
+    ntt_e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- CPU baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) ------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_c as oc
+        oc.build()
+        cores = oc.hardware_threads()
+        ks = min(k, 22)
+        m = 1 << ks
+        s_s = d_scal[: 4 * m].cpu().numpy().view(np.uint64).reshape(m, 4)      # note: d_scal now holds NTT output = still uniform field elements
+        b_s = d_base[: 8 * m].cpu().numpy().view(np.uint64).reshape(m, 8)
+        t0 = time.perf_counter()
+        oc.best_multiexp(s_s, b_s, cores)
+        cpu_msm = m / (time.perf_counter() - t0)
+        kf = min(k, 22)
+        t0 = time.perf_counter()
+        oc.best_fft(s_s[: 1 << kf], omega_words(kf), kf, cores)
+        cpu_ntt = (1 << kf) / (time.perf_counter() - t0)
+        cpu_baseline = {"value": cpu_msm, "unit": "points/s", "cores": cores, "kind": "port",
+                        "sample": "one best_multiexp over the first 2^%d of the 2^%d points, %d threads (C++ restatement of halo2_proofs v2023_02_02)" % (ks, k, cores),
+                        "ntt_value": cpu_ntt, "ntt_unit": "elements/s", "ntt_sample": "one best_fft at 2^%d, %d threads" % (kf, cores)}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
+        acc_avg = sum(acc_ms) / max(1, len(acc_ms))
+        roofline = {
+            "kernel": "msm_accumulate_kernel", "bound": "imad", "unit": "TIMAD/s",
+            "achieved": IMADS_PER_POINT * n / (acc_avg / 1e3) / 1e12 if acc_avg else None,
+            "peak": imad_peak / 1e12,
+            "peak_source": "measured in this run: h2b_imad_bench, independent mad.lo.u32 chains on all SMs (MEASURED_PEAKS.json has no integer-pipe figure)",
+            "frac": (IMADS_PER_POINT * n / (acc_avg / 1e3)) / imad_peak if acc_avg else None,
+            "frac_whole_step": (IMADS_PER_POINT * n * K / (msm_ms / 1e3)) / imad_peak,
+            "algorithmic_per_launch": "21760 IMAD x 2^%d points (SURVEY.md 8d canonical figure)" % k,
+            "kernel_ms_avg": acc_avg, "kernel_share_of_step": acc_avg * K / msm_ms if msm_ms else None,
+            "fq_mul_peak_gmul_s": fqmul_peak / 1e9,
+            "traffic": ncu.get("msm_accumulate_kernel"),
+        }
+        pass_avg = sum(pass_ms) / max(1, len(pass_ms))
+        passes_per_ntt = max(1, len(pass_ms) // max(1, K))
+        ntt = {
+            "metric": "bn254_fr_ntt_elements_per_s", "value": ntt_value, "unit": "elements/s", "k": k, "ms_per_step": ntt_ms / K,
+            "e2e": {"value": world * n * K / ntt_e2e_s, "unit": "elements/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n},
+            "roofline": {
+                "kernel": "ntt_pass_kernel", "bound": "hbm", "unit": "GB/s",
+                "achieved": 64.0 * n / (pass_avg / 1e3) / 1e9 if pass_avg else None, "peak": hbm_peak, "peak_source": hbm_src,
+                "frac": (64.0 * n / (pass_avg / 1e3) / 1e9) / hbm_peak if pass_avg else None,
+                "frac_whole_ntt": (64.0 * n / (ntt_ms / K / 1e3) / 1e9) / hbm_peak,
+                "algorithmic_per_launch": "64 B x 2^%d elements per pass launch (each pass reads and writes the vector once); %d passes per NTT" % (k, passes_per_ntt),
+                "kernel_ms_avg": pass_avg, "passes": passes_per_ntt,
+                "imad_frac_whole_ntt": (MACS_PER_FR_MUL * (n / 2) * k * K / (ntt_ms / 1e3)) / imad_peak,
+                "traffic": ncu.get("ntt_pass_kernel"),
+            },
+        }
+        line = {
+            "metric": "bn254_g1_msm_points_per_s", "value": msm_value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": msm_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": config_for(args, world),
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ntt": ntt,
+            "msm_phase_ms": {str(t): round(v, 4) for t, v in sorted(phase_ms.items())},
+            "result_x_limb0": int(result_host[0]),
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -29,9 +29,10 @@ _EXPORTS = [
     "h2b_init", "h2b_init_device", "h2b_shutdown", "h2b_device_count", "h2b_last_error", "h2b_version",
     "h2b_is_emulator", "h2b_msm_bn254_g1", "h2b_ntt_bn254_fr", "h2b_register_bases", "h2b_unregister_bases",
     "h2b_msm_bn254_g1_registered", "h2b_ntt_bn254_fr_dev", "h2b_msm_bn254_g1_dev",
-    "h2b_msm_bn254_g1_dev_partial", "h2b_msm_fold_partials", "h2b_fr_scale_dev",
+    "h2b_msm_bn254_g1_dev_partial", "h2b_msm_fold_partials", "h2b_msm_fold_partials_dev", "h2b_fr_scale_dev",
     "h2b_dev_alloc", "h2b_dev_free", "h2b_memcpy_h2d", "h2b_memcpy_d2h", "h2b_dev_sync", "h2b_gen_points_dev",
     "h2b_gen_scalars_dev", "h2b_field_op", "h2b_ec_op", "h2b_imad_bench", "h2b_set_msm_window",
+    "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read",
 ]
 
 
@@ -69,6 +70,7 @@ class Lib:
         L.h2b_msm_bn254_g1_dev.argtypes = [i32, vp, vp, sz, vp, vp]
         L.h2b_msm_bn254_g1_dev_partial.argtypes = [i32, vp, vp, sz, vp, vp]
         L.h2b_msm_fold_partials.argtypes = [i32, vp, sz, vp]
+        L.h2b_msm_fold_partials_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_fr_scale_dev.argtypes = [i32, vp, sz, vp, i32, vp]
         L.h2b_dev_alloc.argtypes = [i32, sz, ctypes.POINTER(vp)]
         L.h2b_dev_free.argtypes = [i32, vp]
@@ -81,6 +83,9 @@ class Lib:
         L.h2b_ec_op.argtypes = [i32, vp, vp, sz, vp]
         L.h2b_imad_bench.argtypes = [i32, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
         L.h2b_set_msm_window.argtypes = [i32]
+        L.h2b_launch_count.restype = ctypes.c_ulonglong
+        L.h2b_profile_enable.argtypes = [i32, i32]
+        L.h2b_profile_read.argtypes = [i32, vp, vp, i32, ctypes.POINTER(i32)]
         self.L = L
         self.is_emulator = bool(L.h2b_is_emulator())
         if self.is_emulator and not allow_emulator:
@@ -158,6 +163,9 @@ class Lib:
         self.check(self.L.h2b_msm_fold_partials(device, blocks.ctypes.data, blocks.shape[0], out.ctypes.data))
         return out
 
+    def msm_fold_partials_dev(self, device: int, d_blocks: int, count: int, d_out: int, stream: int = 0):
+        self.check(self.L.h2b_msm_fold_partials_dev(device, d_blocks, count, d_out, stream))
+
     def fr_scale_dev(self, device: int, d_a: int, n: int, factors: np.ndarray, stream: int = 0):
         factors = _u64(factors).reshape(-1, 4)
         self.check(self.L.h2b_fr_scale_dev(device, d_a, n, factors.ctypes.data, factors.shape[0], stream))
@@ -230,6 +238,21 @@ class Lib:
         ms, ops = ctypes.c_float(0), ctypes.c_double(0)
         self.check(self.L.h2b_imad_bench(device, kind, iters, ctypes.byref(ms), ctypes.byref(ops)))
         return ms.value, ops.value
+
+    def launch_count(self) -> int:
+        return int(self.L.h2b_launch_count())
+
+    def profile_enable(self, on: bool, device: int = 0):
+        self.check(self.L.h2b_profile_enable(device, 1 if on else 0))
+
+    def profile_read(self, device: int = 0):
+        """-> list of (tag, ms) in launch order; clears the record."""
+        cap = 8192
+        tags = np.zeros(cap, dtype=np.int32)
+        ms = np.zeros(cap, dtype=np.float32)
+        cnt = ctypes.c_int(0)
+        self.check(self.L.h2b_profile_read(device, tags.ctypes.data, ms.ctypes.data, cap, ctypes.byref(cnt)))
+        return [(int(tags[i]), float(ms[i])) for i in range(cnt.value)]
 
     def set_msm_window(self, c: int):
         self.check(self.L.h2b_set_msm_window(c))

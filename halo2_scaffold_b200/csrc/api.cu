@@ -10,6 +10,7 @@
 
 namespace h2b {
 
+unsigned long long g_launch_count = 0;
 static thread_local std::string t_error;
 void set_error(const char* fmt, ...) {
     char buf[1024];
@@ -393,6 +394,13 @@ int h2b_msm_fold_partials(int device, const uint64_t* host_blocks, size_t count,
     return H2B_OK;
 }
 
+int h2b_msm_fold_partials_dev(int device, const void* d_blocks, size_t count, void* d_out_jac, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_blocks || !d_out_jac || count == 0 || count > 4096) { set_error("h2b_msm_fold_partials_dev: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
+    return msm_sum_partials_run(*c, d_blocks, (uint32_t)count, d_out_jac, (cudaStream_t)stream);
+}
+
 int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, int count, void* stream) {
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
@@ -485,5 +493,43 @@ int h2b_imad_bench(int device, int kind, int iters, float* ms_out, double* ops_o
 }
 
 int h2b_set_msm_window(int c) { return msm_set_window(c); }
+
+unsigned long long h2b_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
+
+int h2b_profile_enable(int device, int on) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    Profiler& p = c->prof;
+    if (on && p.ev.empty()) {
+        p.ev.resize(8192);
+        p.tag.resize(8192);
+        for (auto& e : p.ev) H2B_CUDA(cudaEventCreate(&e));
+    }
+    p.enabled = on != 0;
+    p.used = 0;
+    return H2B_OK;
+}
+
+int h2b_profile_read(int device, int* tags, float* ms, int cap, int* count) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!tags || !ms || !count) { set_error("h2b_profile_read: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    Profiler& p = c->prof;
+    H2B_CUDA(cudaDeviceSynchronize());
+    int n = 0;
+    for (size_t i = 1; i < p.used && n < cap; ++i) {
+        if (p.tag[i] == PROF_BEGIN) continue;
+        float t = 0.f;
+        H2B_CUDA(cudaEventElapsedTime(&t, p.ev[i - 1], p.ev[i]));
+        tags[n] = p.tag[i];
+        ms[n] = t;
+        ++n;
+    }
+    *count = n;
+    p.used = 0;
+    return H2B_OK;
+}
 
 }  // extern "C"

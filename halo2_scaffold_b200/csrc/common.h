@@ -60,6 +60,21 @@ struct DevBuf {
     }
 };
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+enum ProfTag { PROF_BEGIN = 0, PROF_MSM_DECOMPOSE = 1, PROF_MSM_SCAN = 2, PROF_MSM_SCATTER = 3, PROF_MSM_PLAN = 4, PROF_MSM_ACCUMULATE = 5,
+               PROF_MSM_COMBINE = 6, PROF_MSM_REDUCE = 7, PROF_MSM_FINAL = 8, PROF_NTT_TWIDDLE = 15, PROF_NTT_PASS0 = 16 };
+struct Profiler {
+    bool enabled = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    size_t used = 0;
+    void mark(int t, cudaStream_t stream) {
+        if (!enabled || used >= ev.size()) return;
+        cudaEventRecord(ev[used], stream);
+        tag[used++] = t;
+    }
+};
+
 struct NttTwiddles;   // ntt.cu
 struct MsmScratch;    // msm.cu
 struct BaseSet;       // api.cu
@@ -76,6 +91,7 @@ struct DeviceCtx {
     DevBuf msm_out;                    // 96-byte result
     std::vector<NttTwiddles*> twiddles;  // small LRU cache keyed by (omega, log_n)
     MsmScratch* msm = nullptr;
+    Profiler prof;
     void* pinned = nullptr;            // small pinned bounce buffer
     size_t pinned_cap = 0;
 };

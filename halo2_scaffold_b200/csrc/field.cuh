@@ -12,7 +12,8 @@
 #include "cuda_emu.h"
 #else
 #include <cuda_runtime.h>
-#define H2B_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define H2B_LAUNCH(kern, grid, block, smem, stream, ...) \
+    (h2b::count_launch(), kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define H2B_DYN_SMEM(T, name)                                   \
     extern __shared__ __align__(16) unsigned char _h2b_dsm[];   \
     T* name = reinterpret_cast<T*>(_h2b_dsm)
@@ -20,6 +21,10 @@
 #endif
 
 namespace h2b {
+
+// number of kernels this library has launched (reported by bench.py as `gpu_launches`)
+extern unsigned long long g_launch_count;
+inline void count_launch() { __atomic_fetch_add(&g_launch_count, 1ull, __ATOMIC_RELAXED); }
 
 enum FieldId { FR = 0, FQ = 1 };
 

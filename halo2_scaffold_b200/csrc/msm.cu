@@ -398,17 +398,24 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const v
     H2B_CUDA(cudaMemsetAsync(ctrl, 0, 16, stream));
 
     const uint32_t nblk = (n + 255) / 256;
+    ctx.prof.mark(PROF_BEGIN, stream);
     H2B_LAUNCH(msm_decompose_kernel, nblk, 256, 0, stream, (const uint4*)d_scalars, pl, (uint32_t*)s.digits.p, counts);
+    ctx.prof.mark(PROF_MSM_DECOMPOSE, stream);
     H2B_TRY(exclusive_scan(s, counts, pl.B, offsets, cursor, stream));
+    ctx.prof.mark(PROF_MSM_SCAN, stream);
     H2B_LAUNCH(msm_scatter_kernel, nblk, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, (uint32_t*)s.sorted.p);
+    ctx.prof.mark(PROF_MSM_SCATTER, stream);
     H2B_LAUNCH(msm_plan_kernel, (pl.B + 255) / 256, 256, 0, stream, pl, (const uint32_t*)offsets, ctrl, (uint2*)s.overflow_desc.p,
                (uint2*)s.bucket_extra.p, (uint32_t*)s.heavy.p);
+    ctx.prof.mark(PROF_MSM_PLAN, stream);
     const uint32_t acc_threads = pl.B + pl.max_overflow;
     H2B_LAUNCH(msm_accumulate_kernel, (acc_threads + 255) / 256, 256, 0, stream, pl, (const uint4*)d_bases, (const uint32_t*)offsets,
                (const uint32_t*)s.sorted.p, (const uint32_t*)ctrl, (const uint2*)s.overflow_desc.p, (uint4*)s.bucket_acc.p, (uint4*)s.partial.p);
+    ctx.prof.mark(PROF_MSM_ACCUMULATE, stream);
     H2B_LAUNCH(msm_combine_kernel, ctx.sm_count * 2, 128, 0, stream, (const uint32_t*)ctrl, (const uint32_t*)s.heavy.p,
                (const uint2*)s.bucket_extra.p, (const uint4*)s.partial.p, (uint4*)s.bucket_acc.p);
     H2B_CUDA(cudaGetLastError());
+    ctx.prof.mark(PROF_MSM_COMBINE, stream);
 
     // bucket reduction hierarchy
     const uint32_t logm = 4;
@@ -433,8 +440,10 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const v
         N = J;
         if (J == 1) break;
     }
+    ctx.prof.mark(PROF_MSM_REDUCE, stream);
     H2B_LAUNCH(msm_final_kernel, 1, 32, 0, stream, Din, pl.W, pl.c, (uint4*)d_result, accumulate ? 1u : 0u);
     H2B_CUDA(cudaGetLastError());
+    ctx.prof.mark(PROF_MSM_FINAL, stream);
     return H2B_OK;
 }
 

@@ -280,7 +280,9 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
     if (log_n == 0) return H2B_OK;
     if (!d_a) { set_error("ntt: null data pointer"); return H2B_ERR_BAD_ARGUMENT; }
     NttTwiddles* tw = nullptr;
+    ctx.prof.mark(PROF_BEGIN, stream);
     H2B_TRY(ntt_get_twiddles(ctx, omega, log_n, stream, &tw));
+    ctx.prof.mark(PROF_NTT_TWIDDLE, stream);
     const size_t n = (size_t)1 << log_n;
     if (tw->npass > 1) H2B_TRY(ctx.ntt_work.reserve(n * 32));
     auto kfn = ntt_pass_kernel;
@@ -312,6 +314,7 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
         const size_t smem = ((size_t)32 << logE) + 32 * ((size_t)1 << (a.b - 1));
         H2B_LAUNCH(kfn, grid, threads, smem, stream, a);
         H2B_CUDA(cudaGetLastError());
+        ctx.prof.mark(PROF_NTT_PASS0 + (int)p, stream);
     }
     return H2B_OK;
 }

@@ -186,7 +186,8 @@ int ec_selftest_run(DeviceCtx& ctx, int op, const void* d_p, const void* d_q, si
 // accumulate);  kind 2: dependent Fq Montgomery multiplications (the real inner loop: 128 IMAD.WIDE + 8 IMAD each);
 // kind 3: dependent XYZZ mixed additions.   ops_out = multiply-adds (kind 0/1), field muls (2), point adds (3).
 #ifndef H2B_EMU
-__global__ void __launch_bounds__(256) imad_bench_kernel(int kind, int iters, uint32_t* sink) {
+template <int kind>
+__global__ void __launch_bounds__(256) imad_bench_kernel(int iters, uint32_t* sink) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (kind == 0) {
         uint32_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7, m = t | 1, k = t * 3 + 1;
@@ -246,9 +247,10 @@ int imad_bench_run(DeviceCtx& ctx, int kind, int iters, int blocks, int threads,
     cudaEvent_t e0, e1;
     H2B_CUDA(cudaEventCreate(&e0));
     H2B_CUDA(cudaEventCreate(&e1));
-    imad_bench_kernel<<<blocks, threads, 0, stream>>>(kind, iters / 8 + 1, (uint32_t*)sink.p);   // warm-up
+    void (*kfn)(int, uint32_t*) = kind == 0 ? imad_bench_kernel<0> : kind == 1 ? imad_bench_kernel<1> : kind == 2 ? imad_bench_kernel<2> : imad_bench_kernel<3>;
+    H2B_LAUNCH(kfn, blocks, threads, 0, stream, iters / 8 + 1, (uint32_t*)sink.p);   // warm-up
     H2B_CUDA(cudaEventRecord(e0, stream));
-    imad_bench_kernel<<<blocks, threads, 0, stream>>>(kind, iters, (uint32_t*)sink.p);
+    H2B_LAUNCH(kfn, blocks, threads, 0, stream, iters, (uint32_t*)sink.p);
     H2B_CUDA(cudaEventRecord(e1, stream));
     H2B_CUDA(cudaEventSynchronize(e1));
     H2B_CUDA(cudaGetLastError());

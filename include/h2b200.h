@@ -91,6 +91,8 @@ int h2b_msm_bn254_g1_dev(int device, const void* d_scalars, const void* d_bases,
  * caller (e.g. torch.distributed.all_gather) and folded on one device. */
 int h2b_msm_bn254_g1_dev_partial(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_block /* 224 B */, void* stream);
 int h2b_msm_fold_partials(int device, const uint64_t* host_blocks /* count x 28 u64 */, size_t count, uint64_t out_jac[12]);
+/* same, blocks and result in device memory, asynchronous on `stream` */
+int h2b_msm_fold_partials_dev(int device, const void* d_blocks, size_t count, void* d_out_jac /* 96 B */, void* stream);
 /* a[i] *= factors[i % count], count in {1, 3}: the 1/n scaling of lagrange_to_coeff / extended_to_coeff and
  * the (1, zeta, zeta^2) coset pattern of coeff_to_extended ([UP] halo2_proofs/src/poly/domain.rs). */
 int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, int count, void* stream);
@@ -116,6 +118,14 @@ int h2b_ec_op(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* 
 /* integer-pipe micro-benchmark; kind 0 IMAD, 1 IMAD.WIDE, 2 dependent Fq multiplications, 3 dependent
  * XYZZ mixed additions.  Returns elapsed milliseconds and the number of operations executed. */
 int h2b_imad_bench(int device, int kind, int iters, float* ms_out, double* ops_out);
+/* number of CUDA kernels this library has launched since it was loaded */
+unsigned long long h2b_launch_count(void);
+/* per-kernel timing with CUDA events recorded on the launching stream. After h2b_profile_enable(device, 1) every
+ * MSM / NTT call records one event per phase; h2b_profile_read synchronises the device and returns (tag, ms) pairs
+ * in launch order.  MSM tags: 1 decompose, 2 scan, 3 scatter, 4 plan, 5 accumulate, 6 combine, 7 bucket reduction,
+ * 8 final;  NTT tags: 15 twiddle tables, 16 + p = pass p. */
+int h2b_profile_enable(int device, int on);
+int h2b_profile_read(int device, int* tags, float* ms, int cap, int* count);
 /* force the MSM window size (0 = automatic) -- tuning / tests only */
 int h2b_set_msm_window(int c);
 

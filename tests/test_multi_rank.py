@@ -1,0 +1,60 @@
+"""
+CPU, world_size = 2 over gloo: the multi-GPU protocol of bench.py / SURVEY.md section 8e -- point-range sharding of one
+MSM, all-gather of the 224-byte partial blocks, fold on one rank -- with the kernel-logic emulator standing in for
+the two GPUs.  Also checks the in-library multi-device fold entry point.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys
+sys.path[:0] = [%(root)r, %(root)r + '/oracle', %(root)r + '/tests']
+import numpy as np, torch, torch.distributed as dist
+import oracle_c as oc, parity_cases as pc
+from halo2_scaffold_b200._lib import Lib
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', rank=rank, world_size=world)
+L = Lib(%(emu)r, allow_emulator=True); L.init(1)
+n = 3000
+s, P = oc.random_fr(41, n), oc.gen_points(42, n)          # every rank derives the same global problem ...
+lo, hi = n * rank // world, n * (rank + 1) // world       # ... and owns one point range
+d_s, d_p, d_b = L.dev_alloc(0, (hi - lo) * 32), L.dev_alloc(0, (hi - lo) * 64), L.dev_alloc(0, 224)
+L.h2d(0, d_s, s[lo:hi]); L.h2d(0, d_p, P[lo:hi])
+L.msm_dev_partial(0, d_s, d_p, hi - lo, d_b); L.dev_sync(0)
+block = np.zeros(28, dtype=np.uint64); L.d2h(0, block, d_b)
+mine = torch.from_numpy(block.view(np.int64).copy())
+gathered = [torch.zeros(28, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(gathered, mine)
+if rank == 0:
+    blocks = np.stack([g.numpy().view(np.uint64) for g in gathered])
+    got = pc.affine_of(oc, L.msm_fold_partials(blocks))
+    want = pc.affine_of(oc, oc.best_multiexp(s, P))
+    assert (got == want).all()
+    print('FOLD_OK')
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_point_range_sharding_two_ranks(emu, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "emu": emu.path})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", H2B_EMU_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "FOLD_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--k", "12", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["impl"] == "reference" and line["value"] > 0

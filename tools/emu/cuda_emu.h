@@ -199,6 +199,7 @@ static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigne
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = (size_t)8 << 30; *t = (size_t)8 << 30; return cudaSuccess; }
 
 // kernel launch: H2B_LAUNCH(kernel, grid, block, smem, stream, args...)
+namespace h2b { inline void count_launch(); }
 #define H2B_LAUNCH(kern, grid, block, smem, stream, ...) \
-    emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
+    (h2b::count_launch(), emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); }))
 #define H2B_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::dyn_smem_ptr)
