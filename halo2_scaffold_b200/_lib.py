@@ -32,7 +32,8 @@ _EXPORTS = [
     "h2b_msm_bn254_g1_dev_partial", "h2b_msm_fold_partials", "h2b_msm_fold_partials_dev", "h2b_fr_scale_dev",
     "h2b_dev_alloc", "h2b_dev_free", "h2b_memcpy_h2d", "h2b_memcpy_d2h", "h2b_dev_sync", "h2b_gen_points_dev",
     "h2b_gen_scalars_dev", "h2b_field_op", "h2b_ec_op", "h2b_imad_bench", "h2b_set_msm_window",
-    "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read",
+    "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read", "h2b_msm_bn254_g1_dev_registered",
+    "h2b_set_msm_precomp", "h2b_base_set_info",
 ]
 
 
@@ -69,6 +70,9 @@ class Lib:
         L.h2b_ntt_bn254_fr_dev.argtypes = [i32, vp, vp, u32, vp]
         L.h2b_msm_bn254_g1_dev.argtypes = [i32, vp, vp, sz, vp, vp]
         L.h2b_msm_bn254_g1_dev_partial.argtypes = [i32, vp, vp, sz, vp, vp]
+        L.h2b_msm_bn254_g1_dev_registered.argtypes = [i32, vp, u64, sz, sz, vp, vp]
+        L.h2b_set_msm_precomp.argtypes = [i32]
+        L.h2b_base_set_info.argtypes = [u64, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u64)]
         L.h2b_msm_fold_partials.argtypes = [i32, vp, sz, vp]
         L.h2b_msm_fold_partials_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_fr_scale_dev.argtypes = [i32, vp, sz, vp, i32, vp]
@@ -156,6 +160,17 @@ class Lib:
 
     def msm_dev_partial(self, device: int, d_scalars: int, d_bases: int, n: int, d_out_block: int, stream: int = 0):
         self.check(self.L.h2b_msm_bn254_g1_dev_partial(device, d_scalars, d_bases, n, d_out_block, stream))
+
+    def msm_dev_registered(self, device: int, d_scalars: int, handle: int, offset: int, n: int, d_out_block: int, stream: int = 0):
+        self.check(self.L.h2b_msm_bn254_g1_dev_registered(device, d_scalars, handle, offset, n, d_out_block, stream))
+
+    def set_msm_precomp(self, spacing: int):
+        self.check(self.L.h2b_set_msm_precomp(spacing))
+
+    def base_set_info(self, handle: int):
+        nt, sp, by = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint64(0)
+        self.check(self.L.h2b_base_set_info(handle, ctypes.byref(nt), ctypes.byref(sp), ctypes.byref(by)))
+        return {"n_tables": nt.value, "spacing": sp.value, "device_bytes": by.value}
 
     def msm_fold_partials(self, blocks: np.ndarray, device: int = 0) -> np.ndarray:
         blocks = _u64(blocks).reshape(-1, 28)

@@ -62,7 +62,7 @@ struct DevBuf {
 
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
 enum ProfTag { PROF_BEGIN = 0, PROF_MSM_DECOMPOSE = 1, PROF_MSM_SCAN = 2, PROF_MSM_SCATTER = 3, PROF_MSM_PLAN = 4, PROF_MSM_ACCUMULATE = 5,
-               PROF_MSM_COMBINE = 6, PROF_MSM_REDUCE = 7, PROF_MSM_FINAL = 8, PROF_NTT_TWIDDLE = 15, PROF_NTT_PASS0 = 16 };
+               PROF_MSM_COMBINE = 6, PROF_MSM_REDUCE = 7, PROF_MSM_FINAL = 8, PROF_MSM_PRECOMPUTE = 9, PROF_NTT_TWIDDLE = 15, PROF_NTT_PASS0 = 16 };
 struct Profiler {
     bool enabled = false;
     std::vector<cudaEvent_t> ev;
@@ -101,7 +101,19 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);
 void ntt_release(DeviceCtx& ctx);
 // ---- msm.cu ----
-int msm_run(DeviceCtx& ctx, const void* d_scalars, const void* d_bases, size_t n, void* d_out, bool with_xyzz, cudaStream_t stream);
+// The points of an MSM: table j (j < n_tables) holds 2^(c0*j) * P_i at rows [0, stride); the call uses rows
+// [row0, row0 + n) of every table.  n_tables == 1 is the plain, table-less mode (c0 ignored).
+struct MsmBases {
+    const void* tables = nullptr;
+    uint32_t n_tables = 1;
+    uint32_t c0 = 0;
+    size_t stride = 0;
+    size_t row0 = 0;
+};
+int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t n, void* d_out, bool with_xyzz, cudaStream_t stream);
+int msm_precompute_run(DeviceCtx& ctx, const void* d_src, void* d_dst, size_t n, uint32_t c0, cudaStream_t stream);
+uint32_t msm_pick_table_spacing(size_t n, uint32_t max_tables);
+uint32_t msm_tables_for(uint32_t c0);
 int msm_sum_partials_run(DeviceCtx& ctx, const void* d_blocks, uint32_t count, void* d_out_jac, cudaStream_t stream);
 void msm_release(DeviceCtx& ctx);
 int msm_set_window(int c);   // 0 = automatic

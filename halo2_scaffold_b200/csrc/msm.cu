@@ -8,17 +8,22 @@
 // affine value is the unique group element the reference computes.
 //
 // Algorithm (all on the device, no host arithmetic):
-//   1. decompose: leave Montgomery form, map s > (r-1)/2 to (r - s, -P) so that "small negative"
-//      witness values stay small, recode into W signed c-bit digits |d| <= 2^(c-1), histogram the
-//      (window, |d|) buckets with global reductions;
-//   2. exclusive scan of the histogram; counting-sort scatter of (point index | sign) by bucket;
-//   3. plan: buckets longer than a cap L are split into tasks so that skewed inputs (50 % of a
-//      witness column equal to 1 ...) cannot serialise on one thread;
-//   4. accumulate: one thread per task walks its slice of the sorted list and adds the gathered
-//      affine bases into an XYZZ accumulator (8M + 2S per point, next point prefetched);
-//   5. combine the partial sums of split buckets (one warp per split bucket, shuffle tree);
-//   6. bucket reduction sum_b b * B_b as a hierarchy of chunked running sums (m buckets per thread
-//      per level), then Horner over the windows and conversion to Jacobian.
+//   0. (registered SRS vectors only, once) precompute T_j[i] = 2^(c0*j) * P_i, j < W0, in affine form.  With the
+//      tables resident every window of a scalar lands in ONE shared bucket set, so the MSM needs no doublings at
+//      all and its bucket reduction shrinks from W sets to c0/c sets ("precomputed multiples");
+//   1. decompose: leave Montgomery form, map s > (r-1)/2 to (r - s, -P) so that "small negative" witness values
+//      stay small, recode into W signed c-bit digits |d| <= 2^(c-1); window w uses table w / m and bucket set
+//      w % m (plain, table-less mode: m = W, i.e. one bucket set per window); histogram with global reductions;
+//   2. exclusive scan of the histogram; counting-sort scatter of (table row | sign) by bucket;
+//   3. accumulate: the sorted list is cut into G equal slices, one per thread, regardless of bucket boundaries
+//      (perfect balance for any scalar distribution: 50 % zeros, a bucket holding 20 % of the column ...).  A
+//      thread adds the gathered affine points of its slice into an XYZZ accumulator (8M + 2S per point, next
+//      point prefetched) and flushes it whenever the bucket changes; the piece of a bucket that started in an
+//      earlier slice goes to a per-thread "head partial" instead;
+//   4. combine: buckets cut by a slice boundary get their head partials added (one thread per bucket; one CTA
+//      per bucket for buckets cut into many pieces);
+//   5. bucket reduction sum_b b * B_b per set as a hierarchy of chunked running sums, Horner over the (few)
+//      sets, conversion to Jacobian.
 #include "common.h"
 #include "ec.cuh"
 
@@ -27,19 +32,20 @@ namespace h2b {
 static const uint32_t SIGN_BIT = 0x80000000u;
 
 struct MsmPlan {
-    uint32_t n;          // points in this (sub-)MSM, <= 2^26
+    uint32_t n;          // scalars in this (sub-)MSM
     uint32_t c;          // window bits
-    uint32_t W;          // windows
-    uint32_t Nb;         // buckets per window = 2^(c-1), ids 1..Nb
-    uint32_t B;          // W * Nb
-    uint32_t L;          // task length cap
-    uint32_t max_overflow;
+    uint32_t W;          // windows over the scalar
+    uint32_t m;          // bucket sets: window w -> set w % m, table w / m
+    uint32_t Nb;         // buckets per set = 2^(c-1), ids 1..Nb
+    uint32_t B;          // m * Nb
+    uint32_t stride;     // rows between consecutive tables
+    uint32_t row0;       // first row of this call inside each table
+    uint32_t G;          // slices (accumulate threads)
 };
 
-// (r - 1) / 2 and r as canonical 32-bit limbs
+// (r - 1) / 2 as canonical 32-bit limbs
 __device__ __forceinline__ bool fr_gt_half(const Fr& s) {
     const uint32_t H[8] = {0xf8000000u, 0xa1f0fac9u, 0x3cdcb848u, 0x9419f424u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
-    // lexicographic compare from the top limb
 #pragma unroll
     for (int i = 7; i >= 0; --i) {
         if (s.l[i] > H[i]) return true;
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(256) msm_decompose_kernel(const uint4* __restr
         neg = SIGN_BIT;
     }
     const uint32_t c = pl.c, half = 1u << (c - 1);
-    uint32_t carry = 0;
+    uint32_t carry = 0, set = 0;
     for (uint32_t w = 0; w < pl.W; ++w) {
         uint32_t d = limb_bits(s, w * c, c) + carry;
         uint32_t sign = neg;
@@ -92,9 +98,10 @@ __global__ void __launch_bounds__(256) msm_decompose_kernel(const uint4* __restr
         uint32_t entry = 0;
         if (d != 0) {
             entry = d | sign;
-            atomicAdd(&counts[w * pl.Nb + d - 1], 1u);
+            atomicAdd(&counts[set * pl.Nb + d - 1], 1u);
         }
         digits[(size_t)w * pl.n + i] = entry;
+        if (++set == pl.m) set = 0;
     }
 }
 
@@ -172,114 +179,185 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(MsmPlan pl, const uint
                                                         uint32_t* __restrict__ sorted) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.n) return;
+    uint32_t set = 0, row = pl.row0 + i;
     for (uint32_t w = 0; w < pl.W; ++w) {
         uint32_t e = digits[(size_t)w * pl.n + i];
-        if (e == 0) continue;
-        uint32_t d = e & ~SIGN_BIT;
-        uint32_t pos = atomicAdd(&cursor[w * pl.Nb + d - 1], 1u);
-        sorted[pos] = i | (e & SIGN_BIT);
-    }
-}
-
-// ---- 3. plan: split long buckets ------------------------------------------------------------------
-// ctrl[0] = overflow tasks allocated, ctrl[1] = split buckets
-__global__ void __launch_bounds__(256) msm_plan_kernel(MsmPlan pl, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ctrl,
-                                                     uint2* __restrict__ overflow_desc, uint2* __restrict__ bucket_extra, uint32_t* __restrict__ heavy_list) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= pl.B) return;
-    uint32_t cnt = offsets[b + 1] - offsets[b];
-    uint32_t extra = cnt > pl.L ? (cnt - 1) / pl.L : 0;
-    uint32_t slot0 = 0;
-    if (extra) {
-        slot0 = atomicAdd(&ctrl[0], extra);
-        for (uint32_t s = 0; s < extra; ++s) overflow_desc[slot0 + s] = make_uint2(b, s + 1);
-        heavy_list[atomicAdd(&ctrl[1], 1u)] = b;
-    }
-    bucket_extra[b] = make_uint2(slot0, extra);
-}
-
-// ---- 4. accumulate ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const uint4* __restrict__ bases, const uint32_t* __restrict__ offsets,
-                                                           const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ ctrl,
-                                                           const uint2* __restrict__ overflow_desc, uint4* __restrict__ bucket_acc, uint4* __restrict__ partial) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t b, seg;
-    uint4* dst;
-    if (t < pl.B) { b = t; seg = 0; dst = bucket_acc + 8 * (size_t)t; }
-    else {
-        uint32_t slot = t - pl.B;
-        if (slot >= ctrl[0]) return;
-        uint2 d = overflow_desc[slot];
-        b = d.x; seg = d.y;
-        dst = partial + 8 * (size_t)slot;
-    }
-    uint32_t beg = offsets[b], end = offsets[b + 1];
-    beg += seg * pl.L;
-    if (end - beg > pl.L) end = beg + pl.L;
-    XYZZ acc = xyzz_identity();
-    if (beg < end) {
-        uint32_t e = sorted[beg];
-        Affine p = affine_load(bases + 4 * (size_t)(e & ~SIGN_BIT));
-        for (uint32_t j = beg; j < end; ++j) {
-            uint32_t e_next = 0;
-            Affine p_next = p;
-            if (j + 1 < end) {      // prefetch the next point while this one is added
-                e_next = sorted[j + 1];
-                p_next = affine_load(bases + 4 * (size_t)(e_next & ~SIGN_BIT));
-            }
-            xyzz_add_affine(acc, p, (e & SIGN_BIT) != 0);
-            e = e_next;
-            p = p_next;
+        if (e != 0) {
+            uint32_t d = e & ~SIGN_BIT;
+            uint32_t pos = atomicAdd(&cursor[set * pl.Nb + d - 1], 1u);
+            sorted[pos] = row | (e & SIGN_BIT);
         }
+        if (++set == pl.m) { set = 0; row += pl.stride; }
     }
-    xyzz_store(dst, acc);
 }
 
-// ---- 5. combine split buckets: one warp per split bucket ------------------------------------------
-__device__ __forceinline__ XYZZ xyzz_shfl_down(const XYZZ& v, int delta) {
-    XYZZ r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], delta);
-        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], delta);
-        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], delta);
-        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], delta);
-    }
-    return r;
+// ---- 3. accumulate: equal slices of the sorted list ----------------------------------------------------
+// slice length for `total` sorted entries cut into at most G slices.  The host sizes G for the worst case (every
+// digit non-zero); skewed columns sort far fewer entries, so slices never get shorter than SLICE_MIN and the
+// surplus threads simply exit.
+static const uint32_t SLICE_MIN = 32;
+__device__ __forceinline__ uint32_t slice_len(uint32_t total, uint32_t G) {
+    uint32_t S = (total + G - 1) / G;
+    return S < SLICE_MIN ? SLICE_MIN : S;
 }
 
-__global__ void __launch_bounds__(128) msm_combine_kernel(const uint32_t* __restrict__ ctrl, const uint32_t* __restrict__ heavy_list,
-                                                        const uint2* __restrict__ bucket_extra, const uint4* __restrict__ partial, uint4* __restrict__ bucket_acc) {
-    uint32_t lane = threadIdx.x & 31;
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t nheavy = ctrl[1];
-    for (uint32_t h = warp; h < nheavy; h += nwarps) {
-        uint32_t b = heavy_list[h];
-        uint2 ex = bucket_extra[b];
+// ctrl[0] = buckets cut by a slice boundary (split_list), ctrl[1] = those cut into many pieces (heavy_list)
+__global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const uint4* __restrict__ tables, const uint32_t* __restrict__ offsets,
+                                                           const uint32_t* __restrict__ sorted, uint32_t* __restrict__ ctrl,
+                                                           uint32_t* __restrict__ split_list, uint4* __restrict__ bucket_acc,
+                                                           uint4* __restrict__ head_partial) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pl.G) return;
+    const uint32_t total = offsets[pl.B];
+    const uint32_t S = slice_len(total, pl.G);
+    if ((uint64_t)t * S >= total) return;
+    const uint32_t start = t * S;
+    const uint32_t end = (total - start > S) ? start + S : total;
+    // b = the bucket that holds entry `start`: offsets[b] <= start < offsets[b + 1]
+    uint32_t lo = 0, hi = pl.B;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    uint32_t next = offsets[b + 1];
+    bool head = offsets[b] < start;      // the bucket began in an earlier slice
+
+    XYZZ acc = xyzz_identity();
+    uint32_t e = sorted[start];
+    Affine p = affine_load(tables + 4 * (size_t)(e & ~SIGN_BIT));
+    for (uint32_t j = start; j < end; ++j) {
+        uint32_t e_next = 0;
+        Affine p_next = p;
+        if (j + 1 < end) {      // prefetch the next point while this one is added
+            e_next = sorted[j + 1];
+            p_next = affine_load(tables + 4 * (size_t)(e_next & ~SIGN_BIT));
+        }
+        if (j == next) {        // bucket b is complete: flush, move to the next non-empty bucket
+            if (head) xyzz_store(head_partial + 8 * (size_t)t, acc);
+            else xyzz_store(bucket_acc + 8 * (size_t)b, acc);
+            head = false;
+            acc = xyzz_identity();
+            do { ++b; next = offsets[b + 1]; } while (next <= j);
+        }
+        xyzz_add_affine(acc, p, (e & SIGN_BIT) != 0);
+        e = e_next;
+        p = p_next;
+    }
+    if (head) {
+        xyzz_store(head_partial + 8 * (size_t)t, acc);
+    } else {
+        xyzz_store(bucket_acc + 8 * (size_t)b, acc);
+        if (next > end) split_list[atomicAdd(&ctrl[0], 1u)] = b;      // continues in later slices
+    }
+}
+
+// ---- 4. combine the pieces of buckets cut by slice boundaries --------------------------------------------
+// Light buckets (a few pieces: the common case, one thread each) are finished by msm_combine_light_kernel.  A bucket
+// cut into many pieces (a witness column whose value 1 fills 20 % of the rows ...) is reduced by a two-level tree:
+// chunks of COMBINE_CHUNK pieces by one CTA each, then one CTA per bucket over the chunk sums.
+static const uint32_t COMBINE_HEAVY = 24;      // more pieces than this: tree
+static const uint32_t COMBINE_CHUNK = 1024;    // pieces per CTA in the first tree level
+
+struct HeavyDesc { uint32_t bucket, chunk0, nchunks, pad; };
+
+// ctrl[0] = split buckets, ctrl[1] = heavy buckets, ctrl[2] = chunks
+__global__ void __launch_bounds__(128) msm_combine_light_kernel(MsmPlan pl, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ctrl,
+                                                              const uint32_t* __restrict__ split_list, HeavyDesc* __restrict__ heavy,
+                                                              uint2* __restrict__ chunk_desc, const uint4* __restrict__ head_partial,
+                                                              uint4* __restrict__ bucket_acc) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ctrl[0]) return;
+    const uint32_t S = slice_len(offsets[pl.B], pl.G);
+    const uint32_t b = split_list[idx];
+    const uint32_t first = offsets[b] / S, last = (offsets[b + 1] - 1) / S;
+    const uint32_t pieces = last - first;
+    if (pieces > COMBINE_HEAVY) {
+        HeavyDesc d;
+        d.bucket = b;
+        d.nchunks = (pieces + COMBINE_CHUNK - 1) / COMBINE_CHUNK;
+        d.chunk0 = atomicAdd(&ctrl[2], d.nchunks);
+        d.pad = 0;
+        const uint32_t h = atomicAdd(&ctrl[1], 1u);
+        heavy[h] = d;
+        for (uint32_t i = 0; i < d.nchunks; ++i) chunk_desc[d.chunk0 + i] = make_uint2(h, i);
+        return;
+    }
+    XYZZ acc = xyzz_load(bucket_acc + 8 * (size_t)b);
+    for (uint32_t t = first + 1; t <= last; ++t) {
+        XYZZ q = xyzz_load(head_partial + 8 * (size_t)t);
+        xyzz_add(acc, q);
+    }
+    xyzz_store(bucket_acc + 8 * (size_t)b, acc);
+}
+
+// sum of `acc` over the 256 threads of the CTA, valid in thread 0
+__device__ __forceinline__ void block_sum_xyzz(XYZZ& acc, uint4* sh) {
+    xyzz_store(sh + 8 * threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            XYZZ o = xyzz_load(sh + 8 * (threadIdx.x + d));
+            xyzz_add(acc, o);
+            xyzz_store(sh + 8 * threadIdx.x, acc);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) msm_combine_chunk_kernel(MsmPlan pl, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ctrl,
+                                                              const HeavyDesc* __restrict__ heavy, const uint2* __restrict__ chunk_desc,
+                                                              const uint4* __restrict__ head_partial, uint4* __restrict__ chunk_out) {
+    __shared__ uint4 sh[256 * 8];
+    const uint32_t S = slice_len(offsets[pl.B], pl.G);
+    const uint32_t nchunks = ctrl[2];
+    for (uint32_t item = blockIdx.x; item < nchunks; item += gridDim.x) {
+        const uint2 cd = chunk_desc[item];
+        const uint32_t b = heavy[cd.x].bucket;
+        const uint32_t first = offsets[b] / S, last = (offsets[b + 1] - 1) / S;
+        const uint32_t lo = first + 1 + cd.y * COMBINE_CHUNK;
+        uint32_t hi = lo + COMBINE_CHUNK;
+        if (hi > last + 1) hi = last + 1;
         XYZZ acc = xyzz_identity();
-        for (uint32_t s = lane; s < ex.y; s += 32) {
-            XYZZ q = xyzz_load(partial + 8 * (size_t)(ex.x + s));
+        for (uint32_t t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+            XYZZ q = xyzz_load(head_partial + 8 * (size_t)t);
             xyzz_add(acc, q);
         }
-        for (int d = 16; d > 0; d >>= 1) {
-            XYZZ o = xyzz_shfl_down(acc, d);
-            if (lane < (uint32_t)d) xyzz_add(acc, o);
-        }
-        if (lane == 0) {
-            XYZZ cur = xyzz_load(bucket_acc + 8 * (size_t)b);
-            xyzz_add(cur, acc);
-            xyzz_store(bucket_acc + 8 * (size_t)b, cur);
-        }
+        block_sum_xyzz(acc, sh);
+        if (threadIdx.x == 0) xyzz_store(chunk_out + 8 * (size_t)item, acc);
+        __syncthreads();
     }
 }
 
-// ---- 6. bucket reduction ------------------------------------------------------------------------------
-// One level of  S_w = sum_u (u+1) * Bw[u] + sum_u Dw[u]  over N items per window, m items per thread:
+__global__ void __launch_bounds__(256) msm_combine_heavy_kernel(const uint32_t* __restrict__ ctrl, const HeavyDesc* __restrict__ heavy,
+                                                              const uint4* __restrict__ chunk_out, uint4* __restrict__ bucket_acc) {
+    __shared__ uint4 sh[256 * 8];
+    const uint32_t nheavy = ctrl[1];
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const HeavyDesc d = heavy[h];
+        XYZZ acc = xyzz_identity();
+        for (uint32_t i = threadIdx.x; i < d.nchunks; i += blockDim.x) {
+            XYZZ q = xyzz_load(chunk_out + 8 * (size_t)(d.chunk0 + i));
+            xyzz_add(acc, q);
+        }
+        block_sum_xyzz(acc, sh);
+        if (threadIdx.x == 0) {
+            XYZZ cur = xyzz_load(bucket_acc + 8 * (size_t)d.bucket);
+            xyzz_add(cur, acc);
+            xyzz_store(bucket_acc + 8 * (size_t)d.bucket, cur);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- 5. bucket reduction ------------------------------------------------------------------------------
+// One level of  S_w = sum_u (u+1) * Bw[u] + sum_u Dw[u]  over N items per set, m items per thread:
 //   A_j = sum_i B[jm+i],  C_j = sum_i (i+1) B[jm+i] + sum_i D[jm+i]
 //   S_w = sum_j C_j + m * sum_{j>=1} j * A_j  ->  next level: B'[j-1] = m*A_j, B'[J-1] = 0, D'[j] = C_j.
-__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, uint32_t N, uint32_t logm,
-                                                             uint32_t W, uint4* __restrict__ Bout, uint4* __restrict__ Dout) {
+// Level 0 reads the bucket accumulators; `offsets` (level 0 only) tells which buckets are empty and were
+// therefore never written.
+__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, const uint32_t* __restrict__ offsets,
+                                                             uint32_t N, uint32_t logm, uint32_t W, uint4* __restrict__ Bout, uint4* __restrict__ Dout) {
     uint32_t m = 1u << logm;
     uint32_t J = (N + m - 1) >> logm;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,12 +365,15 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint4* __re
     uint32_t w = t / J, j = t - w * J;
     const uint4* Bw = Bin + 8 * (size_t)w * N;
     const uint4* Dw = Din ? Din + 8 * (size_t)w * N : nullptr;
+    const uint32_t* Ow = offsets ? offsets + (size_t)w * N : nullptr;
     uint32_t lo = j << logm, hi = lo + m;
     if (hi > N) hi = N;
     XYZZ running = xyzz_identity(), acc = xyzz_identity();
     for (uint32_t u = hi; u-- > lo;) {
-        XYZZ bu = xyzz_load(Bw + 8 * (size_t)u);
-        xyzz_add(running, bu);
+        if (!Ow || Ow[u + 1] != Ow[u]) {
+            XYZZ bu = xyzz_load(Bw + 8 * (size_t)u);
+            xyzz_add(running, bu);
+        }
         xyzz_add(acc, running);
         if (Dw) {
             XYZZ du = xyzz_load(Dw + 8 * (size_t)u);
@@ -308,7 +389,7 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint4* __re
     }
 }
 
-// Horner over the window sums (S[w] = Dfinal[w]) and conversion to a Jacobian triple
+// Horner over the set sums (S[w] = Dfinal[w], weight 2^(c*w)) and conversion to a Jacobian triple
 __global__ void msm_final_kernel(const uint4* __restrict__ S, uint32_t W, uint32_t c, uint4* __restrict__ out_jac, uint32_t accumulate) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     XYZZ acc = xyzz_load(S + 8 * (size_t)(W - 1));
@@ -329,28 +410,120 @@ __global__ void msm_final_kernel(const uint4* __restrict__ S, uint32_t W, uint32
     fp_store<FQ>(out_jac + 4, Z);
 }
 
+// ---- 0. table precomputation: dst[i] = 2^c0 * src[i], affine in, affine out --------------------------------
+// Each thread owns PRE_G points so that one field inversion (Fermat) serves PRE_G conversions to affine.
+static const int PRE_G = 8;
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint32_t n, uint32_t c0) {
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PRE_G;
+    if (i0 >= n) return;
+    XYZZ q[PRE_G];
+    Fq pre[PRE_G];
+    Fq run = fp_one<FQ>();
+#pragma unroll 1
+    for (int g = 0; g < PRE_G; ++g) {
+        XYZZ v = xyzz_identity();
+        if (i0 + g < n) {
+            v = xyzz_from_affine(affine_load(src + 4 * (size_t)(i0 + g)));
+#pragma unroll 1
+            for (uint32_t k = 0; k < c0; ++k) v = xyzz_double(v);
+        }
+        q[g] = v;
+        pre[g] = run;
+        if (!xyzz_is_identity(v)) run = fp_mul(run, fp_mul(v.zz, v.zzz));
+    }
+    Fq inv = fp_inv(run);
+#pragma unroll 1
+    for (int g = PRE_G - 1; g >= 0; --g) {
+        if (i0 + g >= n) continue;
+        XYZZ v = q[g];
+        Affine a;
+        if (xyzz_is_identity(v)) {
+            a.x = fp_zero<FQ>();
+            a.y = fp_zero<FQ>();
+        } else {
+            Fq zi = fp_mul(inv, pre[g]);                 // 1 / (ZZ * ZZZ)
+            inv = fp_mul(inv, fp_mul(v.zz, v.zzz));
+            a.x = fp_mul(v.x, fp_mul(v.zzz, zi));        // X / ZZ
+            a.y = fp_mul(v.y, fp_mul(v.zz, zi));         // Y / ZZZ
+        }
+        affine_store(dst + 4 * (size_t)(i0 + g), a);
+    }
+}
+
+int msm_precompute_run(DeviceCtx& ctx, const void* d_src, void* d_dst, size_t n, uint32_t c0, cudaStream_t stream) {
+    (void)ctx;
+    if (n == 0) return H2B_OK;
+    if (n > ((size_t)1 << 26)) { set_error("msm precompute: at most 2^26 points per table"); return H2B_ERR_BAD_ARGUMENT; }
+    const uint32_t threads = (uint32_t)((n + PRE_G - 1) / PRE_G);
+    H2B_LAUNCH(msm_precompute_kernel, (threads + 127) / 128, 128, 0, stream, (const uint4*)d_src, (uint4*)d_dst, (uint32_t)n, c0);
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
 // ---- host orchestration ----------------------------------------------------------------------------------
 struct MsmScratch {
-    DevBuf digits, counts, offsets, cursor, block_sums, sorted, ctrl, overflow_desc, bucket_extra, heavy, bucket_acc, partial, redA, redB, redC, redD, result;
+    DevBuf digits, counts, offsets, cursor, block_sums, sorted, ctrl, split_list, heavy, chunk_desc, chunk_out, bucket_acc, head_partial, redA, redB, redC, redD, result;
 };
 
 static int g_forced_c = 0;
 int msm_set_window(int c) {
-    if (c != 0 && (c < 2 || c > 22)) { set_error("msm window must be 0 (auto) or in [2, 22]"); return H2B_ERR_BAD_ARGUMENT; }
+    if (c != 0 && (c < 2 || c > 24)) { set_error("msm window must be 0 (auto) or in [2, 24]"); return H2B_ERR_BAD_ARGUMENT; }
     g_forced_c = c;
     return H2B_OK;
 }
 
-static uint32_t msm_pick_window(size_t n) {
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static uint32_t windows_for(uint32_t c) { return 253 / c + 1; }
+
+// Cost model in units of one sorted entry (sort + one mixed addition, 0.18 ns on a B200), fitted to measurements at
+// 2^16..2^24 (profiles/): the counting sort slows down by about 4 % per bit once the bucket set outgrows the L2-friendly
+// 2^18 counters, and a bucket costs about 17 entries because the running-sum reduction is latency bound.
+static double msm_cost(double n, uint32_t c, uint32_t sets) {
+    double per_entry = 1.0 + (c > 19 ? 0.04 * (c - 19) : 0.0);
+    return n * windows_for(c) * per_entry + 17.0 * sets * (double)(1u << (c - 1));
+}
+
+// plain mode (no tables): one bucket set per window
+static uint32_t msm_pick_window_plain(size_t n) {
     if (g_forced_c) return (uint32_t)g_forced_c;
     static int env_c = -1;
-    if (env_c < 0) { const char* e = getenv("H2B_MSM_C"); env_c = e ? atoi(e) : 0; }
-    if (env_c >= 2 && env_c <= 22) return (uint32_t)env_c;
+    if (env_c < 0) env_c = env_int("H2B_MSM_C", 0);
+    if (env_c >= 2 && env_c <= 24) return (uint32_t)env_c;
     uint32_t best = 2;
     double best_cost = 1e300;
     for (uint32_t c = 2; c <= 20; ++c) {
-        double W = 253 / c + 1;
-        double cost = (double)n * W + 16.0 * W * (double)(1u << (c - 1));
+        double cost = msm_cost((double)n, c, windows_for(c));
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+// table spacing for a base set of n points: even c0 minimising the cost of a full-length MSM, within `max_tables`
+uint32_t msm_pick_table_spacing(size_t n, uint32_t max_tables) {
+    uint32_t best = 0;
+    double best_cost = 1e300;
+    for (uint32_t c0 = 4; c0 <= 24; c0 += 2) {
+        if (windows_for(c0) > max_tables) continue;
+        double cost = msm_cost((double)n, c0, 1);
+        if (cost < best_cost) { best_cost = cost; best = c0; }
+    }
+    return best;
+}
+uint32_t msm_tables_for(uint32_t c0) { return windows_for(c0); }
+
+// precomputed mode: window bits must divide the table spacing c0
+static uint32_t msm_pick_window_tables(size_t n, uint32_t c0) {
+    if (g_forced_c && c0 % (uint32_t)g_forced_c == 0) return (uint32_t)g_forced_c;
+    uint32_t best = c0;
+    double best_cost = 1e300;
+    for (uint32_t sets = 1; sets <= c0 / 2; ++sets) {
+        if (c0 % sets) continue;
+        uint32_t c = c0 / sets;
+        double cost = msm_cost((double)n, c, sets);
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
@@ -367,28 +540,42 @@ static int exclusive_scan(MsmScratch& s, const uint32_t* in, uint32_t count, uin
     return H2B_OK;
 }
 
-static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const void* d_bases, uint32_t n, void* d_result, bool accumulate, cudaStream_t stream) {
+static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const MsmBases& bases, size_t row0, uint32_t n, void* d_result, bool accumulate,
+                   cudaStream_t stream) {
     MsmPlan pl;
+    const bool tables = bases.n_tables > 1;
     pl.n = n;
-    pl.c = msm_pick_window(n);
-    pl.W = 253 / pl.c + 1;
+    pl.c = tables ? msm_pick_window_tables(n, bases.c0) : msm_pick_window_plain(n);
+    pl.W = windows_for(pl.c);
+    pl.m = tables ? bases.c0 / pl.c : pl.W;
     pl.Nb = 1u << (pl.c - 1);
-    pl.B = pl.W * pl.Nb;
-    uint32_t mean = (n + pl.Nb - 1) / pl.Nb;
-    pl.L = 2 * mean < 32 ? 32 : 2 * mean;
-    pl.max_overflow = (uint32_t)(((uint64_t)n * pl.W) / pl.L + 1);
+    pl.B = pl.m * pl.Nb;
+    pl.stride = tables ? (uint32_t)bases.stride : 0u;
+    pl.row0 = (uint32_t)row0;
+    if (tables && (pl.W + pl.m - 1) / pl.m > bases.n_tables) { set_error("msm: %u tables cannot serve %u windows in %u sets", bases.n_tables, pl.W, pl.m); return H2B_ERR_BAD_ARGUMENT; }
+    const uint64_t upper = (uint64_t)n * pl.W;          // sorted entries, at most
+    if (upper >= 0xffffffffull) { set_error("msm: %u points x %u windows exceed the 32-bit sort index", n, pl.W); return H2B_ERR_BAD_ARGUMENT; }
+    // slices: about 256 entries each once the GPU is full, never fewer than 64 (latency of tiny MSMs)
+    const uint64_t resident = (uint64_t)ctx.sm_count * 512;
+    static int env_slice = -1;
+    if (env_slice < 0) env_slice = env_int("H2B_MSM_SLICE", 256);
+    if (upper >= resident * 64) pl.G = (uint32_t)(resident * ((upper + resident * env_slice - 1) / (resident * env_slice)));
+    else pl.G = (uint32_t)((upper + 63) / 64);
+    if (pl.G == 0) pl.G = 1;
 
-    H2B_TRY(s.digits.reserve((size_t)n * pl.W * 4));
+    H2B_TRY(s.digits.reserve((size_t)upper * 4));
     H2B_TRY(s.counts.reserve((size_t)pl.B * 4));
     H2B_TRY(s.offsets.reserve(((size_t)pl.B + 1) * 4));
     H2B_TRY(s.cursor.reserve((size_t)pl.B * 4));
-    H2B_TRY(s.sorted.reserve((size_t)n * pl.W * 4));
+    H2B_TRY(s.sorted.reserve((size_t)upper * 4 + 4));
     H2B_TRY(s.ctrl.reserve(16));
-    H2B_TRY(s.overflow_desc.reserve((size_t)pl.max_overflow * 8));
-    H2B_TRY(s.bucket_extra.reserve((size_t)pl.B * 8));
-    H2B_TRY(s.heavy.reserve((size_t)pl.max_overflow * 4));
+    H2B_TRY(s.split_list.reserve((size_t)pl.G * 4));
+    const size_t max_heavy = pl.G / COMBINE_HEAVY + 1, max_chunks = pl.G / COMBINE_CHUNK + max_heavy + 1;
+    H2B_TRY(s.heavy.reserve(max_heavy * sizeof(HeavyDesc)));
+    H2B_TRY(s.chunk_desc.reserve(max_chunks * 8));
+    H2B_TRY(s.chunk_out.reserve(max_chunks * 128));
     H2B_TRY(s.bucket_acc.reserve((size_t)pl.B * 128));
-    H2B_TRY(s.partial.reserve((size_t)pl.max_overflow * 128));
+    H2B_TRY(s.head_partial.reserve((size_t)pl.G * 128));
 
     uint32_t* counts = (uint32_t*)s.counts.p;
     uint32_t* offsets = (uint32_t*)s.offsets.p;
@@ -405,15 +592,15 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const v
     ctx.prof.mark(PROF_MSM_SCAN, stream);
     H2B_LAUNCH(msm_scatter_kernel, nblk, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, (uint32_t*)s.sorted.p);
     ctx.prof.mark(PROF_MSM_SCATTER, stream);
-    H2B_LAUNCH(msm_plan_kernel, (pl.B + 255) / 256, 256, 0, stream, pl, (const uint32_t*)offsets, ctrl, (uint2*)s.overflow_desc.p,
-               (uint2*)s.bucket_extra.p, (uint32_t*)s.heavy.p);
-    ctx.prof.mark(PROF_MSM_PLAN, stream);
-    const uint32_t acc_threads = pl.B + pl.max_overflow;
-    H2B_LAUNCH(msm_accumulate_kernel, (acc_threads + 255) / 256, 256, 0, stream, pl, (const uint4*)d_bases, (const uint32_t*)offsets,
-               (const uint32_t*)s.sorted.p, (const uint32_t*)ctrl, (const uint2*)s.overflow_desc.p, (uint4*)s.bucket_acc.p, (uint4*)s.partial.p);
+    H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)bases.tables, (const uint32_t*)offsets,
+               (const uint32_t*)s.sorted.p, ctrl, (uint32_t*)s.split_list.p, (uint4*)s.bucket_acc.p, (uint4*)s.head_partial.p);
     ctx.prof.mark(PROF_MSM_ACCUMULATE, stream);
-    H2B_LAUNCH(msm_combine_kernel, ctx.sm_count * 2, 128, 0, stream, (const uint32_t*)ctrl, (const uint32_t*)s.heavy.p,
-               (const uint2*)s.bucket_extra.p, (const uint4*)s.partial.p, (uint4*)s.bucket_acc.p);
+    H2B_LAUNCH(msm_combine_light_kernel, (pl.G + 127) / 128, 128, 0, stream, pl, (const uint32_t*)offsets, ctrl, (const uint32_t*)s.split_list.p,
+               (HeavyDesc*)s.heavy.p, (uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, (uint4*)s.bucket_acc.p);
+    H2B_LAUNCH(msm_combine_chunk_kernel, ctx.sm_count * 2, 256, 0, stream, pl, (const uint32_t*)offsets, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p,
+               (const uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, (uint4*)s.chunk_out.p);
+    H2B_LAUNCH(msm_combine_heavy_kernel, ctx.sm_count, 256, 0, stream, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p, (const uint4*)s.chunk_out.p,
+               (uint4*)s.bucket_acc.p);
     H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_COMBINE, stream);
 
@@ -421,34 +608,36 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const v
     const uint32_t logm = 4;
     uint32_t N = pl.Nb;
     uint32_t J0 = (N + (1u << logm) - 1) >> logm;
-    H2B_TRY(s.redA.reserve((size_t)pl.W * J0 * 128));
-    H2B_TRY(s.redB.reserve((size_t)pl.W * J0 * 128));
-    H2B_TRY(s.redC.reserve((size_t)pl.W * J0 * 128));
-    H2B_TRY(s.redD.reserve((size_t)pl.W * J0 * 128));
+    H2B_TRY(s.redA.reserve((size_t)pl.m * J0 * 128));
+    H2B_TRY(s.redB.reserve((size_t)pl.m * J0 * 128));
+    H2B_TRY(s.redC.reserve((size_t)pl.m * J0 * 128));
+    H2B_TRY(s.redD.reserve((size_t)pl.m * J0 * 128));
     const uint4* Bin = (const uint4*)s.bucket_acc.p;
     const uint4* Din = nullptr;
+    const uint32_t* offs = offsets;
     uint4* Bping[2] = {(uint4*)s.redA.p, (uint4*)s.redB.p};
     uint4* Dping[2] = {(uint4*)s.redC.p, (uint4*)s.redD.p};
     int pp = 0;
     for (;;) {
         uint32_t J = (N + (1u << logm) - 1) >> logm;
-        uint32_t threads = pl.W * J;
-        H2B_LAUNCH(msm_reduce_level_kernel, (threads + 127) / 128, 128, 0, stream, Bin, Din, N, logm, pl.W, Bping[pp], Dping[pp]);
+        uint32_t threads = pl.m * J;
+        H2B_LAUNCH(msm_reduce_level_kernel, (threads + 127) / 128, 128, 0, stream, Bin, Din, offs, N, logm, pl.m, Bping[pp], Dping[pp]);
         Bin = Bping[pp];
         Din = Dping[pp];
+        offs = nullptr;
         pp ^= 1;
         N = J;
         if (J == 1) break;
     }
     ctx.prof.mark(PROF_MSM_REDUCE, stream);
-    H2B_LAUNCH(msm_final_kernel, 1, 32, 0, stream, Din, pl.W, pl.c, (uint4*)d_result, accumulate ? 1u : 0u);
+    H2B_LAUNCH(msm_final_kernel, 1, 32, 0, stream, Din, pl.m, pl.c, (uint4*)d_result, accumulate ? 1u : 0u);
     H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_FINAL, stream);
     return H2B_OK;
 }
 
 // d_out_jac: 96 bytes (x|y|z Montgomery). Internally a 224-byte result block is used (Jacobian + XYZZ total).
-int msm_run(DeviceCtx& ctx, const void* d_scalars, const void* d_bases, size_t n, void* d_out_jac, bool with_xyzz, cudaStream_t stream) {
+int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t n, void* d_out_jac, bool with_xyzz, cudaStream_t stream) {
     if (!ctx.msm) ctx.msm = new MsmScratch();
     MsmScratch& s = *ctx.msm;
     H2B_TRY(s.result.reserve(256));
@@ -462,12 +651,22 @@ int msm_run(DeviceCtx& ctx, const void* d_scalars, const void* d_bases, size_t n
         H2B_CUDA(cudaStreamSynchronize(stream));
         return H2B_OK;
     }
-    if (!d_scalars || !d_bases || !d_out_jac) { set_error("msm: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (!d_scalars || !bases.tables || !d_out_jac) { set_error("msm: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (bases.n_tables > 1 && (bases.row0 + n > bases.stride || (uint64_t)bases.stride * bases.n_tables >= 0x80000000ull)) {
+        set_error("msm: range [%zu, %zu) does not fit the %u x %zu table set", bases.row0, bases.row0 + n, bases.n_tables, bases.stride);
+        return H2B_ERR_BAD_ARGUMENT;
+    }
     const size_t MAX_SUB = (size_t)1 << 26;
     bool first = true;
     for (size_t done = 0; done < n; done += MAX_SUB) {
         uint32_t m = (uint32_t)((n - done < MAX_SUB) ? (n - done) : MAX_SUB);
-        H2B_TRY(msm_sub(ctx, s, (const char*)d_scalars + done * 32, (const char*)d_bases + done * 64, m, s.result.p, !first, stream));
+        MsmBases sub = bases;
+        size_t row0 = bases.row0 + done;
+        if (bases.n_tables <= 1) {       // plain mode: rows are relative to the first point of this chunk
+            sub.tables = (const char*)bases.tables + row0 * 64;
+            row0 = 0;
+        }
+        H2B_TRY(msm_sub(ctx, s, (const char*)d_scalars + done * 32, sub, row0, m, s.result.p, !first, stream));
         first = false;
     }
     H2B_CUDA(cudaMemcpyAsync(d_out_jac, s.result.p, out_bytes, cudaMemcpyDeviceToDevice, stream));
@@ -499,8 +698,8 @@ int msm_sum_partials_run(DeviceCtx& ctx, const void* d_blocks, uint32_t count, v
 void msm_release(DeviceCtx& ctx) {
     if (!ctx.msm) return;
     MsmScratch& s = *ctx.msm;
-    DevBuf* all[] = {&s.digits, &s.counts, &s.offsets, &s.cursor, &s.block_sums, &s.sorted, &s.ctrl, &s.overflow_desc, &s.bucket_extra,
-                     &s.heavy, &s.bucket_acc, &s.partial, &s.redA, &s.redB, &s.redC, &s.redD, &s.result};
+    DevBuf* all[] = {&s.digits, &s.counts, &s.offsets, &s.cursor, &s.block_sums, &s.sorted, &s.ctrl, &s.split_list, &s.heavy, &s.chunk_desc, &s.chunk_out,
+                     &s.bucket_acc, &s.head_partial, &s.redA, &s.redB, &s.redC, &s.redD, &s.result};
     for (DevBuf* b : all) b->release();
     delete ctx.msm;
     ctx.msm = nullptr;

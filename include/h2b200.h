@@ -75,7 +75,11 @@ int h2b_msm_bn254_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, u
  * a has 2^log_n elements, log_n <= 28. */
 int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n);
 
-/* Explicit device residency for an SRS vector (copied; the host array may be freed afterwards). */
+/* Explicit device residency for an SRS vector (copied; the host array may be freed afterwards).  Registration
+ * also precomputes the window tables T_j[i] = 2^(spacing*j) * bases[i] on the device (one-off cost of a few MSMs;
+ * memory n_tables x n x 64 B, see h2b_base_set_info) so that later MSMs over the set need no doublings and a
+ * single shared bucket set.  ParamsKZG's `g` and `g_lagrange` ([UP] halo2_proofs/src/poly/kzg/commitment.rs) are
+ * the two vectors a prover registers.  Implicitly cached arrays (h2b_msm_bn254_g1) get their tables on second use. */
 int h2b_register_bases(const uint64_t* bases, size_t n, uint64_t* handle);
 int h2b_unregister_bases(uint64_t handle);
 /* MSM over bases[offset .. offset+n) of a registered set. */
@@ -90,6 +94,8 @@ int h2b_msm_bn254_g1_dev(int device, const void* d_scalars, const void* d_bases,
  * result block (224 B: Jacobian x|y|z followed by the XYZZ form) for its slice, the blocks are gathered by the
  * caller (e.g. torch.distributed.all_gather) and folded on one device. */
 int h2b_msm_bn254_g1_dev_partial(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_block /* 224 B */, void* stream);
+/* same over rows [offset, offset + n) of a registered base set (uses its window tables); d_scalars on `device` */
+int h2b_msm_bn254_g1_dev_registered(int device, const void* d_scalars, uint64_t handle, size_t offset, size_t n, void* d_out_block /* 224 B */, void* stream);
 int h2b_msm_fold_partials(int device, const uint64_t* host_blocks /* count x 28 u64 */, size_t count, uint64_t out_jac[12]);
 /* same, blocks and result in device memory, asynchronous on `stream` */
 int h2b_msm_fold_partials_dev(int device, const void* d_blocks, size_t count, void* d_out_jac /* 96 B */, void* stream);
@@ -128,6 +134,11 @@ int h2b_profile_enable(int device, int on);
 int h2b_profile_read(int device, int* tags, float* ms, int cap, int* count);
 /* force the MSM window size (0 = automatic) -- tuning / tests only */
 int h2b_set_msm_window(int c);
+/* window-table policy for base sets registered from now on: -1 no tables, 0 automatic spacing, 2..24 forced
+ * spacing (tuning / tests; the environment variable H2B_MSM_PRECOMP sets the initial value) */
+int h2b_set_msm_precomp(int spacing);
+/* tables, spacing (bits) and device bytes per device of a registered base set */
+int h2b_base_set_info(uint64_t handle, uint32_t* n_tables, uint32_t* spacing, uint64_t* device_bytes);
 
 #ifdef __cplusplus
 }

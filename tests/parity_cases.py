@@ -87,6 +87,47 @@ def check_msm(L, oc, n, kind=0, windows=(0,), seed=1):
         assert (got == want).all(), "MSM mismatch n=%d kind=%d window=%d" % (n, kind, cw)
 
 
+def check_msm_tables(L, oc, n, spacing, kind=0, seed=5, windows=(0,), ranges=None):
+    """Registered base set with precomputed window tables: full range and sub-ranges, forced table spacing."""
+    s, P = edge_msm_inputs(L, oc, n, kind, seed + n)
+    L.set_msm_precomp(spacing)
+    try:
+        h = L.register_bases(P)
+    finally:
+        L.set_msm_precomp(0)
+    try:
+        info = L.base_set_info(h)
+        assert info["n_tables"] > 1 and info["spacing"] == (spacing or info["spacing"]), info
+        for (off, m) in (ranges or [(0, n)]):
+            want = affine_of(oc, oc.best_multiexp(s[off:off + m], P[off:off + m]))
+            for cw in windows:
+                L.set_msm_window(cw)
+                try:
+                    got = affine_of(oc, L.msm_registered(s[off:off + m], h, off))
+                finally:
+                    L.set_msm_window(0)
+                assert (got == want).all(), "table MSM mismatch n=%d range=(%d,%d) spacing=%d window=%d" % (n, off, m, spacing, cw)
+    finally:
+        L.unregister_bases(h)
+
+
+def check_msm_single_bucket(L, oc, n, scalar=1, tables=True):
+    """Every scalar equal: the whole sorted list is one bucket, cut into many slices (multi-chunk tree combine)."""
+    P = oc.gen_points(901, n) if n <= (1 << 16) else L.gen_points(901, n)
+    one = oc.fr_to_mont(np.array([[scalar, 0, 0, 0]], dtype=np.uint64))
+    s = np.repeat(one, n, axis=0)
+    want = affine_of(oc, oc.best_multiexp(s, P))
+    if tables:
+        h = L.register_bases(P)
+        try:
+            got = affine_of(oc, L.msm_registered(s, h))
+        finally:
+            L.unregister_bases(h)
+    else:
+        got = affine_of(oc, L.msm(s, P))
+    assert (got == want).all()
+
+
 def check_golden_ntt(L, g):
     for k in (1, 2, 3, 5, 8):
         for tag, wkey in (("fwd", "omega"), ("inv", "omega_inv")):

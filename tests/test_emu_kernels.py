@@ -93,3 +93,31 @@ def test_length_mismatch_asserts_like_the_reference(emu, oc):
         emu.msm(oc.random_fr(1, 4), oc.gen_points(1, 5))
     with pytest.raises(AssertionError):
         emu.ntt(np.zeros((3, 4), dtype=np.uint64), np.zeros(4, dtype=np.uint64), 2)
+
+
+@pytest.mark.parametrize("n,spacing,windows", [(1, 4, (0,)), (3, 6, (0, 3)), (33, 8, (0, 4, 2)), (200, 0, (0,)), (1000, 12, (0, 6, 4, 3)), (700, 10, (0, 5))])
+def test_msm_with_window_tables(emu, oc, n, spacing, windows):
+    pc.check_msm_tables(emu, oc, n, spacing, windows=windows, ranges=[(0, n), (n // 3, n - n // 3), (n - 1, 1)])
+
+
+def test_msm_with_window_tables_witness_like(emu, oc):
+    # skewed scalars: one bucket holds a large share of the sorted list -> slices cut it into many pieces (heavy combine)
+    pc.check_msm_tables(emu, oc, 4000, 8, kind=1, windows=(0, 8))
+
+
+def test_implicit_base_cache_builds_tables_on_second_use_and_follows_reloaded_srs(emu, oc):
+    n = 300
+    s, P = pc.edge_msm_inputs(emu, oc, n, 0, 77)
+    want = pc.affine_of(oc, oc.best_multiexp(s, P))
+    for _ in range(3):      # 1st call: plain upload, 2nd: tables are built, 3rd: tables reused
+        assert (pc.affine_of(oc, emu.msm(s, P)) == want).all()
+    P2 = P.copy()           # the same SRS vector at a new address (scaffold.rs:174 re-reads the params file per proof)
+    assert (pc.affine_of(oc, emu.msm(s, P2)) == want).all()
+    P2[0] = P2[11]          # ... and a different vector at that same address (a sampled point differs) must not hit the cache
+    want2 = pc.affine_of(oc, oc.best_multiexp(s, P2))
+    assert (pc.affine_of(oc, emu.msm(s, P2)) == want2).all()
+
+
+@pytest.mark.parametrize("tables", [False, True])
+def test_msm_one_bucket_holds_everything(emu, oc, tables):
+    pc.check_msm_single_bucket(emu, oc, 40000, scalar=1, tables=tables)

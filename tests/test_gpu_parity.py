@@ -88,6 +88,18 @@ def test_registered_bases_ranges(gpu, oc):
         gpu.msm_registered(s, h, 0)
 
 
+@pytest.mark.parametrize("n,spacing,kind,windows", [(1, 4, 0, (0,)), (33, 8, 0, (0, 4)), (1000, 12, 0, (0, 6, 4)), (4096, 0, 1, (0,)),
+                                                     (1 << 16, 0, 0, (0,)), (1 << 16, 16, 1, (0, 8)), ((1 << 18) + 777, 18, 0, (0, 9)),
+                                                     (1 << 20, 0, 0, (0,)), (1 << 20, 20, 1, (0, 10))])
+def test_msm_with_window_tables_matches_oracle(gpu, oc, n, spacing, kind, windows):
+    pc.check_msm_tables(gpu, oc, n, spacing, kind=kind, windows=windows, ranges=[(0, n), (n // 3, n - n // 3)])
+
+
+@pytest.mark.parametrize("n,scalar,tables", [(1 << 20, 1, True), (1 << 20, 3, False), (300000, 0xffff, True)])
+def test_msm_one_bucket_holds_everything(gpu, oc, n, scalar, tables):
+    pc.check_msm_single_bucket(gpu, oc, n, scalar=scalar, tables=tables)
+
+
 def test_error_behaviour_matches_reference_asserts(gpu, oc):
     with pytest.raises(AssertionError):
         gpu.msm(oc.random_fr(1, 4), oc.gen_points(1, 5))
@@ -180,6 +192,33 @@ def test_msm_full_size_checksum(gpu, oc, k, kind):
     got_w = oc.words_to_ints(pc.affine_of(oc, out).reshape(2, 4))
     got = (o.from_mont(got_w[0], o.P_MOD), o.from_mont(got_w[1], o.P_MOD))
     assert got == want
+
+
+@pytest.mark.parametrize("k,kind", [(22, 1), (24, 0), (24, 1)])
+def test_msm_window_tables_full_size_checksum(gpu, oc, k, kind):
+    """Same O(n) checksum through the registered-SRS path (window tables, one shared bucket set, device-resident scalars)."""
+    n = 1 << k
+    seed_p = 0xB2001000 + k
+    s = gpu.gen_scalars(0xB2000000 + k, n, kind)
+    h = gpu.register_bases(gpu.gen_points(seed_p, n))
+    d_s, d_o = gpu.dev_alloc(0, n * 32), gpu.dev_alloc(0, 224)
+    try:
+        assert gpu.base_set_info(h)["n_tables"] > 1
+        gpu.h2d(0, d_s, s)
+        gpu.msm_dev_registered(0, d_s, h, 0, n, d_o)
+        gpu.dev_sync(0)
+        out = np.zeros(28, dtype=np.uint64)
+        gpu.d2h(0, out, d_o)
+        host = gpu.msm_registered(s, h)            # host-pointer entry point over the same tables
+    finally:
+        gpu.unregister_bases(h)
+        for p in (d_s, d_o):
+            gpu.dev_free(0, p)
+    t = _dot_with_generator_scalars(oc, s, seed_p, n)
+    want = o.g1_mul(o.G1_GEN, t)
+    for res in (out[:12], host):
+        got_w = oc.words_to_ints(pc.affine_of(oc, res).reshape(2, 4))
+        assert (o.from_mont(got_w[0], o.P_MOD), o.from_mont(got_w[1], o.P_MOD)) == want
 
 
 def test_ntt_full_size_round_trip_and_spot_values(gpu, oc):
