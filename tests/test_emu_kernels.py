@@ -121,3 +121,10 @@ def test_implicit_base_cache_builds_tables_on_second_use_and_follows_reloaded_sr
 @pytest.mark.parametrize("tables", [False, True])
 def test_msm_one_bucket_holds_everything(emu, oc, tables):
     pc.check_msm_single_bucket(emu, oc, 40000, scalar=1, tables=tables)
+
+
+def test_cpp_host_mirror_over_the_c_abi(emu, oc, tmp_path):
+    # halo2_scaffold_b200/host/h2b200.hpp (best_multiexp / best_fft / EvaluationDomain / ParamsKZG in C++) linked against
+    # the emulator build of the same C ABI; the GPU suite repeats this against libh2b200.so
+    from host_mirror_case import run_host_mirror
+    run_host_mirror(oc, emu.path, tmp_path, k=6, j=4)

@@ -145,6 +145,12 @@ def test_domain_and_kzg_mirrors(gpu, oc, golden):
     assert (c1 == c2).all()
 
 
+def test_cpp_host_mirror_over_the_c_abi(gpu, oc, tmp_path):
+    from host_mirror_case import run_host_mirror
+    run_host_mirror(oc, gpu.path, tmp_path, k=10, j=4)
+    run_host_mirror(oc, gpu.path, tmp_path, k=5, j=3)       # examples/standard_plonk.rs: k = 5, degree 3
+
+
 # ---- full benchmark sizes: size-independent properties -------------------------------------------------------------
 def _dot_with_generator_scalars(oc, scalars_mont, seed, n):
     """sum_i s_i * z_i mod r for the synthetic bases P_i = [z_i] G (z_i = SplitMix64 stream `seed`)."""
