@@ -19,8 +19,10 @@
 
 namespace h2b {
 
-static const int NTT_MAX_TILE_LOG = 11;      // 2048 elements = 64 KiB of shared memory per CTA
+static const int NTT_MAX_TILE_LOG = 12;      // 4096 elements: 146 KiB of (skewed) shared memory + 73 KiB of stage twiddles
+static const int NTT_DEFAULT_TILE_LOG = 11;  // measured best on B200 (profiles/r01_ntt_tiles.jsonl): 2048-element tiles, two CTAs per SM
 static const int NTT_MAX_PASSES = 4;
+static const int NTT_SINGLE_CTA_LOG = 10;    // up to 2^10 elements one CTA does the whole transform (latency)
 
 struct NttPassParams {
     const uint4* in;
@@ -36,114 +38,193 @@ struct NttPassParams {
     uint32_t last;
 };
 
+// Shared-memory slot of element e.  Elements live in two 16-byte planes; the skew keeps every access pattern of the
+// radix-8 rounds (strides 1, 8, 64, 512 elements) spread over all 32 banks.
+__host__ __device__ __forceinline__ uint32_t sm_slot(uint32_t e) { return e + (e >> 3) + (e >> 6) + (e >> 9); }
+
 __device__ __forceinline__ Fr sm_get(const uint4* lo, const uint4* hi, uint32_t e) {
-    uint4 a = lo[e], b = hi[e];
+    const uint32_t k = sm_slot(e);
+    uint4 a = lo[k], b = hi[k];
     Fr r;
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
 __device__ __forceinline__ void sm_put(uint4* lo, uint4* hi, uint32_t e, const Fr& v) {
-    lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    const uint32_t k = sm_slot(e);
+    lo[k] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[k] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPassParams p) {
+// 16-byte global -> shared copy that does not pass through registers (LDGSTS): a thread issues all its copies of a
+// tile back to back and waits once, so the tile load costs one memory latency instead of one per element.
+__device__ __forceinline__ void copy16_async(uint4* smem_dst, const uint4* gmem_src) {
+#ifdef H2B_EMU
+    *smem_dst = *gmem_src;
+#else
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void copy_async_wait_all() {
+#ifndef H2B_EMU
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// R consecutive DIF stages (first stage index s) on 2^R elements held in registers: the elements of one work item
+// differ in bits [b-s-R, b-s) of the digit q.  Stage s' multiplies the lower output of each butterfly by
+// Omega^(r * 2^s'), r = position inside the half block (the table index never exceeds N/2).
+template <int R>
+__device__ __forceinline__ void ntt_round(uint4* lo, uint4* hi, const uint4* tlo, const uint4* thi, uint32_t item, uint32_t b, uint32_t s,
+                                          uint32_t logT, bool last) {
+    constexpr int K = 1 << R;
+    const uint32_t loghmin = b - s - R;
+    uint32_t t, g;
+    if (!last) { t = item & ((1u << logT) - 1); g = item >> logT; }
+    else { g = item & ((1u << (b - R)) - 1); t = item >> (b - R); }
+    const uint32_t lo_part = g & ((1u << loghmin) - 1);
+    const uint32_t q0 = ((g >> loghmin) << (loghmin + R)) + lo_part;
+    Fr x[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const uint32_t q = q0 + ((uint32_t)j << loghmin);
+        x[j] = sm_get(lo, hi, last ? ((t << b) + q) : ((q << logT) + t));
+    }
+#pragma unroll
+    for (int st = 0; st < R; ++st) {
+        const int dj = K >> (st + 1);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j & dj) continue;
+            const uint32_t r = ((uint32_t)(j & (dj - 1)) << loghmin) + lo_part;
+            const uint32_t twi = r << (s + st);
+            Fr sum = fp_add(x[j], x[j + dj]), dif = fp_sub(x[j], x[j + dj]);
+            if (twi != 0) dif = fp_mul(dif, sm_get(tlo, thi, twi));
+            x[j] = sum;
+            x[j + dj] = dif;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const uint32_t q = q0 + ((uint32_t)j << loghmin);
+        sm_put(lo, hi, last ? ((t << b) + q) : ((q << logT) + t), x[j]);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) ntt_pass_kernel(NttPassParams p) {
     H2B_DYN_SMEM(uint4, sm);
     const uint32_t b = p.b, logT = p.logT;
     const uint32_t N = 1u << b, T = 1u << logT, E = N << logT;
+    const uint32_t data_slots = sm_slot(E - 1) + 1, tw_slots = sm_slot((N >> 1) ? (N >> 1) - 1 : 0) + 1;
     uint4* lo = sm;
-    uint4* hi = sm + E;
-    uint4* tlo = sm + 2 * E;              // small twiddles, split in the same two planes
-    uint4* thi = tlo + (N >> 1);
+    uint4* hi = sm + data_slots;
+    uint4* tlo = sm + 2 * data_slots;       // stage twiddles, same two planes
+    uint4* thi = tlo + tw_slots;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-    const uint32_t blk = blockIdx.x;
+    const bool last = p.last != 0;
+    const uint32_t ntiles = 1u << (p.log_n - b - logT);
+    // non-last pass: tile (q, t), q < N, t < T  <->  global base + q*M + t ; shared e = q*T + t
+    // last pass: T segments that differ in the TOP logT bits of the position;
+    //            element (q, t) <-> global ((t*nseg + tile) << b) + q ; shared e = t*N + q
+    const uint32_t logM = last ? 0u : p.logL - b;
+    const uint32_t M = 1u << logM;
+    const uint32_t log_tiles_per_seg = logM - (last ? 0u : logT);
+    const uint32_t nseg = (1u << (p.log_n - b)) >> logT;
 
-    uint32_t base = 0, M = 0, tau = 0, nseg = 0;
-    if (!p.last) {
-        // tile (q, t), q < N, t < T  <->  global base + q*M + t ; shared e = q*T + t
-        const uint32_t logM = p.logL - b;
-        M = 1u << logM;
-        const uint32_t tiles_per_seg = M >> logT;
-        const uint32_t seg = blk / tiles_per_seg;
-        tau = blk - seg * tiles_per_seg;
-        base = (seg << p.logL) + (tau << logT);
-        for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
-            uint32_t half = idx & 1, t = (idx >> 1) & (T - 1), q = idx >> (1 + logT);
-            uint32_t g = base + q * M + t;
-            uint4 v = p.in[2 * (size_t)g + half];
-            uint32_t e = (q << logT) + t;
-            if (half) hi[e] = v; else lo[e] = v;
-        }
-    } else {
-        // last pass: T segments that differ in the TOP logT bits of the position;
-        // element (q, t) <-> global ((t*nseg + blk) << b) + q ; shared e = t*N + q
-        nseg = (1u << (p.log_n - b)) >> logT;
-        for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
-            uint32_t half = idx & 1, q = (idx >> 1) & (N - 1), t = idx >> (1 + b);
-            uint32_t g = ((t * nseg + blk) << b) + q;
-            uint4 v = p.in[2 * (size_t)g + half];
-            uint32_t e = (t << b) + q;
-            if (half) hi[e] = v; else lo[e] = v;
-        }
-    }
+    // stage twiddles: once per CTA
     for (uint32_t idx = tid; idx < N; idx += nthr) {
         uint32_t half = idx & 1, j = idx >> 1;
-        uint4 v = p.tw_small[2 * j + half];
-        if (half) thi[j] = v; else tlo[j] = v;
+        copy16_async((half ? thi : tlo) + sm_slot(j), p.tw_small + 2 * j + half);
     }
-    __syncthreads();
-
-    const uint32_t SQ = p.last ? 1u : T;
-    uint32_t logh = b - 1;
-    for (uint32_t h = N >> 1; h >= 1; h >>= 1, --logh) {
-        for (uint32_t i = tid; i < (E >> 1); i += nthr) {
-            uint32_t t, bq;
-            if (!p.last) { t = i & (T - 1); bq = i >> logT; }
-            else { bq = i & ((N >> 1) - 1); t = i >> (b - 1); }
-            uint32_t r = bq & (h - 1);
-            uint32_t q = ((bq - r) << 1) | r;
-            uint32_t e0 = p.last ? ((t << b) + q) : ((q << logT) + t);
-            uint32_t e1 = e0 + h * SQ;
-            Fr x = sm_get(lo, hi, e0), y = sm_get(lo, hi, e1);
-            Fr s = fp_add(x, y), d = fp_sub(x, y);
-            uint32_t twi = r << (b - 1 - logh);
-            if (twi != 0) d = fp_mul(d, sm_get(tlo, thi, twi));
-            sm_put(lo, hi, e0, s);
-            sm_put(lo, hi, e1, d);
-        }
-        __syncthreads();
-        if (h == 1) break;
-    }
-
-    if (!p.last) {
-        const uint32_t logS = p.log_n - p.logL;          // S_p = n / L_p
-        const uint32_t hmask = (1u << p.h) - 1;
-        for (uint32_t i = tid; i < E; i += nthr) {
-            uint32_t t = i & (T - 1), q = i >> logT;
-            Fr v = sm_get(lo, hi, i);
-            uint32_t ip = __brev(q) >> (32 - b);
-            uint32_t jr = (tau << logT) + t;
-            uint32_t ex = (jr * ip) << logS;
-            if (ex != 0) {
-                Fr w = fp_load<FR>(p.tw_lo + 2 * (size_t)(ex & hmask));
-                uint32_t eh = ex >> p.h;
-                if (eh != 0) w = fp_mul(w, fp_load<FR>(p.tw_hi + 2 * (size_t)eh));
-                v = fp_mul(v, w);
+    // first tile of this CTA (persistent: tiles blockIdx.x, blockIdx.x + gridDim.x, ...)
+    {
+        const uint32_t tile = blockIdx.x;
+        if (!last) {
+            const uint32_t seg = tile >> log_tiles_per_seg, tau = tile & ((1u << log_tiles_per_seg) - 1);
+            const uint32_t base = (seg << p.logL) + (tau << logT);
+            for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
+                uint32_t half = idx & 1, t = (idx >> 1) & (T - 1), q = idx >> (1 + logT);
+                copy16_async((half ? hi : lo) + sm_slot((q << logT) + t), p.in + 2 * (size_t)(base + q * M + t) + half);
             }
-            uint32_t g = base + q * M + t;
-            fp_store<FR>(p.out + 2 * (size_t)g, v);
-        }
-    } else {
-        for (uint32_t i = tid; i < E; i += nthr) {
-            uint32_t tr = i & (T - 1), q = i >> logT;
-            uint32_t t = logT ? (__brev(tr) >> (32 - logT)) : 0u;
-            Fr v = sm_get(lo, hi, (t << b) + q);
-            uint32_t pos = ((t * nseg + blk) << b) + q;
-            uint32_t oidx = __brev(pos) >> (32 - p.log_n);
-            fp_store<FR>(p.out + 2 * (size_t)oidx, v);
+        } else {
+            for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
+                uint32_t half = idx & 1, q = (idx >> 1) & (N - 1), t = idx >> (1 + b);
+                copy16_async((half ? hi : lo) + sm_slot((t << b) + q), p.in + 2 * (size_t)(((t * nseg + tile) << b) + q) + half);
+            }
         }
     }
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        copy_async_wait_all();
+        __syncthreads();
+
+        // b DIF stages: one partial round (b mod 3 stages) followed by radix-8 rounds, all out of registers
+        uint32_t s = 0;
+        if (b % 3 == 1) {
+            for (uint32_t item = tid; item < (E >> 1); item += nthr) ntt_round<1>(lo, hi, tlo, thi, item, b, 0, logT, last);
+            s = 1;
+            __syncthreads();
+        } else if (b % 3 == 2) {
+            for (uint32_t item = tid; item < (E >> 2); item += nthr) ntt_round<2>(lo, hi, tlo, thi, item, b, 0, logT, last);
+            s = 2;
+            __syncthreads();
+        }
+        for (; s < b; s += 3) {
+            for (uint32_t item = tid; item < (E >> 3); item += nthr) ntt_round<3>(lo, hi, tlo, thi, item, b, s, logT, last);
+            __syncthreads();
+        }
+
+        // Write-out.  Every shared slot is read by exactly one thread, which right afterwards refills it with the
+        // matching element of this CTA's NEXT tile: the next tile's load overlaps the twiddle multiplications and
+        // stores of this one without a second buffer.
+        const uint32_t next = tile + gridDim.x;
+        const bool has_next = next < ntiles;
+        if (!last) {
+            const uint32_t seg = tile >> log_tiles_per_seg, tau = tile & ((1u << log_tiles_per_seg) - 1);
+            const uint32_t base = (seg << p.logL) + (tau << logT);
+            const uint32_t nseg2 = next >> log_tiles_per_seg, ntau = next & ((1u << log_tiles_per_seg) - 1);
+            const uint32_t nbase = (nseg2 << p.logL) + (ntau << logT);
+            const uint32_t logS = p.log_n - p.logL;          // S_p = n / L_p
+            const uint32_t hmask = (1u << p.h) - 1;
+#pragma unroll 2
+            for (uint32_t i = tid; i < E; i += nthr) {
+                uint32_t t = i & (T - 1), q = i >> logT;
+                Fr v = sm_get(lo, hi, i);
+                uint32_t ip = __brev(q) >> (32 - b);
+                uint32_t jr = (tau << logT) + t;
+                uint32_t ex = (jr * ip) << logS;
+                if (ex != 0) {
+                    Fr w = fp_load<FR>(p.tw_lo + 2 * (size_t)(ex & hmask));
+                    uint32_t eh = ex >> p.h;
+                    if (eh != 0) w = fp_mul(w, fp_load<FR>(p.tw_hi + 2 * (size_t)eh));
+                    v = fp_mul(v, w);
+                }
+                fp_store<FR>(p.out + 2 * (size_t)(base + q * M + t), v);
+                if (has_next) {
+                    const uint4* src = p.in + 2 * (size_t)(nbase + q * M + t);
+                    copy16_async(lo + sm_slot(i), src);
+                    copy16_async(hi + sm_slot(i), src + 1);
+                }
+            }
+        } else {
+            for (uint32_t i = tid; i < E; i += nthr) {
+                uint32_t tr = i & (T - 1), q = i >> logT;
+                uint32_t t = logT ? (__brev(tr) >> (32 - logT)) : 0u;
+                const uint32_t e = (t << b) + q;
+                Fr v = sm_get(lo, hi, e);
+                uint32_t pos = ((t * nseg + tile) << b) + q;
+                uint32_t oidx = __brev(pos) >> (32 - p.log_n);
+                fp_store<FR>(p.out + 2 * (size_t)oidx, v);
+                if (has_next) {
+                    const uint4* src = p.in + 2 * (size_t)(((t * nseg + next) << b) + q);
+                    copy16_async(lo + sm_slot(e), src);
+                    copy16_async(hi + sm_slot(e), src + 1);
+                }
+            }
+        }
+    }
+    copy_async_wait_all();
 }
 
 // ---- twiddle tables ---------------------------------------------------------------------------
@@ -193,26 +274,44 @@ struct NttTwiddles {
 
 static uint64_t g_use_counter = 0;
 
+static int ntt_tile_log() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("H2B_NTT_TILE");
+        v = e ? atoi(e) : NTT_DEFAULT_TILE_LOG;
+        if (v < 3 || v > NTT_MAX_TILE_LOG) v = NTT_DEFAULT_TILE_LOG;
+    }
+    return v;
+}
+
 static int ntt_bmax() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("H2B_NTT_BMAX");
-        v = e ? atoi(e) : 9;
-        if (v < 1 || v > NTT_MAX_TILE_LOG) v = 9;
+        v = e ? atoi(e) : ntt_tile_log();
+        if (v < 1 || v > ntt_tile_log()) v = ntt_tile_log();
     }
     return v;
 }
 
 static void ntt_plan(uint32_t log_n, NttTwiddles& tw) {
     uint32_t P;
-    if (log_n <= (uint32_t)NTT_MAX_TILE_LOG) P = 1;
+    static int single_env = -1;
+    if (single_env < 0) {
+        const char* e = getenv("H2B_NTT_SINGLE");
+        single_env = e ? atoi(e) : NTT_SINGLE_CTA_LOG;
+        if (single_env < 1 || single_env > ntt_tile_log()) single_env = NTT_SINGLE_CTA_LOG;
+    }
+    const uint32_t single = (uint32_t)(ntt_bmax() < single_env ? ntt_bmax() : single_env);
+    if (log_n <= single) P = 1;
     else P = (log_n + ntt_bmax() - 1) / ntt_bmax();
-    if (P > (uint32_t)NTT_MAX_PASSES) P = NTT_MAX_PASSES;   // log_n <= 28 < 4 * 9
+    if (P < 2 && log_n > single) P = 2;
+    if (P > (uint32_t)NTT_MAX_PASSES) P = NTT_MAX_PASSES;   // log_n <= 28 < 4 * 7 needs H2B_NTT_BMAX >= 7
     tw.npass = P;
     uint32_t logL = log_n;
     for (uint32_t p = 0; p < P; ++p) {
         uint32_t b = log_n / P + (p < log_n % P ? 1 : 0);
-        uint32_t logT = NTT_MAX_TILE_LOG - b;
+        uint32_t logT = (uint32_t)ntt_tile_log() - b;
         uint32_t room = (p + 1 < P) ? (logL - b) : (log_n - b);   // tile cannot exceed the stride / segment count
         if (logT > room) logT = room;
         tw.pass[p].b = b;
@@ -287,7 +386,8 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
     if (tw->npass > 1) H2B_TRY(ctx.ntt_work.reserve(n * 32));
     auto kfn = ntt_pass_kernel;
     if (!ctx.ntt_attr_set) {
-        H2B_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 << NTT_MAX_TILE_LOG) + 32 * (1 << (NTT_MAX_TILE_LOG - 1))));
+        H2B_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      32 * (int)(sm_slot((1u << NTT_MAX_TILE_LOG) - 1) + 1 + sm_slot((1u << (NTT_MAX_TILE_LOG - 1)) - 1) + 1)));
         ctx.ntt_attr_set = true;
     }
     const uint4* tbl = (const uint4*)tw->buf.p;
@@ -307,11 +407,26 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
         a.h = tw->h;
         a.last = last ? 1u : 0u;
         const uint32_t logE = a.b + a.logT;
-        const uint32_t grid = 1u << (log_n - logE);
-        uint32_t threads = (1u << logE) / 2;
-        if (threads > 256) threads = 256;
+        const uint32_t ntiles = 1u << (log_n - logE);
+        uint32_t threads = (1u << logE) / 8;
+        if (threads > 512) threads = 512;
         if (threads < 32) threads = 32;
-        const size_t smem = ((size_t)32 << logE) + 32 * ((size_t)1 << (a.b - 1));
+        const size_t smem = 32 * ((size_t)sm_slot((1u << logE) - 1) + 1 + sm_slot(a.b > 1 ? (1u << (a.b - 1)) - 1 : 0) + 1);
+        // One tile per CTA by default: CTAs of different ages overlap their load, butterfly and store phases on an SM.
+        // H2B_NTT_PERSIST=1 instead keeps as many CTAs as fit on the GPU and lets each loop over tiles with the
+        // next tile prefetched into the slots the write-out frees (measured 7 % slower at 2^24: lock-step phases).
+        static int persist = -1;
+        if (persist < 0) { const char* e = getenv("H2B_NTT_PERSIST"); persist = e ? atoi(e) : 0; }
+        uint32_t per_sm = (uint32_t)(232448 / (smem + 1024));
+        const uint32_t by_regs = 65536 / (threads * 128);
+        if (per_sm > by_regs) per_sm = by_regs;
+        if (per_sm > 16) per_sm = 16;
+        if (per_sm < 1) per_sm = 1;
+        uint32_t grid = persist ? (uint32_t)ctx.sm_count * per_sm : ntiles;
+        static int grid_cap = -1;      // tests: force several tiles per CTA at small sizes
+        if (grid_cap < 0) { const char* e = getenv("H2B_NTT_GRID"); grid_cap = e ? atoi(e) : 0; }
+        if (grid_cap > 0 && grid > (uint32_t)grid_cap) grid = (uint32_t)grid_cap;
+        if (grid > ntiles) grid = ntiles;
         H2B_LAUNCH(kfn, grid, threads, smem, stream, a);
         H2B_CUDA(cudaGetLastError());
         ctx.prof.mark(PROF_NTT_PASS0 + (int)p, stream);

@@ -47,6 +47,14 @@ def test_ntt_three_and_four_pass_plans(emu, oc, monkeypatch):
     env = dict(os.environ, H2B_NTT_BMAX="4")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+    # persistent CTAs looping over several tiles (the next tile is prefetched into the slots the write-out frees)
+    env = dict(os.environ, H2B_NTT_BMAX="5", H2B_NTT_GRID="3")
+    out = subprocess.run([sys.executable, "-c", code.replace("(12, 13, 14, 16)", "(11, 13, 15, 16)")], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+    # one CTA holding a full 2^11 / 2^12 tile (the tile size of the two-pass plan at 2^22..2^24)
+    env = dict(os.environ, H2B_NTT_SINGLE="12")
+    out = subprocess.run([sys.executable, "-c", code.replace("(12, 13, 14, 16)", "(11, 12)")], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 32, 33, 100, 1000])
