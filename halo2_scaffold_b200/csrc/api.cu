@@ -263,12 +263,7 @@ static MsmBases bases_of(const BaseSet& bs, size_t d, size_t row0) {
 static int msm_on_device(DeviceCtx& c, const uint64_t* scalars, const MsmBases& d_bases, size_t n, uint64_t* out_block /*28 x u64*/) {
     H2B_CUDA(cudaSetDevice(c.device));
     H2B_TRY(c.msm_scalars.reserve(n * 32 + 32));
-    H2B_TRY(c.msm_out.reserve(256));
-    if (n) H2B_CUDA(cudaMemcpyAsync(c.msm_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, c.stream));
-    H2B_TRY(msm_run(c, c.msm_scalars.p, d_bases, n, c.msm_out.p, true, c.stream));
-    H2B_CUDA(cudaMemcpyAsync(out_block, c.msm_out.p, 224, cudaMemcpyDeviceToHost, c.stream));
-    H2B_CUDA(cudaStreamSynchronize(c.stream));
-    return H2B_OK;
+    return msm_run_host(c, scalars, c.msm_scalars.p, d_bases, n, out_block);
 }
 
 static int msm_host(const uint64_t* scalars, BaseSet& bs, size_t offset, size_t n, uint64_t out_jac[12]) {
@@ -355,6 +350,9 @@ void h2b_shutdown(void) {
         msm_release(*c);
         c->msm_scalars.release();
         c->msm_out.release();
+        for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+        c->copy_events.clear();
+        if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
         cudaStreamDestroy(c->stream);
     }
     G.devs.clear();

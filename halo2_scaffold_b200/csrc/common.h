@@ -83,6 +83,8 @@ struct DeviceCtx {
     int device = -1;
     int sm_count = 148;
     cudaStream_t stream = nullptr;     // stream used by the host-pointer entry points
+    cudaStream_t copy_stream = nullptr;   // chunked scalar uploads of the host-pointer MSM (overlap with compute)
+    std::vector<cudaEvent_t> copy_events;
     std::mutex mu;                     // serialises calls that share this context's scratch
     DevBuf ntt_work;                   // ping-pong buffer of the multi-pass NTT
     bool ntt_attr_set = false;
@@ -111,6 +113,7 @@ struct MsmBases {
     size_t row0 = 0;
 };
 int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t n, void* d_out, bool with_xyzz, cudaStream_t stream);
+int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const MsmBases& bases, size_t n, void* h_out_block);
 int msm_precompute_run(DeviceCtx& ctx, const void* d_src, void* d_dst, size_t n, uint32_t c0, cudaStream_t stream);
 uint32_t msm_pick_table_spacing(size_t n, uint32_t max_tables);
 uint32_t msm_tables_for(uint32_t c0);

@@ -41,6 +41,7 @@ struct MsmPlan {
     uint32_t stride;     // rows between consecutive tables
     uint32_t row0;       // first row of this call inside each table
     uint32_t G;          // slices (accumulate threads)
+    uint32_t add_into;   // 1: bucket accumulators already hold the sums of earlier chunks (flushes add to them)
 };
 
 // (r - 1) / 2 as canonical 32-bit limbs
@@ -201,6 +202,15 @@ __device__ __forceinline__ uint32_t slice_len(uint32_t total, uint32_t G) {
     return S < SLICE_MIN ? SLICE_MIN : S;
 }
 
+// Exactly one thread flushes a given bucket in one launch (the slice in which the bucket starts), so the
+// read-modify-write of the chunked mode needs no atomics; chunks are ordered by the stream.
+__device__ __forceinline__ void bucket_flush(uint4* slot, const XYZZ& acc, uint32_t add_into) {
+    if (!add_into) { xyzz_store(slot, acc); return; }
+    XYZZ cur = xyzz_load(slot);
+    xyzz_add(cur, acc);
+    xyzz_store(slot, cur);
+}
+
 // ctrl[0] = buckets cut by a slice boundary (split_list), ctrl[1] = those cut into many pieces (heavy_list)
 __global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const uint4* __restrict__ tables, const uint32_t* __restrict__ offsets,
                                                            const uint32_t* __restrict__ sorted, uint32_t* __restrict__ ctrl,
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const u
         }
         if (j == next) {        // bucket b is complete: flush, move to the next non-empty bucket
             if (head) xyzz_store(head_partial + 8 * (size_t)t, acc);
-            else xyzz_store(bucket_acc + 8 * (size_t)b, acc);
+            else bucket_flush(bucket_acc + 8 * (size_t)b, acc, pl.add_into);
             head = false;
             acc = xyzz_identity();
             do { ++b; next = offsets[b + 1]; } while (next <= j);
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const u
     if (head) {
         xyzz_store(head_partial + 8 * (size_t)t, acc);
     } else {
-        xyzz_store(bucket_acc + 8 * (size_t)b, acc);
+        bucket_flush(bucket_acc + 8 * (size_t)b, acc, pl.add_into);
         if (next > end) split_list[atomicAdd(&ctrl[0], 1u)] = b;      // continues in later slices
     }
 }
@@ -540,19 +550,32 @@ static int exclusive_scan(MsmScratch& s, const uint32_t* in, uint32_t count, uin
     return H2B_OK;
 }
 
-static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const MsmBases& bases, size_t row0, uint32_t n, void* d_result, bool accumulate,
-                   cudaStream_t stream) {
-    MsmPlan pl;
+// ---- an MSM = plan + one or more chunks of scalars accumulated into the same buckets + one bucket reduction ----
+static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t n_total, bool chunked, cudaStream_t stream, MsmPlan& pl) {
+    (void)ctx;
     const bool tables = bases.n_tables > 1;
-    pl.n = n;
-    pl.c = tables ? msm_pick_window_tables(n, bases.c0) : msm_pick_window_plain(n);
+    memset(&pl, 0, sizeof(pl));
+    pl.c = tables ? msm_pick_window_tables(n_total, bases.c0) : msm_pick_window_plain(n_total);
     pl.W = windows_for(pl.c);
     pl.m = tables ? bases.c0 / pl.c : pl.W;
     pl.Nb = 1u << (pl.c - 1);
     pl.B = pl.m * pl.Nb;
     pl.stride = tables ? (uint32_t)bases.stride : 0u;
-    pl.row0 = (uint32_t)row0;
+    pl.add_into = chunked ? 1u : 0u;
     if (tables && (pl.W + pl.m - 1) / pl.m > bases.n_tables) { set_error("msm: %u tables cannot serve %u windows in %u sets", bases.n_tables, pl.W, pl.m); return H2B_ERR_BAD_ARGUMENT; }
+    H2B_TRY(s.counts.reserve((size_t)pl.B * 4));
+    H2B_TRY(s.offsets.reserve(((size_t)pl.B + 1) * 4));
+    H2B_TRY(s.cursor.reserve((size_t)pl.B * 4));
+    H2B_TRY(s.ctrl.reserve(16));
+    H2B_TRY(s.bucket_acc.reserve((size_t)pl.B * 128));
+    if (chunked) H2B_CUDA(cudaMemsetAsync(s.bucket_acc.p, 0, (size_t)pl.B * 128, stream));     // XYZZ identity = all zero
+    return H2B_OK;
+}
+
+// sort one chunk of scalars and add its points into the buckets.  `tables`/`row0` locate the chunk's points.
+static int msm_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_scalars, const void* tables, size_t row0, uint32_t n, cudaStream_t stream) {
+    pl.n = n;
+    pl.row0 = (uint32_t)row0;
     const uint64_t upper = (uint64_t)n * pl.W;          // sorted entries, at most
     if (upper >= 0xffffffffull) { set_error("msm: %u points x %u windows exceed the 32-bit sort index", n, pl.W); return H2B_ERR_BAD_ARGUMENT; }
     // slices: about 256 entries each once the GPU is full, never fewer than 64 (latency of tiny MSMs)
@@ -564,17 +587,12 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const M
     if (pl.G == 0) pl.G = 1;
 
     H2B_TRY(s.digits.reserve((size_t)upper * 4));
-    H2B_TRY(s.counts.reserve((size_t)pl.B * 4));
-    H2B_TRY(s.offsets.reserve(((size_t)pl.B + 1) * 4));
-    H2B_TRY(s.cursor.reserve((size_t)pl.B * 4));
     H2B_TRY(s.sorted.reserve((size_t)upper * 4 + 4));
-    H2B_TRY(s.ctrl.reserve(16));
     H2B_TRY(s.split_list.reserve((size_t)pl.G * 4));
     const size_t max_heavy = pl.G / COMBINE_HEAVY + 1, max_chunks = pl.G / COMBINE_CHUNK + max_heavy + 1;
     H2B_TRY(s.heavy.reserve(max_heavy * sizeof(HeavyDesc)));
     H2B_TRY(s.chunk_desc.reserve(max_chunks * 8));
     H2B_TRY(s.chunk_out.reserve(max_chunks * 128));
-    H2B_TRY(s.bucket_acc.reserve((size_t)pl.B * 128));
     H2B_TRY(s.head_partial.reserve((size_t)pl.G * 128));
 
     uint32_t* counts = (uint32_t*)s.counts.p;
@@ -592,7 +610,7 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const M
     ctx.prof.mark(PROF_MSM_SCAN, stream);
     H2B_LAUNCH(msm_scatter_kernel, nblk, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, (uint32_t*)s.sorted.p);
     ctx.prof.mark(PROF_MSM_SCATTER, stream);
-    H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)bases.tables, (const uint32_t*)offsets,
+    H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)tables, (const uint32_t*)offsets,
                (const uint32_t*)s.sorted.p, ctrl, (uint32_t*)s.split_list.p, (uint4*)s.bucket_acc.p, (uint4*)s.head_partial.p);
     ctx.prof.mark(PROF_MSM_ACCUMULATE, stream);
     H2B_LAUNCH(msm_combine_light_kernel, (pl.G + 127) / 128, 128, 0, stream, pl, (const uint32_t*)offsets, ctrl, (const uint32_t*)s.split_list.p,
@@ -603,8 +621,11 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const M
                (uint4*)s.bucket_acc.p);
     H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_COMBINE, stream);
+    return H2B_OK;
+}
 
-    // bucket reduction hierarchy
+// bucket reduction hierarchy + Horner over the sets -> 224-byte result block (Jacobian | XYZZ)
+static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_result, bool accumulate, cudaStream_t stream) {
     const uint32_t logm = 4;
     uint32_t N = pl.Nb;
     uint32_t J0 = (N + (1u << logm) - 1) >> logm;
@@ -612,9 +633,11 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const M
     H2B_TRY(s.redB.reserve((size_t)pl.m * J0 * 128));
     H2B_TRY(s.redC.reserve((size_t)pl.m * J0 * 128));
     H2B_TRY(s.redD.reserve((size_t)pl.m * J0 * 128));
+    ctx.prof.mark(PROF_BEGIN, stream);
     const uint4* Bin = (const uint4*)s.bucket_acc.p;
     const uint4* Din = nullptr;
-    const uint32_t* offs = offsets;
+    // single-chunk MSMs never wrote their empty buckets: level 0 skips them by their sorted count
+    const uint32_t* offs = pl.add_into ? nullptr : (const uint32_t*)s.offsets.p;
     uint4* Bping[2] = {(uint4*)s.redA.p, (uint4*)s.redB.p};
     uint4* Dping[2] = {(uint4*)s.redC.p, (uint4*)s.redD.p};
     int pp = 0;
@@ -636,40 +659,108 @@ static int msm_sub(DeviceCtx& ctx, MsmScratch& s, const void* d_scalars, const M
     return H2B_OK;
 }
 
-// d_out_jac: 96 bytes (x|y|z Montgomery). Internally a 224-byte result block is used (Jacobian + XYZZ total).
+static int msm_check_args(const void* scalars, const MsmBases& bases, size_t n, const void* out) {
+    if (!scalars || !bases.tables || !out) { set_error("msm: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (bases.n_tables > 1 && (bases.row0 + n > bases.stride || (uint64_t)bases.stride * bases.n_tables >= 0x80000000ull)) {
+        set_error("msm: range [%zu, %zu) does not fit the %u x %zu table set", bases.row0, bases.row0 + n, bases.n_tables, bases.stride);
+        return H2B_ERR_BAD_ARGUMENT;
+    }
+    return H2B_OK;
+}
+
+static int msm_identity(void* d_out, size_t out_bytes, cudaStream_t stream) {
+    // identity: Jacobian (0, 1, 0), XYZZ all-zero
+    uint32_t host[56];
+    memset(host, 0, sizeof(host));
+    for (int i = 0; i < 8; ++i) host[8 + i] = FpParams<FQ>::ONE(i);
+    H2B_CUDA(cudaMemcpyAsync(d_out, host, out_bytes, cudaMemcpyHostToDevice, stream));
+    H2B_CUDA(cudaStreamSynchronize(stream));
+    return H2B_OK;
+}
+
+// where chunk [done, done + m) of the call finds its points
+static void chunk_points(const MsmBases& bases, size_t done, const void** tables, size_t* row0) {
+    *row0 = bases.row0 + done;
+    *tables = bases.tables;
+    if (bases.n_tables <= 1) {       // plain mode: rows are relative to the first point of the chunk
+        *tables = (const char*)bases.tables + *row0 * 64;
+        *row0 = 0;
+    }
+}
+
+// Scalars already on the device.  d_out_jac: 96 bytes (x|y|z Montgomery), or the 224-byte block (Jacobian | XYZZ).
 int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t n, void* d_out_jac, bool with_xyzz, cudaStream_t stream) {
     if (!ctx.msm) ctx.msm = new MsmScratch();
     MsmScratch& s = *ctx.msm;
     H2B_TRY(s.result.reserve(256));
     const size_t out_bytes = with_xyzz ? 224 : 96;
+    if (n == 0) return msm_identity(d_out_jac, out_bytes, stream);
+    H2B_TRY(msm_check_args(d_scalars, bases, n, d_out_jac));
+    const size_t MAX_CHUNK = (size_t)1 << 26;
+    MsmPlan pl;
+    H2B_TRY(msm_plan(ctx, s, bases, n, n > MAX_CHUNK, stream, pl));
+    for (size_t done = 0; done < n; done += MAX_CHUNK) {
+        uint32_t m = (uint32_t)((n - done < MAX_CHUNK) ? (n - done) : MAX_CHUNK);
+        const void* tables;
+        size_t row0;
+        chunk_points(bases, done, &tables, &row0);
+        H2B_TRY(msm_chunk(ctx, s, pl, (const char*)d_scalars + done * 32, tables, row0, m, stream));
+    }
+    H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
+    H2B_CUDA(cudaMemcpyAsync(d_out_jac, s.result.p, out_bytes, cudaMemcpyDeviceToDevice, stream));
+    return H2B_OK;
+}
+
+// Scalars in host memory (the drop-in entry points): the upload is cut into chunks on a second stream, and chunk
+// j + 1 crosses PCIe while chunk j is sorted and accumulated, so only the first chunk's transfer is exposed.
+// d_staging: device buffer of at least n * 32 bytes.  Synchronous: returns with the result block in `h_out_block`.
+int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const MsmBases& bases, size_t n, void* h_out_block /* 224 B */) {
+    if (!ctx.msm) ctx.msm = new MsmScratch();
+    MsmScratch& s = *ctx.msm;
+    cudaStream_t stream = ctx.stream;
+    H2B_TRY(s.result.reserve(256));
     if (n == 0) {
-        // identity: Jacobian (0, 1, 0), XYZZ all-zero
-        uint32_t host[56];
-        memset(host, 0, sizeof(host));
-        for (int i = 0; i < 8; ++i) host[8 + i] = FpParams<FQ>::ONE(i);
-        H2B_CUDA(cudaMemcpyAsync(d_out_jac, host, out_bytes, cudaMemcpyHostToDevice, stream));
+        H2B_TRY(msm_identity(s.result.p, 224, stream));
+        H2B_CUDA(cudaMemcpyAsync(h_out_block, s.result.p, 224, cudaMemcpyDeviceToHost, stream));
         H2B_CUDA(cudaStreamSynchronize(stream));
         return H2B_OK;
     }
-    if (!d_scalars || !bases.tables || !d_out_jac) { set_error("msm: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
-    if (bases.n_tables > 1 && (bases.row0 + n > bases.stride || (uint64_t)bases.stride * bases.n_tables >= 0x80000000ull)) {
-        set_error("msm: range [%zu, %zu) does not fit the %u x %zu table set", bases.row0, bases.row0 + n, bases.n_tables, bases.stride);
-        return H2B_ERR_BAD_ARGUMENT;
+    H2B_TRY(msm_check_args(h_scalars, bases, n, h_out_block));
+    static int env_chunk = -1;
+    if (env_chunk < 0) env_chunk = env_int("H2B_MSM_UPLOAD_CHUNK_LOG", 21);
+    size_t chunk = (size_t)1 << (env_chunk < 10 ? 10 : (env_chunk > 26 ? 26 : env_chunk));
+    if (n < 2 * chunk) chunk = n;                 // small MSMs: one upload, one chunk
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    if (!ctx.copy_stream) H2B_CUDA(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
+    while (ctx.copy_events.size() < nchunks) {
+        cudaEvent_t e;
+        H2B_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx.copy_events.push_back(e);
     }
-    const size_t MAX_SUB = (size_t)1 << 26;
-    bool first = true;
-    for (size_t done = 0; done < n; done += MAX_SUB) {
-        uint32_t m = (uint32_t)((n - done < MAX_SUB) ? (n - done) : MAX_SUB);
-        MsmBases sub = bases;
-        size_t row0 = bases.row0 + done;
-        if (bases.n_tables <= 1) {       // plain mode: rows are relative to the first point of this chunk
-            sub.tables = (const char*)bases.tables + row0 * 64;
-            row0 = 0;
-        }
-        H2B_TRY(msm_sub(ctx, s, (const char*)d_scalars + done * 32, sub, row0, m, s.result.p, !first, stream));
-        first = false;
+    MsmPlan pl;
+    H2B_TRY(msm_plan(ctx, s, bases, n, nchunks > 1, stream, pl));
+    // the staging buffer may still be read by the previous call's kernels on `stream`: order the copies after them
+    if (nchunks > 1) {
+        H2B_CUDA(cudaEventRecord(ctx.copy_events[0], stream));
+        H2B_CUDA(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_events[0], 0));
     }
-    H2B_CUDA(cudaMemcpyAsync(d_out_jac, s.result.p, out_bytes, cudaMemcpyDeviceToDevice, stream));
+    for (size_t j = 0; j < nchunks; ++j) {
+        const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+        cudaStream_t cs = nchunks > 1 ? ctx.copy_stream : stream;
+        H2B_CUDA(cudaMemcpyAsync((char*)d_staging + done * 32, (const char*)h_scalars + done * 32, m * 32, cudaMemcpyHostToDevice, cs));
+        if (nchunks > 1) H2B_CUDA(cudaEventRecord(ctx.copy_events[j], cs));
+    }
+    for (size_t j = 0; j < nchunks; ++j) {
+        const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+        if (nchunks > 1) H2B_CUDA(cudaStreamWaitEvent(stream, ctx.copy_events[j], 0));
+        const void* tables;
+        size_t row0;
+        chunk_points(bases, done, &tables, &row0);
+        H2B_TRY(msm_chunk(ctx, s, pl, (const char*)d_staging + done * 32, tables, row0, (uint32_t)m, stream));
+    }
+    H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
+    H2B_CUDA(cudaMemcpyAsync(h_out_block, s.result.p, 224, cudaMemcpyDeviceToHost, stream));
+    H2B_CUDA(cudaStreamSynchronize(stream));
     return H2B_OK;
 }
 

@@ -136,3 +136,24 @@ def test_cpp_host_mirror_over_the_c_abi(emu, oc, tmp_path):
     # the emulator build of the same C ABI; the GPU suite repeats this against libh2b200.so
     from host_mirror_case import run_host_mirror
     run_host_mirror(oc, emu.path, tmp_path, k=6, j=4)
+
+
+def test_msm_chunked_upload_pipeline(emu):
+    # host-pointer MSMs cut into upload chunks that are accumulated into the same buckets (fresh process: the chunk
+    # size is read once); plain and table mode, uniform and witness-like scalars, ragged last chunk
+    import os, subprocess, sys
+    root = pc.__file__.rsplit('/tests/', 1)[0]
+    code = (
+        "import sys; sys.path[:0]=[%r,%r,%r]\n"
+        "import oracle_c as oc, parity_cases as pc\n"
+        "from halo2_scaffold_b200._lib import Lib\n"
+        "L=Lib(%r, allow_emulator=True); L.init(1)\n"
+        "pc.check_msm(L, oc, 5000, kind=0, windows=(0, 7))\n"
+        "pc.check_msm(L, oc, 4097, kind=1, windows=(0,))\n"
+        "pc.check_msm_tables(L, oc, 5000, 8, kind=0, windows=(0, 4), ranges=[(0, 5000), (100, 4500)])\n"
+        "pc.check_msm_tables(L, oc, 6000, 10, kind=1)\n"
+        "pc.check_msm_single_bucket(L, oc, 9000, scalar=1, tables=True)\n"
+        "print('ok')\n") % (root, root + '/oracle', root + '/tests', emu.path)
+    env = dict(os.environ, H2B_MSM_UPLOAD_CHUNK_LOG="10")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
