@@ -41,7 +41,7 @@ struct MsmPlan {
     uint32_t stride;     // rows between consecutive tables
     uint32_t row0;       // first row of this call inside each table
     uint32_t G;          // slices (accumulate threads)
-    uint32_t add_into;   // 1: bucket accumulators already hold the sums of earlier chunks (flushes add to them)
+    uint32_t add_into;   // 1: chunked MSM -- each chunk's bucket sums are merged into running accumulators
 };
 
 // (r - 1) / 2 as canonical 32-bit limbs
@@ -202,15 +202,6 @@ __device__ __forceinline__ uint32_t slice_len(uint32_t total, uint32_t G) {
     return S < SLICE_MIN ? SLICE_MIN : S;
 }
 
-// Exactly one thread flushes a given bucket in one launch (the slice in which the bucket starts), so the
-// read-modify-write of the chunked mode needs no atomics; chunks are ordered by the stream.
-__device__ __forceinline__ void bucket_flush(uint4* slot, const XYZZ& acc, uint32_t add_into) {
-    if (!add_into) { xyzz_store(slot, acc); return; }
-    XYZZ cur = xyzz_load(slot);
-    xyzz_add(cur, acc);
-    xyzz_store(slot, cur);
-}
-
 // ctrl[0] = buckets cut by a slice boundary (split_list), ctrl[1] = those cut into many pieces (heavy_list)
 __global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const uint4* __restrict__ tables, const uint32_t* __restrict__ offsets,
                                                            const uint32_t* __restrict__ sorted, uint32_t* __restrict__ ctrl,
@@ -245,7 +236,7 @@ __global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const u
         }
         if (j == next) {        // bucket b is complete: flush, move to the next non-empty bucket
             if (head) xyzz_store(head_partial + 8 * (size_t)t, acc);
-            else bucket_flush(bucket_acc + 8 * (size_t)b, acc, pl.add_into);
+            else xyzz_store(bucket_acc + 8 * (size_t)b, acc);
             head = false;
             acc = xyzz_identity();
             do { ++b; next = offsets[b + 1]; } while (next <= j);
@@ -257,7 +248,7 @@ __global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const u
     if (head) {
         xyzz_store(head_partial + 8 * (size_t)t, acc);
     } else {
-        bucket_flush(bucket_acc + 8 * (size_t)b, acc, pl.add_into);
+        xyzz_store(bucket_acc + 8 * (size_t)b, acc);
         if (next > end) split_list[atomicAdd(&ctrl[0], 1u)] = b;      // continues in later slices
     }
 }
@@ -358,6 +349,19 @@ __global__ void __launch_bounds__(256) msm_combine_heavy_kernel(const uint32_t* 
         }
         __syncthreads();
     }
+}
+
+// ---- 4b. chunked MSMs: add the bucket sums of one chunk into the running bucket accumulators -------------------
+// (a separate, uniform kernel: doing this addition inside the accumulate kernel's flush would make every lane's
+// flush a divergent 14-multiplication detour for the whole warp)
+__global__ void __launch_bounds__(128) msm_merge_kernel(uint32_t B, const uint32_t* __restrict__ offsets, const uint4* __restrict__ chunk_acc,
+                                                      uint4* __restrict__ bucket_acc) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || offsets[b + 1] == offsets[b]) return;
+    XYZZ cur = xyzz_load(bucket_acc + 8 * (size_t)b);
+    XYZZ add = xyzz_load(chunk_acc + 8 * (size_t)b);
+    xyzz_add(cur, add);
+    xyzz_store(bucket_acc + 8 * (size_t)b, cur);
 }
 
 // ---- 5. bucket reduction ------------------------------------------------------------------------------
@@ -472,7 +476,7 @@ int msm_precompute_run(DeviceCtx& ctx, const void* d_src, void* d_dst, size_t n,
 
 // ---- host orchestration ----------------------------------------------------------------------------------
 struct MsmScratch {
-    DevBuf digits, counts, offsets, cursor, block_sums, sorted, ctrl, split_list, heavy, chunk_desc, chunk_out, bucket_acc, head_partial, redA, redB, redC, redD, result;
+    DevBuf digits, counts, offsets, cursor, block_sums, sorted, ctrl, split_list, heavy, chunk_desc, chunk_out, bucket_acc, bucket_tmp, head_partial, redA, redB, redC, redD, result;
 };
 
 static int g_forced_c = 0;
@@ -568,7 +572,10 @@ static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t
     H2B_TRY(s.cursor.reserve((size_t)pl.B * 4));
     H2B_TRY(s.ctrl.reserve(16));
     H2B_TRY(s.bucket_acc.reserve((size_t)pl.B * 128));
-    if (chunked) H2B_CUDA(cudaMemsetAsync(s.bucket_acc.p, 0, (size_t)pl.B * 128, stream));     // XYZZ identity = all zero
+    if (chunked) {
+        H2B_TRY(s.bucket_tmp.reserve((size_t)pl.B * 128));
+        H2B_CUDA(cudaMemsetAsync(s.bucket_acc.p, 0, (size_t)pl.B * 128, stream));     // XYZZ identity = all zero
+    }
     return H2B_OK;
 }
 
@@ -603,6 +610,7 @@ static int msm_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_sc
     H2B_CUDA(cudaMemsetAsync(ctrl, 0, 16, stream));
 
     const uint32_t nblk = (n + 255) / 256;
+    uint4* target = (uint4*)(pl.add_into ? s.bucket_tmp.p : s.bucket_acc.p);
     ctx.prof.mark(PROF_BEGIN, stream);
     H2B_LAUNCH(msm_decompose_kernel, nblk, 256, 0, stream, (const uint4*)d_scalars, pl, (uint32_t*)s.digits.p, counts);
     ctx.prof.mark(PROF_MSM_DECOMPOSE, stream);
@@ -611,14 +619,16 @@ static int msm_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_sc
     H2B_LAUNCH(msm_scatter_kernel, nblk, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, (uint32_t*)s.sorted.p);
     ctx.prof.mark(PROF_MSM_SCATTER, stream);
     H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)tables, (const uint32_t*)offsets,
-               (const uint32_t*)s.sorted.p, ctrl, (uint32_t*)s.split_list.p, (uint4*)s.bucket_acc.p, (uint4*)s.head_partial.p);
+               (const uint32_t*)s.sorted.p, ctrl, (uint32_t*)s.split_list.p, target, (uint4*)s.head_partial.p);
     ctx.prof.mark(PROF_MSM_ACCUMULATE, stream);
     H2B_LAUNCH(msm_combine_light_kernel, (pl.G + 127) / 128, 128, 0, stream, pl, (const uint32_t*)offsets, ctrl, (const uint32_t*)s.split_list.p,
-               (HeavyDesc*)s.heavy.p, (uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, (uint4*)s.bucket_acc.p);
+               (HeavyDesc*)s.heavy.p, (uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, target);
     H2B_LAUNCH(msm_combine_chunk_kernel, ctx.sm_count * 2, 256, 0, stream, pl, (const uint32_t*)offsets, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p,
                (const uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, (uint4*)s.chunk_out.p);
     H2B_LAUNCH(msm_combine_heavy_kernel, ctx.sm_count, 256, 0, stream, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p, (const uint4*)s.chunk_out.p,
-               (uint4*)s.bucket_acc.p);
+               target);
+    if (pl.add_into)
+        H2B_LAUNCH(msm_merge_kernel, (pl.B + 127) / 128, 128, 0, stream, pl.B, (const uint32_t*)offsets, (const uint4*)target, (uint4*)s.bucket_acc.p);
     H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_COMBINE, stream);
     return H2B_OK;
@@ -726,10 +736,13 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
         return H2B_OK;
     }
     H2B_TRY(msm_check_args(h_scalars, bases, n, h_out_block));
+    // four chunks from 2^22 points up (measured best at 2^24: profiles/r01_msm_e2e_chunks.txt); H2B_MSM_UPLOAD_CHUNK_LOG
+    // forces a chunk size (tests)
     static int env_chunk = -1;
-    if (env_chunk < 0) env_chunk = env_int("H2B_MSM_UPLOAD_CHUNK_LOG", 21);
-    size_t chunk = (size_t)1 << (env_chunk < 10 ? 10 : (env_chunk > 26 ? 26 : env_chunk));
-    if (n < 2 * chunk) chunk = n;                 // small MSMs: one upload, one chunk
+    if (env_chunk < 0) env_chunk = env_int("H2B_MSM_UPLOAD_CHUNK_LOG", 0);
+    size_t chunk = n;
+    if (env_chunk >= 10 && env_chunk <= 26) { chunk = (size_t)1 << env_chunk; if (n < 2 * chunk) chunk = n; }
+    else if (n >= ((size_t)1 << 22)) chunk = (n + 3) / 4;
     const size_t nchunks = (n + chunk - 1) / chunk;
     if (!ctx.copy_stream) H2B_CUDA(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
     while (ctx.copy_events.size() < nchunks) {
@@ -790,7 +803,7 @@ void msm_release(DeviceCtx& ctx) {
     if (!ctx.msm) return;
     MsmScratch& s = *ctx.msm;
     DevBuf* all[] = {&s.digits, &s.counts, &s.offsets, &s.cursor, &s.block_sums, &s.sorted, &s.ctrl, &s.split_list, &s.heavy, &s.chunk_desc, &s.chunk_out,
-                     &s.bucket_acc, &s.head_partial, &s.redA, &s.redB, &s.redC, &s.redD, &s.result};
+                     &s.bucket_acc, &s.bucket_tmp, &s.head_partial, &s.redA, &s.redB, &s.redC, &s.redD, &s.result};
     for (DevBuf* b : all) b->release();
     delete ctx.msm;
     ctx.msm = nullptr;
