@@ -107,7 +107,15 @@ __device__ __forceinline__ void xyzz_add_affine(XYZZ& acc, const Affine& q_in, b
     Fq ppp = fp_mul(p, pp);
     Fq qq = fp_mul(acc.x, pp);
     Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
+    // Y3 = R*(Q - X3) - Y1*PPP.  fp_mul2 (two products, one Montgomery reduction) saves 72 of this addition's 1260
+    // FMA-pipe instructions, but measured 2 % SLOWER here (profiles/r01_field_primitives.jsonl): at the 16 warps per
+    // SM this kernel's 126 registers allow, the longer dependency chains of the separated product/reduction form
+    // cost more than the saved dispatch cycles.  Kept behind a switch for kernels with more resident warps.
+#ifdef H2B_MADD_MUL2
+    Fq y3 = fp_mul2(r, fp_sub(qq, x3), fp_neg(acc.y), ppp);
+#else
     Fq y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(acc.y, ppp));
+#endif
     acc.x = x3;
     acc.y = y3;
     acc.zz = fp_mul(acc.zz, pp);

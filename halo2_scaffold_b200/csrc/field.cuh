@@ -114,8 +114,18 @@ template <int F> __device__ __forceinline__ Fp<F> fp_mul(const Fp<F>& a, const F
     return r;
 }
 template <int F> __device__ __forceinline__ Fp<F> fp_sqr(const Fp<F>& a) {
+#ifdef H2B_SQR_AS_MUL
+    return fp_mul(a, a);
+#else
     Fp<F> r;
     if (F == FR) fr_sqr_asm(r.l, a.l); else fq_sqr_asm(r.l, a.l);
+    return r;
+#endif
+}
+// a*b + c*d with a single Montgomery reduction (a*b + c*d < 2 p^2 < p * 2^256)
+template <int F> __device__ __forceinline__ Fp<F> fp_mul2(const Fp<F>& a, const Fp<F>& b, const Fp<F>& c, const Fp<F>& d) {
+    Fp<F> r;
+    if (F == FR) fr_mul2_asm(r.l, a.l, b.l, c.l, d.l); else fq_mul2_asm(r.l, a.l, b.l, c.l, d.l);
     return r;
 }
 template <int F> __device__ __forceinline__ Fp<F> fp_add(const Fp<F>& a, const Fp<F>& b) {
@@ -162,6 +172,8 @@ template <int F> inline Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
     return r;
 }
 template <int F> inline Fp<F> fp_sqr(const Fp<F>& a) { return fp_mul(a, a); }
+template <int F> inline Fp<F> fp_add(const Fp<F>& a, const Fp<F>& b);
+template <int F> inline Fp<F> fp_mul2(const Fp<F>& a, const Fp<F>& b, const Fp<F>& c, const Fp<F>& d) { return fp_add(fp_mul(a, b), fp_mul(c, d)); }
 template <int F> inline Fp<F> fp_add(const Fp<F>& a, const Fp<F>& b) {
     uint32_t t[8]; uint64_t c = 0;
     for (int i = 0; i < 8; ++i) { c += (uint64_t)a.l[i] + b.l[i]; t[i] = (uint32_t)c; c >>= 32; }

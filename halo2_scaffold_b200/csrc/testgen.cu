@@ -222,6 +222,19 @@ __global__ void __launch_bounds__(256) imad_bench_kernel(int iters, uint32_t* si
             a = b; b = c;
         }
         sink[t] = b.l[0] ^ b.l[7];
+    } else if (kind == 4) {
+        Fq a = fp_one<FQ>();
+        a.l[0] ^= t; a.l[3] ^= t * 7;
+        for (int i = 0; i < iters; ++i) a = fp_sqr(a);
+        sink[t] = a.l[0] ^ a.l[7];
+    } else if (kind == 5) {
+        Fq a = fp_one<FQ>(), b = fp_one<FQ>();
+        a.l[0] ^= t; b.l[1] ^= t;
+        for (int i = 0; i < iters; ++i) {
+            Fq c = fp_mul2(a, b, b, a);
+            a = b; b = c;
+        }
+        sink[t] = b.l[0] ^ b.l[7];
     } else {
         Affine g;
         g.x = fp_one<FQ>();
@@ -240,14 +253,15 @@ int imad_bench_run(DeviceCtx& ctx, int kind, int iters, int blocks, int threads,
     set_error("imad_bench: not available in the kernel-logic emulator");
     return H2B_ERR_BAD_ARGUMENT;
 #else
-    if (kind < 0 || kind > 3 || iters < 1 || blocks < 1 || threads < 32 || threads > 256) { set_error("imad_bench: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
+    if (kind < 0 || kind > 5 || iters < 1 || blocks < 1 || threads < 32 || threads > 256) { set_error("imad_bench: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
     (void)ctx;
     DevBuf sink;
     H2B_TRY(sink.reserve((size_t)blocks * threads * 4));
     cudaEvent_t e0, e1;
     H2B_CUDA(cudaEventCreate(&e0));
     H2B_CUDA(cudaEventCreate(&e1));
-    void (*kfn)(int, uint32_t*) = kind == 0 ? imad_bench_kernel<0> : kind == 1 ? imad_bench_kernel<1> : kind == 2 ? imad_bench_kernel<2> : imad_bench_kernel<3>;
+    void (*kfn)(int, uint32_t*) = kind == 0 ? imad_bench_kernel<0> : kind == 1 ? imad_bench_kernel<1> : kind == 2 ? imad_bench_kernel<2> : kind == 3 ? imad_bench_kernel<3> :
+                                   kind == 4 ? imad_bench_kernel<4> : imad_bench_kernel<5>;
     H2B_LAUNCH(kfn, blocks, threads, 0, stream, iters / 8 + 1, (uint32_t*)sink.p);   // warm-up
     H2B_CUDA(cudaEventRecord(e0, stream));
     H2B_LAUNCH(kfn, blocks, threads, 0, stream, iters, (uint32_t*)sink.p);

@@ -122,7 +122,7 @@ int h2b_field_op(int field, int op, const uint64_t* a, const uint64_t* b, size_t
  * XYZZ adder and doubling, 3 p+q through the Jacobian conversion.  out: affine. */
 int h2b_ec_op(int op, const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out);
 /* integer-pipe micro-benchmark; kind 0 IMAD, 1 IMAD.WIDE, 2 dependent Fq multiplications, 3 dependent
- * XYZZ mixed additions.  Returns elapsed milliseconds and the number of operations executed. */
+ * XYZZ mixed additions, 4 dependent Fq squarings, 5 dependent a*b + c*d with one reduction.  Returns elapsed milliseconds and the number of operations executed. */
 int h2b_imad_bench(int device, int kind, int iters, float* ms_out, double* ops_out);
 /* number of CUDA kernels this library has launched since it was loaded */
 unsigned long long h2b_launch_count(void);

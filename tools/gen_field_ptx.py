@@ -91,6 +91,11 @@ class Prog:
                     cf = 1 if s < 0 else 0
             elif op == "and":
                 reg[dst] = v[0] & v[1]
+            elif op == "shl1":        # dst = low 32 bits of ((v1:v0) << 1) >> 32 = (v1 << 1) | (v0 >> 31)   (shf.l.wrap)
+                reg[dst] = ((v[1] << 1) | (v[0] >> 31)) & M32
+            elif op == "chk0":        # generator-side assertion: the carry flag must be clear here (emits nothing)
+                if cf:
+                    raise OverflowError("lost carry in %s" % self.name)
             elif op == "selnz":       # dst = (v0 != 0) ? v1 : v2   (emitted as setp + selp)
                 reg[dst] = v[1] if v[0] != 0 else v[2]
             else:
@@ -135,6 +140,10 @@ class Prog:
                 lines.append("selp.u32 %s, %s, %s, pz;" % (r(dst), r(srcs[1]), r(srcs[2])))
             elif op == "mov":
                 lines.append("mov.u32 %s, %s;" % (r(dst), r(srcs[0])))
+            elif op == "shl1":
+                lines.append("shf.l.wrap.b32 %s, %s, %s, 1;" % (r(dst), r(srcs[0]), r(srcs[1])))
+            elif op == "chk0":
+                pass
             elif op == "and":
                 lines.append("and.b32 %s, %s, %s;" % (r(dst), r(srcs[0]), r(srcs[1])))
             else:
@@ -282,6 +291,180 @@ def gen_mont_mul_rows(name, mod, square=False):
     return P
 
 
+# =====================================================================================
+# Separated product / reduction ("full-width even/odd accumulators")
+#   AE holds the 64-bit product slots that start at even limbs, AO those that start at odd limbs
+#   (AO[k] is limb k+1 of the total); every row of partial products is one mad.lo.cc/madc.hi.cc
+#   chain inside ONE accumulator, so ptxas keeps it as IMAD.WIDE.U32(.X).  The Montgomery
+#   reduction adds its m_i * p rows into the same accumulators; a carry that leaves a chain goes
+#   into a small per-limb counter C[pos] (or initialises a still untouched limb), never ripples.
+#   Used for the operations whose product phase differs from a plain a*b:
+#     * squaring (28 doubled cross products + 8 squares instead of 64 products),
+#     * a*b + c*d with ONE reduction (the Y3 of the XYZZ mixed addition).
+# =====================================================================================
+class WideAcc:
+    def __init__(self, P, nlimbs=16):
+        self.P = P
+        self.n = nlimbs
+        self.ae = [P.tmp("x%d" % k) for k in range(nlimbs)]          # limb k
+        self.ao = [P.tmp("y%d" % k) for k in range(nlimbs)]          # limb k + 1
+        self.te = [False] * nlimbs
+        self.to = [False] * nlimbs
+        self.c = {}                                                  # total limb position -> counter register
+
+    def _counter(self, pos):
+        if pos not in self.c:
+            self.c[pos] = self.P.tmp("k%d" % pos)
+            return self.c[pos], 0
+        return self.c[pos], self.c[pos]
+
+    def chain(self, limb, products):
+        """add sum_j products[j] << 64*j at total limb position `limb` (one carry chain)."""
+        P = self.P
+        even = (limb % 2 == 0)
+        regs, touched, start = (self.ae, self.te, limb) if even else (self.ao, self.to, limb - 1)
+        for j, (x, y) in enumerate(products):
+            k = start + 2 * j
+            lo_src = regs[k] if touched[k] else 0
+            hi_src = regs[k + 1] if touched[k + 1] else 0
+            P.emit("mad.lo.cc" if j == 0 else "madc.lo.cc", regs[k], x, y, lo_src)
+            P.emit("madc.hi.cc", regs[k + 1], x, y, hi_src)
+            touched[k] = touched[k + 1] = True
+        top = start + 2 * len(products)
+        if top >= self.n:
+            P.emit("chk0", None)
+            return
+        if not touched[top]:
+            P.emit("addc", regs[top], 0, 0)
+            touched[top] = True
+        else:
+            pos = top if even else top + 1
+            if pos >= self.n:
+                P.emit("chk0", None)
+            else:
+                creg, csrc = self._counter(pos)
+                P.emit("addc", creg, csrc, 0)
+
+    def limb_e(self, k):
+        return self.ae[k] if (0 <= k < self.n and self.te[k]) else 0
+
+    def limb_o(self, k):          # AO register that holds total limb k
+        return self.ao[k - 1] if (1 <= k <= self.n and self.to[k - 1]) else 0
+
+    def double(self):
+        """AE <- 2*AE, AO <- 2*AO with funnel shifts (no carry chain); the small carry counters are doubled too."""
+        P = self.P
+        for creg in self.c.values():
+            P.emit("add", creg, creg, creg)
+        for regs, touched in ((self.ae, self.te), (self.ao, self.to)):
+            for k in range(self.n - 1, -1, -1):
+                if not touched[k]:
+                    if k > 0 and touched[k - 1]:
+                        P.emit("shl1", regs[k], regs[k - 1], 0)       # only the bit shifted out of the limb below
+                        touched[k] = True
+                    continue
+                P.emit("shl1", regs[k], regs[k - 1] if (k > 0 and touched[k - 1]) else 0, regs[k])
+
+
+def redc_tail(P, acc, p, inv, R):
+    """Montgomery reduction of the value held in acc (< p * 2^256) into R (canonical)."""
+    NLp = NL
+    p_even = [p[0], p[2], p[4], p[6]]
+    p_odd = [p[1], p[3], p[5], p[7]]
+    m = P.tmp("m")
+    v = P.tmp("v")
+    cw = None                      # carry word into limb i (0..2)
+    s1, s2, c1 = P.tmp("s1"), P.tmp("s2"), P.tmp("c1")
+    for i in range(NLp):
+        if i > 0:
+            # limb i-1 of the running total is 0 mod 2^32; its carry goes into limb i
+            P.emit("add.cc", s1, acc.limb_e(i - 1), acc.limb_o(i - 1))
+            P.emit("addc", c1, 0, 0)
+            ncw = P.tmp("w%d" % i)
+            if cw is None:
+                P.emit("mov", ncw, c1)
+            else:
+                P.emit("add.cc", s2, s1, cw)
+                P.emit("addc", ncw, c1, 0)
+            cw = ncw
+        P.emit("add", v, acc.limb_e(i), acc.limb_o(i))
+        if cw is not None:
+            P.emit("add", v, v, cw)
+        P.emit("mul.lo", m, v, inv)
+        acc.chain(i, [(m, pj) for pj in p_even])
+        acc.chain(i + 1, [(m, pj) for pj in p_odd])
+    # carry out of limb 7 into limb 8
+    P.emit("add.cc", s1, acc.limb_e(NLp - 1), acc.limb_o(NLp - 1))
+    P.emit("addc", c1, 0, 0)
+    P.emit("add.cc", s2, s1, cw)
+    cw8 = P.tmp("w8")
+    P.emit("addc", cw8, c1, 0)
+    creg, csrc = acc._counter(NLp)
+    P.emit("add", creg, csrc, cw8)
+    # t = limbs 8..15 of AE + (AO << 32) + counters
+    x = [P.tmp("q%d" % k) for k in range(NLp)]
+    t = [P.tmp("t%d" % k) for k in range(NLp)]
+    for k in range(NLp):
+        op = "add.cc" if k == 0 else ("addc.cc" if k < NLp - 1 else "addc")
+        P.emit(op, x[k], acc.limb_e(NLp + k), acc.limb_o(NLp + k))
+    for k in range(NLp):
+        op = "add.cc" if k == 0 else ("addc.cc" if k < NLp - 1 else "addc")
+        P.emit(op, t[k], x[k], acc.c.get(NLp + k, 0))
+    s = [P.tmp("s%d" % i) for i in range(NLp)]
+    bw = P.tmp("bw")
+    for i in range(NLp):
+        P.emit("sub.cc" if i == 0 else "subc.cc", s[i], t[i], p[i])
+    P.emit("subc", bw, 0, 0)
+    for i in range(NLp):
+        P.emit("selnz", R[i], bw, t[i], s[i])
+
+
+def product_rows(acc, X, Y):
+    """acc += X * Y (8 x 8 limbs), operand scanning, two chains per row."""
+    for i in range(NL):
+        acc.chain(i, [(X[j], Y[i]) for j in (0, 2, 4, 6)])
+        acc.chain(i + 1, [(X[j], Y[i]) for j in (1, 3, 5, 7)])
+
+
+def gen_mont_sqr_sep(name, mod):
+    p = limbs(mod)
+    inv = (-pow(mod, -1, 1 << 32)) & M32
+    A = ["a%d" % i for i in range(NL)]
+    R = ["r%d" % i for i in range(NL)]
+    P = Prog(name, A, R)
+    acc = WideAcc(P)
+    # cross products a_i * a_j, i < j: row i has one chain per parity class of j
+    for i in range(NL):
+        for par in (1, 0):
+            js = [j for j in range(i + 1, NL) if (j - i) % 2 == par]
+            if js:
+                acc.chain(i + js[0], [(A[i], A[j]) for j in js])
+    acc.double()
+    # squares a_i^2 at limb 2i: one chain over the whole even accumulator
+    acc.chain(0, [(A[i], A[i]) for i in range(NL)])
+    redc_tail(P, acc, p, inv, R)
+    return P
+
+
+def gen_mont_mul2_sep(name, mod):
+    """r = (a*b + c*d) / R mod p with a single reduction (a*b + c*d < 2 p^2 < p * 2^256)."""
+    p = limbs(mod)
+    inv = (-pow(mod, -1, 1 << 32)) & M32
+    A = ["a%d" % i for i in range(NL)]
+    B = ["b%d" % i for i in range(NL)]
+    C = ["c%d" % i for i in range(NL)]
+    D = ["d%d" % i for i in range(NL)]
+    R = ["r%d" % i for i in range(NL)]
+    P = Prog(name, A + B + C + D, R)
+    acc = WideAcc(P)
+    product_rows(acc, A, B)
+    product_rows(acc, C, D)
+    redc_tail(P, acc, p, inv, R)
+    return P
+
+
+
+
 def gen_add(name, mod):
     p = limbs(mod)
     A = ["a%d" % i for i in range(NL)]
@@ -330,17 +513,33 @@ def check(prog, mod, kind, trials=3000):
             0xFFFFFFFF, 0xFFFFFFFF00000000, (1 << 224) - 1, mod - 0xFFFFFFFF]
     cases = [(x, y) for x in edge for y in edge]
     cases += [(rng.randrange(mod), rng.randrange(mod)) for _ in range(trials)]
-    for x, y in cases:
+    # values with long runs of one-bits in every limb position (carry propagation across accumulator tops)
+    for sh in range(0, 256, 16):
+        v1 = ((1 << 256) - 1 - ((1 << sh) - 1)) % mod
+        v2 = ((1 << sh) - 1) % mod
+        cases += [(v1, v1), (v1, v2), (v2, v2), (mod - 1 - v2 if v2 < mod else 0, v1)]
+    for idx, (x, y) in enumerate(cases):
         env = {}
         for i, l in enumerate(limbs(x)):
             env["a%d" % i] = l
         for i, l in enumerate(limbs(y)):
             env["b%d" % i] = l
+        z, w = 0, 0
+        if kind == "mul2":
+            z, w = cases[(idx * 7 + 3) % len(cases)]
+            if idx % 5 == 0:
+                z, w = mod - 1, mod - 1
+            for i, l in enumerate(limbs(z)):
+                env["c%d" % i] = l
+            for i, l in enumerate(limbs(w)):
+                env["d%d" % i] = l
         env["z0"] = 0
         out = prog.run(env)
         got = sum(v << (32 * i) for i, v in enumerate(out))
         if kind == "mul":
             want = x * y * Rinv % mod
+        elif kind == "mul2":
+            want = (x * y + z * w) * Rinv % mod
         elif kind == "sqr":
             want = x * x * Rinv % mod
         elif kind == "add":
@@ -361,12 +560,14 @@ def main():
     ]
     total = 0
     for tag, mod in (("fr", FR), ("fq", FQ)):
-        for kind, gen in (("mul", gen_mont_mul), ("sqr", lambda n, m: gen_mont_mul(n, m, square=True)),
-                          ("mulw", gen_mont_mul_rows), ("sqrw", lambda n, m: gen_mont_mul_rows(n, m, square=True)),
+        for kind, gen in (("mul", gen_mont_mul), ("sqr", gen_mont_sqr_sep), ("mul2", gen_mont_mul2_sep),
                           ("add", gen_add), ("sub", gen_sub)):
             prog = gen("%s_%s" % (tag, kind), mod)
-            total += check(prog, mod, kind.replace("w", ""))
-            if kind == "sqr":
+            total += check(prog, mod, kind)
+            if kind == "mul2":
+                sig = ("__device__ __forceinline__ void %s_%s_asm(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], "
+                       "const uint32_t (&c)[8], const uint32_t (&d)[8])" % (tag, kind))
+            elif kind == "sqr":
                 sig = "__device__ __forceinline__ void %s_%s_asm(uint32_t (&r)[8], const uint32_t (&a)[8])" % (tag, kind)
             elif kind == "sqrw":
                 sig = "__device__ __forceinline__ void %s_%s_asm(uint32_t (&r)[8], const uint32_t (&a)[8], uint32_t z)" % (tag, kind)
