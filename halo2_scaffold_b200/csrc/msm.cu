@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(MsmPlan pl, const uint
 // slice length for `total` sorted entries cut into at most G slices.  The host sizes G for the worst case (every
 // digit non-zero); skewed columns sort far fewer entries, so slices never get shorter than SLICE_MIN and the
 // surplus threads simply exit.
-static const uint32_t SLICE_MIN = 32;
+static const uint32_t SLICE_MIN = 16;
 __device__ __forceinline__ uint32_t slice_len(uint32_t total, uint32_t G) {
     uint32_t S = (total + G - 1) / G;
     return S < SLICE_MIN ? SLICE_MIN : S;
@@ -403,6 +403,42 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint4* __re
     }
 }
 
+// Tail of the reduction, one CTA per set, N <= 512 items: S_w = sum_u (u+1) * B[u] + sum_u D[u] as a suffix scan
+// (sum_u (u+1) B[u] = sum_u suffix_u) followed by a tree sum, both in shared memory.  2 log2(N) + 1 additions deep
+// instead of the 2 m per level of the chunked running sums: small MSMs are pure latency.
+static const uint32_t REDUCE_TAIL_MAX = 512;
+__global__ void __launch_bounds__(512) msm_reduce_tail_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, const uint32_t* __restrict__ offsets,
+                                                            uint32_t N, uint4* __restrict__ out) {
+    H2B_DYN_SMEM(uint4, sh);
+    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    XYZZ x = xyzz_identity();
+    if (tid < N && (!offsets || offsets[(size_t)w * N + tid + 1] != offsets[(size_t)w * N + tid])) x = xyzz_load(Bin + 8 * ((size_t)w * N + tid));
+    for (uint32_t d = 1; d < N; d <<= 1) {
+        xyzz_store(sh + 8 * tid, x);
+        __syncthreads();
+        if (tid + d < N) {
+            XYZZ o = xyzz_load(sh + 8 * (tid + d));
+            xyzz_add(x, o);
+        }
+        __syncthreads();
+    }
+    if (Din && tid < N) {
+        XYZZ dd = xyzz_load(Din + 8 * ((size_t)w * N + tid));
+        xyzz_add(x, dd);
+    }
+    xyzz_store(sh + 8 * tid, x);
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if (tid < d) {
+            XYZZ o = xyzz_load(sh + 8 * (tid + d));
+            xyzz_add(x, o);
+            xyzz_store(sh + 8 * tid, x);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) xyzz_store(out + 8 * (size_t)w, x);
+}
+
 // Horner over the set sums (S[w] = Dfinal[w], weight 2^(c*w)) and conversion to a Jacobian triple
 __global__ void msm_final_kernel(const uint4* __restrict__ S, uint32_t W, uint32_t c, uint4* __restrict__ out_jac, uint32_t accumulate) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -589,8 +625,11 @@ static int msm_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_sc
     const uint64_t resident = (uint64_t)ctx.sm_count * 512;
     static int env_slice = -1;
     if (env_slice < 0) env_slice = env_int("H2B_MSM_SLICE", 256);
+    // below one full wave the slices shrink down to SLICE_MIN entries: a small MSM is latency bound, and a slice is a
+    // serial chain of mixed additions
     if (upper >= resident * 64) pl.G = (uint32_t)(resident * ((upper + resident * env_slice - 1) / (resident * env_slice)));
-    else pl.G = (uint32_t)((upper + 63) / 64);
+    else if (upper >= resident * SLICE_MIN) pl.G = (uint32_t)resident;
+    else pl.G = (uint32_t)((upper + SLICE_MIN - 1) / SLICE_MIN);
     if (pl.G == 0) pl.G = 1;
 
     H2B_TRY(s.digits.reserve((size_t)upper * 4));
@@ -636,9 +675,15 @@ static int msm_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_sc
 
 // bucket reduction hierarchy + Horner over the sets -> 224-byte result block (Jacobian | XYZZ)
 static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_result, bool accumulate, cudaStream_t stream) {
-    const uint32_t logm = 4;
+    // running sums over m = 2^logm buckets per thread and level: 16 while a level still fills the GPU (throughput),
+    // 4 below that (each level is then a serial chain of 2m additions, and latency is all that matters)
+    static int env_logm = -1;
+    if (env_logm < 0) env_logm = env_int("H2B_MSM_REDUCE_LOGM", 0);
+    uint32_t logm = (uint64_t)pl.m * pl.Nb >= (1u << 21) ? 4u : 2u;
+    if (env_logm >= 1 && env_logm <= 6) logm = (uint32_t)env_logm;
     uint32_t N = pl.Nb;
     uint32_t J0 = (N + (1u << logm) - 1) >> logm;
+    if (J0 < 1) J0 = 1;
     H2B_TRY(s.redA.reserve((size_t)pl.m * J0 * 128));
     H2B_TRY(s.redB.reserve((size_t)pl.m * J0 * 128));
     H2B_TRY(s.redC.reserve((size_t)pl.m * J0 * 128));
@@ -651,7 +696,7 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
     uint4* Bping[2] = {(uint4*)s.redA.p, (uint4*)s.redB.p};
     uint4* Dping[2] = {(uint4*)s.redC.p, (uint4*)s.redD.p};
     int pp = 0;
-    for (;;) {
+    while (N > REDUCE_TAIL_MAX) {
         uint32_t J = (N + (1u << logm) - 1) >> logm;
         uint32_t threads = pl.m * J;
         H2B_LAUNCH(msm_reduce_level_kernel, (threads + 127) / 128, 128, 0, stream, Bin, Din, offs, N, logm, pl.m, Bping[pp], Dping[pp]);
@@ -660,7 +705,18 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
         offs = nullptr;
         pp ^= 1;
         N = J;
-        if (J == 1) break;
+        if (env_logm < 1 && (uint64_t)pl.m * N < (1u << 21)) logm = 2;
+    }
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            H2B_CUDA(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REDUCE_TAIL_MAX * 128)));
+            attr_set = true;
+        }
+        uint32_t tthreads = 32;
+        while (tthreads < N) tthreads <<= 1;
+        H2B_LAUNCH(msm_reduce_tail_kernel, pl.m, tthreads, (size_t)tthreads * 128, stream, Bin, Din, offs, N, Dping[pp]);
+        Din = Dping[pp];
     }
     ctx.prof.mark(PROF_MSM_REDUCE, stream);
     H2B_LAUNCH(msm_final_kernel, 1, 32, 0, stream, Din, pl.m, pl.c, (uint4*)d_result, accumulate ? 1u : 0u);
