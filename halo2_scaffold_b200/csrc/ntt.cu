@@ -30,6 +30,7 @@ struct NttPassParams {
     const uint4* tw_small;   // Omega^t, t < N/2, Omega = w^(n/N)
     const uint4* tw_lo;      // w^j,          j < 2^h
     const uint4* tw_hi;      // w^(j * 2^h),  j < 2^(log_n - h)
+    const uint4* tw_direct;  // optional: w^(S * jr * bitrev(q)) at [q * M + jr] -- the inter-pass twiddle in ONE load, no multiplication
     uint32_t log_n;
     uint32_t b;              // digit bits of this pass
     uint32_t logT;           // tile width
@@ -195,9 +196,14 @@ __global__ void __launch_bounds__(512, 1) ntt_pass_kernel(NttPassParams p) {
                 uint32_t jr = (tau << logT) + t;
                 uint32_t ex = (jr * ip) << logS;
                 if (ex != 0) {
-                    Fr w = fp_load<FR>(p.tw_lo + 2 * (size_t)(ex & hmask));
-                    uint32_t eh = ex >> p.h;
-                    if (eh != 0) w = fp_mul(w, fp_load<FR>(p.tw_hi + 2 * (size_t)eh));
+                    Fr w;
+                    if (p.tw_direct) {
+                        w = fp_load<FR>(p.tw_direct + 2 * (((size_t)q << logM) + jr));
+                    } else {
+                        w = fp_load<FR>(p.tw_lo + 2 * (size_t)(ex & hmask));
+                        uint32_t eh = ex >> p.h;
+                        if (eh != 0) w = fp_mul(w, fp_load<FR>(p.tw_hi + 2 * (size_t)eh));
+                    }
                     v = fp_mul(v, w);
                 }
                 fp_store<FR>(p.out + 2 * (size_t)(base + q * M + t), v);
@@ -260,6 +266,26 @@ __global__ void __launch_bounds__(128) ntt_twiddle_kernel(TwGenParams g) {
     fp_store<FR>(g.out + 2 * (size_t)(g.tab[k].offset + j), r);
 }
 
+// direct inter-pass twiddle table of one pass: entry [q * M + jr] = w^(S * jr * bitrev_b(q)), built from the two-level tables
+struct TwDirectParams {
+    const uint4* tw_lo;
+    const uint4* tw_hi;
+    uint4* out;
+    uint32_t log_n, b, logL, h;
+};
+__global__ void __launch_bounds__(256) ntt_direct_twiddle_kernel(TwDirectParams g) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >> g.logL) return;
+    const uint32_t logM = g.logL - g.b;
+    const uint32_t q = (uint32_t)(idx >> logM), jr = (uint32_t)idx & ((1u << logM) - 1);
+    const uint32_t ip = g.b ? (__brev(q) >> (32 - g.b)) : 0u;
+    const uint32_t ex = (jr * ip) << (g.log_n - g.logL);
+    Fr w = fp_load<FR>(g.tw_lo + 2 * (size_t)(ex & ((1u << g.h) - 1)));
+    const uint32_t eh = ex >> g.h;
+    if (eh != 0) w = fp_mul(w, fp_load<FR>(g.tw_hi + 2 * (size_t)eh));
+    fp_store<FR>(g.out + 2 * idx, w);
+}
+
 struct NttPass { uint32_t b, logT, logL; };
 struct NttTwiddles {
     uint64_t omega[4];
@@ -270,6 +296,9 @@ struct NttTwiddles {
     NttPass pass[NTT_MAX_PASSES];
     uint32_t small_off[NTT_MAX_PASSES];
     uint32_t lo_off, hi_off, h;
+    DevBuf direct;                              // direct inter-pass tables of the non-last passes (optional)
+    size_t direct_off[NTT_MAX_PASSES];          // element offsets into `direct`
+    bool has_direct = false;
 };
 
 static uint64_t g_use_counter = 0;
@@ -329,6 +358,21 @@ static int ntt_get_twiddles(DeviceCtx& ctx, const uint64_t omega[4], uint32_t lo
             return H2B_OK;
         }
     }
+    // the direct tables are big (32 * n bytes): keep the cache under a byte budget as well as under 16 entries
+    for (;;) {
+        size_t bytes = 0, victim = 0;
+        for (size_t i = 0; i < ctx.twiddles.size(); ++i) {
+            bytes += ctx.twiddles[i]->direct.cap;
+            if (ctx.twiddles[i]->last_use < ctx.twiddles[victim]->last_use) victim = i;
+        }
+        if (bytes <= ((size_t)12 << 30) || ctx.twiddles.size() <= 1) break;
+        H2B_CUDA(cudaStreamSynchronize(stream));
+        NttTwiddles* v = ctx.twiddles[victim];
+        ctx.twiddles.erase(ctx.twiddles.begin() + victim);
+        v->buf.release();
+        v->direct.release();
+        delete v;
+    }
     NttTwiddles* t;
     if (ctx.twiddles.size() >= 16) {   // evict the least recently used entry
         size_t victim = 0;
@@ -369,6 +413,34 @@ static int ntt_get_twiddles(DeviceCtx& ctx, const uint64_t omega[4], uint32_t lo
     g.out = (uint4*)t->buf.p;
     H2B_LAUNCH(ntt_twiddle_kernel, (g.total + 127) / 128, 128, 0, stream, g);
     H2B_CUDA(cudaGetLastError());
+    // Direct inter-pass tables (one 32-byte load replaces two loads and a multiplication per element and pass
+    // boundary; about n entries in total).  Only while they stay affordable: H2B_NTT_DIRECT_MB per (omega, log n),
+    // default 2304 MiB = up to 2^26.
+    static long direct_mb = -1;
+    if (direct_mb < 0) { const char* e = getenv("H2B_NTT_DIRECT_MB"); direct_mb = e ? atol(e) : 2304; }
+    t->has_direct = false;
+    if (t->npass > 1) {
+        size_t entries = 0;
+        for (uint32_t p = 0; p + 1 < t->npass; ++p) { t->direct_off[p] = entries; entries += (size_t)1 << t->pass[p].logL; }
+        if (entries * 32 <= (size_t)direct_mb << 20 && t->direct.reserve(entries * 32) == H2B_OK) {
+            for (uint32_t p = 0; p + 1 < t->npass; ++p) {
+                TwDirectParams d;
+                d.tw_lo = (const uint4*)t->buf.p + 2 * (size_t)t->lo_off;
+                d.tw_hi = (const uint4*)t->buf.p + 2 * (size_t)t->hi_off;
+                d.out = (uint4*)t->direct.p + 2 * t->direct_off[p];
+                d.log_n = log_n; d.b = t->pass[p].b; d.logL = t->pass[p].logL; d.h = t->h;
+                const size_t cnt = (size_t)1 << d.logL;
+                H2B_LAUNCH(ntt_direct_twiddle_kernel, (unsigned)((cnt + 255) / 256), 256, 0, stream, d);
+            }
+            H2B_CUDA(cudaGetLastError());
+            t->has_direct = true;
+        } else {
+            t->direct.release();
+            cudaGetLastError();
+        }
+    } else {
+        t->direct.release();
+    }
     ctx.twiddles.push_back(t);
     *out = t;
     return H2B_OK;
@@ -400,6 +472,7 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
         a.tw_small = tbl + 2 * (size_t)tw->small_off[p];
         a.tw_lo = tbl + 2 * (size_t)tw->lo_off;
         a.tw_hi = tbl + 2 * (size_t)tw->hi_off;
+        a.tw_direct = (tw->has_direct && !last) ? (const uint4*)tw->direct.p + 2 * tw->direct_off[p] : nullptr;
         a.log_n = log_n;
         a.b = tw->pass[p].b;
         a.logT = tw->pass[p].logT;
@@ -462,7 +535,7 @@ int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors, 
 }
 
 void ntt_release(DeviceCtx& ctx) {
-    for (NttTwiddles* t : ctx.twiddles) { t->buf.release(); delete t; }
+    for (NttTwiddles* t : ctx.twiddles) { t->buf.release(); t->direct.release(); delete t; }
     ctx.twiddles.clear();
     ctx.ntt_work.release();
     ctx.ntt_io.release();
