@@ -264,6 +264,30 @@ def run_ours(args):
     msm_value = world * n * K / (msm_ms / 1e3)
     result_host = d_out.cpu().numpy().astype(np.uint64)
 
+    # ---- the same MSM over a witness-like column (50 % zero, 20 % one, 20 % < 2^19, 10 % r - small) ---------
+    witness = None
+    if args.scalars == "uniform":
+        d_wit = torch.empty(n * 4, dtype=torch.int64, device=dev)
+        L.gen_scalars_dev(0, 0xB2000000 + k + 1000 * rank + 77, n, 1, d_wit.data_ptr(), st)
+
+        def wit_step():
+            if handle is not None:
+                L.msm_dev_registered(0, d_wit.data_ptr(), handle, 0, n, d_block.data_ptr(), st)
+            else:
+                L.msm_dev_partial(0, d_wit.data_ptr(), d_base.data_ptr(), n, d_block.data_ptr(), st)
+        for _ in range(W):
+            wit_step()
+        barrier()
+        e0.record()
+        for _ in range(K):
+            wit_step()
+        e1.record()
+        barrier()
+        wit_ms = max_over_ranks(e0.elapsed_time(e1))
+        witness = {"value": world * n * K / (wit_ms / 1e3), "unit": "points/s", "ms_per_step": wit_ms / K,
+                   "scalars": "50% zero, 20% one, 20% uniform < 2^19, 10% r - small"}
+        del d_wit
+
     # ---- MSM, end to end through the host-pointer drop-in ---------------------------------------------------
     h_scal = torch.empty(n * 4, dtype=torch.int64).pin_memory()
     h_scal.copy_(d_scal)
@@ -386,6 +410,8 @@ def run_ours(args):
             "srs": dict(set_info, registration_ms=reg_ms, plain=bool(args.plain)),
             "result_x_limb0": int(result_host[0]),
         }
+        if witness:
+            line["witness_like"] = witness
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)

@@ -1,8 +1,10 @@
 #!/usr/bin/env python3
-"""Minimal device-resident workload for ncu captures: W+1 MSMs and NTTs at 2^k (default 24) through the C ABI."""
+"""Minimal device-resident workload for ncu captures: `reps` MSMs over a registered SRS vector (window tables) and
+`reps` NTTs at 2^k (default 24) through the C ABI."""
 import os, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
+import numpy as np
 import torch
 import halo2_scaffold_b200 as h2
 from bench import omega_words
@@ -18,8 +20,12 @@ d_b = torch.empty(n * 8, dtype=torch.int64, device="cuda")
 d_o = torch.empty(28, dtype=torch.int64, device="cuda")
 L.gen_scalars_dev(0, 1, n, 0, d_s.data_ptr(), st)
 L.gen_points_dev(0, 2, n, d_b.data_ptr(), st)
+torch.cuda.synchronize()
+hb = d_b.cpu()
+handle = L.register_bases(hb.numpy().view(np.uint64))
+del hb, d_b
 for _ in range(reps):
-    L.msm_dev_partial(0, d_s.data_ptr(), d_b.data_ptr(), n, d_o.data_ptr(), st)
+    L.msm_dev_registered(0, d_s.data_ptr(), handle, 0, n, d_o.data_ptr(), st)
 w = omega_words(k)
 for _ in range(reps):
     L.ntt_dev(0, d_s.data_ptr(), w, k, st)
