@@ -42,7 +42,11 @@ struct MsmPlan {
     uint32_t row0;       // first row of this call inside each table
     uint32_t G;          // slices (accumulate threads)
     uint32_t add_into;   // 1: chunked MSM -- each chunk's bucket sums are merged into running accumulators
+    uint32_t top_bins;   // > 0: the top window only has this many digit values (few scalar bits left): its histogram and
+                         //      cursor atomics are aggregated per CTA in shared memory instead of hammering 2-4 counters
 };
+
+static const uint32_t TOP_BINS_MAX = 1026;      // top windows of up to 10 bits (+ carry) are aggregated
 
 // (r - 1) / 2 as canonical 32-bit limbs
 __device__ __forceinline__ bool fr_gt_half(const Fr& s) {
@@ -69,40 +73,63 @@ __device__ __forceinline__ uint32_t limb_bits(const Fr& s, uint32_t bit, uint32_
 }
 
 // ---- 1. decompose + histogram ------------------------------------------------------------------
+// (grid-stride over blocks of 256 scalars so that the per-CTA aggregation of a narrow top window is flushed rarely)
 __global__ void __launch_bounds__(256) msm_decompose_kernel(const uint4* __restrict__ scalars, MsmPlan pl,
                                                           uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pl.n) return;
-    Fr s = fp_from_mont(fp_load<FR>(scalars + 2 * (size_t)i));
-    uint32_t neg = 0;
-    if (fr_gt_half(s)) {
-        // s <- r - s  (canonical, non-zero)
-        Fr r;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r.l[k] = FpParams<FR>::P(k);
-        uint32_t borrow = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint64_t d = (uint64_t)r.l[k] - s.l[k] - borrow;
-            s.l[k] = (uint32_t)d;
-            borrow = (uint32_t)(d >> 63);
-        }
-        neg = SIGN_BIT;
+    __shared__ uint32_t top_hist[TOP_BINS_MAX];
+    const uint32_t top_set = (pl.W - 1) % pl.m;
+    if (pl.top_bins) {
+        for (uint32_t b = threadIdx.x; b < pl.top_bins; b += blockDim.x) top_hist[b] = 0;
+        __syncthreads();
     }
     const uint32_t c = pl.c, half = 1u << (c - 1);
-    uint32_t carry = 0, set = 0;
-    for (uint32_t w = 0; w < pl.W; ++w) {
-        uint32_t d = limb_bits(s, w * c, c) + carry;
-        uint32_t sign = neg;
-        if (d > half) { d = (1u << c) - d; carry = 1; sign ^= SIGN_BIT; }
-        else carry = 0;
-        uint32_t entry = 0;
-        if (d != 0) {
-            entry = d | sign;
-            atomicAdd(&counts[set * pl.Nb + d - 1], 1u);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rounds = (pl.n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t round = 0; round < rounds; ++round) {
+        const uint32_t i = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        const bool live = i < pl.n;
+        Fr s = fp_zero<FR>();
+        uint32_t neg = 0;
+        if (live) {
+            s = fp_from_mont(fp_load<FR>(scalars + 2 * (size_t)i));
+            if (fr_gt_half(s)) {
+                // s <- r - s  (canonical, non-zero)
+                Fr r;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r.l[k] = FpParams<FR>::P(k);
+                uint32_t borrow = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint64_t d = (uint64_t)r.l[k] - s.l[k] - borrow;
+                    s.l[k] = (uint32_t)d;
+                    borrow = (uint32_t)(d >> 63);
+                }
+                neg = SIGN_BIT;
+            }
         }
-        digits[(size_t)w * pl.n + i] = entry;
-        if (++set == pl.m) set = 0;
+        uint32_t carry = 0, set = 0;
+        for (uint32_t w = 0; w < pl.W; ++w) {
+            uint32_t d = limb_bits(s, w * c, c) + carry;
+            uint32_t sign = neg;
+            if (d > half) { d = (1u << c) - d; carry = 1; sign ^= SIGN_BIT; }
+            else carry = 0;
+            if (w == 0) {
+                // Window 0 is where witness columns pile up (a fifth of the rows equal to 1, small lookup limbs ...):
+                // lanes of a warp that hit the same bucket send ONE reduction.  (Every lane takes part; d == 0 = no entry.)
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (d != 0 && lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&counts[d - 1], (uint32_t)__popc(peers));
+            } else if (d != 0) {
+                if (pl.top_bins && w + 1 == pl.W) atomicAdd(&top_hist[d], 1u);
+                else atomicAdd(&counts[set * pl.Nb + d - 1], 1u);
+            }
+            if (live) digits[(size_t)w * pl.n + i] = d ? (d | sign) : 0u;
+            if (++set == pl.m) set = 0;
+        }
+    }
+    if (pl.top_bins) {
+        __syncthreads();
+        for (uint32_t b = 1 + threadIdx.x; b < pl.top_bins; b += blockDim.x)
+            if (top_hist[b]) atomicAdd(&counts[top_set * pl.Nb + b - 1], top_hist[b]);
     }
 }
 
@@ -178,17 +205,50 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t* __restr
 
 __global__ void __launch_bounds__(256) msm_scatter_kernel(MsmPlan pl, const uint32_t* __restrict__ digits, uint32_t* __restrict__ cursor,
                                                         uint32_t* __restrict__ sorted) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pl.n) return;
-    uint32_t set = 0, row = pl.row0 + i;
-    for (uint32_t w = 0; w < pl.W; ++w) {
-        uint32_t e = digits[(size_t)w * pl.n + i];
-        if (e != 0) {
-            uint32_t d = e & ~SIGN_BIT;
-            uint32_t pos = atomicAdd(&cursor[set * pl.Nb + d - 1], 1u);
-            sorted[pos] = row | (e & SIGN_BIT);
+    __shared__ uint32_t top_cnt[TOP_BINS_MAX];      // per-round count, then the round's base position, of each top-window digit
+    const uint32_t top_set = (pl.W - 1) % pl.m;
+    const uint32_t rounds = (pl.n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t round = 0; round < rounds; ++round) {
+        const uint32_t i = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        const bool live = i < pl.n;
+        uint32_t set = 0, row = pl.row0 + i;
+        const uint32_t lower = pl.top_bins ? pl.W - 1 : pl.W;
+        {   // window 0: one cursor update per warp and bucket (see msm_decompose_kernel)
+            const uint32_t e = live ? digits[i] : 0u;
+            const uint32_t d = e & ~SIGN_BIT;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t lane = threadIdx.x & 31, leader = (uint32_t)(__ffs((int)peers) - 1);
+            uint32_t base = 0;
+            if (d != 0 && lane == leader) base = atomicAdd(&cursor[d - 1], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, (int)leader);
+            if (d != 0) sorted[base + (uint32_t)__popc(peers & ((1u << lane) - 1))] = row | (e & SIGN_BIT);
+            if (++set == pl.m) { set = 0; row += pl.stride; }
         }
-        if (++set == pl.m) { set = 0; row += pl.stride; }
+        if (live) {
+            for (uint32_t w = 1; w < lower; ++w) {
+                uint32_t e = digits[(size_t)w * pl.n + i];
+                if (e != 0) {
+                    uint32_t d = e & ~SIGN_BIT;
+                    uint32_t pos = atomicAdd(&cursor[set * pl.Nb + d - 1], 1u);
+                    sorted[pos] = row | (e & SIGN_BIT);
+                }
+                if (++set == pl.m) { set = 0; row += pl.stride; }
+            }
+        }
+        if (pl.top_bins) {
+            // narrow top window: rank inside the CTA in shared memory, one global cursor update per digit value and round
+            for (uint32_t b = threadIdx.x; b < pl.top_bins; b += blockDim.x) top_cnt[b] = 0;
+            __syncthreads();
+            uint32_t e = live ? digits[(size_t)(pl.W - 1) * pl.n + i] : 0u;
+            uint32_t d = e & ~SIGN_BIT, rank = 0;
+            if (d) rank = atomicAdd(&top_cnt[d], 1u);
+            __syncthreads();
+            for (uint32_t b = 1 + threadIdx.x; b < pl.top_bins; b += blockDim.x)
+                if (top_cnt[b]) top_cnt[b] = atomicAdd(&cursor[top_set * pl.Nb + b - 1], top_cnt[b]);
+            __syncthreads();
+            if (d) sorted[top_cnt[d] + rank] = (pl.row0 + i + ((pl.W - 1) / pl.m) * pl.stride) | (e & SIGN_BIT);
+            __syncthreads();
+        }
     }
 }
 
@@ -530,11 +590,11 @@ static int env_int(const char* name, int dflt) {
 static uint32_t windows_for(uint32_t c) { return 253 / c + 1; }
 
 // Cost model in units of one sorted entry (sort + one mixed addition, 0.18 ns on a B200), fitted to measurements at
-// 2^16..2^24 (profiles/): the counting sort slows down by about 4 % per bit once the bucket set outgrows the L2-friendly
-// 2^18 counters, and a bucket costs about 17 entries because the running-sum reduction is latency bound.
+// 2^16..2^26 (profiles/r01_msm_spacing.jsonl): the counting sort slows down by about 3.5 % per bit once the bucket set
+// outgrows the L2-friendly 2^19 counters, and a bucket costs about 8 entries (the reduction is latency bound).
 static double msm_cost(double n, uint32_t c, uint32_t sets) {
-    double per_entry = 1.0 + (c > 19 ? 0.04 * (c - 19) : 0.0);
-    return n * windows_for(c) * per_entry + 17.0 * sets * (double)(1u << (c - 1));
+    double per_entry = 1.0 + (c > 20 ? 0.035 * (c - 20) : 0.0);
+    return n * windows_for(c) * per_entry + 8.0 * sets * (double)(1u << (c - 1));
 }
 
 // plain mode (no tables): one bucket set per window
@@ -602,6 +662,11 @@ static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t
     pl.B = pl.m * pl.Nb;
     pl.stride = tables ? (uint32_t)bases.stride : 0u;
     pl.add_into = chunked ? 1u : 0u;
+    {   // scalar bits left for the top window (the recoded scalar is < 2^253) -> number of digit values it can take
+        const uint32_t top_bits = 253 - pl.c * (pl.W - 1);
+        const uint64_t bins = ((uint64_t)1 << top_bits) + 2;      // digits 0 .. 2^top_bits (carry) inclusive
+        pl.top_bins = (bins <= TOP_BINS_MAX && bins <= (uint64_t)pl.Nb + 1) ? (uint32_t)bins : 0u;
+    }
     if (tables && (pl.W + pl.m - 1) / pl.m > bases.n_tables) { set_error("msm: %u tables cannot serve %u windows in %u sets", bases.n_tables, pl.W, pl.m); return H2B_ERR_BAD_ARGUMENT; }
     H2B_TRY(s.counts.reserve((size_t)pl.B * 4));
     H2B_TRY(s.offsets.reserve(((size_t)pl.B + 1) * 4));
@@ -651,11 +716,12 @@ static int msm_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_sc
     const uint32_t nblk = (n + 255) / 256;
     uint4* target = (uint4*)(pl.add_into ? s.bucket_tmp.p : s.bucket_acc.p);
     ctx.prof.mark(PROF_BEGIN, stream);
-    H2B_LAUNCH(msm_decompose_kernel, nblk, 256, 0, stream, (const uint4*)d_scalars, pl, (uint32_t*)s.digits.p, counts);
+    const uint32_t sort_grid = nblk < (uint32_t)ctx.sm_count * 32 ? nblk : (uint32_t)ctx.sm_count * 32;
+    H2B_LAUNCH(msm_decompose_kernel, sort_grid, 256, 0, stream, (const uint4*)d_scalars, pl, (uint32_t*)s.digits.p, counts);
     ctx.prof.mark(PROF_MSM_DECOMPOSE, stream);
     H2B_TRY(exclusive_scan(s, counts, pl.B, offsets, cursor, stream));
     ctx.prof.mark(PROF_MSM_SCAN, stream);
-    H2B_LAUNCH(msm_scatter_kernel, nblk, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, (uint32_t*)s.sorted.p);
+    H2B_LAUNCH(msm_scatter_kernel, sort_grid, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, (uint32_t*)s.sorted.p);
     ctx.prof.mark(PROF_MSM_SCATTER, stream);
     H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)tables, (const uint32_t*)offsets,
                (const uint32_t*)s.sorted.p, ctrl, (uint32_t*)s.split_list.p, target, (uint4*)s.head_partial.p);

@@ -131,6 +131,11 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     for (int i = 0; i < 32; ++i) r |= (emu::shfl_generic<unsigned>(pred ? 1u : 0u, i) & 1u) << i;
     return r;
 }
+static inline unsigned __match_any_sync(unsigned, unsigned key) {
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= (emu::shfl_generic<unsigned>(key, i) == key ? 1u : 0u) << i;
+    return r;
+}
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
