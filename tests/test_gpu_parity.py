@@ -151,6 +151,14 @@ def test_cpp_host_mirror_over_the_c_abi(gpu, oc, tmp_path):
     run_host_mirror(oc, gpu.path, tmp_path, k=5, j=3)       # examples/standard_plonk.rs: k = 5, degree 3
 
 
+def test_in_process_multi_device_paths(gpu):
+    """Point-range sharding of one MSM across every visible GPU + concurrent callers (fresh process: own library instance)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "multi_device_check.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTI_DEVICE_OK" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])
+
+
 # ---- full benchmark sizes: size-independent properties -------------------------------------------------------------
 def _dot_with_generator_scalars(oc, scalars_mont, seed, n):
     """sum_i s_i * z_i mod r for the synthetic bases P_i = [z_i] G (z_i = SplitMix64 stream `seed`)."""
