@@ -88,6 +88,7 @@ struct DeviceCtx {
     std::mutex mu;                     // serialises calls that share this context's scratch
     DevBuf ntt_work;                   // ping-pong buffer of the multi-pass NTT
     bool ntt_attr_set = false;
+    bool msm_attr_set = false;
     DevBuf ntt_io;                     // staging for the host-pointer NTT entry point
     DevBuf msm_scalars;                // staging for host-pointer MSM scalars
     DevBuf msm_out;                    // 96-byte result

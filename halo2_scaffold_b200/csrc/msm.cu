@@ -774,10 +774,9 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
         if (env_logm < 1 && (uint64_t)pl.m * N < (1u << 21)) logm = 2;
     }
     {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx.msm_attr_set) {      // a per-device function attribute
             H2B_CUDA(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REDUCE_TAIL_MAX * 128)));
-            attr_set = true;
+            ctx.msm_attr_set = true;
         }
         uint32_t tthreads = 32;
         while (tthreads < N) tthreads <<= 1;
