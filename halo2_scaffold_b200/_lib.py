@@ -33,7 +33,7 @@ _EXPORTS = [
     "h2b_dev_alloc", "h2b_dev_free", "h2b_memcpy_h2d", "h2b_memcpy_d2h", "h2b_dev_sync", "h2b_gen_points_dev",
     "h2b_gen_scalars_dev", "h2b_field_op", "h2b_ec_op", "h2b_imad_bench", "h2b_set_msm_window",
     "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read", "h2b_msm_bn254_g1_dev_registered",
-    "h2b_set_msm_precomp", "h2b_base_set_info",
+    "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
 ]
 
 
@@ -73,6 +73,8 @@ class Lib:
         L.h2b_msm_bn254_g1_dev_registered.argtypes = [i32, vp, u64, sz, sz, vp, vp]
         L.h2b_set_msm_precomp.argtypes = [i32]
         L.h2b_base_set_info.argtypes = [u64, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u64)]
+        L.h2b_msm_bn254_g1_batch_registered.argtypes = [vp, vp, sz, u64, vp]
+        L.h2b_ntt_bn254_fr_batch.argtypes = [vp, sz, vp, u32]
         L.h2b_msm_fold_partials.argtypes = [i32, vp, sz, vp]
         L.h2b_msm_fold_partials_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_fr_scale_dev.argtypes = [i32, vp, sz, vp, i32, vp]
@@ -149,6 +151,42 @@ class Lib:
         out = np.zeros(12, dtype=np.uint64)
         self.check(self.L.h2b_msm_bn254_g1_registered(scalars.ctypes.data, handle, offset, scalars.size // 4, out.ctypes.data))
         return out
+
+    def msm_batch_registered(self, columns, handle: int) -> np.ndarray:
+        """columns: list of (n_j, 4) uint64 arrays -> (len(columns), 12) Jacobian results"""
+        cols = [_u64(c).reshape(-1, 4) for c in columns]
+        ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        lens = (ctypes.c_size_t * len(cols))(*[c.shape[0] for c in cols])
+        out = np.zeros((len(cols), 12), dtype=np.uint64)
+        self.check(self.L.h2b_msm_bn254_g1_batch_registered(ptrs, lens, len(cols), handle, out.ctypes.data))
+        return out
+
+    def ntt_batch(self, polys, omega: np.ndarray, log_n: int):
+        """In place on each C-contiguous uint64 (2^log_n, 4) array of the list."""
+        for a in polys:
+            assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"] and a.size == 4 << log_n
+        ptrs = (ctypes.c_void_p * len(polys))(*[a.ctypes.data for a in polys])
+        omega = _u64(omega)
+        self.check(self.L.h2b_ntt_bn254_fr_batch(ptrs, len(polys), omega.ctypes.data, log_n))
+        return polys
+
+    def msm_batch_registered(self, columns, handle: int) -> np.ndarray:
+        """columns: list of (n_j, 4) uint64 arrays -> (len(columns), 12) Jacobian results"""
+        cols = [_u64(c).reshape(-1, 4) for c in columns]
+        ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        lens = (ctypes.c_size_t * len(cols))(*[c.shape[0] for c in cols])
+        out = np.zeros((len(cols), 12), dtype=np.uint64)
+        self.check(self.L.h2b_msm_bn254_g1_batch_registered(ptrs, lens, len(cols), handle, out.ctypes.data))
+        return out
+
+    def ntt_batch(self, polys, omega: np.ndarray, log_n: int):
+        """In place on each C-contiguous uint64 (2^log_n, 4) array of the list."""
+        for a in polys:
+            assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"] and a.size == 4 << log_n
+        ptrs = (ctypes.c_void_p * len(polys))(*[a.ctypes.data for a in polys])
+        omega = _u64(omega)
+        self.check(self.L.h2b_ntt_bn254_fr_batch(ptrs, len(polys), omega.ctypes.data, log_n))
+        return polys
 
     # ---- device-pointer entry points ------------------------------------------------------------
     def ntt_dev(self, device: int, d_a: int, omega: np.ndarray, log_n: int, stream: int = 0):

@@ -306,6 +306,33 @@ static int msm_host(const uint64_t* scalars, BaseSet& bs, size_t offset, size_t 
     return H2B_OK;
 }
 
+// ---- batched entry points: independent columns, round-robin over the devices ------------
+// One worker thread per device; worker d takes columns d, d + D, d + 2D, ...  Each column is a complete single-device
+// call (no sharding inside a column), so D columns are in flight at once and the SRS tables of every device are used.
+template <class F>
+static int run_round_robin(size_t count, F one_column) {
+    const size_t nd = G.devs.size();
+    const size_t workers = count < nd ? count : nd;
+    if (workers <= 1) {
+        for (size_t j = 0; j < count; ++j) H2B_TRY(one_column(j, 0));
+        return H2B_OK;
+    }
+    std::vector<int> rcs(workers, 0);
+    std::vector<std::string> errs(workers);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < workers; ++d) {
+        th.emplace_back([&, d] {
+            for (size_t j = d; j < count && rcs[d] == 0; j += workers) {
+                rcs[d] = one_column(j, d);
+                if (rcs[d]) errs[d] = get_error();
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t d = 0; d < workers; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
+    return H2B_OK;
+}
+
 }  // namespace h2b
 
 using namespace h2b;
@@ -453,6 +480,51 @@ int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
     H2B_CUDA(cudaMemcpyAsync(a, c->ntt_io.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     H2B_CUDA(cudaStreamSynchronize(c->stream));
     return H2B_OK;
+}
+
+int h2b_msm_bn254_g1_batch_registered(const uint64_t* const* scalars, const size_t* lens, size_t count, uint64_t handle, uint64_t* out_jac) {
+    H2B_TRY(require_init());
+    if (count == 0) return H2B_OK;
+    if (!scalars || !lens || !out_jac) { set_error("h2b_msm_bn254_g1_batch_registered: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    BaseSet* bs = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        for (auto& up : G.sets) if (up->handle == handle) bs = up.get();
+    }
+    if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
+    for (size_t j = 0; j < count; ++j) {
+        if (lens[j] > bs->n) { set_error("column %zu: %zu scalars exceed the registered set of %zu points", j, lens[j], bs->n); return H2B_ERR_BAD_ARGUMENT; }
+        if (lens[j] && !scalars[j]) { set_error("column %zu: null scalars", j); return H2B_ERR_BAD_ARGUMENT; }
+    }
+    return run_round_robin(count, [&](size_t j, size_t d) -> int {
+        DeviceCtx& c = *G.devs[d];
+        std::lock_guard<std::mutex> lk(c.mu);
+        uint64_t block[28];
+        H2B_TRY(msm_on_device(c, scalars[j], bases_of(*bs, d, 0), lens[j], block));
+        memcpy(out_jac + 12 * j, block, 96);
+        return H2B_OK;
+    });
+}
+
+int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omega[4], uint32_t log_n) {
+    H2B_TRY(require_init());
+    if (count == 0) return H2B_OK;
+    if (!a || !omega) { set_error("h2b_ntt_bn254_fr_batch: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (log_n > 28) { set_error("h2b_ntt_bn254_fr_batch: log_n = %u exceeds the two-adicity of Fr (28)", log_n); return H2B_ERR_BAD_ARGUMENT; }
+    for (size_t j = 0; j < count; ++j) if (!a[j]) { set_error("polynomial %zu: null pointer", j); return H2B_ERR_BAD_ARGUMENT; }
+    if (log_n == 0) return H2B_OK;
+    const size_t bytes = (size_t)32 << log_n;
+    return run_round_robin(count, [&](size_t j, size_t d) -> int {
+        DeviceCtx& c = *G.devs[d];
+        std::lock_guard<std::mutex> lk(c.mu);
+        H2B_CUDA(cudaSetDevice(c.device));
+        H2B_TRY(c.ntt_io.reserve(bytes));
+        H2B_CUDA(cudaMemcpyAsync(c.ntt_io.p, a[j], bytes, cudaMemcpyHostToDevice, c.stream));
+        H2B_TRY(ntt_run(c, c.ntt_io.p, omega, log_n, c.stream));
+        H2B_CUDA(cudaMemcpyAsync(a[j], c.ntt_io.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+        H2B_CUDA(cudaStreamSynchronize(c.stream));
+        return H2B_OK;
+    });
 }
 
 int h2b_ntt_bn254_fr_dev(int device, void* d_a, const uint64_t omega[4], uint32_t log_n, void* stream) {

@@ -85,6 +85,14 @@ int h2b_unregister_bases(uint64_t handle);
 /* MSM over bases[offset .. offset+n) of a registered set. */
 int h2b_msm_bn254_g1_registered(const uint64_t* scalars, uint64_t handle, size_t offset, size_t n, uint64_t out_jac[12]);
 
+/* ---- batched drop-ins: independent columns / polynomials, distributed round-robin over the devices ------------------
+ * The advice, lookup and permutation columns a proof phase commits are independent MSMs over the same SRS vector, and
+ * its per-polynomial (i)NTTs are independent too: with D devices, D columns are in flight at
+ * once, each on a device that holds its own copy of the SRS tables.  Results are identical to `count` single calls. */
+int h2b_msm_bn254_g1_batch_registered(const uint64_t* const* scalars, const size_t* lens, size_t count, uint64_t handle,
+                                      uint64_t* out_jac /* count x 12 */);
+int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omega[4], uint32_t log_n);
+
 /* ---- device-resident entry points (device pointers on `device`, caller's CUDA stream) ------------- */
 /* Asynchronous with respect to the host: work is enqueued on `stream` (a cudaStream_t; NULL = the
  * legacy default stream).  `device` is an index into the devices given to h2b_init. */

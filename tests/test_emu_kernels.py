@@ -157,3 +157,22 @@ def test_msm_chunked_upload_pipeline(emu):
     env = dict(os.environ, H2B_MSM_UPLOAD_CHUNK_LOG="10")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_batched_columns_match_single_calls(emu, oc):
+    n = 600
+    P = oc.gen_points(71, n)
+    cols = [oc.random_fr(80 + j, n - 37 * j) for j in range(5)] + [np.zeros((0, 4), dtype=np.uint64)]
+    h = emu.register_bases(P)
+    try:
+        got = emu.msm_batch_registered(cols, h)
+        for j, c in enumerate(cols):
+            assert (pc.affine_of(oc, got[j]) == pc.affine_of(oc, oc.best_multiexp(c, P[:c.shape[0]]))).all(), j
+    finally:
+        emu.unregister_bases(h)
+    k = 9
+    polys = [oc.random_fr(90 + j, 1 << k) for j in range(4)]
+    want = [oc.best_fft(a, pc.omega_words(oc, k), k) for a in polys]
+    emu.ntt_batch(polys, pc.omega_words(oc, k), k)
+    for a, w in zip(polys, want):
+        assert (a == w).all()

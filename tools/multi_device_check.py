@@ -29,7 +29,17 @@ h = L.register_bases(P)
 assert (pc.affine_of(oc, L.msm_registered(s, h)) == want).all()
 off, m = 12345, 1 << 19
 assert (pc.affine_of(oc, L.msm_registered(s[:m], h, off)) == pc.affine_of(oc, oc.best_multiexp(s[:m], P[off:off + m]))).all()
+# batched columns, round-robin over the devices (results identical to single calls)
+cols = [L.gen_scalars(400 + j, (1 << 18) - 1000 * j, j % 2) for j in range(2 * nd + 1)]
+got = L.msm_batch_registered(cols, h)
+for j, c in enumerate(cols):
+    assert (pc.affine_of(oc, got[j]) == pc.affine_of(oc, oc.best_multiexp(c, P[:c.shape[0]]))).all(), j
 L.unregister_bases(h)
+polys = [oc.random_fr(500 + j, 1 << 16) for j in range(2 * nd + 1)]
+wantp = [oc.best_fft(a, pc.omega_words(oc, 16), 16) for a in polys]
+L.ntt_batch(polys, pc.omega_words(oc, 16), 16)
+for a, w_ in zip(polys, wantp):
+    assert (a == w_).all()
 
 # concurrent callers: 2 * nd threads, each an NTT round trip and a small MSM
 errs = []
