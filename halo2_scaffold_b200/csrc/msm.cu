@@ -571,8 +571,12 @@ int msm_precompute_run(DeviceCtx& ctx, const void* d_src, void* d_dst, size_t n,
 }
 
 // ---- host orchestration ----------------------------------------------------------------------------------
+// The sort of chunk j + 1 (L2-atomic bound) runs on its own high-priority stream while chunk j is accumulated
+// (integer-pipe bound): the two stages keep their outputs (offsets, sorted list) in alternating buffers.
 struct MsmScratch {
-    DevBuf digits, counts, offsets, cursor, block_sums, sorted, ctrl, split_list, heavy, chunk_desc, chunk_out, bucket_acc, bucket_tmp, head_partial, redA, redB, redC, redD, result;
+    cudaStream_t sort_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_sorted[2] = {nullptr, nullptr}, ev_accumulated[2] = {nullptr, nullptr};
+    DevBuf digits, counts, offsets, offsets2, cursor, block_sums, sorted, sorted2, ctrl, split_list, heavy, chunk_desc, chunk_out, bucket_acc, bucket_tmp, head_partial, redA, redB, redC, redD, result;
 };
 
 static int g_forced_c = 0;
@@ -680,62 +684,137 @@ static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t
     return H2B_OK;
 }
 
-// sort one chunk of scalars and add its points into the buckets.  `tables`/`row0` locate the chunk's points.
-static int msm_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_scalars, const void* tables, size_t row0, uint32_t n, cudaStream_t stream) {
+// where chunk [done, done + m) of the call finds its points
+static void chunk_points(const MsmBases& bases, size_t done, const void** tables, size_t* row0) {
+    *row0 = bases.row0 + done;
+    *tables = bases.tables;
+    if (bases.n_tables <= 1) {       // plain mode: rows are relative to the first point of the chunk
+        *tables = (const char*)bases.tables + *row0 * 64;
+        *row0 = 0;
+    }
+}
+
+// slices and scratch of one chunk
+static int msm_size_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan& pl, size_t row0, uint32_t n, int b) {
     pl.n = n;
     pl.row0 = (uint32_t)row0;
     const uint64_t upper = (uint64_t)n * pl.W;          // sorted entries, at most
     if (upper >= 0xffffffffull) { set_error("msm: %u points x %u windows exceed the 32-bit sort index", n, pl.W); return H2B_ERR_BAD_ARGUMENT; }
-    // slices: about 256 entries each once the GPU is full, never fewer than 64 (latency of tiny MSMs)
+    // slices: about 256 entries each once the GPU is full; below one full wave they shrink down to SLICE_MIN entries
+    // (a small MSM is latency bound, and a slice is a serial chain of mixed additions)
     const uint64_t resident = (uint64_t)ctx.sm_count * 512;
     static int env_slice = -1;
     if (env_slice < 0) env_slice = env_int("H2B_MSM_SLICE", 256);
-    // below one full wave the slices shrink down to SLICE_MIN entries: a small MSM is latency bound, and a slice is a
-    // serial chain of mixed additions
     if (upper >= resident * 64) pl.G = (uint32_t)(resident * ((upper + resident * env_slice - 1) / (resident * env_slice)));
     else if (upper >= resident * SLICE_MIN) pl.G = (uint32_t)resident;
     else pl.G = (uint32_t)((upper + SLICE_MIN - 1) / SLICE_MIN);
     if (pl.G == 0) pl.G = 1;
-
     H2B_TRY(s.digits.reserve((size_t)upper * 4));
-    H2B_TRY(s.sorted.reserve((size_t)upper * 4 + 4));
+    H2B_TRY((b ? s.sorted2 : s.sorted).reserve((size_t)upper * 4 + 4));
+    H2B_TRY((b ? s.offsets2 : s.offsets).reserve(((size_t)pl.B + 1) * 4));
     H2B_TRY(s.split_list.reserve((size_t)pl.G * 4));
     const size_t max_heavy = pl.G / COMBINE_HEAVY + 1, max_chunks = pl.G / COMBINE_CHUNK + max_heavy + 1;
     H2B_TRY(s.heavy.reserve(max_heavy * sizeof(HeavyDesc)));
     H2B_TRY(s.chunk_desc.reserve(max_chunks * 8));
     H2B_TRY(s.chunk_out.reserve(max_chunks * 128));
     H2B_TRY(s.head_partial.reserve((size_t)pl.G * 128));
+    return H2B_OK;
+}
 
+// stage 1 of a chunk: digits, histogram, scan, counting-sort scatter -> offsets[b], sorted[b]
+static int msm_sort_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, const void* d_scalars, int b, cudaStream_t stream) {
     uint32_t* counts = (uint32_t*)s.counts.p;
-    uint32_t* offsets = (uint32_t*)s.offsets.p;
+    uint32_t* offsets = (uint32_t*)(b ? s.offsets2 : s.offsets).p;
     uint32_t* cursor = (uint32_t*)s.cursor.p;
-    uint32_t* ctrl = (uint32_t*)s.ctrl.p;
+    uint32_t* sorted = (uint32_t*)(b ? s.sorted2 : s.sorted).p;
     H2B_CUDA(cudaMemsetAsync(counts, 0, (size_t)pl.B * 4, stream));
-    H2B_CUDA(cudaMemsetAsync(ctrl, 0, 16, stream));
-
-    const uint32_t nblk = (n + 255) / 256;
-    uint4* target = (uint4*)(pl.add_into ? s.bucket_tmp.p : s.bucket_acc.p);
+    const uint32_t nblk = (pl.n + 255) / 256;
+    // grid-stride only when a narrow top window is aggregated per CTA (fewer, longer-lived CTAs flush less often)
+    const uint32_t sort_grid = (pl.top_bins && nblk > (uint32_t)ctx.sm_count * 32) ? (uint32_t)ctx.sm_count * 32 : nblk;
     ctx.prof.mark(PROF_BEGIN, stream);
-    const uint32_t sort_grid = nblk < (uint32_t)ctx.sm_count * 32 ? nblk : (uint32_t)ctx.sm_count * 32;
     H2B_LAUNCH(msm_decompose_kernel, sort_grid, 256, 0, stream, (const uint4*)d_scalars, pl, (uint32_t*)s.digits.p, counts);
     ctx.prof.mark(PROF_MSM_DECOMPOSE, stream);
     H2B_TRY(exclusive_scan(s, counts, pl.B, offsets, cursor, stream));
     ctx.prof.mark(PROF_MSM_SCAN, stream);
-    H2B_LAUNCH(msm_scatter_kernel, sort_grid, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, (uint32_t*)s.sorted.p);
+    H2B_LAUNCH(msm_scatter_kernel, sort_grid, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, sorted);
+    H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_SCATTER, stream);
-    H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)tables, (const uint32_t*)offsets,
-               (const uint32_t*)s.sorted.p, ctrl, (uint32_t*)s.split_list.p, target, (uint4*)s.head_partial.p);
+    return H2B_OK;
+}
+
+// stage 2 of a chunk: accumulate the sorted list into the buckets, combine cut buckets, merge (chunked MSMs)
+static int msm_accumulate_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, const void* tables, int b, cudaStream_t stream) {
+    const uint32_t* offsets = (const uint32_t*)(b ? s.offsets2 : s.offsets).p;
+    const uint32_t* sorted = (const uint32_t*)(b ? s.sorted2 : s.sorted).p;
+    uint32_t* ctrl = (uint32_t*)s.ctrl.p;
+    uint4* target = (uint4*)(pl.add_into ? s.bucket_tmp.p : s.bucket_acc.p);
+    H2B_CUDA(cudaMemsetAsync(ctrl, 0, 16, stream));
+    ctx.prof.mark(PROF_BEGIN, stream);
+    H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)tables, offsets, sorted, ctrl, (uint32_t*)s.split_list.p, target,
+               (uint4*)s.head_partial.p);
     ctx.prof.mark(PROF_MSM_ACCUMULATE, stream);
-    H2B_LAUNCH(msm_combine_light_kernel, (pl.G + 127) / 128, 128, 0, stream, pl, (const uint32_t*)offsets, ctrl, (const uint32_t*)s.split_list.p,
+    H2B_LAUNCH(msm_combine_light_kernel, (pl.G + 127) / 128, 128, 0, stream, pl, offsets, ctrl, (const uint32_t*)s.split_list.p,
                (HeavyDesc*)s.heavy.p, (uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, target);
-    H2B_LAUNCH(msm_combine_chunk_kernel, ctx.sm_count * 2, 256, 0, stream, pl, (const uint32_t*)offsets, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p,
+    H2B_LAUNCH(msm_combine_chunk_kernel, ctx.sm_count * 2, 256, 0, stream, pl, offsets, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p,
                (const uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, (uint4*)s.chunk_out.p);
     H2B_LAUNCH(msm_combine_heavy_kernel, ctx.sm_count, 256, 0, stream, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p, (const uint4*)s.chunk_out.p,
                target);
     if (pl.add_into)
-        H2B_LAUNCH(msm_merge_kernel, (pl.B + 127) / 128, 128, 0, stream, pl.B, (const uint32_t*)offsets, (const uint4*)target, (uint4*)s.bucket_acc.p);
+        H2B_LAUNCH(msm_merge_kernel, (pl.B + 127) / 128, 128, 0, stream, pl.B, offsets, (const uint4*)target, (uint4*)s.bucket_acc.p);
     H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_COMBINE, stream);
+    return H2B_OK;
+}
+
+static int msm_pipeline_init(MsmScratch& s) {
+    if (s.sort_stream) return H2B_OK;
+    int lo = 0, hi = 0;
+    H2B_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    H2B_CUDA(cudaStreamCreateWithPriority(&s.sort_stream, cudaStreamNonBlocking, hi));     // numerically lowest = highest priority
+    H2B_CUDA(cudaEventCreateWithFlags(&s.ev_start, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        H2B_CUDA(cudaEventCreateWithFlags(&s.ev_sorted[b], cudaEventDisableTiming));
+        H2B_CUDA(cudaEventCreateWithFlags(&s.ev_accumulated[b], cudaEventDisableTiming));
+    }
+    return H2B_OK;
+}
+
+// All chunks of one MSM.  `stream` carries the accumulate stage (and is the stream the caller synchronises with);
+// with more than one chunk the sort stage of the next chunk overlaps it on s.sort_stream.  uploaded[j], when given, is
+// the event after which chunk j's scalars are in device memory.
+static int msm_run_chunks(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_scalars, const MsmBases& bases, size_t n, size_t chunk,
+                          const cudaEvent_t* uploaded, cudaStream_t stream) {
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    // Measured at 2^24 (profiles/r01_msm_spacing.jsonl): overlapping the two stages gains nothing -- both want every SM,
+    // the sort slows down 2x and the accumulation 15 % while they share the GPU (41.4 ms unsplit, 43.3 ms as 4
+    // overlapped chunks).  Off by default; H2B_MSM_OVERLAP_SORT=1 turns it on.
+    static int env_overlap = -1;
+    if (env_overlap < 0) env_overlap = env_int("H2B_MSM_OVERLAP_SORT", 0);
+    const bool overlap = nchunks > 1 && env_overlap > 0;
+    if (overlap) {
+        H2B_TRY(msm_pipeline_init(s));
+        // the sort stage starts after everything already queued on the caller's stream (inputs, the previous MSM)
+        H2B_CUDA(cudaEventRecord(s.ev_start, stream));
+        H2B_CUDA(cudaStreamWaitEvent(s.sort_stream, s.ev_start, 0));
+    }
+    for (size_t j = 0; j < nchunks; ++j) {
+        const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+        const int b = overlap ? (int)(j & 1) : 0;
+        const void* tables;
+        size_t row0;
+        chunk_points(bases, done, &tables, &row0);
+        H2B_TRY(msm_size_chunk(ctx, s, pl, row0, (uint32_t)m, b));
+        cudaStream_t ss = overlap ? s.sort_stream : stream;
+        if (uploaded) H2B_CUDA(cudaStreamWaitEvent(ss, uploaded[j], 0));
+        if (overlap && j >= 2) H2B_CUDA(cudaStreamWaitEvent(ss, s.ev_accumulated[b], 0));      // buffers b are free again
+        H2B_TRY(msm_sort_chunk(ctx, s, pl, (const char*)d_scalars + done * 32, b, ss));
+        if (overlap) {
+            H2B_CUDA(cudaEventRecord(s.ev_sorted[b], ss));
+            H2B_CUDA(cudaStreamWaitEvent(stream, s.ev_sorted[b], 0));
+        }
+        H2B_TRY(msm_accumulate_chunk(ctx, s, pl, tables, b, stream));
+        if (overlap) H2B_CUDA(cudaEventRecord(s.ev_accumulated[b], stream));
+    }
     return H2B_OK;
 }
 
@@ -809,16 +888,6 @@ static int msm_identity(void* d_out, size_t out_bytes, cudaStream_t stream) {
     return H2B_OK;
 }
 
-// where chunk [done, done + m) of the call finds its points
-static void chunk_points(const MsmBases& bases, size_t done, const void** tables, size_t* row0) {
-    *row0 = bases.row0 + done;
-    *tables = bases.tables;
-    if (bases.n_tables <= 1) {       // plain mode: rows are relative to the first point of the chunk
-        *tables = (const char*)bases.tables + *row0 * 64;
-        *row0 = 0;
-    }
-}
-
 // Scalars already on the device.  d_out_jac: 96 bytes (x|y|z Montgomery), or the 224-byte block (Jacobian | XYZZ).
 int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t n, void* d_out_jac, bool with_xyzz, cudaStream_t stream) {
     if (!ctx.msm) ctx.msm = new MsmScratch();
@@ -827,16 +896,18 @@ int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t
     const size_t out_bytes = with_xyzz ? 224 : 96;
     if (n == 0) return msm_identity(d_out_jac, out_bytes, stream);
     H2B_TRY(msm_check_args(d_scalars, bases, n, d_out_jac));
+    // device-resident scalars need no chunks below 2^26 points (H2B_MSM_DEVICE_CHUNKS > 1 splits anyway: tests, tuning)
     const size_t MAX_CHUNK = (size_t)1 << 26;
+    static int env_dev_chunks = -1;
+    if (env_dev_chunks < 0) env_dev_chunks = env_int("H2B_MSM_DEVICE_CHUNKS", 1);
+    size_t chunk = n;
+    static int env_dev_min = -1;
+    if (env_dev_min < 0) env_dev_min = env_int("H2B_MSM_DEVICE_CHUNK_MIN_LOG", 22);      // tests lower it
+    if (env_dev_chunks > 1 && n >= ((size_t)1 << env_dev_min)) chunk = (n + env_dev_chunks - 1) / env_dev_chunks;
+    if (chunk > MAX_CHUNK) chunk = MAX_CHUNK;
     MsmPlan pl;
-    H2B_TRY(msm_plan(ctx, s, bases, n, n > MAX_CHUNK, stream, pl));
-    for (size_t done = 0; done < n; done += MAX_CHUNK) {
-        uint32_t m = (uint32_t)((n - done < MAX_CHUNK) ? (n - done) : MAX_CHUNK);
-        const void* tables;
-        size_t row0;
-        chunk_points(bases, done, &tables, &row0);
-        H2B_TRY(msm_chunk(ctx, s, pl, (const char*)d_scalars + done * 32, tables, row0, m, stream));
-    }
+    H2B_TRY(msm_plan(ctx, s, bases, n, chunk < n, stream, pl));
+    H2B_TRY(msm_run_chunks(ctx, s, pl, d_scalars, bases, n, chunk, nullptr, stream));
     H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
     H2B_CUDA(cudaMemcpyAsync(d_out_jac, s.result.p, out_bytes, cudaMemcpyDeviceToDevice, stream));
     return H2B_OK;
@@ -884,14 +955,7 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
         H2B_CUDA(cudaMemcpyAsync((char*)d_staging + done * 32, (const char*)h_scalars + done * 32, m * 32, cudaMemcpyHostToDevice, cs));
         if (nchunks > 1) H2B_CUDA(cudaEventRecord(ctx.copy_events[j], cs));
     }
-    for (size_t j = 0; j < nchunks; ++j) {
-        const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
-        if (nchunks > 1) H2B_CUDA(cudaStreamWaitEvent(stream, ctx.copy_events[j], 0));
-        const void* tables;
-        size_t row0;
-        chunk_points(bases, done, &tables, &row0);
-        H2B_TRY(msm_chunk(ctx, s, pl, (const char*)d_staging + done * 32, tables, row0, (uint32_t)m, stream));
-    }
+    H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, n, chunk, nchunks > 1 ? ctx.copy_events.data() : nullptr, stream));
     H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
     H2B_CUDA(cudaMemcpyAsync(h_out_block, s.result.p, 224, cudaMemcpyDeviceToHost, stream));
     H2B_CUDA(cudaStreamSynchronize(stream));
@@ -923,7 +987,12 @@ int msm_sum_partials_run(DeviceCtx& ctx, const void* d_blocks, uint32_t count, v
 void msm_release(DeviceCtx& ctx) {
     if (!ctx.msm) return;
     MsmScratch& s = *ctx.msm;
-    DevBuf* all[] = {&s.digits, &s.counts, &s.offsets, &s.cursor, &s.block_sums, &s.sorted, &s.ctrl, &s.split_list, &s.heavy, &s.chunk_desc, &s.chunk_out,
+    if (s.sort_stream) {
+        cudaStreamDestroy(s.sort_stream);
+        cudaEventDestroy(s.ev_start);
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(s.ev_sorted[b]); cudaEventDestroy(s.ev_accumulated[b]); }
+    }
+    DevBuf* all[] = {&s.digits, &s.counts, &s.offsets, &s.offsets2, &s.sorted2, &s.cursor, &s.block_sums, &s.sorted, &s.ctrl, &s.split_list, &s.heavy, &s.chunk_desc, &s.chunk_out,
                      &s.bucket_acc, &s.bucket_tmp, &s.head_partial, &s.redA, &s.redB, &s.redC, &s.redD, &s.result};
     for (DevBuf* b : all) b->release();
     delete ctx.msm;

@@ -157,6 +157,27 @@ def test_msm_chunked_upload_pipeline(emu):
     env = dict(os.environ, H2B_MSM_UPLOAD_CHUNK_LOG="10")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+    # device-resident scalars: 4 (or 3) chunks whose sort overlaps the previous chunk's accumulation
+    code2 = (
+        "import sys; sys.path[:0]=[%r,%r,%r]\n"
+        "import numpy as np, oracle_c as oc, parity_cases as pc\n"
+        "from halo2_scaffold_b200._lib import Lib\n"
+        "L=Lib(%r, allow_emulator=True); L.init(1)\n"
+        "for n, kind, chunks in ((5000, 0, 4), (4099, 1, 3)):\n"
+        "    s, P = pc.edge_msm_inputs(L, oc, n, kind, 900 + n)\n"
+        "    want = pc.affine_of(oc, oc.best_multiexp(s, P))\n"
+        "    h = L.register_bases(P)\n"
+        "    d_s, d_p, d_o = L.dev_alloc(0, n * 32), L.dev_alloc(0, n * 64), L.dev_alloc(0, 224)\n"
+        "    L.h2d(0, d_s, s); L.h2d(0, d_p, P)\n"
+        "    out = np.zeros(28, dtype=np.uint64)\n"
+        "    L.msm_dev_registered(0, d_s, h, 0, n, d_o); L.dev_sync(0); L.d2h(0, out, d_o)\n"
+        "    assert (pc.affine_of(oc, out[:12]) == want).all()\n"
+        "    L.msm_dev_partial(0, d_s, d_p, n, d_o); L.dev_sync(0); L.d2h(0, out, d_o)\n"
+        "    assert (pc.affine_of(oc, out[:12]) == want).all()\n"
+        "print('ok')\n") % (root, root + '/oracle', root + '/tests', emu.path)
+    env = dict(os.environ, H2B_MSM_DEVICE_CHUNK_MIN_LOG="10", H2B_MSM_DEVICE_CHUNKS="4", H2B_MSM_OVERLAP_SORT="1")
+    out = subprocess.run([sys.executable, "-c", code2], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
 def test_batched_columns_match_single_calls(emu, oc):
