@@ -375,6 +375,7 @@ void h2b_shutdown(void) {
         cudaStreamSynchronize(c->stream);
         ntt_release(*c);
         msm_release(*c);
+        stager_release(*c);
         c->msm_scalars.release();
         c->msm_out.release();
         for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
@@ -475,11 +476,9 @@ int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
     H2B_CUDA(cudaSetDevice(c->device));
     const size_t bytes = (size_t)32 << log_n;
     H2B_TRY(c->ntt_io.reserve(bytes));
-    H2B_CUDA(cudaMemcpyAsync(c->ntt_io.p, a, bytes, cudaMemcpyHostToDevice, c->stream));
+    H2B_TRY(host_upload(*c, c->ntt_io.p, a, bytes, c->stream));
     H2B_TRY(ntt_run(*c, c->ntt_io.p, omega, log_n, c->stream));
-    H2B_CUDA(cudaMemcpyAsync(a, c->ntt_io.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-    H2B_CUDA(cudaStreamSynchronize(c->stream));
-    return H2B_OK;
+    return host_download(*c, a, c->ntt_io.p, bytes, c->stream);
 }
 
 int h2b_msm_bn254_g1_batch_registered(const uint64_t* const* scalars, const size_t* lens, size_t count, uint64_t handle, uint64_t* out_jac) {
@@ -519,11 +518,9 @@ int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omeg
         std::lock_guard<std::mutex> lk(c.mu);
         H2B_CUDA(cudaSetDevice(c.device));
         H2B_TRY(c.ntt_io.reserve(bytes));
-        H2B_CUDA(cudaMemcpyAsync(c.ntt_io.p, a[j], bytes, cudaMemcpyHostToDevice, c.stream));
+        H2B_TRY(host_upload(c, c.ntt_io.p, a[j], bytes, c.stream));
         H2B_TRY(ntt_run(c, c.ntt_io.p, omega, log_n, c.stream));
-        H2B_CUDA(cudaMemcpyAsync(a[j], c.ntt_io.p, bytes, cudaMemcpyDeviceToHost, c.stream));
-        H2B_CUDA(cudaStreamSynchronize(c.stream));
-        return H2B_OK;
+        return host_download(c, a[j], c.ntt_io.p, bytes, c.stream);
     });
 }
 

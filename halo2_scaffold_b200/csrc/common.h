@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -75,6 +76,7 @@ struct Profiler {
     }
 };
 
+struct Stager;        // stage.cu
 struct NttTwiddles;   // ntt.cu
 struct MsmScratch;    // msm.cu
 struct BaseSet;       // api.cu
@@ -95,10 +97,16 @@ struct DeviceCtx {
     std::vector<NttTwiddles*> twiddles;  // small LRU cache keyed by (omega, log_n)
     MsmScratch* msm = nullptr;
     Profiler prof;
+    Stager* stager = nullptr;          // pinned slots + worker streams for pageable host buffers
     void* pinned = nullptr;            // small pinned bounce buffer
     size_t pinned_cap = 0;
 };
 
+// ---- stage.cu ----
+int host_upload(DeviceCtx& ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t consumer, bool order_after_consumer = true);
+int host_download(DeviceCtx& ctx, void* h_dst, const void* d_src, size_t bytes, cudaStream_t producer);
+void stager_release(DeviceCtx& ctx);
+bool host_is_pageable(const void* p);
 // ---- ntt.cu ----
 int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);

@@ -783,7 +783,7 @@ static int msm_pipeline_init(MsmScratch& s) {
 // with more than one chunk the sort stage of the next chunk overlaps it on s.sort_stream.  uploaded[j], when given, is
 // the event after which chunk j's scalars are in device memory.
 static int msm_run_chunks(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_scalars, const MsmBases& bases, size_t n, size_t chunk,
-                          const cudaEvent_t* uploaded, cudaStream_t stream) {
+                          const cudaEvent_t* uploaded, cudaStream_t stream, const std::function<int(size_t)>* before_chunk = nullptr) {
     const size_t nchunks = (n + chunk - 1) / chunk;
     // Measured at 2^24 (profiles/r01_msm_spacing.jsonl): overlapping the two stages gains nothing -- both want every SM,
     // the sort slows down 2x and the accumulation 15 % while they share the GPU (41.4 ms unsplit, 43.3 ms as 4
@@ -805,6 +805,7 @@ static int msm_run_chunks(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void*
         chunk_points(bases, done, &tables, &row0);
         H2B_TRY(msm_size_chunk(ctx, s, pl, row0, (uint32_t)m, b));
         cudaStream_t ss = overlap ? s.sort_stream : stream;
+        if (before_chunk) H2B_TRY((*before_chunk)(j));          // e.g. the staged upload of this chunk's scalars onto `stream`
         if (uploaded) H2B_CUDA(cudaStreamWaitEvent(ss, uploaded[j], 0));
         if (overlap && j >= 2) H2B_CUDA(cudaStreamWaitEvent(ss, s.ev_accumulated[b], 0));      // buffers b are free again
         H2B_TRY(msm_sort_chunk(ctx, s, pl, (const char*)d_scalars + done * 32, b, ss));
@@ -944,18 +945,31 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
     }
     MsmPlan pl;
     H2B_TRY(msm_plan(ctx, s, bases, n, nchunks > 1, stream, pl));
-    // the staging buffer may still be read by the previous call's kernels on `stream`: order the copies after them
-    if (nchunks > 1) {
-        H2B_CUDA(cudaEventRecord(ctx.copy_events[0], stream));
-        H2B_CUDA(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_events[0], 0));
+    if (host_is_pageable(h_scalars)) {
+        // pageable caller memory (a Rust Vec): chunk j is copied through pinned slots by a few host threads right before
+        // its kernels are queued, so the CPU copy of chunk j + 1 overlaps the GPU work of chunk j (stage.cu)
+        std::function<int(size_t)> upload = [&](size_t j) -> int {
+            const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+            // only chunk 0 has to wait for the previous call's kernels (they may still read the staging buffer); the
+            // other chunks land in regions nothing in flight touches, so their DMA overlaps the GPU work of chunk j - 1
+            return host_upload(ctx, (char*)d_staging + done * 32, (const char*)h_scalars + done * 32, m * 32, stream, j == 0);
+        };
+        H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, n, chunk, nullptr, stream, &upload));
+    } else {
+        // pinned caller memory: every chunk's DMA is queued up front on the copy stream
+        // (the staging buffer may still be read by the previous call's kernels on `stream`: order the copies after them)
+        if (nchunks > 1) {
+            H2B_CUDA(cudaEventRecord(ctx.copy_events[0], stream));
+            H2B_CUDA(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_events[0], 0));
+        }
+        for (size_t j = 0; j < nchunks; ++j) {
+            const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+            cudaStream_t cs = nchunks > 1 ? ctx.copy_stream : stream;
+            H2B_CUDA(cudaMemcpyAsync((char*)d_staging + done * 32, (const char*)h_scalars + done * 32, m * 32, cudaMemcpyHostToDevice, cs));
+            if (nchunks > 1) H2B_CUDA(cudaEventRecord(ctx.copy_events[j], cs));
+        }
+        H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, n, chunk, nchunks > 1 ? ctx.copy_events.data() : nullptr, stream));
     }
-    for (size_t j = 0; j < nchunks; ++j) {
-        const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
-        cudaStream_t cs = nchunks > 1 ? ctx.copy_stream : stream;
-        H2B_CUDA(cudaMemcpyAsync((char*)d_staging + done * 32, (const char*)h_scalars + done * 32, m * 32, cudaMemcpyHostToDevice, cs));
-        if (nchunks > 1) H2B_CUDA(cudaEventRecord(ctx.copy_events[j], cs));
-    }
-    H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, n, chunk, nchunks > 1 ? ctx.copy_events.data() : nullptr, stream));
     H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
     H2B_CUDA(cudaMemcpyAsync(h_out_block, s.result.p, 224, cudaMemcpyDeviceToHost, stream));
     H2B_CUDA(cudaStreamSynchronize(stream));

@@ -197,3 +197,23 @@ def test_batched_columns_match_single_calls(emu, oc):
     emu.ntt_batch(polys, pc.omega_words(oc, k), k)
     for a, w in zip(polys, want):
         assert (a == w).all()
+
+
+def test_pageable_host_buffers_go_through_the_pinned_staging_threads(emu):
+    # stage.cu: host threads copy pieces of the caller's (pageable) buffers through pinned slots, both directions;
+    # tiny pieces force many pieces per worker and the slot recycling at CPU-test sizes
+    import os, subprocess, sys
+    root = pc.__file__.rsplit('/tests/', 1)[0]
+    code = (
+        "import sys; sys.path[:0]=[%r,%r,%r]\n"
+        "import oracle_c as oc, parity_cases as pc\n"
+        "from halo2_scaffold_b200._lib import Lib\n"
+        "L=Lib(%r, allow_emulator=True); L.init(1)\n"
+        "[pc.check_ntt(L, oc, k) for k in (7, 10, 12)]\n"
+        "pc.check_msm(L, oc, 5000, kind=0)\n"
+        "pc.check_msm_tables(L, oc, 3000, 8, kind=1, ranges=[(0, 3000), (17, 2500)])\n"
+        "print('ok')\n") % (root, root + '/oracle', root + '/tests', emu.path)
+    for threads in ("1", "3"):
+        env = dict(os.environ, H2B_STAGE_PIECE_LOG="10", H2B_STAGE_THREADS=threads, H2B_MSM_UPLOAD_CHUNK_LOG="11")
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
