@@ -71,14 +71,6 @@ class Prog:
                 reg[dst] = s & M32
                 if op.endswith(".cc"):
                     cf = s >> 32
-            elif op == "madwide":      # (dst_lo, dst_hi) = v0 * v1 + (v3:v2)   -- one IMAD.WIDE.U32, result mod 2^64
-                lo_name, hi_name = dst
-                r = (v[0] * v[1] + v[2] + (v[3] << 32))
-                if r >> 64:
-                    raise OverflowError("madwide overflow in %s" % self.name)
-                reg[lo_name] = r & M32
-                reg[hi_name] = r >> 32
-                continue
             elif op in ("add", "add.cc", "addc", "addc.cc"):
                 s = v[0] + v[1] + (cf if op.startswith("addc") else 0)
                 reg[dst] = s & M32
@@ -121,21 +113,8 @@ class Prog:
         if self.temps:
             lines.append(".reg .u32 " + ", ".join(self.temps) + ";")
         lines.append(".reg .pred pz;")
-        lines.append(".reg .u64 w64, p64, zhi;")
-        if "z0" in opnum:
-            lines.append("cvt.u64.u32 zhi, %s;" % r("z0"))
-            lines.append("shl.b64 zhi, zhi, 32;")
         for op, dst, srcs in self.ins:
-            if op == "madwide":
-                lo_name, hi_name = dst
-                # (t | z<<32) as a genuine 64-bit value + mul.wide + add.s64: the form ptxas keeps as ONE
-                # IMAD.WIDE.U32 with a register-pair addend (a mov.b64 pack makes it split the MAD instead)
-                lines.append("cvt.u64.u32 w64, %s;" % r(srcs[2]))
-                lines.append("or.b64 w64, w64, zhi;")
-                lines.append("mul.wide.u32 p64, %s, %s;" % (r(srcs[0]), r(srcs[1])))
-                lines.append("add.s64 w64, p64, w64;")
-                lines.append("mov.b64 {%s, %s}, w64;" % (r(lo_name), r(hi_name)))
-            elif op == "selnz":
+            if op == "selnz":
                 lines.append("setp.ne.u32 pz, %s, 0;" % r(srcs[0]))
                 lines.append("selp.u32 %s, %s, %s, pz;" % (r(dst), r(srcs[1]), r(srcs[2])))
             elif op == "mov":
@@ -233,62 +212,6 @@ def gen_mont_mul(name, mod, square=False):
         P.emit("selnz", R[i], bw, t[i], s[i])
     return P
 
-
-
-# =====================================================================================
-# Montgomery multiplication, carry-free wide MADs ("CIOS rows")
-#   Measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 issues every 2 clk per warp, but
-#   the carry-chained IMAD.WIDE.U32.X (what the even/odd scheme compiles to) only every 4 clk, and
-#   the FMA-heavy pipe was 89 % busy in msm_accumulate_kernel.  This variant keeps the FMA pipe on
-#   full-rate instructions: every partial product is  a_j*b_i + t_j  with a *32-bit* addend, which
-#   cannot overflow 64 bits ((2^32-1)^2 + 2^32-1 < 2^64), so the 8 MADs of a row are independent
-#   and carry-free; the carries are resolved by one add.cc chain per row on the ALU pipe, which
-#   runs concurrently.  The 64-bit addend is the register pair (t_j, z) where z is a zero the
-#   compiler cannot see through (otherwise ptxas splits the MAD into mul + 64-bit add).
-# =====================================================================================
-def gen_mont_mul_rows(name, mod, square=False):
-    p = limbs(mod)
-    inv = (-pow(mod, -1, 1 << 32)) & M32
-    A = ["a%d" % i for i in range(NL)]
-    B = A if square else ["b%d" % i for i in range(NL)]
-    R = ["r%d" % i for i in range(NL)]
-    P = Prog(name, A + ([] if square else B) + ["z0"], R)
-    t = [P.tmp("t%d" % i) for i in range(NL)]
-    u = [P.tmp("u%d" % i) for i in range(NL + 1)]
-    lo = [P.tmp("l%d" % i) for i in range(NL)]
-    hi = [P.tmp("h%d" % i) for i in range(NL)]
-    m = P.tmp("m")
-    Z = "z0"
-    for i in range(NL):
-        bi = B[i]
-        # row A: (lo_j, hi_j) = a_j * b_i + t_j
-        for j in range(NL):
-            if i == 0:
-                P.emit("mul.lo", lo[j], A[j], bi)      # ptxas fuses the lo/hi pair into one IMAD.WIDE
-                P.emit("mul.hi", hi[j], A[j], bi)
-            else:
-                P.emit("madwide", (lo[j], hi[j]), A[j], bi, t[j], Z)
-        # carry chain A: u = row sum (9 limbs); u0 = lo0
-        P.emit("mov", u[0], lo[0])
-        for j in range(1, NL):
-            P.emit("add.cc" if j == 1 else "addc.cc", u[j], lo[j], hi[j - 1])
-        P.emit("addc", u[NL], hi[NL - 1], 0)
-        P.emit("mul.lo", m, u[0], inv)
-        # row B: (lo_j, hi_j) = m * p_j + u_j
-        for j in range(NL):
-            P.emit("madwide", (lo[j], hi[j]), m, p[j], u[j], Z)
-        # carry chain B with the division by 2^32: t_j = lo_{j+1} + hi_j
-        for j in range(NL - 1):
-            P.emit("add.cc" if j == 0 else "addc.cc", t[j], lo[j + 1], hi[j])
-        P.emit("addc", t[NL - 1], u[NL], hi[NL - 1])
-    s = [P.tmp("s%d" % i) for i in range(NL)]
-    bw = P.tmp("bw")
-    for i in range(NL):
-        P.emit("sub.cc" if i == 0 else "subc.cc", s[i], t[i], p[i])
-    P.emit("subc", bw, 0, 0)
-    for i in range(NL):
-        P.emit("selnz", R[i], bw, t[i], s[i])
-    return P
 
 
 # =====================================================================================
@@ -569,10 +492,6 @@ def main():
                        "const uint32_t (&c)[8], const uint32_t (&d)[8])" % (tag, kind))
             elif kind == "sqr":
                 sig = "__device__ __forceinline__ void %s_%s_asm(uint32_t (&r)[8], const uint32_t (&a)[8])" % (tag, kind)
-            elif kind == "sqrw":
-                sig = "__device__ __forceinline__ void %s_%s_asm(uint32_t (&r)[8], const uint32_t (&a)[8], uint32_t z)" % (tag, kind)
-            elif kind == "mulw":
-                sig = "__device__ __forceinline__ void %s_%s_asm(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t z)" % (tag, kind)
             else:
                 sig = "__device__ __forceinline__ void %s_%s_asm(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8])" % (tag, kind)
             chunks.append("// %s: %d PTX instructions\n" % (prog.name, len(prog.ins)))
