@@ -34,6 +34,7 @@ _EXPORTS = [
     "h2b_gen_scalars_dev", "h2b_field_op", "h2b_ec_op", "h2b_imad_bench", "h2b_set_msm_window",
     "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read", "h2b_msm_bn254_g1_dev_registered",
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
+    "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
 ]
 
 
@@ -78,6 +79,9 @@ class Lib:
         L.h2b_msm_fold_partials.argtypes = [i32, vp, sz, vp]
         L.h2b_msm_fold_partials_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_fr_scale_dev.argtypes = [i32, vp, sz, vp, i32, vp]
+        L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
+        L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
+        L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_dev_alloc.argtypes = [i32, sz, ctypes.POINTER(vp)]
         L.h2b_dev_free.argtypes = [i32, vp]
         L.h2b_memcpy_h2d.argtypes = [i32, vp, vp, sz]
@@ -222,6 +226,18 @@ class Lib:
     def fr_scale_dev(self, device: int, d_a: int, n: int, factors: np.ndarray, stream: int = 0):
         factors = _u64(factors).reshape(-1, 4)
         self.check(self.L.h2b_fr_scale_dev(device, d_a, n, factors.ctypes.data, factors.shape[0], stream))
+
+    def lagrange_to_coeff_dev(self, device: int, d_a: int, k: int, omega_inv: np.ndarray, ifft_divisor: np.ndarray, stream: int = 0):
+        omega_inv, ifft_divisor = _u64(omega_inv), _u64(ifft_divisor)
+        self.check(self.L.h2b_lagrange_to_coeff_dev(device, d_a, k, omega_inv.ctypes.data, ifft_divisor.ctypes.data, stream))
+
+    def coeff_to_extended_dev(self, device: int, d_a: int, k: int, extended_k: int, extended_omega: np.ndarray, zeta_powers: np.ndarray, stream: int = 0):
+        extended_omega, zeta_powers = _u64(extended_omega), _u64(zeta_powers).reshape(3, 4)
+        self.check(self.L.h2b_coeff_to_extended_dev(device, d_a, k, extended_k, extended_omega.ctypes.data, zeta_powers.ctypes.data, stream))
+
+    def extended_to_coeff_dev(self, device: int, d_a: int, extended_k: int, extended_omega_inv: np.ndarray, factors: np.ndarray, stream: int = 0):
+        extended_omega_inv, factors = _u64(extended_omega_inv), _u64(factors).reshape(3, 4)
+        self.check(self.L.h2b_extended_to_coeff_dev(device, d_a, extended_k, extended_omega_inv.ctypes.data, factors.ctypes.data, stream))
 
     def dev_alloc(self, device: int, nbytes: int) -> int:
         p = ctypes.c_void_p(0)

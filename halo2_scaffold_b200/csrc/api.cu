@@ -617,6 +617,41 @@ int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, i
     return ntt_scale_run(*c, d_a, n, factors, count, (cudaStream_t)stream);
 }
 
+// ---- EvaluationDomain on the device ([UP] halo2_proofs/src/poly/domain.rs) --------------------------
+// The column stays in device memory between the scaling, padding and transform steps of each conversion; the constants
+// (omega, divisors, zeta) are the caller's: EvaluationDomain::new computes them once per domain on the host.
+int h2b_lagrange_to_coeff_dev(int device, void* d_a, uint32_t k, const uint64_t omega_inv[4], const uint64_t ifft_divisor[4], void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_a || !omega_inv || !ifft_divisor) { set_error("h2b_lagrange_to_coeff_dev: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    H2B_TRY(ntt_run(*c, d_a, omega_inv, k, (cudaStream_t)stream));
+    return ntt_scale_run(*c, d_a, (size_t)1 << k, ifft_divisor, 1, (cudaStream_t)stream);
+}
+
+int h2b_coeff_to_extended_dev(int device, void* d_a, uint32_t k, uint32_t extended_k, const uint64_t extended_omega[4], const uint64_t zeta_powers[12],
+                              void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_a || !extended_omega || !zeta_powers) { set_error("h2b_coeff_to_extended_dev: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (extended_k < k || extended_k > 28) { set_error("h2b_coeff_to_extended_dev: need k <= extended_k <= 28"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t n = (size_t)1 << k, en = (size_t)1 << extended_k;
+    H2B_TRY(ntt_scale_run(*c, d_a, n, zeta_powers, 3, (cudaStream_t)stream));                         // a[i] *= zeta^(i mod 3)
+    if (en > n) H2B_CUDA(cudaMemsetAsync((char*)d_a + n * 32, 0, (en - n) * 32, (cudaStream_t)stream));   // zero-pad
+    return ntt_run(*c, d_a, extended_omega, extended_k, (cudaStream_t)stream);
+}
+
+int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const uint64_t extended_omega_inv[4], const uint64_t factors[12], void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_a || !extended_omega_inv || !factors) { set_error("h2b_extended_to_coeff_dev: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    H2B_TRY(ntt_run(*c, d_a, extended_omega_inv, extended_k, (cudaStream_t)stream));
+    // factors[j] = extended_ifft_divisor * (1, zeta^-1, zeta^-2)[j]: one pass undoes the scaling and the coset
+    return ntt_scale_run(*c, d_a, (size_t)1 << extended_k, factors, 3, (cudaStream_t)stream);
+}
+
 int h2b_dev_alloc(int device, size_t bytes, void** out) {
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));

@@ -55,17 +55,18 @@ class EvaluationDomain:
         self.g_coset_inv = FR_ZETA * FR_ZETA % FR_MODULUS
 
     # -- helpers ----------------------------------------------------------------------------------
-    def _run(self, a: np.ndarray, out_len: int, work_len: int, steps):
+    def _run(self, a: np.ndarray, out_len: int, work_len: int, steps, alloc_len: int | None = None):
+        """upload `work_len` elements into a device buffer of `alloc_len` (default work_len), run `steps`, download `out_len`"""
         L, dev = self.lib, self.device
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
-        d = L.dev_alloc(dev, work_len * 32)
+        d = L.dev_alloc(dev, (alloc_len or work_len) * 32)
         try:
             if work_len > a.shape[0]:
                 pad = np.zeros((work_len, 4), dtype=np.uint64)
                 pad[: a.shape[0]] = a
                 L.h2d(dev, d, pad)
             else:
-                L.h2d(dev, d, a)
+                L.h2d(dev, d, a[:work_len])
             for step in steps:
                 step(d)
             L.dev_sync(dev)
@@ -80,8 +81,7 @@ class EvaluationDomain:
         assert a.size == 4 * self.n
         L, dev = self.lib, self.device
         return self._run(a, self.n, self.n, [
-            lambda d: L.ntt_dev(dev, d, fr_to_words(self.omega_inv), self.k),
-            lambda d: L.fr_scale_dev(dev, d, self.n, fr_to_words(self.ifft_divisor)),
+            lambda d: L.lagrange_to_coeff_dev(dev, d, self.k, fr_to_words(self.omega_inv), fr_to_words(self.ifft_divisor)),
         ])
 
     def coeff_to_extended(self, a: np.ndarray) -> np.ndarray:
@@ -90,10 +90,9 @@ class EvaluationDomain:
         L, dev = self.lib, self.device
         en = 1 << self.extended_k
         zs = np.stack([fr_to_words(1), fr_to_words(self.g_coset), fr_to_words(self.g_coset_inv)])
-        return self._run(a, en, en, [
-            lambda d: L.fr_scale_dev(dev, d, self.n, zs),
-            lambda d: L.ntt_dev(dev, d, fr_to_words(self.extended_omega), self.extended_k),
-        ])
+        return self._run(a, en, self.n, [
+            lambda d: L.coeff_to_extended_dev(dev, d, self.k, self.extended_k, fr_to_words(self.extended_omega), zs),
+        ], alloc_len=en)
 
     def extended_to_coeff(self, a: np.ndarray) -> np.ndarray:
         """best_fft(a, extended_omega_inv, extended_k); scale by 1/2^ek and un-zeta; truncate to n*(j-1)"""
@@ -104,6 +103,5 @@ class EvaluationDomain:
                        fr_to_words(self.extended_ifft_divisor * self.g_coset_inv),
                        fr_to_words(self.extended_ifft_divisor * self.g_coset)])
         return self._run(a, self.n * self.quotient_poly_degree, en, [
-            lambda d: L.ntt_dev(dev, d, fr_to_words(self.extended_omega_inv), self.extended_k),
-            lambda d: L.fr_scale_dev(dev, d, en, zs),
+            lambda d: L.extended_to_coeff_dev(dev, d, self.extended_k, fr_to_words(self.extended_omega_inv), zs),
         ])

@@ -202,41 +202,34 @@ class EvaluationDomain {
     // pub fn lagrange_to_coeff(&self, a: Polynomial<_, LagrangeCoeff>) -> Polynomial<_, Coeff>
     std::vector<Fr> lagrange_to_coeff(const std::vector<Fr>& a) const {
         if (a.size() != n_) throw Panic("assertion failed: a.len() == 1 << self.k");
-        return run(a, n_, n_, [&](void* d) {
-            check(h2b_ntt_bn254_fr_dev(device_, d, omega_inv_.l, k_, nullptr), "ifft");
-            check(h2b_fr_scale_dev(device_, d, n_, ifft_divisor_.l, 1, nullptr), "ifft divisor");
+        return run(a, n_, n_, n_, [&](void* d) {
+            check(h2b_lagrange_to_coeff_dev(device_, d, k_, omega_inv_.l, ifft_divisor_.l, nullptr), "lagrange_to_coeff");
         });
     }
     // pub fn coeff_to_extended(&self, a: Polynomial<_, Coeff>) -> Polynomial<_, ExtendedLagrangeCoeff>
     std::vector<Fr> coeff_to_extended(const std::vector<Fr>& a) const {
         if (a.size() != n_) throw Panic("assertion failed: a.len() == 1 << self.k");
         const Fr z[3] = {fr::one(), g_coset_, g_coset_inv_};
-        return run(a, extended_len(), extended_len(), [&](void* d) {
-            check(h2b_fr_scale_dev(device_, d, n_, z[0].l, 3, nullptr), "distribute_powers_zeta");
-            check(h2b_ntt_bn254_fr_dev(device_, d, extended_omega_.l, extended_k_, nullptr), "extended fft");
+        // only the 2^k coefficients cross PCIe; scaling by zeta powers, zero-padding and the extended FFT run on the device
+        return run(a, extended_len(), n_, extended_len(), [&](void* d) {
+            check(h2b_coeff_to_extended_dev(device_, d, k_, extended_k_, extended_omega_.l, z[0].l, nullptr), "coeff_to_extended");
         });
     }
     // pub fn extended_to_coeff(&self, a: Polynomial<_, ExtendedLagrangeCoeff>) -> Vec<G>
     std::vector<Fr> extended_to_coeff(const std::vector<Fr>& a) const {
         if (a.size() != extended_len()) throw Panic("assertion failed: a.len() == self.extended_len()");
         const Fr z[3] = {extended_ifft_divisor_, fr::mul(extended_ifft_divisor_, g_coset_inv_), fr::mul(extended_ifft_divisor_, g_coset_)};
-        return run(a, n_ * quotient_poly_degree_, extended_len(), [&](void* d) {
-            check(h2b_ntt_bn254_fr_dev(device_, d, extended_omega_inv_.l, extended_k_, nullptr), "extended ifft");
-            check(h2b_fr_scale_dev(device_, d, extended_len(), z[0].l, 3, nullptr), "divisor and inverse zeta powers");
+        return run(a, n_ * quotient_poly_degree_, extended_len(), extended_len(), [&](void* d) {
+            check(h2b_extended_to_coeff_dev(device_, d, extended_k_, extended_omega_inv_.l, z[0].l, nullptr), "extended_to_coeff");
         });
     }
 
   private:
+    // upload `upload_len` elements of `a` into a device buffer of `alloc_len`, run `steps`, download `out_len`
     template <class F>
-    std::vector<Fr> run(const std::vector<Fr>& a, size_t out_len, size_t work_len, F steps) const {
-        DeviceBuffer d(device_, work_len * sizeof(Fr));
-        if (work_len > a.size()) {
-            std::vector<Fr> padded(work_len, Fr{{0, 0, 0, 0}});
-            std::memcpy(padded.data(), a.data(), a.size() * sizeof(Fr));
-            check(h2b_memcpy_h2d(device_, d.get(), padded.data(), work_len * sizeof(Fr)), "h2d");
-        } else {
-            check(h2b_memcpy_h2d(device_, d.get(), a.data(), work_len * sizeof(Fr)), "h2d");
-        }
+    std::vector<Fr> run(const std::vector<Fr>& a, size_t out_len, size_t upload_len, size_t alloc_len, F steps) const {
+        DeviceBuffer d(device_, alloc_len * sizeof(Fr));
+        check(h2b_memcpy_h2d(device_, d.get(), a.data(), upload_len * sizeof(Fr)), "h2d");
         steps(d.get());
         check(h2b_dev_sync(device_), "sync");
         std::vector<Fr> out(out_len);

@@ -111,6 +111,18 @@ int h2b_msm_fold_partials_dev(int device, const void* d_blocks, size_t count, vo
  * the (1, zeta, zeta^2) coset pattern of coeff_to_extended ([UP] halo2_proofs/src/poly/domain.rs). */
 int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, int count, void* stream);
 
+/* EvaluationDomain's three conversions on a device-resident column ([UP] halo2_proofs/src/poly/domain.rs, SURVEY.md row
+ * a6); the domain constants are the caller's (computed once per domain on the host, as EvaluationDomain::new does):
+ *   lagrange_to_coeff : best_fft(a, omega_inv, k); a[i] *= ifft_divisor                         (2^k elements, in place)
+ *   coeff_to_extended : a[i] *= zeta_powers[i mod 3] for i < 2^k; zero-pad to 2^extended_k; best_fft(a, extended_omega, extended_k)
+ *                       (d_a must hold 2^extended_k elements; zeta_powers = 1, zeta, zeta^2)
+ *   extended_to_coeff : best_fft(a, extended_omega_inv, extended_k); a[i] *= factors[i mod 3]
+ *                       (factors = extended_ifft_divisor * (1, zeta^2, zeta); the caller truncates to n * (j - 1)) */
+int h2b_lagrange_to_coeff_dev(int device, void* d_a, uint32_t k, const uint64_t omega_inv[4], const uint64_t ifft_divisor[4], void* stream);
+int h2b_coeff_to_extended_dev(int device, void* d_a, uint32_t k, uint32_t extended_k, const uint64_t extended_omega[4], const uint64_t zeta_powers[12],
+                              void* stream);
+int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const uint64_t extended_omega_inv[4], const uint64_t factors[12], void* stream);
+
 /* ---- raw device memory helpers (so that non-CUDA hosts -- ctypes, Rust -- can hold device buffers) --- */
 int h2b_dev_alloc(int device, size_t bytes, void** out);
 int h2b_dev_free(int device, void* p);

@@ -217,3 +217,16 @@ def test_pageable_host_buffers_go_through_the_pinned_staging_threads(emu):
         env = dict(os.environ, H2B_STAGE_PIECE_LOG="10", H2B_STAGE_THREADS=threads, H2B_MSM_UPLOAD_CHUNK_LOG="11")
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
         assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_evaluation_domain_mirror_matches_golden(emu, golden):
+    # halo2_scaffold_b200.EvaluationDomain over the h2b_*_dev domain entry points (row a6) against the fixture that
+    # tests/golden/make_golden.py produced with the big-int oracle
+    import halo2_scaffold_b200 as h2
+    g = golden["domain"]
+    d = h2.EvaluationDomain(int(g["j"]), int(g["k"]), lib=emu)
+    coeff = d.lagrange_to_coeff(g["lagrange"])
+    assert (coeff == g["coeff"]).all()
+    ext = d.coeff_to_extended(coeff)
+    assert (ext == g["extended"]).all()
+    assert (d.extended_to_coeff(ext) == g["back"]).all()
