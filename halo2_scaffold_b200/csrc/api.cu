@@ -669,14 +669,19 @@ int h2b_dev_free(int device, void* p) {
 int h2b_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes) {
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
-    H2B_CUDA(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    // pageable sources go through the pinned staging threads (stage.cu); synchronous like cudaMemcpy
+    std::lock_guard<std::mutex> lk(c->mu);
+    H2B_CUDA(cudaDeviceSynchronize());            // cudaMemcpy semantics: ordered after everything queued on the device
+    H2B_TRY(host_upload(*c, d_dst, h_src, bytes, c->stream));
+    H2B_CUDA(cudaStreamSynchronize(c->stream));
     return H2B_OK;
 }
 int h2b_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes) {
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
-    H2B_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
-    return H2B_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    H2B_CUDA(cudaDeviceSynchronize());
+    return host_download(*c, h_dst, d_src, bytes, c->stream);
 }
 int h2b_dev_sync(int device) {
     DeviceCtx* c = nullptr;

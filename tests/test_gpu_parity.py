@@ -151,6 +151,25 @@ def test_cpp_host_mirror_over_the_c_abi(gpu, oc, tmp_path):
     run_host_mirror(oc, gpu.path, tmp_path, k=5, j=3)       # examples/standard_plonk.rs: k = 5, degree 3
 
 
+def test_batched_columns_match_single_calls(gpu, oc):
+    n = 1 << 14
+    P = oc.gen_points(71, n)
+    cols = [gpu.gen_scalars(80 + j, n - 1000 * j, j % 2) for j in range(5)] + [np.zeros((0, 4), dtype=np.uint64)]
+    h = gpu.register_bases(P)
+    try:
+        got = gpu.msm_batch_registered(cols, h)
+        for j, c in enumerate(cols):
+            assert (pc.affine_of(oc, got[j]) == pc.affine_of(oc, oc.best_multiexp(c, P[:c.shape[0]]))).all(), j
+    finally:
+        gpu.unregister_bases(h)
+    k = 15
+    polys = [oc.random_fr(90 + j, 1 << k) for j in range(3)]
+    want = [oc.best_fft(a, pc.omega_words(oc, k), k) for a in polys]
+    gpu.ntt_batch(polys, pc.omega_words(oc, k), k)
+    for a, w in zip(polys, want):
+        assert (a == w).all()
+
+
 def test_in_process_multi_device_paths(gpu):
     """Point-range sharding of one MSM across every visible GPU + concurrent callers (fresh process: own library instance)."""
     import os, subprocess, sys
