@@ -782,9 +782,10 @@ static int msm_pipeline_init(MsmScratch& s) {
 // All chunks of one MSM.  `stream` carries the accumulate stage (and is the stream the caller synchronises with);
 // with more than one chunk the sort stage of the next chunk overlaps it on s.sort_stream.  uploaded[j], when given, is
 // the event after which chunk j's scalars are in device memory.
-static int msm_run_chunks(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_scalars, const MsmBases& bases, size_t n, size_t chunk,
+// bounds: nchunks + 1 ascending scalar indices, bounds[0] = 0, bounds[nchunks] = n
+static int msm_run_chunks(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void* d_scalars, const MsmBases& bases, const std::vector<size_t>& bounds,
                           const cudaEvent_t* uploaded, cudaStream_t stream, const std::function<int(size_t)>* before_chunk = nullptr) {
-    const size_t nchunks = (n + chunk - 1) / chunk;
+    const size_t nchunks = bounds.size() - 1;
     // Measured at 2^24 (profiles/r01_msm_spacing.jsonl): overlapping the two stages gains nothing -- both want every SM,
     // the sort slows down 2x and the accumulation 15 % while they share the GPU (41.4 ms unsplit, 43.3 ms as 4
     // overlapped chunks).  Off by default; H2B_MSM_OVERLAP_SORT=1 turns it on.
@@ -798,7 +799,7 @@ static int msm_run_chunks(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void*
         H2B_CUDA(cudaStreamWaitEvent(s.sort_stream, s.ev_start, 0));
     }
     for (size_t j = 0; j < nchunks; ++j) {
-        const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+        const size_t done = bounds[j], m = bounds[j + 1] - bounds[j];
         const int b = overlap ? (int)(j & 1) : 0;
         const void* tables;
         size_t row0;
@@ -908,7 +909,10 @@ int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t
     if (chunk > MAX_CHUNK) chunk = MAX_CHUNK;
     MsmPlan pl;
     H2B_TRY(msm_plan(ctx, s, bases, n, chunk < n, stream, pl));
-    H2B_TRY(msm_run_chunks(ctx, s, pl, d_scalars, bases, n, chunk, nullptr, stream));
+    std::vector<size_t> bounds;
+    for (size_t done = 0; done < n; done += chunk) bounds.push_back(done);
+    bounds.push_back(n);
+    H2B_TRY(msm_run_chunks(ctx, s, pl, d_scalars, bases, bounds, nullptr, stream));
     H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
     H2B_CUDA(cudaMemcpyAsync(d_out_jac, s.result.p, out_bytes, cudaMemcpyDeviceToDevice, stream));
     return H2B_OK;
@@ -929,14 +933,22 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
         return H2B_OK;
     }
     H2B_TRY(msm_check_args(h_scalars, bases, n, h_out_block));
-    // four chunks from 2^22 points up (measured best at 2^24: profiles/r01_msm_e2e_chunks.txt); H2B_MSM_UPLOAD_CHUNK_LOG
-    // forces a chunk size (tests)
+    // From 2^22 points up the upload is cut into a short first chunk (1/16: the only transfer nothing can hide) and three
+    // chunks of 5/16 whose transfers hide behind the previous chunk's kernels (profiles/r01_msm_e2e_chunks.txt).
+    // H2B_MSM_UPLOAD_CHUNK_LOG forces a uniform chunk size (tests).
     static int env_chunk = -1;
     if (env_chunk < 0) env_chunk = env_int("H2B_MSM_UPLOAD_CHUNK_LOG", 0);
-    size_t chunk = n;
-    if (env_chunk >= 10 && env_chunk <= 26) { chunk = (size_t)1 << env_chunk; if (n < 2 * chunk) chunk = n; }
-    else if (n >= ((size_t)1 << 22)) chunk = (n + 3) / 4;
-    const size_t nchunks = (n + chunk - 1) / chunk;
+    std::vector<size_t> bounds;
+    if (env_chunk >= 10 && env_chunk <= 26 && n >= ((size_t)2 << env_chunk)) {
+        for (size_t done = 0; done < n; done += (size_t)1 << env_chunk) bounds.push_back(done);
+    } else if (env_chunk == 0 && n >= ((size_t)1 << env_int("H2B_MSM_UPLOAD_MIN_LOG", 22))) {
+        const size_t u = n / 16;
+        bounds = {0, u, 6 * u, 11 * u};
+    } else {
+        bounds.push_back(0);
+    }
+    bounds.push_back(n);
+    const size_t nchunks = bounds.size() - 1;
     if (!ctx.copy_stream) H2B_CUDA(cudaStreamCreateWithFlags(&ctx.copy_stream, cudaStreamNonBlocking));
     while (ctx.copy_events.size() < nchunks) {
         cudaEvent_t e;
@@ -949,12 +961,12 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
         // pageable caller memory (a Rust Vec): chunk j is copied through pinned slots by a few host threads right before
         // its kernels are queued, so the CPU copy of chunk j + 1 overlaps the GPU work of chunk j (stage.cu)
         std::function<int(size_t)> upload = [&](size_t j) -> int {
-            const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+            const size_t done = bounds[j], m = bounds[j + 1] - bounds[j];
             // only chunk 0 has to wait for the previous call's kernels (they may still read the staging buffer); the
             // other chunks land in regions nothing in flight touches, so their DMA overlaps the GPU work of chunk j - 1
             return host_upload(ctx, (char*)d_staging + done * 32, (const char*)h_scalars + done * 32, m * 32, stream, j == 0);
         };
-        H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, n, chunk, nullptr, stream, &upload));
+        H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, bounds, nullptr, stream, &upload));
     } else {
         // pinned caller memory: every chunk's DMA is queued up front on the copy stream
         // (the staging buffer may still be read by the previous call's kernels on `stream`: order the copies after them)
@@ -963,12 +975,12 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
             H2B_CUDA(cudaStreamWaitEvent(ctx.copy_stream, ctx.copy_events[0], 0));
         }
         for (size_t j = 0; j < nchunks; ++j) {
-            const size_t done = j * chunk, m = (n - done < chunk) ? (n - done) : chunk;
+            const size_t done = bounds[j], m = bounds[j + 1] - bounds[j];
             cudaStream_t cs = nchunks > 1 ? ctx.copy_stream : stream;
             H2B_CUDA(cudaMemcpyAsync((char*)d_staging + done * 32, (const char*)h_scalars + done * 32, m * 32, cudaMemcpyHostToDevice, cs));
             if (nchunks > 1) H2B_CUDA(cudaEventRecord(ctx.copy_events[j], cs));
         }
-        H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, n, chunk, nchunks > 1 ? ctx.copy_events.data() : nullptr, stream));
+        H2B_TRY(msm_run_chunks(ctx, s, pl, d_staging, bases, bounds, nchunks > 1 ? ctx.copy_events.data() : nullptr, stream));
     }
     H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
     H2B_CUDA(cudaMemcpyAsync(h_out_block, s.result.p, 224, cudaMemcpyDeviceToHost, stream));

@@ -157,6 +157,10 @@ def test_msm_chunked_upload_pipeline(emu):
     env = dict(os.environ, H2B_MSM_UPLOAD_CHUNK_LOG="10")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+    # the production schedule (1/16 + 3 x 5/16) at a CPU-test size
+    env = dict(os.environ, H2B_MSM_UPLOAD_MIN_LOG="10")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
     # device-resident scalars: 4 (or 3) chunks whose sort overlaps the previous chunk's accumulation
     code2 = (
         "import sys; sys.path[:0]=[%r,%r,%r]\n"
