@@ -128,6 +128,60 @@ def check_msm_single_bucket(L, oc, n, scalar=1, tables=True):
     assert (got == want).all()
 
 
+def check_msm_random(L, oc, examples, max_n, spacings, windows):
+    """Property test over the MSM's shape space: random length, scalar mix (incl. 0, 1, r-1, duplicates, identity bases),
+    table spacing / plain mode (-1), forced window, sub-range of a registered set -- always the oracle's affine result."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    one = oc.fr_to_mont(np.array([[1, 0, 0, 0]], dtype=np.uint64))[0]
+    minus_one = oc.field_op("fr", "sub", np.zeros((1, 4), dtype=np.uint64), one.reshape(1, 4))[0]
+
+    @settings(max_examples=examples, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(n=st.integers(1, max_n), seed=st.integers(0, 10 ** 6), spacing=st.sampled_from(list(spacings)),
+           window=st.sampled_from(list(windows)), kind=st.integers(0, 1), off_frac=st.floats(0, 0.9))
+    def run(n, seed, spacing, window, kind, off_frac):
+        s = L.gen_scalars(seed, n, kind)
+        P = oc.gen_points(seed + 1, n)
+        rng = np.random.default_rng(seed)
+        for i in rng.integers(0, n, size=min(n, 6)):
+            choice = rng.integers(0, 5)
+            if choice == 0:
+                s[i] = 0
+            elif choice == 1:
+                s[i] = one
+            elif choice == 2:
+                s[i] = minus_one
+            elif choice == 3:
+                P[i] = 0
+            else:
+                P[i] = P[rng.integers(0, n)]
+        if spacing < 0:
+            L.set_msm_window(window)
+            try:
+                got = affine_of(oc, L.msm(s, P))
+            finally:
+                L.set_msm_window(0)
+            want = affine_of(oc, oc.best_multiexp(s, P))
+        else:
+            off = int(off_frac * n)
+            m = n - off
+            L.set_msm_precomp(spacing)
+            try:
+                h = L.register_bases(P)
+            finally:
+                L.set_msm_precomp(0)
+            try:
+                L.set_msm_window(window)
+                got = affine_of(oc, L.msm_registered(s[:m], h, off))
+            finally:
+                L.set_msm_window(0)
+                L.unregister_bases(h)
+            want = affine_of(oc, oc.best_multiexp(s[:m], P[off:off + m]))
+        assert (got == want).all(), (n, seed, spacing, window, kind, off_frac)
+
+    run()
+
+
 def check_golden_ntt(L, g):
     for k in (1, 2, 3, 5, 8):
         for tag, wkey in (("fwd", "omega"), ("inv", "omega_inv")):

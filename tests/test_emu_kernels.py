@@ -234,3 +234,24 @@ def test_evaluation_domain_mirror_matches_golden(emu, golden):
     ext = d.coeff_to_extended(coeff)
     assert (ext == g["extended"]).all()
     assert (d.extended_to_coeff(ext) == g["back"]).all()
+
+
+def test_msm_randomised_shapes(emu, oc):
+    pc.check_msm_random(emu, oc, examples=30, max_n=400, spacings=(-1, 4, 6, 8, 10, 12), windows=(0, 0, 2, 3, 4, 5, 6))
+
+
+def test_ntt_randomised_inputs(emu, oc):
+    """NTT against the oracle for random sizes and structured inputs (zeros, a single spike, all-equal, r-1 everywhere)."""
+    rng = np.random.default_rng(5)
+    one = oc.fr_to_mont(np.array([[1, 0, 0, 0]], dtype=np.uint64))[0]
+    minus_one = oc.field_op("fr", "sub", np.zeros((1, 4), dtype=np.uint64), one.reshape(1, 4))[0]
+    for k in (1, 2, 4, 6, 9, 11, 13):
+        n = 1 << k
+        cases = [np.zeros((n, 4), dtype=np.uint64), np.repeat(minus_one.reshape(1, 4), n, axis=0), oc.random_fr(int(rng.integers(1 << 30)), n)]
+        spike = np.zeros((n, 4), dtype=np.uint64)
+        spike[int(rng.integers(0, n))] = one
+        cases.append(spike)
+        for a in cases:
+            for inverse in (False, True):
+                w = pc.omega_words(oc, k, inverse)
+                assert (emu.ntt(a.copy(), w, k) == oc.best_fft(a, w, k)).all(), (k, inverse)

@@ -151,6 +151,10 @@ def test_cpp_host_mirror_over_the_c_abi(gpu, oc, tmp_path):
     run_host_mirror(oc, gpu.path, tmp_path, k=5, j=3)       # examples/standard_plonk.rs: k = 5, degree 3
 
 
+def test_msm_randomised_shapes(gpu, oc):
+    pc.check_msm_random(gpu, oc, examples=25, max_n=40000, spacings=(-1, 0, 8, 12, 14, 16), windows=(0, 0, 0, 2, 4, 7, 8))
+
+
 def test_batched_columns_match_single_calls(gpu, oc):
     n = 1 << 14
     P = oc.gen_points(71, n)
