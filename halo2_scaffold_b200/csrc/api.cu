@@ -144,9 +144,12 @@ static int build_tables(BaseSet& bs) {
     if ((uint64_t)bs.n * nt >= 0x7fffffffull) return H2B_OK;
     std::vector<void*> fresh(G.devs.size(), nullptr);
     bool ok = true;
+    // every device builds its own copy; the kernels of all devices are queued first and awaited afterwards, so the
+    // devices work concurrently (registration time does not grow with the device count)
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (size_t d = 0; d < G.devs.size(); ++d) locks.emplace_back(G.devs[d]->mu);
     for (size_t d = 0; d < G.devs.size() && ok; ++d) {
         DeviceCtx& c = *G.devs[d];
-        std::lock_guard<std::mutex> lk(c.mu);
         cudaSetDevice(c.device);
         if (cudaMalloc(&fresh[d], (size_t)nt * bs.n * 64 + 64) != cudaSuccess) { cudaGetLastError(); fresh[d] = nullptr; ok = false; break; }
         c.prof.mark(PROF_BEGIN, c.stream);
@@ -154,8 +157,13 @@ static int build_tables(BaseSet& bs) {
         for (uint32_t j = 1; j < nt && ok; ++j)
             ok = msm_precompute_run(c, (const char*)fresh[d] + (size_t)(j - 1) * bs.n * 64, (char*)fresh[d] + (size_t)j * bs.n * 64, bs.n, c0, c.stream) == H2B_OK;
         c.prof.mark(PROF_MSM_PRECOMPUTE, c.stream);
-        if (cudaStreamSynchronize(c.stream) != cudaSuccess) ok = false;
     }
+    for (size_t d = 0; d < G.devs.size(); ++d) {
+        if (!fresh[d]) continue;
+        cudaSetDevice(G.devs[d]->device);
+        if (cudaStreamSynchronize(G.devs[d]->stream) != cudaSuccess) ok = false;
+    }
+    locks.clear();
     if (!ok) {
         for (size_t d = 0; d < fresh.size(); ++d) if (fresh[d]) { cudaSetDevice(G.devs[d]->device); cudaFree(fresh[d]); }
         cudaGetLastError();
@@ -181,8 +189,25 @@ static int upload_set(BaseSet& bs, const uint64_t* bases, size_t n, bool with_ta
         H2B_CUDA(cudaSetDevice(G.devs[d]->device));
         cudaError_t e = cudaMalloc(&bs.dev[d], n * 64 + 64);
         if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes for SRS bases failed: %s", n * 64, cudaGetErrorString(e)); return H2B_ERR_OOM; }
-        H2B_CUDA(cudaMemcpy(bs.dev[d], bases, n * 64, cudaMemcpyHostToDevice));
     }
+    // one upload per device, concurrently (pageable arrays go through each device's pinned staging threads)
+    std::vector<int> rcs(G.devs.size(), 0);
+    std::vector<std::string> errs(G.devs.size());
+    auto upload_one = [&](size_t d) {
+        DeviceCtx& c = *G.devs[d];
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (cudaSetDevice(c.device) != cudaSuccess) { rcs[d] = H2B_ERR_CUDA; return; }
+        rcs[d] = host_upload(c, bs.dev[d], bases, n * 64, c.stream);
+        if (!rcs[d] && cudaStreamSynchronize(c.stream) != cudaSuccess) { set_error("SRS upload: %s", cudaGetErrorString(cudaGetLastError())); rcs[d] = H2B_ERR_CUDA; }
+        if (rcs[d]) errs[d] = get_error();
+    };
+    if (G.devs.size() == 1) upload_one(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < G.devs.size(); ++d) th.emplace_back(upload_one, d);
+        for (auto& t : th) t.join();
+    }
+    for (size_t d = 0; d < G.devs.size(); ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
     if (with_tables) H2B_TRY(build_tables(bs));
     return H2B_OK;
 }
