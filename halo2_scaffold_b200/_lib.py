@@ -35,6 +35,7 @@ _EXPORTS = [
     "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read", "h2b_msm_bn254_g1_dev_registered",
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
+    "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev",
 ]
 
 
@@ -79,6 +80,8 @@ class Lib:
         L.h2b_msm_fold_partials.argtypes = [i32, vp, sz, vp]
         L.h2b_msm_fold_partials_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_fr_scale_dev.argtypes = [i32, vp, sz, vp, i32, vp]
+        L.h2b_fr_batch_invert_dev.argtypes = [i32, vp, sz, vp]
+        L.h2b_fr_prefix_product_dev.argtypes = [i32, vp, vp, sz, vp]
         L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
         L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
@@ -238,6 +241,35 @@ class Lib:
     def extended_to_coeff_dev(self, device: int, d_a: int, extended_k: int, extended_omega_inv: np.ndarray, factors: np.ndarray, stream: int = 0):
         extended_omega_inv, factors = _u64(extended_omega_inv), _u64(factors).reshape(3, 4)
         self.check(self.L.h2b_extended_to_coeff_dev(device, d_a, extended_k, extended_omega_inv.ctypes.data, factors.ctypes.data, stream))
+
+    def fr_batch_invert_dev(self, device: int, d_a: int, n: int, stream: int = 0):
+        self.check(self.L.h2b_fr_batch_invert_dev(device, d_a, n, stream))
+
+    def fr_prefix_product_dev(self, device: int, d_in: int, d_out: int, n: int, stream: int = 0):
+        self.check(self.L.h2b_fr_prefix_product_dev(device, d_in, d_out, n, stream))
+
+    def _column_op(self, a: np.ndarray, op, device: int = 0) -> np.ndarray:
+        a = _u64(a).reshape(-1, 4)
+        n = a.shape[0]
+        out = np.empty_like(a)
+        d = self.dev_alloc(device, max(n, 1) * 32)
+        try:
+            if n:
+                self.h2d(device, d, a)
+                op(d, n)
+                self.dev_sync(device)
+                self.d2h(device, out, d)
+        finally:
+            self.dev_free(device, d)
+        return out
+
+    def fr_batch_invert(self, a: np.ndarray, device: int = 0) -> np.ndarray:
+        """a[i] -> 1 / a[i] (zeros stay zero), through device memory"""
+        return self._column_op(a, lambda d, n: self.fr_batch_invert_dev(device, d, n), device)
+
+    def fr_prefix_product(self, a: np.ndarray, device: int = 0) -> np.ndarray:
+        """out[0] = 1, out[i] = a[0] * ... * a[i-1], through device memory (in place on the device)"""
+        return self._column_op(a, lambda d, n: self.fr_prefix_product_dev(device, d, d, n), device)
 
     def dev_alloc(self, device: int, nbytes: int) -> int:
         p = ctypes.c_void_p(0)

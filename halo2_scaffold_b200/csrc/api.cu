@@ -403,6 +403,7 @@ void h2b_shutdown(void) {
         stager_release(*c);
         c->msm_scalars.release();
         c->msm_out.release();
+        c->scan_scratch.release();
         for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
         c->copy_events.clear();
         if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
@@ -675,6 +676,21 @@ int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const 
     H2B_TRY(ntt_run(*c, d_a, extended_omega_inv, extended_k, (cudaStream_t)stream));
     // factors[j] = extended_ifft_divisor * (1, zeta^-1, zeta^-2)[j]: one pass undoes the scaling and the coset
     return ntt_scale_run(*c, d_a, (size_t)1 << extended_k, factors, 3, (cudaStream_t)stream);
+}
+
+// ---- grand-product building blocks ---------------------------------------------------------------
+int h2b_fr_batch_invert_dev(int device, void* d_a, size_t n, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return fr_batch_invert_run(*c, d_a, n, (cudaStream_t)stream);
+}
+
+int h2b_fr_prefix_product_dev(int device, const void* d_in, void* d_out, size_t n, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return fr_prefix_product_run(*c, d_in, d_out, n, (cudaStream_t)stream);
 }
 
 int h2b_dev_alloc(int device, size_t bytes, void** out) {

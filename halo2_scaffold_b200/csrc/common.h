@@ -94,6 +94,7 @@ struct DeviceCtx {
     DevBuf ntt_io;                     // staging for the host-pointer NTT entry point
     DevBuf msm_scalars;                // staging for host-pointer MSM scalars
     DevBuf msm_out;                    // 96-byte result
+    DevBuf scan_scratch;               // batch inversion / prefix product scratch (scan.cu)
     std::vector<NttTwiddles*> twiddles;  // small LRU cache keyed by (omega, log_n)
     MsmScratch* msm = nullptr;
     Profiler prof;
@@ -107,6 +108,9 @@ int host_upload(DeviceCtx& ctx, void* d_dst, const void* h_src, size_t bytes, cu
 int host_download(DeviceCtx& ctx, void* h_dst, const void* d_src, size_t bytes, cudaStream_t producer);
 void stager_release(DeviceCtx& ctx);
 bool host_is_pageable(const void* p);
+// ---- scan.cu ----
+int fr_batch_invert_run(DeviceCtx& ctx, void* d_a, size_t n, cudaStream_t stream);
+int fr_prefix_product_run(DeviceCtx& ctx, const void* d_in, void* d_out, size_t n, cudaStream_t stream);
 // ---- ntt.cu ----
 int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);

@@ -123,6 +123,14 @@ int h2b_coeff_to_extended_dev(int device, void* d_a, uint32_t k, uint32_t extend
                               void* stream);
 int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const uint64_t extended_omega_inv[4], const uint64_t factors[12], void* stream);
 
+/* Grand-product building blocks on a device-resident Fr column ([UP] halo2_proofs
+ * plonk/permutation/prover.rs, plonk/lookup/prover.rs): z(omega^i) is the exclusive running product of
+ * numerator[i] / denominator[i], the denominators inverted with ff::BatchInvert.
+ *   batch_invert   : a[i] <- 1 / a[i] in place; zeros stay zero
+ *   prefix_product : out[0] = 1, out[i] = in[0] * ... * in[i-1]   (n outputs; out may alias in) */
+int h2b_fr_batch_invert_dev(int device, void* d_a, size_t n, void* stream);
+int h2b_fr_prefix_product_dev(int device, const void* d_in, void* d_out, size_t n, void* stream);
+
 /* ---- raw device memory helpers (so that non-CUDA hosts -- ctypes, Rust -- can hold device buffers) --- */
 int h2b_dev_alloc(int device, size_t bytes, void** out);
 int h2b_dev_free(int device, void* p);

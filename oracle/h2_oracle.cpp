@@ -354,6 +354,36 @@ void orc_fr_scale(u64* a, size_t n, const u64* s) {
     Fr w; memcpy(w.l, s, 32);
     for (size_t i = 0; i < n; ++i) { Fr x; memcpy(x.l, a + 4 * i, 32); x = x * w; memcpy(a + 4 * i, x.l, 32); }
 }
+// ---- grand-product building blocks ([UP] halo2_proofs plonk/permutation/prover.rs and
+// plonk/lookup/prover.rs build z(X) as a running product of numerator / denominator, the denominators inverted with
+// ff::BatchInvert, which leaves zeros untouched) ---------------------------------------------------------------------
+// a[i] <- 1 / a[i]; a[i] == 0 stays 0
+void orc_fr_batch_invert(u64* a, size_t n) {
+    std::vector<Fr> pre(n);
+    Fr run = Fr::one();
+    for (size_t i = 0; i < n; ++i) {
+        Fr x; memcpy(x.l, a + 4 * i, 32);
+        pre[i] = run;
+        if (!x.is_zero()) run = run * x;
+    }
+    Fr inv = run.inv();
+    for (size_t i = n; i-- > 0;) {
+        Fr x; memcpy(x.l, a + 4 * i, 32);
+        if (x.is_zero()) continue;
+        Fr xi = inv * pre[i];
+        inv = inv * x;
+        memcpy(a + 4 * i, xi.l, 32);
+    }
+}
+// out[0] = 1, out[i] = a[0] * ... * a[i-1]  (n outputs: the exclusive running product that z(omega^i) is)
+void orc_fr_prefix_product(const u64* a, size_t n, u64* out) {
+    Fr run = Fr::one();
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(out + 4 * i, run.l, 32);
+        Fr x; memcpy(x.l, a + 4 * i, 32);
+        run = run * x;
+    }
+}
 // uniform scalars in Montgomery form: 512-bit SplitMix64 draw reduced mod r (same stream as oracle/bn254.py random_fr)
 void orc_random_fr(u64 seed, size_t n, u64* out) {
     Fr two64; two64.l[0] = 0; two64.l[1] = 1; two64.l[2] = two64.l[3] = 0; two64 = two64.to_mont();

@@ -39,6 +39,8 @@ def lib():
         L.orc_fr_to_mont.argtypes = [u64p, ctypes.c_size_t, u64p]
         L.orc_fr_from_mont.argtypes = [u64p, ctypes.c_size_t, u64p]
         L.orc_fr_scale.argtypes = [u64p, ctypes.c_size_t, u64p]
+        L.orc_fr_batch_invert.argtypes = [u64p, ctypes.c_size_t]
+        L.orc_fr_prefix_product.argtypes = [u64p, ctypes.c_size_t, u64p]
         L.orc_random_fr.argtypes = [ctypes.c_uint64, ctypes.c_size_t, u64p]
         L.orc_gen_points.argtypes = [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int, u64p]
         _lib = L
@@ -102,6 +104,21 @@ def fr_scale(a: np.ndarray, s: np.ndarray) -> np.ndarray:
     s = np.ascontiguousarray(s, dtype=np.uint64)
     lib().orc_fr_scale(_p(a), a.shape[0], _p(s))
     return a
+
+
+def fr_batch_invert(a: np.ndarray) -> np.ndarray:
+    """a[i] -> 1 / a[i], zeros stay zero (ff::BatchInvert semantics)"""
+    a = np.array(a, dtype=np.uint64, order="C", copy=True)
+    lib().orc_fr_batch_invert(_p(a), a.shape[0])
+    return a
+
+
+def fr_prefix_product(a: np.ndarray) -> np.ndarray:
+    """out[0] = 1, out[i] = a[0] * ... * a[i-1]"""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().orc_fr_prefix_product(_p(a), a.shape[0], _p(out))
+    return out
 
 
 def field_op(field: str, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -182,6 +182,22 @@ def check_msm_random(L, oc, examples, max_n, spacings, windows):
     run()
 
 
+def check_grand_product_blocks(L, oc, sizes):
+    """batch inversion (zeros stay zero) and exclusive prefix product against the oracle, ragged sizes"""
+    for n in sizes:
+        a = oc.random_fr(0xD000 + n, n)
+        if n > 3:
+            a[1] = 0
+            a[n - 1] = 0
+            a[n // 2] = a[n // 2 - 1]
+        assert (L.fr_batch_invert(a) == oc.fr_batch_invert(a)).all(), ("batch_invert", n)
+        assert (L.fr_prefix_product(a) == oc.fr_prefix_product(a)).all(), ("prefix_product", n)
+        if n > 8:
+            b = a.copy()
+            b[b.sum(axis=1) == 0] = a[0]                                   # no zeros: the product never collapses
+            assert (L.fr_prefix_product(b) == oc.fr_prefix_product(b)).all(), ("prefix_product nz", n)
+
+
 def check_golden_ntt(L, g):
     for k in (1, 2, 3, 5, 8):
         for tag, wkey in (("fwd", "omega"), ("inv", "omega_inv")):

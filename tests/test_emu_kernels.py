@@ -255,3 +255,7 @@ def test_ntt_randomised_inputs(emu, oc):
             for inverse in (False, True):
                 w = pc.omega_words(oc, k, inverse)
                 assert (emu.ntt(a.copy(), w, k) == oc.best_fft(a, w, k)).all(), (k, inverse)
+
+
+def test_grand_product_building_blocks(emu, oc):
+    pc.check_grand_product_blocks(emu, oc, [1, 2, 3, 15, 16, 17, 100, 1023, 1024, 1025, 5000, 20000])

@@ -151,6 +151,10 @@ def test_cpp_host_mirror_over_the_c_abi(gpu, oc, tmp_path):
     run_host_mirror(oc, gpu.path, tmp_path, k=5, j=3)       # examples/standard_plonk.rs: k = 5, degree 3
 
 
+def test_grand_product_building_blocks(gpu, oc):
+    pc.check_grand_product_blocks(gpu, oc, [1, 17, 1024, 1025, 16385, (1 << 18) + 3, 1 << 22])
+
+
 def test_msm_randomised_shapes(gpu, oc):
     pc.check_msm_random(gpu, oc, examples=25, max_n=40000, spacings=(-1, 0, 8, 12, 14, 16), windows=(0, 0, 0, 2, 4, 7, 8))
 

@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Device-resident batch inversion and exclusive prefix product of an Fr column (grand-product building blocks):
+ms and GB/s of algorithmic traffic (64 B per element: read + write once).  usage: python tools/scan_bench.py [k ...]"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import halo2_scaffold_b200 as h2
+L = h2.load(); L.init_device(0)
+dev = torch.device("cuda", 0)
+st = torch.cuda.current_stream().cuda_stream
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for k in [int(a) for a in (sys.argv[1:] or ["20", "22", "24"])]:
+    n = 1 << k
+    d = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    L.gen_scalars_dev(0, 7 + k, n, 0, d.data_ptr(), st)
+    out = {"k": k}
+    for name, fn in (("batch_invert", lambda: L.fr_batch_invert_dev(0, d.data_ptr(), n, st)), ("prefix_product", lambda: L.fr_prefix_product_dev(0, d.data_ptr(), d.data_ptr(), n, st))):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name + "_ms"] = round(ms, 4)
+        out[name + "_elements_per_s"] = n / ms * 1e3
+        out[name + "_algorithmic_gb_s"] = round(64.0 * n / ms / 1e6, 1)
+    print(json.dumps(out), flush=True)
