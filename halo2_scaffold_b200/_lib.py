@@ -35,7 +35,7 @@ _EXPORTS = [
     "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read", "h2b_msm_bn254_g1_dev_registered",
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
-    "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev",
+    "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
 ]
 
 
@@ -82,6 +82,8 @@ class Lib:
         L.h2b_fr_scale_dev.argtypes = [i32, vp, sz, vp, i32, vp]
         L.h2b_fr_batch_invert_dev.argtypes = [i32, vp, sz, vp]
         L.h2b_fr_prefix_product_dev.argtypes = [i32, vp, vp, sz, vp]
+        L.h2b_fr_eval_polynomial_dev.argtypes = [i32, vp, sz, vp, vp, vp]
+        L.h2b_fr_kate_division_dev.argtypes = [i32, vp, sz, vp, vp, vp]
         L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
         L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
@@ -270,6 +272,41 @@ class Lib:
     def fr_prefix_product(self, a: np.ndarray, device: int = 0) -> np.ndarray:
         """out[0] = 1, out[i] = a[0] * ... * a[i-1], through device memory (in place on the device)"""
         return self._column_op(a, lambda d, n: self.fr_prefix_product_dev(device, d, d, n), device)
+
+    def fr_eval_polynomial(self, coeffs: np.ndarray, x: np.ndarray, device: int = 0) -> np.ndarray:
+        """eval_polynomial(poly, point) through device memory -> (4,) uint64"""
+        coeffs, x = _u64(coeffs).reshape(-1, 4), _u64(x)
+        n = coeffs.shape[0]
+        out = np.zeros(4, dtype=np.uint64)
+        d, d_o = self.dev_alloc(device, max(n, 1) * 32), self.dev_alloc(device, 32)
+        try:
+            if n:
+                self.h2d(device, d, coeffs)
+            self.check(self.L.h2b_fr_eval_polynomial_dev(device, d, n, x.ctypes.data, d_o, 0))
+            self.dev_sync(device)
+            self.d2h(device, out, d_o)
+        finally:
+            self.dev_free(device, d)
+            self.dev_free(device, d_o)
+        return out
+
+    def fr_kate_division(self, a: np.ndarray, b: np.ndarray, device: int = 0) -> np.ndarray:
+        """kate_division(a, b) through device memory -> (n - 1, 4) uint64"""
+        a, b = _u64(a).reshape(-1, 4), _u64(b)
+        n = a.shape[0]
+        q = np.zeros((max(n - 1, 0), 4), dtype=np.uint64)
+        if n <= 1:
+            return q
+        d, d_q = self.dev_alloc(device, n * 32), self.dev_alloc(device, n * 32)
+        try:
+            self.h2d(device, d, a)
+            self.check(self.L.h2b_fr_kate_division_dev(device, d, n, b.ctypes.data, d_q, 0))
+            self.dev_sync(device)
+            self.d2h(device, q, d_q)
+        finally:
+            self.dev_free(device, d)
+            self.dev_free(device, d_q)
+        return q
 
     def dev_alloc(self, device: int, nbytes: int) -> int:
         p = ctypes.c_void_p(0)

@@ -693,6 +693,20 @@ int h2b_fr_prefix_product_dev(int device, const void* d_in, void* d_out, size_t 
     return fr_prefix_product_run(*c, d_in, d_out, n, (cudaStream_t)stream);
 }
 
+int h2b_fr_eval_polynomial_dev(int device, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return fr_eval_polynomial_run(*c, d_coeffs, n, x, d_out, (cudaStream_t)stream);
+}
+
+int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return fr_kate_division_run(*c, d_a, n, b, d_q, (cudaStream_t)stream);
+}
+
 int h2b_dev_alloc(int device, size_t bytes, void** out) {
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));

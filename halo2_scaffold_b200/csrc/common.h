@@ -111,6 +111,8 @@ bool host_is_pageable(const void* p);
 // ---- scan.cu ----
 int fr_batch_invert_run(DeviceCtx& ctx, void* d_a, size_t n, cudaStream_t stream);
 int fr_prefix_product_run(DeviceCtx& ctx, const void* d_in, void* d_out, size_t n, cudaStream_t stream);
+int fr_eval_polynomial_run(DeviceCtx& ctx, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, cudaStream_t stream);
+int fr_kate_division_run(DeviceCtx& ctx, const void* d_a, size_t n, const uint64_t b[4], void* d_q, cudaStream_t stream);
 // ---- ntt.cu ----
 int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);

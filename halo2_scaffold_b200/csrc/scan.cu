@@ -120,4 +120,123 @@ int fr_prefix_product_run(DeviceCtx& ctx, const void* d_in, void* d_out, size_t 
     return prefix_product_rec(ctx, (const uint4*)d_in, (uint4*)d_out, n, (uint4*)ctx.scan_scratch.p, stream);
 }
 
+// ---- polynomial evaluation and division by (X - b) ---------------------------------------------------------------------
+// [UP] halo2_proofs::arithmetic::{eval_polynomial, kate_division} (layer L0): the prover evaluates
+// every committed polynomial at the challenge points and divides by (X - x) for the multi-open argument.
+// Both are first-order linear recurrences with a constant multiplier, so they telescope through levels of 16:
+//   eval:  P(x) = sum_t p_t * (x^16)^t with p_t the Horner value of 16 consecutive coefficients -> evaluate {p_t} at x^16;
+//   kate:  q[i-1] = a[i] + b * q[i]  (q = all suffix Horner values): chunk sums with zero carry-in, the same recurrence
+//          on the chunk sums with multiplier b^16 gives every chunk's carry-in, then the chunks replay.
+static const uint32_t POLY_K = 16;
+static const uint32_t POLY_LEVELS_MAX = 9;          // 16^8 > 2^31
+
+// pts[l] = x^(16^l), l < levels (one thread; a handful of squarings)
+__global__ void fr_point_powers_kernel(const uint4* __restrict__ x, uint32_t levels, uint4* __restrict__ pts) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Fr p = fp_load<FR>(x);
+    for (uint32_t l = 0; l < levels; ++l) {
+        fp_store<FR>(pts + 2 * l, p);
+        for (int k = 0; k < 4; ++k) p = fp_sqr(p);
+    }
+}
+
+// out[t] = sum_{i < 16} in[16 t + i] * x^i
+__global__ void __launch_bounds__(128) fr_horner_chunk_kernel(const uint4* __restrict__ in, size_t n, const uint4* __restrict__ x, uint4* __restrict__ out, uint32_t chunks) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks) return;
+    const size_t lo = (size_t)t * POLY_K;
+    const size_t hi = lo + POLY_K < n ? lo + POLY_K : n;
+    const Fr xx = fp_load<FR>(x);
+    Fr r = fp_load<FR>(in + 2 * (hi - 1));
+    for (size_t i = hi - 1; i-- > lo;) r = fp_add(fp_mul(r, xx), fp_load<FR>(in + 2 * i));
+    fp_store<FR>(out + 2 * (size_t)t, r);
+}
+
+int fr_eval_polynomial_run(DeviceCtx& ctx, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, cudaStream_t stream) {
+    if (!d_out || !x || (n && !d_coeffs)) { set_error("eval_polynomial: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) { H2B_CUDA(cudaMemsetAsync(d_out, 0, 32, stream)); return H2B_OK; }
+    if (n > ((size_t)1 << 31)) { set_error("eval_polynomial: at most 2^31 coefficients"); return H2B_ERR_BAD_ARGUMENT; }
+    // scratch: point powers (POLY_LEVELS_MAX + 1 elements) | the partial values of all levels (< n/15 + slack)
+    H2B_TRY(ctx.scan_scratch.reserve((n / 15 + 64) * 32));
+    uint4* pts = (uint4*)ctx.scan_scratch.p;
+    uint4* buf = pts + 2 * (POLY_LEVELS_MAX + 1);
+    H2B_CUDA(cudaMemcpyAsync(pts + 2 * POLY_LEVELS_MAX, x, 32, cudaMemcpyHostToDevice, stream));
+    H2B_LAUNCH(fr_point_powers_kernel, 1, 32, 0, stream, (const uint4*)(pts + 2 * POLY_LEVELS_MAX), POLY_LEVELS_MAX, pts);
+    const uint4* in = (const uint4*)d_coeffs;
+    size_t m = n;
+    for (uint32_t l = 0;; ++l) {
+        const uint32_t chunks = (uint32_t)((m + POLY_K - 1) / POLY_K);
+        uint4* out = chunks == 1 ? (uint4*)d_out : buf;
+        H2B_LAUNCH(fr_horner_chunk_kernel, (chunks + 127) / 128, 128, 0, stream, in, m, (const uint4*)(pts + 2 * l), out, chunks);
+        if (chunks == 1) break;
+        in = buf;
+        buf += 2 * (size_t)chunks;
+        m = chunks;
+    }
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
+// chunk sums with zero carry-in: s[t] = sum_{i < 16} a[16 t + i] * b^i   (the same kernel as the Horner chunks), then
+// carry[t] = s[t+1] + b^16 * carry[t+1] solved recursively, then the replay:
+//   q[i-1] = a[i] + b * q[i] inside chunk t, starting from q[hi-1] = carry[t]
+// `q` has n - 1 coefficients (q[i-1] for i = 1 .. n-1); a[0] only enters the remainder, which the caller does not need.
+__global__ void __launch_bounds__(128) fr_kate_replay_kernel(const uint4* __restrict__ a, size_t n, const uint4* __restrict__ b, const uint4* __restrict__ carry,
+                                                           uint4* __restrict__ q, uint32_t chunks) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= chunks) return;
+    const size_t lo = (size_t)t * POLY_K;
+    const size_t hi = lo + POLY_K < n ? lo + POLY_K : n;
+    const Fr bb = fp_load<FR>(b);
+    Fr run = carry ? fp_load<FR>(carry + 2 * (size_t)t) : fp_zero<FR>();       // value of q at index hi - 1
+    for (size_t i = hi; i-- > lo;) {
+        // run = q[i];  q[i-1] = a[i] + b * q[i]
+        if (i == 0) break;
+        run = fp_add(fp_load<FR>(a + 2 * i), fp_mul(bb, run));
+        fp_store<FR>(q + 2 * (i - 1), run);
+    }
+}
+
+// carry-in of every chunk at one level: c[t] = value the recurrence has reached when it enters chunk t from above,
+// i.e. c[chunks-1] = 0 and c[t] = s[t+1] + m * c[t+1] with m = b^(16^(level+1)).  Solved by recursion on {s[t+1]}.
+static int kate_carries(DeviceCtx& ctx, const uint4* s, uint32_t chunks, const uint4* pts, uint32_t level, uint4* carry, uint4* scratch, cudaStream_t stream);
+
+// q_out[i-1] = a[i] + m * q[i] for a vector a of length n with multiplier pts[level]; writes n - 1 values ... as a reusable
+// step: solve the recurrence for `a` (length n) at `level`, producing q (length n - 1, q[n-1] taken as 0)
+static int kate_level(DeviceCtx& ctx, const uint4* a, size_t n, const uint4* pts, uint32_t level, uint4* q, uint4* scratch, cudaStream_t stream) {
+    const uint32_t chunks = (uint32_t)((n + POLY_K - 1) / POLY_K);
+    if (chunks == 1) {
+        H2B_LAUNCH(fr_kate_replay_kernel, 1, 128, 0, stream, a, n, pts + 2 * level, (const uint4*)nullptr, q, 1u);
+        return H2B_OK;
+    }
+    uint4* s = scratch;                     // chunk sums
+    uint4* carry = s + 2 * (size_t)chunks;  // carry-ins
+    uint4* rest = carry + 2 * (size_t)chunks;
+    H2B_LAUNCH(fr_horner_chunk_kernel, (chunks + 127) / 128, 128, 0, stream, a, n, pts + 2 * level, s, chunks);
+    H2B_TRY(kate_carries(ctx, s, chunks, pts, level, carry, rest, stream));
+    H2B_LAUNCH(fr_kate_replay_kernel, (chunks + 127) / 128, 128, 0, stream, a, n, pts + 2 * level, (const uint4*)carry, q, chunks);
+    return H2B_OK;
+}
+
+static int kate_carries(DeviceCtx& ctx, const uint4* s, uint32_t chunks, const uint4* pts, uint32_t level, uint4* carry, uint4* scratch, cudaStream_t stream) {
+    // c[t-1] = s[t] + m * c[t] for t = chunks-1 .. 1, c[chunks-1] = 0: exactly the kate recurrence on the vector s with
+    // multiplier m = pts[level + 1]; its solution q has q[t-1] = c[t-1], and c[chunks-1] = 0 completes it
+    H2B_CUDA(cudaMemsetAsync(carry + 2 * (size_t)(chunks - 1), 0, 32, stream));
+    return kate_level(ctx, s, chunks, pts, level + 1, carry, scratch, stream);
+}
+
+int fr_kate_division_run(DeviceCtx& ctx, const void* d_a, size_t n, const uint64_t b[4], void* d_q, cudaStream_t stream) {
+    if (!b || (n && (!d_a || !d_q))) { set_error("kate_division: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (n <= 1) return H2B_OK;                 // the quotient of a constant is empty
+    if (n > ((size_t)1 << 31)) { set_error("kate_division: at most 2^31 coefficients"); return H2B_ERR_BAD_ARGUMENT; }
+    H2B_TRY(ctx.scan_scratch.reserve((n / 7 + 256) * 32));
+    uint4* pts = (uint4*)ctx.scan_scratch.p;
+    uint4* buf = pts + 2 * (POLY_LEVELS_MAX + 1);
+    H2B_CUDA(cudaMemcpyAsync(pts + 2 * POLY_LEVELS_MAX, b, 32, cudaMemcpyHostToDevice, stream));
+    H2B_LAUNCH(fr_point_powers_kernel, 1, 32, 0, stream, (const uint4*)(pts + 2 * POLY_LEVELS_MAX), POLY_LEVELS_MAX, pts);
+    H2B_TRY(kate_level(ctx, (const uint4*)d_a, n, pts, 0, (uint4*)d_q, buf, stream));
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
 }  // namespace h2b

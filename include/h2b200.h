@@ -130,6 +130,10 @@ int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const 
  *   prefix_product : out[0] = 1, out[i] = in[0] * ... * in[i-1]   (n outputs; out may alias in) */
 int h2b_fr_batch_invert_dev(int device, void* d_a, size_t n, void* stream);
 int h2b_fr_prefix_product_dev(int device, const void* d_in, void* d_out, size_t n, void* stream);
+/* [UP] halo2_proofs::arithmetic::eval_polynomial(poly, point) = sum_i poly[i] * point^i  -> one Fr (32 B) at d_out;
+ * [UP] halo2_proofs::arithmetic::kate_division(a, b): the n - 1 coefficients of a(X) / (X - b) -> d_q (must not alias d_a) */
+int h2b_fr_eval_polynomial_dev(int device, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, void* stream);
+int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream);
 
 /* ---- raw device memory helpers (so that non-CUDA hosts -- ctypes, Rust -- can hold device buffers) --- */
 int h2b_dev_alloc(int device, size_t bytes, void** out);

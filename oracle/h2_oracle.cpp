@@ -384,6 +384,25 @@ void orc_fr_prefix_product(const u64* a, size_t n, u64* out) {
         run = run * x;
     }
 }
+// [UP] halo2_proofs::arithmetic::eval_polynomial: sum_i poly[i] * point^i (Horner from the top)
+void orc_fr_eval_polynomial(const u64* a, size_t n, const u64* x, u64* out) {
+    Fr xx; memcpy(xx.l, x, 32);
+    Fr r = Fr::zero();
+    for (size_t i = n; i-- > 0;) { Fr c; memcpy(c.l, a + 4 * i, 32); r = r * xx + c; }
+    memcpy(out, r.l, 32);
+}
+// [UP] halo2_proofs::arithmetic::kate_division(a, b): the quotient of a(X) by (X - b), n - 1 coefficients:
+// q[n-2] = a[n-1], q[i-1] = a[i] + b * q[i]
+void orc_fr_kate_division(const u64* a, size_t n, const u64* b, u64* q) {
+    if (n <= 1) return;
+    Fr bb; memcpy(bb.l, b, 32);
+    Fr run = Fr::zero();
+    for (size_t i = n - 1; i >= 1; --i) {
+        Fr c; memcpy(c.l, a + 4 * i, 32);
+        run = c + bb * run;
+        memcpy(q + 4 * (i - 1), run.l, 32);
+    }
+}
 // uniform scalars in Montgomery form: 512-bit SplitMix64 draw reduced mod r (same stream as oracle/bn254.py random_fr)
 void orc_random_fr(u64 seed, size_t n, u64* out) {
     Fr two64; two64.l[0] = 0; two64.l[1] = 1; two64.l[2] = two64.l[3] = 0; two64 = two64.to_mont();

@@ -41,6 +41,8 @@ def lib():
         L.orc_fr_scale.argtypes = [u64p, ctypes.c_size_t, u64p]
         L.orc_fr_batch_invert.argtypes = [u64p, ctypes.c_size_t]
         L.orc_fr_prefix_product.argtypes = [u64p, ctypes.c_size_t, u64p]
+        L.orc_fr_eval_polynomial.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
+        L.orc_fr_kate_division.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_random_fr.argtypes = [ctypes.c_uint64, ctypes.c_size_t, u64p]
         L.orc_gen_points.argtypes = [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int, u64p]
         _lib = L
@@ -119,6 +121,23 @@ def fr_prefix_product(a: np.ndarray) -> np.ndarray:
     out = np.empty_like(a)
     lib().orc_fr_prefix_product(_p(a), a.shape[0], _p(out))
     return out
+
+
+def fr_eval_polynomial(a: np.ndarray, x: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    x = np.ascontiguousarray(x, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_fr_eval_polynomial(_p(a), a.shape[0], _p(x), _p(out))
+    return out
+
+
+def fr_kate_division(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    q = np.zeros((max(a.shape[0] - 1, 0), 4), dtype=np.uint64)
+    if a.shape[0] > 1:
+        lib().orc_fr_kate_division(_p(a), a.shape[0], _p(b), _p(q))
+    return q
 
 
 def field_op(field: str, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:

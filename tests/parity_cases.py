@@ -198,6 +198,22 @@ def check_grand_product_blocks(L, oc, sizes):
             assert (L.fr_prefix_product(b) == oc.fr_prefix_product(b)).all(), ("prefix_product nz", n)
 
 
+def check_poly_eval_and_division(L, oc, sizes):
+    """eval_polynomial and kate_division against the oracle, plus the identity a(X) = q(X) (X - b) + a(b) at a random point"""
+    for n in sizes:
+        a = oc.random_fr(0xE000 + n, n)
+        x, b = oc.random_fr(0xE100 + n, 1)[0], oc.random_fr(0xE200 + n, 1)[0]
+        assert (L.fr_eval_polynomial(a, x) == oc.fr_eval_polynomial(a, x)).all(), ("eval", n)
+        q = L.fr_kate_division(a, b)
+        assert (q == oc.fr_kate_division(a, b)).all(), ("kate", n)
+        if n > 1:
+            # a(x) == q(x) * (x - b) + a(b), all through the device evaluation
+            ax, qx, ab = L.fr_eval_polynomial(a, x), L.fr_eval_polynomial(q, x), L.fr_eval_polynomial(a, b)
+            xmb = oc.field_op("fr", "sub", x.reshape(1, 4), b.reshape(1, 4))
+            rhs = oc.field_op("fr", "add", oc.field_op("fr", "mul", qx.reshape(1, 4), xmb), ab.reshape(1, 4))
+            assert (rhs[0] == ax).all(), ("identity", n)
+
+
 def check_golden_ntt(L, g):
     for k in (1, 2, 3, 5, 8):
         for tag, wkey in (("fwd", "omega"), ("inv", "omega_inv")):

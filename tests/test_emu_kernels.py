@@ -259,3 +259,7 @@ def test_ntt_randomised_inputs(emu, oc):
 
 def test_grand_product_building_blocks(emu, oc):
     pc.check_grand_product_blocks(emu, oc, [1, 2, 3, 15, 16, 17, 100, 1023, 1024, 1025, 5000, 20000])
+
+
+def test_polynomial_evaluation_and_kate_division(emu, oc):
+    pc.check_poly_eval_and_division(emu, oc, [1, 2, 3, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 70000])

@@ -155,6 +155,10 @@ def test_grand_product_building_blocks(gpu, oc):
     pc.check_grand_product_blocks(gpu, oc, [1, 17, 1024, 1025, 16385, (1 << 18) + 3, 1 << 22])
 
 
+def test_polynomial_evaluation_and_kate_division(gpu, oc):
+    pc.check_poly_eval_and_division(gpu, oc, [1, 2, 17, 256, 257, 65537, (1 << 20) - 1, 1 << 22])
+
+
 def test_msm_randomised_shapes(gpu, oc):
     pc.check_msm_random(gpu, oc, examples=25, max_n=40000, spacings=(-1, 0, 8, 12, 14, 16), windows=(0, 0, 0, 2, 4, 7, 8))
 

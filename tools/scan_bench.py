@@ -14,7 +14,13 @@ for k in [int(a) for a in (sys.argv[1:] or ["20", "22", "24"])]:
     d = torch.empty(n * 4, dtype=torch.int64, device=dev)
     L.gen_scalars_dev(0, 7 + k, n, 0, d.data_ptr(), st)
     out = {"k": k}
-    for name, fn in (("batch_invert", lambda: L.fr_batch_invert_dev(0, d.data_ptr(), n, st)), ("prefix_product", lambda: L.fr_prefix_product_dev(0, d.data_ptr(), d.data_ptr(), n, st))):
+    import numpy as np
+    x = np.array([0x1234567, 0x89abcdef, 0x55, 0x1], dtype=np.uint64)
+    d_q = torch.empty(n * 4, dtype=torch.int64, device=dev)
+    d_o = torch.empty(4, dtype=torch.int64, device=dev)
+    for name, fn in (("batch_invert", lambda: L.fr_batch_invert_dev(0, d.data_ptr(), n, st)), ("prefix_product", lambda: L.fr_prefix_product_dev(0, d.data_ptr(), d.data_ptr(), n, st)),
+                     ("eval_polynomial", lambda: L.check(L.L.h2b_fr_eval_polynomial_dev(0, d.data_ptr(), n, x.ctypes.data, d_o.data_ptr(), st))),
+                     ("kate_division", lambda: L.check(L.L.h2b_fr_kate_division_dev(0, d.data_ptr(), n, x.ctypes.data, d_q.data_ptr(), st)))):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
