@@ -31,6 +31,13 @@ namespace h2b {
 
 static const uint32_t SIGN_BIT = 0x80000000u;
 
+// scattered 4-byte stores of the counting sort: evict-first, so that they do not push the bucket cursors out of L2
+#if defined(H2B_EMU) || defined(H2B_NO_STREAMING_STORES)
+#define H2B_STORE_STREAMING(ptr, val) (*(ptr) = (val))
+#else
+#define H2B_STORE_STREAMING(ptr, val) __stcs((ptr), (val))
+#endif
+
 struct MsmPlan {
     uint32_t n;          // scalars in this (sub-)MSM
     uint32_t c;          // window bits
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(MsmPlan pl, const uint
                 if (e != 0) {
                     uint32_t d = e & ~SIGN_BIT;
                     uint32_t pos = atomicAdd(&cursor[set * pl.Nb + d - 1], 1u);
-                    sorted[pos] = row | (e & SIGN_BIT);
+                    H2B_STORE_STREAMING(&sorted[pos], row | (e & SIGN_BIT));
                 }
                 if (++set == pl.m) { set = 0; row += pl.stride; }
             }
