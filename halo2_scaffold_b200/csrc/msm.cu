@@ -605,7 +605,12 @@ static uint32_t windows_for(uint32_t c) { return 253 / c + 1; }
 // outgrows the L2-friendly 2^19 counters, and a bucket costs about 8 entries (the reduction is latency bound).
 static double msm_cost(double n, uint32_t c, uint32_t sets) {
     double per_entry = 1.0 + (c > 20 ? 0.035 * (c - 20) : 0.0);
-    return n * windows_for(c) * per_entry + 8.0 * sets * (double)(1u << (c - 1));
+    double cost = n * windows_for(c) * per_entry + 8.0 * sets * (double)(1u << (c - 1));
+    // a top window with only a few scalar bits left puts n / 2^bits entries into each of its 2^bits buckets; cutting those
+    // into slices and folding the pieces back is a latency-bound tree (0.2 - 0.9 ms at 2^16): worth about 1.5 windows
+    const uint32_t top_bits = 253 - c * (windows_for(c) - 1);
+    if (top_bits <= 4) cost += 1.5 * n;
+    return cost;
 }
 
 // plain mode (no tables): one bucket set per window
@@ -625,6 +630,11 @@ static uint32_t msm_pick_window_plain(size_t n) {
 
 // table spacing for a base set of n points: even c0 minimising the cost of a full-length MSM, within `max_tables`
 uint32_t msm_pick_table_spacing(size_t n, uint32_t max_tables) {
+    // measured on B200 (profiles/r01_msm_spacing.jsonl, r01_sweep.jsonl): small sets are latency bound and want few
+    // buckets (8-bit windows, whose 5-bit top window is harmless), the mid range 16 bits, large sets 20 bits; 10/12/14/18
+    // bits leave a 1-3 bit top window whose hot buckets cost more than they save
+    const uint32_t preferred = n < ((size_t)1 << 15) ? 8u : (n < ((size_t)1 << 21) ? 16u : 20u);
+    if (windows_for(preferred) <= max_tables) return preferred;
     uint32_t best = 0;
     double best_cost = 1e300;
     for (uint32_t c0 = 4; c0 <= 24; c0 += 2) {
