@@ -633,7 +633,7 @@ uint32_t msm_pick_table_spacing(size_t n, uint32_t max_tables) {
     // measured on B200 (profiles/r01_msm_spacing.jsonl, r01_sweep.jsonl): small sets are latency bound and want few
     // buckets (8-bit windows, whose 5-bit top window is harmless), the mid range 16 bits, large sets 20 bits; 10/12/14/18
     // bits leave a 1-3 bit top window whose hot buckets cost more than they save
-    const uint32_t preferred = n < ((size_t)1 << 15) ? 8u : (n < ((size_t)1 << 21) ? 16u : 20u);
+    const uint32_t preferred = n < ((size_t)1 << 15) ? 8u : (n < ((size_t)1 << 20) ? 16u : 20u);
     if (windows_for(preferred) <= max_tables) return preferred;
     uint32_t best = 0;
     double best_cost = 1e300;
