@@ -36,7 +36,69 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
+    "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
+
+
+# ---- include/h2b200.h structs of the quotient evaluation ------------------------------------------------
+class ValueSourceStruct(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_uint32), ("index", ctypes.c_uint32), ("rotation", ctypes.c_uint32)]
+
+
+class CalculationStruct(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_uint32), ("target", ctypes.c_uint32), ("a", ValueSourceStruct), ("b", ValueSourceStruct),
+                ("parts_offset", ctypes.c_uint32), ("parts_len", ctypes.c_uint32)]
+
+
+class GraphStruct(ctypes.Structure):
+    _fields_ = [("constants", ctypes.c_void_p), ("n_constants", ctypes.c_uint32),
+                ("rotations", ctypes.c_void_p), ("n_rotations", ctypes.c_uint32),
+                ("calculations", ctypes.c_void_p), ("n_calculations", ctypes.c_uint32),
+                ("parts", ctypes.c_void_p), ("n_parts", ctypes.c_uint32),
+                ("n_intermediates", ctypes.c_uint32)]
+
+
+class EvalColumnsStruct(ctypes.Structure):
+    _fields_ = [("fixed", ctypes.c_void_p), ("n_fixed", ctypes.c_uint32),
+                ("advice", ctypes.c_void_p), ("n_advice", ctypes.c_uint32),
+                ("instance", ctypes.c_void_p), ("n_instance", ctypes.c_uint32),
+                ("challenges", ctypes.c_void_p), ("n_challenges", ctypes.c_uint32),
+                ("beta", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("theta", ctypes.c_void_p), ("y", ctypes.c_void_p)]
+
+
+assert ctypes.sizeof(CalculationStruct) == 40
+
+
+class GraphArrays:
+    """A GraphEvaluator flattened into the arrays h2b_graph points at (kept alive by this object)."""
+
+    def __init__(self, constants, rotations, calculations, parts, n_intermediates: int):
+        self.constants = np.ascontiguousarray(constants, dtype=np.uint64).reshape(-1, 4)
+        self.rotations = np.ascontiguousarray(rotations, dtype=np.int32).reshape(-1)
+        self.calculations = np.ascontiguousarray(calculations, dtype=np.uint32).reshape(-1, 10)
+        self.parts = np.ascontiguousarray(parts, dtype=np.uint32).reshape(-1, 3)
+        self.n_intermediates = int(n_intermediates)
+
+    def struct(self) -> GraphStruct:
+        return GraphStruct(self.constants.ctypes.data, self.constants.shape[0], self.rotations.ctypes.data, self.rotations.shape[0],
+                           self.calculations.ctypes.data, self.calculations.shape[0], self.parts.ctypes.data, self.parts.shape[0],
+                           self.n_intermediates)
+
+
+class EvalColumns:
+    """Device pointers of the fixed / advice / instance cosets plus the scalars of one evaluate_h call."""
+
+    def __init__(self, fixed, advice, instance, challenges, beta, gamma, theta, y):
+        self.fixed = np.array(list(fixed), dtype=np.uint64)
+        self.advice = np.array(list(advice), dtype=np.uint64)
+        self.instance = np.array(list(instance), dtype=np.uint64)
+        self.challenges = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)
+        self.beta, self.gamma, self.theta, self.y = (np.ascontiguousarray(v, dtype=np.uint64).reshape(4) for v in (beta, gamma, theta, y))
+
+    def struct(self) -> EvalColumnsStruct:
+        return EvalColumnsStruct(self.fixed.ctypes.data, self.fixed.shape[0], self.advice.ctypes.data, self.advice.shape[0],
+                                 self.instance.ctypes.data, self.instance.shape[0], self.challenges.ctypes.data, self.challenges.shape[0],
+                                 self.beta.ctypes.data, self.gamma.ctypes.data, self.theta.ctypes.data, self.y.ctypes.data)
 
 
 def exported_symbols():
@@ -87,6 +149,10 @@ class Lib:
         L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
         L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
+        L.h2b_evaluate_graph_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp]
+        L.h2b_evaluate_h_permutation_dev.argtypes = [i32, vp, u32, i32, vp, u32, vp, vp, u32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.h2b_evaluate_h_lookup_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.h2b_evaluate_graph_info.argtypes = [ctypes.POINTER(u32), ctypes.POINTER(u32)]
         L.h2b_dev_alloc.argtypes = [i32, sz, ctypes.POINTER(vp)]
         L.h2b_dev_free.argtypes = [i32, vp]
         L.h2b_memcpy_h2d.argtypes = [i32, vp, vp, sz]
@@ -307,6 +373,33 @@ class Lib:
             self.dev_free(device, d)
             self.dev_free(device, d_q)
         return q
+
+    # ---- quotient evaluation (evaluate_h) on device-resident extended-coset columns ------------------
+    def evaluate_graph_dev(self, device: int, graph: GraphArrays, cols: EvalColumns, d_values: int, size: int, rot_scale: int, stream: int = 0):
+        g, c = graph.struct(), cols.struct()
+        self.check(self.L.h2b_evaluate_graph_dev(device, ctypes.addressof(g), ctypes.addressof(c), d_values, size, rot_scale, stream))
+
+    def evaluate_h_permutation_dev(self, device: int, d_values: int, size: int, rot_scale: int, product_cosets, columns, perm_cosets, chunk_len: int,
+                                   last_rotation: int, d_l0: int, d_l_last: int, d_l_active_row: int, beta, gamma, y, delta, zeta, extended_omega,
+                                   stream: int = 0):
+        pc, co, pe = (np.array(list(v), dtype=np.uint64) for v in (product_cosets, columns, perm_cosets))
+        assert co.shape[0] == pe.shape[0]
+        w = [np.ascontiguousarray(v, dtype=np.uint64).reshape(4) for v in (beta, gamma, y, delta, zeta, extended_omega)]
+        self.check(self.L.h2b_evaluate_h_permutation_dev(device, d_values, size, rot_scale, pc.ctypes.data, pc.shape[0], co.ctypes.data, pe.ctypes.data,
+                                                         co.shape[0], chunk_len, last_rotation, d_l0, d_l_last, d_l_active_row,
+                                                         *[v.ctypes.data for v in w], stream))
+
+    def evaluate_h_lookup_dev(self, device: int, graph: GraphArrays, cols: EvalColumns, d_values: int, size: int, rot_scale: int, d_product: int,
+                              d_permuted_input: int, d_permuted_table: int, d_l0: int, d_l_last: int, d_l_active_row: int, stream: int = 0):
+        g, c = graph.struct(), cols.struct()
+        self.check(self.L.h2b_evaluate_h_lookup_dev(device, ctypes.addressof(g), ctypes.addressof(c), d_values, size, rot_scale, d_product,
+                                                    d_permuted_input, d_permuted_table, d_l0, d_l_last, d_l_active_row, stream))
+
+    def evaluate_graph_info(self):
+        """-> (live-value slots, micro-operations) of the graph this thread compiled last"""
+        a, b = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self.check(self.L.h2b_evaluate_graph_info(ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def dev_alloc(self, device: int, nbytes: int) -> int:
         p = ctypes.c_void_p(0)

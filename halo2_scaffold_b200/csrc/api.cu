@@ -404,6 +404,7 @@ void h2b_shutdown(void) {
         c->msm_scalars.release();
         c->msm_out.release();
         c->scan_scratch.release();
+        evaluate_release(*c);
         for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
         c->copy_events.clear();
         if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
@@ -705,6 +706,41 @@ int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64
     H2B_TRY(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     return fr_kate_division_run(*c, d_a, n, b, d_q, (cudaStream_t)stream);
+}
+
+// ---- quotient evaluation -----------------------------------------------------------------------
+int h2b_evaluate_graph_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return evaluate_graph_run(*c, graph, cols, d_values, size, rot_scale, (cudaStream_t)stream);
+}
+
+int h2b_evaluate_h_permutation_dev(int device, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
+                                   const void* const* d_columns, const void* const* d_perm_cosets, uint32_t n_columns, uint32_t chunk_len,
+                                   int32_t last_rotation, const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t beta[4],
+                                   const uint64_t gamma[4], const uint64_t y[4], const uint64_t delta[4], const uint64_t zeta[4],
+                                   const uint64_t extended_omega[4], void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return evaluate_h_permutation_run(*c, d_values, size, rot_scale, d_product_cosets, n_sets, d_columns, d_perm_cosets, n_columns, chunk_len, last_rotation,
+                                      d_l0, d_l_last, d_l_active_row, beta, gamma, y, delta, zeta, extended_omega, (cudaStream_t)stream);
+}
+
+int h2b_evaluate_h_lookup_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                              const void* d_product_coset, const void* d_permuted_input_coset, const void* d_permuted_table_coset, const void* d_l0,
+                              const void* d_l_last, const void* d_l_active_row, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return evaluate_h_lookup_run(*c, graph, cols, d_values, size, rot_scale, d_product_coset, d_permuted_input_coset, d_permuted_table_coset, d_l0, d_l_last,
+                                 d_l_active_row, (cudaStream_t)stream);
+}
+
+int h2b_evaluate_graph_info(uint32_t* slots, uint32_t* micro_ops) {
+    evaluate_graph_last_info(slots, micro_ops);
+    return H2B_OK;
 }
 
 int h2b_dev_alloc(int device, size_t bytes, void** out) {

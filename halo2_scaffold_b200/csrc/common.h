@@ -80,6 +80,7 @@ struct Stager;        // stage.cu
 struct NttTwiddles;   // ntt.cu
 struct MsmScratch;    // msm.cu
 struct BaseSet;       // api.cu
+struct EvalScratch;   // evaluate.cu
 
 struct DeviceCtx {
     int device = -1;
@@ -95,6 +96,7 @@ struct DeviceCtx {
     DevBuf msm_scalars;                // staging for host-pointer MSM scalars
     DevBuf msm_out;                    // 96-byte result
     DevBuf scan_scratch;               // batch inversion / prefix product scratch (scan.cu)
+    EvalScratch* eval = nullptr;       // compiled-program ring of the quotient evaluation (evaluate.cu)
     std::vector<NttTwiddles*> twiddles;  // small LRU cache keyed by (omega, log_n)
     MsmScratch* msm = nullptr;
     Profiler prof;
@@ -113,6 +115,17 @@ int fr_batch_invert_run(DeviceCtx& ctx, void* d_a, size_t n, cudaStream_t stream
 int fr_prefix_product_run(DeviceCtx& ctx, const void* d_in, void* d_out, size_t n, cudaStream_t stream);
 int fr_eval_polynomial_run(DeviceCtx& ctx, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, cudaStream_t stream);
 int fr_kate_division_run(DeviceCtx& ctx, const void* d_a, size_t n, const uint64_t b[4], void* d_q, cudaStream_t stream);
+// ---- evaluate.cu ----
+int evaluate_graph_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale, cudaStream_t stream);
+int evaluate_h_lookup_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                          const void* d_product, const void* d_permuted_input, const void* d_permuted_table, const void* d_l0, const void* d_l_last,
+                          const void* d_l_active_row, cudaStream_t stream);
+int evaluate_h_permutation_run(DeviceCtx& ctx, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
+                               const void* const* d_columns, const void* const* d_perm_cosets, uint32_t n_columns, uint32_t chunk_len, int32_t last_rotation,
+                               const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t* beta, const uint64_t* gamma,
+                               const uint64_t* y, const uint64_t* delta, const uint64_t* zeta, const uint64_t* extended_omega, cudaStream_t stream);
+void evaluate_graph_last_info(uint32_t* slots, uint32_t* micro_ops);
+void evaluate_release(DeviceCtx& ctx);
 // ---- ntt.cu ----
 int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);

@@ -135,6 +135,69 @@ int h2b_fr_prefix_product_dev(int device, const void* d_in, void* d_out, size_t 
 int h2b_fr_eval_polynomial_dev(int device, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, void* stream);
 int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream);
 
+/* ---- quotient evaluation: evaluate_h on device-resident extended-coset columns ----------
+ * [UP] halo2_proofs/src/plonk/evaluation.rs.  A GraphEvaluator is passed in the vocabulary upstream builds it in
+ * (ValueSource / Calculation / CalculationInfo), flattened into plain arrays; the Rust shim fills these structs from
+ * `Evaluator { custom_gates, lookups }` once per proving key.  Every column is a device pointer to `size` Fr elements
+ * (the 2^extended_k evaluations over the zeta coset that coeff_to_extended produced). */
+enum h2b_value_kind {          /* [UP] evaluation.rs `enum ValueSource`; index / rotation as upstream's tuple fields */
+    H2B_VS_CONSTANT = 0,       /* constants[index] */
+    H2B_VS_INTERMEDIATE = 1,   /* intermediates[index] */
+    H2B_VS_FIXED = 2,          /* fixed[index][rotations[rotation]] */
+    H2B_VS_ADVICE = 3,         /* advice[index][rotations[rotation]] */
+    H2B_VS_INSTANCE = 4,       /* instance[index][rotations[rotation]] */
+    H2B_VS_CHALLENGE = 5,      /* challenges[index] */
+    H2B_VS_BETA = 6, H2B_VS_GAMMA = 7, H2B_VS_THETA = 8, H2B_VS_Y = 9,
+    H2B_VS_PREVIOUS_VALUE = 10
+};
+enum h2b_calc_op {             /* [UP] evaluation.rs `enum Calculation` */
+    H2B_CALC_ADD = 0, H2B_CALC_SUB = 1, H2B_CALC_MUL = 2, H2B_CALC_SQUARE = 3, H2B_CALC_DOUBLE = 4, H2B_CALC_NEGATE = 5,
+    H2B_CALC_HORNER = 6,       /* value = a; for part in parts: value = value * b + part */
+    H2B_CALC_STORE = 7
+};
+typedef struct h2b_value_source { uint32_t kind, index, rotation; } h2b_value_source;
+typedef struct h2b_calculation {
+    uint32_t op, target;                 /* intermediates[target] = op(...) */
+    h2b_value_source a, b;               /* Horner: a = start value, b = factor */
+    uint32_t parts_offset, parts_len;    /* Horner only: parts[parts_offset .. parts_offset + parts_len) */
+} h2b_calculation;
+typedef struct h2b_graph {               /* [UP] evaluation.rs `struct GraphEvaluator` */
+    const uint64_t* constants; uint32_t n_constants;     /* n x 4, Montgomery */
+    const int32_t* rotations; uint32_t n_rotations;
+    const h2b_calculation* calculations; uint32_t n_calculations;
+    const h2b_value_source* parts; uint32_t n_parts;
+    uint32_t n_intermediates;
+} h2b_graph;
+typedef struct h2b_eval_columns {        /* host arrays of device pointers + the per-proof scalars of evaluate_h */
+    const void* const* fixed; uint32_t n_fixed;
+    const void* const* advice; uint32_t n_advice;
+    const void* const* instance; uint32_t n_instance;
+    const uint64_t* challenges; uint32_t n_challenges;    /* n x 4 */
+    const uint64_t* beta; const uint64_t* gamma; const uint64_t* theta; const uint64_t* y;   /* 4 words each */
+} h2b_eval_columns;
+/* values[idx] = graph.evaluate(.., previous_value = values[idx], idx, rot_scale, isize = size) for every idx < size: the
+ * "Custom gates" loop of evaluate_h.  A graph without calculations writes zero, as upstream does.  The rotated row is
+ * get_rotation_idx(idx, rot, rot_scale, isize) = (idx + rot * rot_scale).rem_euclid(isize). */
+int h2b_evaluate_graph_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                           void* stream);
+/* The "Permutations" loop of evaluate_h: values[idx] is advanced by the l_0 / l_last / set-chaining / product terms.
+ *   d_product_cosets[n_sets]   : permutation_product_coset of every set (z_i)
+ *   d_columns[n_columns]       : the value coset of every column of the argument, in p.columns order (the caller resolves
+ *                                Any::{Advice, Fixed, Instance} to a pointer); d_perm_cosets[n_columns] = pk.permutation.cosets
+ *   chunk_len = cs.degree() - 2; last_rotation = -(blinding_factors + 1); delta = Fr::DELTA; zeta = Fr::ZETA */
+int h2b_evaluate_h_permutation_dev(int device, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
+                                   const void* const* d_columns, const void* const* d_perm_cosets, uint32_t n_columns, uint32_t chunk_len,
+                                   int32_t last_rotation, const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t beta[4],
+                                   const uint64_t gamma[4], const uint64_t y[4], const uint64_t delta[4], const uint64_t zeta[4],
+                                   const uint64_t extended_omega[4], void* stream);
+/* One iteration of the "Lookups" loop of evaluate_h: table_value = graph.evaluate(.., previous_value = 0, ..) and the five
+ * lookup terms on product_coset (z), permuted_input_coset (a') and permuted_table_coset (s'). */
+int h2b_evaluate_h_lookup_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                              const void* d_product_coset, const void* d_permuted_input_coset, const void* d_permuted_table_coset, const void* d_l0,
+                              const void* d_l_last, const void* d_l_active_row, void* stream);
+/* slots (live values per row) and micro-operations the last compiled graph of this thread needed -- diagnostics / tests */
+int h2b_evaluate_graph_info(uint32_t* slots, uint32_t* micro_ops);
+
 /* ---- raw device memory helpers (so that non-CUDA hosts -- ctypes, Rust -- can hold device buffers) --- */
 int h2b_dev_alloc(int device, size_t bytes, void** out);
 int h2b_dev_free(int device, void* p);

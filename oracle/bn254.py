@@ -376,3 +376,56 @@ def random_fr(seed: int, n: int):
             v = (v << 64) | w
         out.append(v % R_MOD)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Quotient evaluation ([UP] halo2_proofs/src/plonk/evaluation.rs): GraphEvaluator::evaluate on canonical
+# integers, one row at a time -- the independent (big-int) check of oracle/h2_oracle.cpp's restatement.
+# Encoding as in h2_oracle.cpp: value source (kind, index, rotation); calculation
+# (op, target, a[3], b[3], parts_offset, parts_len).
+# ---------------------------------------------------------------------------------------------------------
+def graph_evaluate_row(constants, rotations, calcs, parts, n_intermediates, fixed, advice, instance, challenges, beta, gamma, theta, y,
+                       previous_value, idx, rot_scale, isize):
+    rot = [(idx + r * rot_scale) % isize for r in rotations]          # get_rotation_idx (Python % is rem_euclid)
+    inter = [0] * n_intermediates
+
+    def get(vs):
+        kind, index, rotation = vs
+        if kind == 0:
+            return constants[index]
+        if kind == 1:
+            return inter[index]
+        if kind == 2:
+            return fixed[index][rot[rotation]]
+        if kind == 3:
+            return advice[index][rot[rotation]]
+        if kind == 4:
+            return instance[index][rot[rotation]]
+        if kind == 5:
+            return challenges[index]
+        return {6: beta, 7: gamma, 8: theta, 9: y, 10: previous_value}[kind]
+
+    last = None
+    for c in calcs:
+        op, target, a, b, po, pl = c[0], c[1], tuple(c[2:5]), tuple(c[5:8]), c[8], c[9]
+        if op == 0:
+            v = get(a) + get(b)
+        elif op == 1:
+            v = get(a) - get(b)
+        elif op == 2:
+            v = get(a) * get(b)
+        elif op == 3:
+            v = get(a) ** 2
+        elif op == 4:
+            v = 2 * get(a)
+        elif op == 5:
+            v = -get(a)
+        elif op == 6:
+            v, f = get(a), get(b)
+            for j in range(pl):
+                v = (v * f + get(tuple(parts[po + j]))) % R_MOD
+        else:
+            v = get(a)
+        inter[target] = v % R_MOD
+        last = target
+    return inter[last] if last is not None else 0

@@ -403,6 +403,153 @@ void orc_fr_kate_division(const u64* a, size_t n, const u64* b, u64* q) {
         memcpy(q + 4 * (i - 1), run.l, 32);
     }
 }
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------
+// Quotient evaluation ([UP] halo2_proofs/src/plonk/evaluation.rs), restated as upstream
+// runs it: one `intermediates` vector, the calculations walked in order for every row.
+// Flat encoding shared with tests: a value source is 3 u32 (kind, index, rotation), a calculation 10 u32
+// (op, target, a[3], b[3], parts_offset, parts_len); kinds / ops numbered as the enums are declared upstream:
+//   ValueSource: 0 Constant, 1 Intermediate, 2 Fixed, 3 Advice, 4 Instance, 5 Challenge, 6 Beta, 7 Gamma, 8 Theta, 9 Y,
+//                10 PreviousValue;   Calculation: 0 Add, 1 Sub, 2 Mul, 3 Square, 4 Double, 5 Negate, 6 Horner, 7 Store
+// ---------------------------------------------------------------------------------
+struct OrcGraph {
+    const u64* constants; uint32_t n_constants;
+    const int32_t* rotations; uint32_t n_rotations;
+    const uint32_t* calcs; uint32_t n_calcs;
+    const uint32_t* parts; uint32_t n_parts;
+    uint32_t n_intermediates;
+};
+struct OrcColumns {
+    const u64* const* fixed; const u64* const* advice; const u64* const* instance;
+    const u64* challenges; const u64 *beta, *gamma, *theta, *y;
+};
+static inline Fr fr_at(const u64* col, size_t i) { Fr x; memcpy(x.l, col + 4 * i, 32); return x; }
+// [UP] evaluation.rs get_rotation_idx
+static inline size_t get_rotation_idx(size_t idx, int32_t rot, int32_t rot_scale, int64_t isize) {
+    int64_t v = ((int64_t)idx + (int64_t)rot * rot_scale) % isize;
+    if (v < 0) v += isize;
+    return (size_t)v;
+}
+struct OrcEvalData { std::vector<Fr> intermediates; std::vector<size_t> rotations; };
+// [UP] evaluation.rs ValueSource::get
+static Fr value_source_get(const uint32_t* vs, const OrcGraph& g, const OrcColumns& c, const OrcEvalData& d, const Fr& previous_value) {
+    switch (vs[0]) {
+        case 0: return fr_at(g.constants, vs[1]);
+        case 1: return d.intermediates[vs[1]];
+        case 2: return fr_at(c.fixed[vs[1]], d.rotations[vs[2]]);
+        case 3: return fr_at(c.advice[vs[1]], d.rotations[vs[2]]);
+        case 4: return fr_at(c.instance[vs[1]], d.rotations[vs[2]]);
+        case 5: return fr_at(c.challenges, vs[1]);
+        case 6: return fr_at(c.beta, 0);
+        case 7: return fr_at(c.gamma, 0);
+        case 8: return fr_at(c.theta, 0);
+        case 9: return fr_at(c.y, 0);
+        default: return previous_value;
+    }
+}
+// [UP] evaluation.rs GraphEvaluator::evaluate
+static Fr graph_evaluate(const OrcGraph& g, const OrcColumns& c, OrcEvalData& d, const Fr& previous_value, size_t idx, int32_t rot_scale, int64_t isize) {
+    for (uint32_t r = 0; r < g.n_rotations; ++r) d.rotations[r] = get_rotation_idx(idx, g.rotations[r], rot_scale, isize);
+    for (uint32_t i = 0; i < g.n_calcs; ++i) {
+        const uint32_t* k = g.calcs + 10 * (size_t)i;
+        Fr a = value_source_get(k + 2, g, c, d, previous_value), v;
+        switch (k[0]) {
+            case 0: v = a + value_source_get(k + 5, g, c, d, previous_value); break;
+            case 1: v = a - value_source_get(k + 5, g, c, d, previous_value); break;
+            case 2: v = a * value_source_get(k + 5, g, c, d, previous_value); break;
+            case 3: v = a.sqr(); break;
+            case 4: v = a.dbl(); break;
+            case 5: v = a.neg(); break;
+            case 6: {
+                Fr factor = value_source_get(k + 5, g, c, d, previous_value);
+                v = a;
+                for (uint32_t j = 0; j < k[9]; ++j) v = v * factor + value_source_get(g.parts + 3 * (size_t)(k[8] + j), g, c, d, previous_value);
+                break;
+            }
+            default: v = a;
+        }
+        d.intermediates[k[1]] = v;
+    }
+    return g.n_calcs ? d.intermediates[g.calcs[10 * (size_t)(g.n_calcs - 1) + 1]] : Fr::zero();
+}
+static OrcGraph make_graph(const u64* constants, uint32_t n_constants, const int32_t* rotations, uint32_t n_rotations, const uint32_t* calcs, uint32_t n_calcs,
+                           const uint32_t* parts, uint32_t n_parts, uint32_t n_intermediates) {
+    return OrcGraph{constants, n_constants, rotations, n_rotations, calcs, n_calcs, parts, n_parts, n_intermediates};
+}
+
+extern "C" {
+// the "Custom gates" loop of evaluate_h: values[idx] = custom_gates.evaluate(.., previous_value = values[idx], idx, rot_scale, isize)
+void orc_evaluate_graph(const u64* constants, uint32_t n_constants, const int32_t* rotations, uint32_t n_rotations, const uint32_t* calcs, uint32_t n_calcs,
+                        const uint32_t* parts, uint32_t n_parts, uint32_t n_intermediates, const u64* const* fixed, const u64* const* advice,
+                        const u64* const* instance, const u64* challenges, const u64* beta, const u64* gamma, const u64* theta, const u64* y, u64* values,
+                        uint32_t size, int32_t rot_scale) {
+    OrcGraph g = make_graph(constants, n_constants, rotations, n_rotations, calcs, n_calcs, parts, n_parts, n_intermediates);
+    OrcColumns c{fixed, advice, instance, challenges, beta, gamma, theta, y};
+    OrcEvalData d{std::vector<Fr>(n_intermediates, Fr::zero()), std::vector<size_t>(n_rotations, 0)};
+    for (size_t idx = 0; idx < size; ++idx) {
+        Fr v = graph_evaluate(g, c, d, fr_at(values, idx), idx, rot_scale, size);
+        memcpy(values + 4 * idx, v.l, 32);
+    }
+}
+// one iteration of the "Lookups" loop of evaluate_h
+void orc_evaluate_h_lookup(const u64* constants, uint32_t n_constants, const int32_t* rotations, uint32_t n_rotations, const uint32_t* calcs, uint32_t n_calcs,
+                           const uint32_t* parts, uint32_t n_parts, uint32_t n_intermediates, const u64* const* fixed, const u64* const* advice,
+                           const u64* const* instance, const u64* challenges, const u64* beta_w, const u64* gamma_w, const u64* theta, const u64* y_w,
+                           u64* values, uint32_t size, int32_t rot_scale, const u64* product_coset, const u64* permuted_input_coset,
+                           const u64* permuted_table_coset, const u64* l0, const u64* l_last, const u64* l_active_row) {
+    OrcGraph g = make_graph(constants, n_constants, rotations, n_rotations, calcs, n_calcs, parts, n_parts, n_intermediates);
+    OrcColumns c{fixed, advice, instance, challenges, beta_w, gamma_w, theta, y_w};
+    OrcEvalData d{std::vector<Fr>(n_intermediates, Fr::zero()), std::vector<size_t>(n_rotations, 0)};
+    const Fr beta = fr_at(beta_w, 0), gamma = fr_at(gamma_w, 0), y = fr_at(y_w, 0), one = Fr::one();
+    for (size_t idx = 0; idx < size; ++idx) {
+        Fr table_value = graph_evaluate(g, c, d, Fr::zero(), idx, rot_scale, size);
+        size_t r_next = get_rotation_idx(idx, 1, rot_scale, size), r_prev = get_rotation_idx(idx, -1, rot_scale, size);
+        Fr a_minus_s = fr_at(permuted_input_coset, idx) - fr_at(permuted_table_coset, idx);
+        Fr value = fr_at(values, idx);
+        value = value * y + ((one - fr_at(product_coset, idx)) * fr_at(l0, idx));
+        value = value * y + ((fr_at(product_coset, idx) * fr_at(product_coset, idx) - fr_at(product_coset, idx)) * fr_at(l_last, idx));
+        value = value * y + ((fr_at(product_coset, r_next) * (fr_at(permuted_input_coset, idx) + beta) * (fr_at(permuted_table_coset, idx) + gamma) -
+                              fr_at(product_coset, idx) * table_value) * fr_at(l_active_row, idx));
+        value = value * y + (a_minus_s * fr_at(l0, idx));
+        value = value * y + (a_minus_s * (fr_at(permuted_input_coset, idx) - fr_at(permuted_input_coset, r_prev)) * fr_at(l_active_row, idx));
+        memcpy(values + 4 * idx, value.l, 32);
+    }
+}
+// the "Permutations" loop of evaluate_h
+void orc_evaluate_h_permutation(u64* values, uint32_t size, int32_t rot_scale, const u64* const* product_cosets, uint32_t n_sets, const u64* const* columns,
+                                const u64* const* perm_cosets, uint32_t n_columns, uint32_t chunk_len, int32_t last_rotation, const u64* l0, const u64* l_last,
+                                const u64* l_active_row, const u64* beta_w, const u64* gamma_w, const u64* y_w, const u64* delta_w, const u64* zeta_w,
+                                const u64* extended_omega_w) {
+    if (n_sets == 0) return;
+    const Fr beta = fr_at(beta_w, 0), gamma = fr_at(gamma_w, 0), y = fr_at(y_w, 0), delta = fr_at(delta_w, 0), one = Fr::one();
+    const Fr extended_omega = fr_at(extended_omega_w, 0);
+    const Fr delta_start = beta * fr_at(zeta_w, 0);
+    Fr beta_term = Fr::one();                                   // extended_omega^start with start = 0 (one chunk)
+    for (size_t idx = 0; idx < size; ++idx) {
+        size_t r_next = get_rotation_idx(idx, 1, rot_scale, size), r_last = get_rotation_idx(idx, last_rotation, rot_scale, size);
+        Fr value = fr_at(values, idx);
+        value = value * y + ((one - fr_at(product_cosets[0], idx)) * fr_at(l0, idx));
+        const u64* last = product_cosets[n_sets - 1];
+        value = value * y + ((fr_at(last, idx) * fr_at(last, idx) - fr_at(last, idx)) * fr_at(l_last, idx));
+        for (uint32_t s = 1; s < n_sets; ++s)
+            value = value * y + ((fr_at(product_cosets[s], idx) - fr_at(product_cosets[s - 1], r_last)) * fr_at(l0, idx));
+        Fr current_delta = delta_start * beta_term;
+        for (uint32_t s = 0, c0 = 0; s < n_sets && c0 < n_columns; ++s, c0 += chunk_len) {      // sets.zip(columns.chunks(chunk_len))
+            uint32_t c1 = std::min(c0 + chunk_len, n_columns);
+            Fr left = fr_at(product_cosets[s], r_next);
+            for (uint32_t c = c0; c < c1; ++c) left = left * (fr_at(columns[c], idx) + beta * fr_at(perm_cosets[c], idx) + gamma);
+            Fr right = fr_at(product_cosets[s], idx);
+            for (uint32_t c = c0; c < c1; ++c) { right = right * (fr_at(columns[c], idx) + current_delta + gamma); current_delta = current_delta * delta; }
+            value = value * y + ((left - right) * fr_at(l_active_row, idx));
+        }
+        beta_term = beta_term * extended_omega;
+        memcpy(values + 4 * idx, value.l, 32);
+    }
+}
+}  // extern "C"
+
+extern "C" {
 // uniform scalars in Montgomery form: 512-bit SplitMix64 draw reduced mod r (same stream as oracle/bn254.py random_fr)
 void orc_random_fr(u64 seed, size_t n, u64* out) {
     Fr two64; two64.l[0] = 0; two64.l[1] = 1; two64.l[2] = two64.l[3] = 0; two64 = two64.to_mont();

@@ -44,6 +44,12 @@ def lib():
         L.orc_fr_eval_polynomial.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_fr_kate_division.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_random_fr.argtypes = [ctypes.c_uint64, ctypes.c_size_t, u64p]
+        u32, i32 = ctypes.c_uint32, ctypes.c_int32
+        graph = [u64p, u32, u64p, u32, u64p, u32, u64p, u32, u32]           # constants, rotations, calculations, parts, n_intermediates
+        columns = [u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p]          # fixed, advice, instance, challenges, beta, gamma, theta, y
+        L.orc_evaluate_graph.argtypes = graph + columns + [u64p, u32, i32]
+        L.orc_evaluate_h_lookup.argtypes = graph + columns + [u64p, u32, i32, u64p, u64p, u64p, u64p, u64p, u64p]
+        L.orc_evaluate_h_permutation.argtypes = [u64p, u32, i32, u64p, u32, u64p, u64p, u32, u32, i32] + [u64p] * 9
         L.orc_gen_points.argtypes = [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int, u64p]
         _lib = L
     return _lib
@@ -138,6 +144,67 @@ def fr_kate_division(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     if a.shape[0] > 1:
         lib().orc_fr_kate_division(_p(a), a.shape[0], _p(b), _p(q))
     return q
+
+
+# ---- quotient evaluation ([UP] halo2_proofs/src/plonk/evaluation.rs) ------------------------------------------------
+def _col(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+
+
+def _ptrs(cols):
+    cols = [_col(c) for c in cols]
+    return cols, np.array([c.ctypes.data for c in cols], dtype=np.uint64)
+
+
+def _graph_args(graph):
+    """graph: (constants (n,4) u64, rotations int32, calculations (n,10) u32, parts (m,3) u32, n_intermediates)"""
+    constants, rotations, calcs, parts, n_inter = graph
+    constants = _col(constants)
+    rotations = np.ascontiguousarray(rotations, dtype=np.int32).reshape(-1)
+    calcs = np.ascontiguousarray(calcs, dtype=np.uint32).reshape(-1, 10)
+    parts = np.ascontiguousarray(parts, dtype=np.uint32).reshape(-1, 3)
+    keep = (constants, rotations, calcs, parts)
+    return keep, [constants.ctypes.data, constants.shape[0], rotations.ctypes.data, rotations.shape[0], calcs.ctypes.data, calcs.shape[0],
+                  parts.ctypes.data, parts.shape[0], int(n_inter)]
+
+
+def _column_args(fixed, advice, instance, challenges, beta, gamma, theta, y):
+    kf, pf = _ptrs(fixed)
+    ka, pa = _ptrs(advice)
+    ki, pi = _ptrs(instance)
+    scal = [_col(v) for v in (challenges, beta, gamma, theta, y)]
+    return (kf, ka, ki, pf, pa, pi, scal), [pf.ctypes.data, pa.ctypes.data, pi.ctypes.data] + [v.ctypes.data for v in scal]
+
+
+def evaluate_graph(graph, fixed, advice, instance, challenges, beta, gamma, theta, y, values, rot_scale: int) -> np.ndarray:
+    """the "Custom gates" loop of evaluate_h, sequentially as upstream walks it -> new values"""
+    values = np.array(values, dtype=np.uint64, order="C", copy=True).reshape(-1, 4)
+    k1, ga = _graph_args(graph)
+    k2, ca = _column_args(fixed, advice, instance, challenges, beta, gamma, theta, y)
+    lib().orc_evaluate_graph(*ga, *ca, values.ctypes.data, values.shape[0], rot_scale)
+    return values
+
+
+def evaluate_h_lookup(graph, fixed, advice, instance, challenges, beta, gamma, theta, y, values, rot_scale: int, product_coset,
+                      permuted_input_coset, permuted_table_coset, l0, l_last, l_active_row) -> np.ndarray:
+    values = np.array(values, dtype=np.uint64, order="C", copy=True).reshape(-1, 4)
+    k1, ga = _graph_args(graph)
+    k2, ca = _column_args(fixed, advice, instance, challenges, beta, gamma, theta, y)
+    extra = [_col(v) for v in (product_coset, permuted_input_coset, permuted_table_coset, l0, l_last, l_active_row)]
+    lib().orc_evaluate_h_lookup(*ga, *ca, values.ctypes.data, values.shape[0], rot_scale, *[v.ctypes.data for v in extra])
+    return values
+
+
+def evaluate_h_permutation(values, rot_scale: int, product_cosets, columns, perm_cosets, chunk_len: int, last_rotation: int, l0, l_last,
+                           l_active_row, beta, gamma, y, delta, zeta, extended_omega) -> np.ndarray:
+    values = np.array(values, dtype=np.uint64, order="C", copy=True).reshape(-1, 4)
+    kp, pp = _ptrs(product_cosets)
+    kc, pc = _ptrs(columns)
+    ks, ps = _ptrs(perm_cosets)
+    extra = [_col(v) for v in (l0, l_last, l_active_row, beta, gamma, y, delta, zeta, extended_omega)]
+    lib().orc_evaluate_h_permutation(values.ctypes.data, values.shape[0], rot_scale, pp.ctypes.data, len(kp), pc.ctypes.data, ps.ctypes.data, len(kc),
+                                     chunk_len, last_rotation, *[v.ctypes.data for v in extra])
+    return values
 
 
 def field_op(field: str, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -226,3 +226,151 @@ def check_golden_msm(L, oc, g):
     for tag in ("n1", "n2", "n8", "n64", "n200", "cancel", "anchor"):
         got = affine_of(oc, L.msm(g[tag + "_scalars"], g[tag + "_bases"]))
         assert (got == g[tag + "_result"]).all(), tag
+
+
+# ---- quotient evaluation (evaluate_h) ---------------------------------------------------------------------------------
+def random_graph(rng, n_fixed, n_advice, n_instance, n_challenges, n_calcs, n_rot=4, reuse_targets=False):
+    """A random GraphEvaluator in upstream's vocabulary: every Calculation / ValueSource variant, Horner with 0..6 parts,
+    dead calculations, Stores of columns / constants / intermediates.  -> (constants, rotations, calcs, parts, n_intermediates)"""
+    n_const = 3 + int(rng.integers(0, 4))
+    rotations = [0] + [int(v) for v in rng.integers(-3, 4, size=n_rot - 1)]
+    calcs, parts, defined = [], [], []
+    n_inter = n_calcs if not reuse_targets else max(2, n_calcs // 3)
+
+    def source():
+        kinds = [0, 5, 6, 7, 8, 9, 10] if n_challenges else [0, 6, 7, 8, 9, 10]
+        kinds += [2] * (2 if n_fixed else 0) + [3] * (4 if n_advice else 0) + [4] * (1 if n_instance else 0)
+        kinds += [1] * (14 if defined else 0)
+        k = int(rng.choice(kinds))
+        if k == 0:
+            return (0, int(rng.integers(0, n_const)), 0)
+        if k == 1:
+            # mostly recent values (chains), sometimes an old one (long live ranges)
+            return (1, defined[-1 - int(rng.integers(0, min(3, len(defined))))] if rng.random() < 0.7 else int(rng.choice(defined)), 0)
+        if k in (2, 3, 4):
+            return (k, int(rng.integers(0, {2: n_fixed, 3: n_advice, 4: n_instance}[k])), int(rng.integers(0, len(rotations))))
+        if k == 5:
+            return (5, int(rng.integers(0, n_challenges)), 0)
+        return (k, 0, 0)
+
+    for c in range(n_calcs):
+        op = int(rng.choice([0, 1, 2, 2, 2, 3, 4, 5, 6, 6, 7]))
+        a, b = source(), source()
+        po, pl = 0, 0
+        if op == 6:
+            pl = int(rng.integers(0, 7))
+            po = len(parts)
+            parts.extend(source() for _ in range(pl))
+        target = c if not reuse_targets else int(rng.integers(0, n_inter))
+        calcs.append([op, target, *a, *b, po, pl])
+        if target not in defined:
+            defined.append(target)
+    # the result: a Horner in y over a sample of what was defined, so that most of the program is reachable
+    pl = min(len(defined), 24)
+    po = len(parts)
+    parts.extend((1, int(t), 0) for t in rng.choice(defined, size=pl, replace=False))
+    calcs.append([6, defined[-1] if reuse_targets else n_calcs, 10, 0, 0, 9, 0, 0, po, pl])
+    if not reuse_targets:
+        n_inter += 1
+    return (None, np.array(rotations, dtype=np.int32), np.array(calcs, dtype=np.uint32).reshape(-1, 10),
+            np.array(parts, dtype=np.uint32).reshape(-1, 3), n_inter), n_const
+
+
+def wide_graph(n_live):
+    """n_live products that all stay live: each is consumed once by a running sum and once more by a running product"""
+    calcs = [[2, i, 3, 0, 0, 0, 3 + (i % 3), 0, 0, 0] for i in range(n_live)]                  # v_i = advice0 * constant
+    t = n_live
+    calcs.append([0, t, 1, 0, 0, 1, 1, 0, 0, 0])                                              # s = v_0 + v_1
+    for i in range(2, n_live):
+        calcs.append([0, t + 1, 1, t, 0, 1, i, 0, 0, 0])
+        t += 1
+    for i in range(n_live):
+        calcs.append([2 if i % 2 else 1, t + 1, 1, t, 0, 1, i, 0, 0, 0])                      # s = s (* or -) v_i
+        t += 1
+    return (None, np.array([0], dtype=np.int32), np.array(calcs, dtype=np.uint32), np.zeros((0, 3), dtype=np.uint32), t + 1), 6
+
+
+def _graph_pair(oc, graph, n_const, seed):
+    """(oracle tuple, product GraphArrays) of one random graph with random constants"""
+    from halo2_scaffold_b200._lib import GraphArrays
+    constants = oc.random_fr(seed, n_const)
+    constants[0] = 0
+    g = (constants,) + graph[1:]
+    return g, GraphArrays(*g)
+
+
+def check_evaluate_graph(L, oc, cases):
+    """h2b_evaluate_graph_dev against the sequential walk of the oracle on random graphs.  cases: (size, rot_scale, n_calcs, seed)"""
+    from halo2_scaffold_b200 import evaluation as ev
+    for size, rot_scale, n_calcs, seed in cases:
+        rng = np.random.default_rng(seed)
+        nf, na, ni, nch = int(rng.integers(0, 3)), int(rng.integers(1, 5)), int(rng.integers(0, 2)), int(rng.integers(0, 3))
+        graph, n_const = random_graph(rng, nf, na, ni, nch, n_calcs, reuse_targets=bool(seed % 3 == 2))
+        g, ga = _graph_pair(oc, graph, n_const, seed)
+        cols = [oc.random_fr(seed * 131 + j, size) for j in range(nf + na + ni)]
+        fixed, advice, instance = cols[:nf], cols[nf:nf + na], cols[nf + na:]
+        sc = oc.random_fr(seed * 7 + 1, nch + 4)
+        challenges, (beta, gamma, theta, y) = sc[:nch], sc[nch:]
+        values = oc.random_fr(seed * 7 + 2, size)
+        want = oc.evaluate_graph(g, fixed, advice, instance, challenges, beta, gamma, theta, y, values, rot_scale)
+        got = ev.evaluate_graph(L, ga, fixed, advice, instance, challenges, beta, gamma, theta, y, values, rot_scale)
+        assert (got == want).all(), ("evaluate_graph", size, rot_scale, n_calcs, seed, L.evaluate_graph_info())
+
+
+def standard_plonk_like(n_advice_groups=1):
+    """gate polynomials in the shape of examples/standard_plonk.rs (q_a a + q_b b + q_c c + q_ab a b + constant + instance = 0),
+    one per advice triple, plus a rotated term and a lookup argument over the first advice column"""
+    from halo2_scaffold_b200 import evaluation as ev
+    polys, f = [], 0
+    for gidx in range(n_advice_groups):
+        a, b, c = ev.Advice(3 * gidx), ev.Advice(3 * gidx + 1), ev.Advice(3 * gidx + 2)
+        q_a, q_b, q_c, q_ab, const = (ev.Fixed(f + j) for j in range(5))
+        f += 5
+        poly = ev.Sum(ev.Sum(ev.Sum(ev.Sum(ev.Sum(ev.Product(q_a, a), ev.Product(q_b, b)), ev.Product(q_c, c)),
+                                    ev.Product(q_ab, ev.Product(a, b))), const), ev.Instance(0))
+        polys.append(poly)
+        # a * (a[next] - b) - 3 * c[prev] : rotations, Negated, Scaled
+        polys.append(ev.Sum(ev.Product(a, ev.Sum(ev.Advice(3 * gidx, 1), ev.Negated(b))), ev.Negated(ev.Scaled(ev.Advice(3 * gidx + 2, -1), 3))))
+    lookups = [([ev.Product(ev.Fixed(0), ev.Advice(0)), ev.Advice(1, 1)], [ev.Fixed(1), ev.Fixed(2)])]
+    return polys, lookups, f, 3 * n_advice_groups
+
+
+def check_evaluate_h(L, oc, cases):
+    """Evaluator::evaluate_h (custom gates, permutations, lookups) through the host mirror against the oracle's three loops.
+    cases: (extended_k, k, groups, seed)"""
+    from halo2_scaffold_b200 import evaluation as ev
+    from halo2_scaffold_b200.domain import fr_to_words
+    for ek, k, groups, seed in cases:
+        size, rot_scale = 1 << ek, 1 << (ek - k)
+        polys, lookup_exprs, nf, na = standard_plonk_like(groups)
+        E = ev.Evaluator(polys, lookup_exprs)
+        fixed = [oc.random_fr(seed * 1000 + j, size) for j in range(nf)]
+        advice = [oc.random_fr(seed * 1000 + 100 + j, size) for j in range(na)]
+        instance = [oc.random_fr(seed * 1000 + 200, size)]
+        sc = oc.random_fr(seed * 1000 + 300, 8)
+        beta, gamma, theta, y, delta, zeta, extended_omega = sc[:7]
+        extended_omega = fr_to_words(o.omega_for(ek))
+        l0, l_last, l_active = (oc.random_fr(seed * 1000 + 400 + j, size) for j in range(3))
+        # permutation over all advice columns + one fixed column, chunk_len 2 (degree 4): ceil(n_cols / 2) sets
+        perm_cols = [("advice", j) for j in range(na)] + [("fixed", 0)]
+        chunk_len = 2
+        n_sets = (len(perm_cols) + chunk_len - 1) // chunk_len
+        perm = dict(product_cosets=[oc.random_fr(seed * 1000 + 500 + j, size) for j in range(n_sets)], columns=perm_cols,
+                    cosets=[oc.random_fr(seed * 1000 + 600 + j, size) for j in range(len(perm_cols))], chunk_len=chunk_len, last_rotation=-6,
+                    delta=delta, zeta=zeta, extended_omega=extended_omega)
+        lks = [dict(product_coset=oc.random_fr(seed * 1000 + 700, size), permuted_input_coset=oc.random_fr(seed * 1000 + 701, size),
+                    permuted_table_coset=oc.random_fr(seed * 1000 + 702, size))]
+        got = E.evaluate_h(size=size, rot_scale=rot_scale, fixed=fixed, advice=advice, instance=instance, challenges=np.zeros((0, 4), dtype=np.uint64),
+                           y=y, beta=beta, gamma=gamma, theta=theta, l0=l0, l_last=l_last, l_active_row=l_active, permutation=perm, lookups=lks, lib=L)
+
+        def tup(g):
+            a = g.arrays()
+            return (a.constants, a.rotations, a.calculations, a.parts, a.n_intermediates)
+        ch = np.zeros((0, 4), dtype=np.uint64)
+        want = oc.evaluate_graph(tup(E.custom_gates), fixed, advice, instance, ch, beta, gamma, theta, y, np.zeros((size, 4), dtype=np.uint64), rot_scale)
+        by_type = {"advice": advice, "fixed": fixed, "instance": instance}
+        want = oc.evaluate_h_permutation(want, rot_scale, perm["product_cosets"], [by_type[t][i] for t, i in perm_cols], perm["cosets"], chunk_len, -6,
+                                         l0, l_last, l_active, beta, gamma, y, delta, zeta, extended_omega)
+        want = oc.evaluate_h_lookup(tup(E.lookups[0]), fixed, advice, instance, ch, beta, gamma, theta, y, want, rot_scale, lks[0]["product_coset"],
+                                    lks[0]["permuted_input_coset"], lks[0]["permuted_table_coset"], l0, l_last, l_active)
+        assert (got == want).all(), ("evaluate_h", ek, k, groups, seed)

@@ -263,3 +263,96 @@ def test_grand_product_building_blocks(emu, oc):
 
 def test_polynomial_evaluation_and_kate_division(emu, oc):
     pc.check_poly_eval_and_division(emu, oc, [1, 2, 3, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 70000])
+
+
+def test_evaluate_graph_random_programs(emu, oc):
+    # every Calculation / ValueSource variant, dead code, re-used targets, ragged sizes, negative and large rotations
+    cases = [(1, 1, 1, 1), (2, 1, 5, 2), (37, 1, 12, 3), (64, 4, 30, 4), (200, 2, 60, 5), (256, 4, 120, 6), (100, 7, 250, 7), (513, 3, 40, 8),
+             (300, 1, 400, 9), (128, 16, 25, 10), (99, 1, 80, 11)]
+    pc.check_evaluate_graph(emu, oc, cases)
+    slots, ops = emu.evaluate_graph_info()
+    assert ops > 0
+
+
+def test_evaluate_graph_edge_cases(emu, oc):
+    from halo2_scaffold_b200 import evaluation as ev
+    from halo2_scaffold_b200._lib import GraphArrays, H2BError
+    size = 40
+    adv = [oc.random_fr(5, size)]
+    sc = oc.random_fr(6, 4)
+    vals = oc.random_fr(7, size)
+    none = np.zeros((0, 4), dtype=np.uint64)
+
+    def run(calcs, parts=(), n_inter=4, rotations=(0,)):
+        g = (oc.random_fr(8, 3), np.array(rotations, dtype=np.int32), np.array(calcs, dtype=np.uint32).reshape(-1, 10),
+             np.array(parts, dtype=np.uint32).reshape(-1, 3), n_inter)
+        want = oc.evaluate_graph(g, [], adv, [], none, *sc, vals, 1)
+        got = ev.evaluate_graph(emu, GraphArrays(*g), [], adv, [], none, *sc, vals, 1)
+        assert (got == want).all()
+        return got
+    # no calculations: zero, as upstream
+    assert not run([], n_inter=0).any()
+    # the result is a Store of a column / of the previous value / of an intermediate
+    run([[7, 0, 3, 0, 0, 0, 0, 0, 0, 0]])
+    assert (run([[7, 0, 10, 0, 0, 0, 0, 0, 0, 0]]) == vals).all()
+    run([[2, 0, 3, 0, 0, 10, 0, 0, 0, 0], [7, 1, 1, 0, 0, 0, 0, 0, 0, 0]])
+    # Horner without parts is its start value; Horner whose parts repeat one intermediate
+    run([[6, 0, 9, 0, 0, 8, 0, 0, 0, 0]])
+    run([[3, 0, 3, 0, 0, 0, 0, 0, 0, 0], [6, 1, 10, 0, 0, 9, 0, 0, 0, 3]], parts=[[1, 0, 0], [1, 0, 0], [3, 0, 0]])
+    # malformed graphs are refused, not executed
+    for bad in ([[0, 0, 1, 2, 0, 0, 0, 0, 0, 0]],          # reads an intermediate that was never written
+                [[0, 9, 0, 0, 0, 0, 0, 0, 0, 0]],          # target out of range
+                [[0, 0, 3, 5, 0, 0, 0, 0, 0, 0]],          # advice column out of range
+                [[0, 0, 3, 0, 4, 0, 0, 0, 0, 0]],          # rotation out of range
+                [[6, 0, 0, 0, 0, 0, 0, 0, 0, 2]],          # Horner parts out of range
+                [[9, 0, 0, 0, 0, 0, 0, 0, 0, 0]]):         # unknown op
+        g = GraphArrays(oc.random_fr(8, 3), np.array([0], dtype=np.int32), np.array(bad, dtype=np.uint32), np.zeros((0, 3), dtype=np.uint32), 4)
+        with pytest.raises(H2BError):
+            ev.evaluate_graph(emu, g, [], adv, [], none, *sc, vals, 1)
+
+
+def test_evaluate_graph_many_live_values(emu, oc):
+    # 6 / 12 / 24 / 48 values live at once select the 8 / 16 / 32 / 64-slot kernels; more than 64 is refused
+    from halo2_scaffold_b200 import evaluation as ev
+    from halo2_scaffold_b200._lib import H2BError
+    size = 33
+    adv = [oc.random_fr(5, size)]
+    sc = oc.random_fr(6, 4)
+    vals = oc.random_fr(7, size)
+    none = np.zeros((0, 4), dtype=np.uint64)
+    for n_live in (6, 12, 24, 48):
+        graph, n_const = pc.wide_graph(n_live)
+        g, ga = pc._graph_pair(oc, graph, n_const, n_live)
+        want = oc.evaluate_graph(g, [], adv, [], none, *sc, vals, 1)
+        got = ev.evaluate_graph(emu, ga, [], adv, [], none, *sc, vals, 1)
+        assert (got == want).all(), n_live
+        slots, ops = emu.evaluate_graph_info()
+        assert n_live <= slots <= n_live + 2, (n_live, slots)
+    graph, n_const = pc.wide_graph(70)
+    with pytest.raises(H2BError):
+        ev.evaluate_graph(emu, pc._graph_pair(oc, graph, n_const, 1)[1], [], adv, [], none, *sc, vals, 1)
+
+
+def test_evaluate_graph_scheduling_keeps_few_values_live(emu, oc):
+    # 40 gate polynomials combined by one Horner in y: upstream keeps one intermediate per gate; the depth-first schedule
+    # needs a handful of slots
+    from halo2_scaffold_b200 import evaluation as ev
+    polys, lookups, nf, na = pc.standard_plonk_like(20)
+    E = ev.Evaluator(polys, lookups)
+    size = 64
+    fixed = [oc.random_fr(100 + j, size) for j in range(nf)]
+    advice = [oc.random_fr(300 + j, size) for j in range(na)]
+    inst = [oc.random_fr(500, size)]
+    sc = oc.random_fr(6, 4)
+    none = np.zeros((0, 4), dtype=np.uint64)
+    a = E.custom_gates.arrays()
+    got = ev.evaluate_graph(emu, a, fixed, advice, inst, none, *sc, np.zeros((size, 4), dtype=np.uint64), 4)
+    want = oc.evaluate_graph((a.constants, a.rotations, a.calculations, a.parts, a.n_intermediates), fixed, advice, inst, none, *sc,
+                             np.zeros((size, 4), dtype=np.uint64), 4)
+    assert (got == want).all()
+    slots, ops = emu.evaluate_graph_info()
+    assert E.custom_gates.num_intermediates > 300 and slots <= 8, (E.custom_gates.num_intermediates, slots, ops)
+
+
+def test_evaluate_h_all_three_loops(emu, oc):
+    pc.check_evaluate_h(emu, oc, [(5, 3, 1, 1), (7, 5, 2, 2), (6, 6, 1, 3)])

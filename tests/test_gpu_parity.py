@@ -159,6 +159,29 @@ def test_polynomial_evaluation_and_kate_division(gpu, oc):
     pc.check_poly_eval_and_division(gpu, oc, [1, 2, 17, 256, 257, 65537, (1 << 20) - 1, 1 << 22])
 
 
+def test_evaluate_graph_random_programs(gpu, oc):
+    cases = [(1, 1, 3, 21), (1000, 1, 40, 22), (1 << 12, 4, 150, 23), ((1 << 14) + 77, 2, 300, 24), (1 << 16, 4, 80, 25), (1 << 18, 4, 30, 26),
+             (1 << 15, 8, 600, 27), (300000, 3, 50, 29)]
+    pc.check_evaluate_graph(gpu, oc, cases)
+
+
+def test_evaluate_graph_many_live_values(gpu, oc):
+    from halo2_scaffold_b200 import evaluation as ev
+    size = 5000
+    adv = [oc.random_fr(5, size)]
+    sc = oc.random_fr(6, 4)
+    vals = oc.random_fr(7, size)
+    none = np.zeros((0, 4), dtype=np.uint64)
+    for n_live in (6, 12, 24, 48):
+        graph, n_const = pc.wide_graph(n_live)
+        g, ga = pc._graph_pair(oc, graph, n_const, n_live)
+        assert (ev.evaluate_graph(gpu, ga, [], adv, [], none, *sc, vals, 1) == oc.evaluate_graph(g, [], adv, [], none, *sc, vals, 1)).all(), n_live
+
+
+def test_evaluate_h_all_three_loops(gpu, oc):
+    pc.check_evaluate_h(gpu, oc, [(5, 3, 1, 1), (12, 10, 2, 2), (16, 14, 3, 3), (18, 16, 1, 4)])
+
+
 def test_msm_randomised_shapes(gpu, oc):
     pc.check_msm_random(gpu, oc, examples=25, max_n=40000, spacings=(-1, 0, 8, 12, 14, 16), windows=(0, 0, 0, 2, 4, 7, 8))
 

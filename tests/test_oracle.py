@@ -103,3 +103,27 @@ def test_domain_golden_matches_python_oracle(golden):
     # extended_to_coeff(coeff_to_extended(p)) = p (zero padded)
     back = [o.from_mont(x, o.R_MOD) for x in words_to_ints(g["back"])]
     assert back[:16] == coeff and all(v == 0 for v in back[16:])
+
+
+def test_graph_evaluator_restatement_matches_big_int_walk(oc):
+    """oracle/h2_oracle.cpp's GraphEvaluator::evaluate against the independent big-int interpreter of oracle/bn254.py"""
+    import bn254 as o
+    import parity_cases as pc
+    for seed, size, n_calcs in ((1, 9, 6), (2, 16, 40), (5, 12, 90), (8, 7, 25)):
+        rng = np.random.default_rng(seed)
+        graph, n_const = pc.random_graph(rng, 2, 3, 1, 2, n_calcs, reuse_targets=bool(seed % 3 == 2))
+        g, _ = pc._graph_pair(oc, graph, n_const, seed)
+        cols = [oc.random_fr(seed * 31 + j, size) for j in range(6)]
+        sc = oc.random_fr(seed * 7 + 1, 6)
+        values = oc.random_fr(seed * 7 + 2, size)
+        got = oc.evaluate_graph(g, cols[:2], cols[2:5], cols[5:], sc[:2], *sc[2:], values, 3)
+
+        def ints(a):
+            return [o.from_mont(v, o.R_MOD) for v in oc.words_to_ints(np.ascontiguousarray(a).reshape(-1, 4))]
+        ci = [ints(c) for c in cols]
+        si = ints(sc)
+        vi = ints(values)
+        for idx in range(size):
+            w = o.graph_evaluate_row(ints(g[0]), [int(r) for r in g[1]], g[2].tolist(), g[3].tolist(), g[4], ci[:2], ci[2:5], ci[5:], si[:2],
+                                     si[2], si[3], si[4], si[5], vi[idx], idx, 3, size)
+            assert o.from_mont(oc.words_to_ints(got[idx:idx + 1])[0], o.R_MOD) == w, (seed, idx)
