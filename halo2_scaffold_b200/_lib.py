@@ -36,6 +36,7 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
+    "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write",
     "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
 
@@ -149,6 +150,10 @@ class Lib:
         L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
         L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
+        L.h2b_g1_decode_dev.argtypes = [i32, vp, sz, i32, vp, ctypes.POINTER(u64), vp]
+        L.h2b_g1_encode_dev.argtypes = [i32, vp, sz, vp, vp]
+        L.h2b_srs_read.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(u32), vp, vp, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.h2b_srs_write.argtypes = [ctypes.c_char_p, i32, u32, vp, vp, vp, sz]
         L.h2b_evaluate_graph_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp]
         L.h2b_evaluate_h_permutation_dev.argtypes = [i32, vp, u32, i32, vp, u32, vp, vp, u32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_evaluate_h_lookup_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp, vp, vp, vp, vp, vp, vp]
@@ -373,6 +378,63 @@ class Lib:
             self.dev_free(device, d)
             self.dev_free(device, d_q)
         return q
+
+    # ---- SRS on-disk format ---------------------------------------------------------------------------
+    def g1_decode(self, data: np.ndarray, fmt: int, device: int = 0) -> np.ndarray:
+        """encoded points ((n, 32) uint8 compressed or (n, 64) raw) -> (n, 8) uint64 affine; raises H2BError on an invalid point"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        ps = 32 if fmt == 0 else 64
+        n = data.size // ps
+        out = np.empty((n, 8), dtype=np.uint64)
+        d_in, d_out = self.dev_alloc(device, max(n, 1) * ps), self.dev_alloc(device, max(n, 1) * 64)
+        try:
+            if n:
+                self.h2d(device, d_in, data)
+            bad = ctypes.c_uint64(0)
+            self.check(self.L.h2b_g1_decode_dev(device, d_in, n, fmt, d_out, ctypes.byref(bad), 0))
+            if n:
+                self.d2h(device, out, d_out)
+        finally:
+            self.dev_free(device, d_in)
+            self.dev_free(device, d_out)
+        return out
+
+    def g1_encode(self, aff: np.ndarray, device: int = 0) -> np.ndarray:
+        """(n, 8) uint64 affine -> (n, 32) uint8 compressed (G1Affine::to_bytes)"""
+        aff = _u64(aff).reshape(-1, 8)
+        n = aff.shape[0]
+        out = np.empty((n, 32), dtype=np.uint8)
+        d_in, d_out = self.dev_alloc(device, max(n, 1) * 64), self.dev_alloc(device, max(n, 1) * 32)
+        try:
+            if n:
+                self.h2d(device, d_in, aff)
+                self.check(self.L.h2b_g1_encode_dev(device, d_in, n, d_out, 0))
+                self.dev_sync(device)
+                self.d2h(device, out, d_out)
+        finally:
+            self.dev_free(device, d_in)
+            self.dev_free(device, d_out)
+        return out
+
+    def srs_read(self, path: str, fmt: int, want_host: bool = True, register: bool = True):
+        """-> dict(k, g, g_lagrange, g2_bytes, handle_g, handle_g_lagrange); see h2b_srs_read"""
+        with open(path, "rb") as f:
+            k0 = int.from_bytes(f.read(4), "little")
+        n = 1 << min(k0, 28)
+        g = np.empty((n, 8), dtype=np.uint64) if want_host else None
+        gl = np.empty((n, 8), dtype=np.uint64) if want_host else None
+        g2 = np.zeros(256, dtype=np.uint8)
+        k, g2_len, hg, hl = ctypes.c_uint32(0), ctypes.c_size_t(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self.check(self.L.h2b_srs_read(path.encode(), fmt, ctypes.byref(k), g.ctypes.data if want_host else None, gl.ctypes.data if want_host else None,
+                                       g2.ctypes.data, g2.size, ctypes.byref(g2_len), ctypes.byref(hg) if register else None,
+                                       ctypes.byref(hl) if register else None))
+        return dict(k=k.value, g=g, g_lagrange=gl, g2_bytes=bytes(g2[:g2_len.value]), handle_g=hg.value, handle_g_lagrange=hl.value)
+
+    def srs_write(self, path: str, fmt: int, k: int, g: np.ndarray, g_lagrange: np.ndarray, g2_bytes: bytes):
+        g, g_lagrange = _u64(g).reshape(-1, 8), _u64(g_lagrange).reshape(-1, 8)
+        assert g.shape[0] == 1 << k and g_lagrange.shape[0] == 1 << k
+        buf = np.frombuffer(g2_bytes, dtype=np.uint8).copy()
+        self.check(self.L.h2b_srs_write(path.encode(), fmt, k, g.ctypes.data, g_lagrange.ctypes.data, buf.ctypes.data if buf.size else None, buf.size))
 
     # ---- quotient evaluation (evaluate_h) on device-resident extended-coset columns ------------------
     def evaluate_graph_dev(self, device: int, graph: GraphArrays, cols: EvalColumns, d_values: int, size: int, rot_scale: int, stream: int = 0):

@@ -405,6 +405,8 @@ void h2b_shutdown(void) {
         c->msm_out.release();
         c->scan_scratch.release();
         evaluate_release(*c);
+        c->srs_status.release();
+        c->srs_io.release();
         for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
         c->copy_events.clear();
         if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); c->copy_stream = nullptr; }
@@ -706,6 +708,127 @@ int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64
     H2B_TRY(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     return fr_kate_division_run(*c, d_a, n, b, d_q, (cudaStream_t)stream);
+}
+
+// ---- SRS on-disk format -----------------------------------------------------------------------------
+int h2b_g1_decode_dev(int device, const void* d_bytes, size_t n, int format, void* d_out_affine, uint64_t* first_invalid, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return g1_decode_run(*c, d_bytes, n, format, d_out_affine, first_invalid, (cudaStream_t)stream);
+}
+
+int h2b_g1_encode_dev(int device, const void* d_affine, size_t n, void* d_out_bytes, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return g1_encode_run(*c, d_affine, n, d_out_bytes, (cudaStream_t)stream);
+}
+
+namespace {
+struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
+}
+
+// one vector of the file: bytes -> device 0 -> decoded points; optionally downloaded and / or registered on every device
+static int srs_read_vector(FILE* f, const char* what, size_t n, int format, uint64_t* host_out, uint64_t* handle) {
+    const size_t ps = format == H2B_SERDE_PROCESSED ? 32 : 64;
+    std::vector<unsigned char> raw(n * ps);
+    if (fread(raw.data(), 1, raw.size(), f) != raw.size()) { set_error("h2b_srs_read: file ends inside %s", what); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> glk(G.mu);
+    DeviceCtx& c = *G.devs[0];
+    void* d_pts = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        H2B_CUDA(cudaSetDevice(c.device));
+        H2B_TRY(c.srs_io.reserve(raw.size()));
+        cudaError_t e = cudaMalloc(&d_pts, n * 64 + 64);
+        if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes for %s failed: %s", n * 64, what, cudaGetErrorString(e)); return H2B_ERR_OOM; }
+        int rc = host_upload(c, c.srs_io.p, raw.data(), raw.size(), c.stream);
+        uint64_t bad = 0;
+        if (!rc) rc = g1_decode_run(c, c.srs_io.p, n, format, d_pts, &bad, c.stream);
+        if (!rc && host_out) rc = host_download(c, host_out, d_pts, n * 64, c.stream);
+        if (!rc && cudaStreamSynchronize(c.stream) != cudaSuccess) { set_error("h2b_srs_read: %s", cudaGetErrorString(cudaGetLastError())); rc = H2B_ERR_CUDA; }
+        if (rc || !handle) { cudaFree(d_pts); if (rc) set_error("%s: %s", what, std::string(get_error()).c_str()); return rc; }
+    }
+    std::unique_ptr<BaseSet> bs(new BaseSet());
+    bs->handle = G.next_handle++;
+    bs->host_ptr = nullptr;
+    bs->last_use = ++G.use_counter;
+    bs->n = n;
+    bs->dev.assign(G.devs.size(), nullptr);
+    bs->dev[0] = d_pts;
+    for (size_t d = 1; d < G.devs.size(); ++d) {        // the other devices take a peer copy of the decoded points
+        std::lock_guard<std::mutex> lk(G.devs[d]->mu);
+        cudaError_t e = cudaSetDevice(G.devs[d]->device);
+        if (e == cudaSuccess) e = cudaMalloc(&bs->dev[d], n * 64 + 64);
+        if (e == cudaSuccess) e = cudaMemcpyPeer(bs->dev[d], G.devs[d]->device, d_pts, c.device, n * 64);
+        if (e != cudaSuccess) { set_error("h2b_srs_read: copy of %s to device %zu: %s", what, d, cudaGetErrorString(e)); free_set(*bs); return H2B_ERR_CUDA; }
+    }
+    int rc = build_tables(*bs);
+    if (rc != H2B_OK) { free_set(*bs); return rc; }
+    *handle = bs->handle;
+    G.sets.push_back(std::move(bs));
+    return H2B_OK;
+}
+
+int h2b_srs_read(const char* path, int format, uint32_t* k, uint64_t* out_g, uint64_t* out_g_lagrange, uint8_t* g2_bytes, size_t g2_cap, size_t* g2_len,
+                 uint64_t* handle_g, uint64_t* handle_g_lagrange) {
+    H2B_TRY(require_init());
+    if (!path || !k) { set_error("h2b_srs_read: null path / k"); return H2B_ERR_BAD_ARGUMENT; }
+    if (format < H2B_SERDE_PROCESSED || format > H2B_SERDE_RAW_BYTES_UNCHECKED) { set_error("h2b_srs_read: unknown format %d", format); return H2B_ERR_BAD_ARGUMENT; }
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) { set_error("h2b_srs_read: cannot open %s", path); return H2B_ERR_BAD_ARGUMENT; }
+    unsigned char kb[4];
+    if (fread(kb, 1, 4, fc.f) != 4) { set_error("h2b_srs_read: %s is empty", path); return H2B_ERR_BAD_ARGUMENT; }
+    const uint32_t kk = (uint32_t)kb[0] | ((uint32_t)kb[1] << 8) | ((uint32_t)kb[2] << 16) | ((uint32_t)kb[3] << 24);
+    if (kk > 28) { set_error("h2b_srs_read: k = %u in %s (at most 28)", kk, path); return H2B_ERR_BAD_ARGUMENT; }
+    *k = kk;
+    const size_t n = (size_t)1 << kk;
+    uint64_t hg = 0;
+    H2B_TRY(srs_read_vector(fc.f, "g", n, format, out_g, handle_g ? &hg : nullptr));
+    int rc = srs_read_vector(fc.f, "g_lagrange", n, format, out_g_lagrange, handle_g_lagrange);
+    if (rc != H2B_OK) { if (handle_g) h2b_unregister_bases(hg); return rc; }
+    if (handle_g) *handle_g = hg;
+    const size_t want = format == H2B_SERDE_PROCESSED ? 128 : 256;      // g2 | s_g2
+    std::vector<unsigned char> tail(want);
+    const size_t got = fread(tail.data(), 1, want, fc.f);
+    if (got != want) {
+        if (handle_g) h2b_unregister_bases(hg);
+        if (handle_g_lagrange) h2b_unregister_bases(*handle_g_lagrange);
+        set_error("h2b_srs_read: %s ends inside the G2 section", path);
+        return H2B_ERR_BAD_ARGUMENT;
+    }
+    if (g2_len) *g2_len = want;
+    if (g2_bytes) memcpy(g2_bytes, tail.data(), want < g2_cap ? want : g2_cap);
+    return H2B_OK;
+}
+
+int h2b_srs_write(const char* path, int format, uint32_t k, const uint64_t* g, const uint64_t* g_lagrange, const uint8_t* g2_bytes, size_t g2_len) {
+    H2B_TRY(require_init());
+    if (!path || !g || !g_lagrange || (g2_len && !g2_bytes) || k > 28) { set_error("h2b_srs_write: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
+    if (format < H2B_SERDE_PROCESSED || format > H2B_SERDE_RAW_BYTES_UNCHECKED) { set_error("h2b_srs_write: unknown format %d", format); return H2B_ERR_BAD_ARGUMENT; }
+    FileCloser fc{fopen(path, "wb")};
+    if (!fc.f) { set_error("h2b_srs_write: cannot create %s", path); return H2B_ERR_BAD_ARGUMENT; }
+    const unsigned char kb[4] = {(unsigned char)k, (unsigned char)(k >> 8), (unsigned char)(k >> 16), (unsigned char)(k >> 24)};
+    const size_t n = (size_t)1 << k;
+    bool ok = fwrite(kb, 1, 4, fc.f) == 4;
+    for (const uint64_t* v : {g, g_lagrange}) {
+        if (!ok) break;
+        if (format != H2B_SERDE_PROCESSED) { ok = fwrite(v, 64, n, fc.f) == n; continue; }
+        DeviceCtx& c = *G.devs[0];
+        std::lock_guard<std::mutex> lk(c.mu);
+        H2B_CUDA(cudaSetDevice(c.device));
+        H2B_TRY(c.srs_io.reserve(n * 96));
+        std::vector<unsigned char> enc(n * 32);
+        H2B_TRY(host_upload(c, c.srs_io.p, v, n * 64, c.stream));
+        H2B_TRY(g1_encode_run(c, c.srs_io.p, n, (char*)c.srs_io.p + n * 64, c.stream));
+        H2B_TRY(host_download(c, enc.data(), (char*)c.srs_io.p + n * 64, n * 32, c.stream));
+        H2B_CUDA(cudaStreamSynchronize(c.stream));
+        ok = fwrite(enc.data(), 32, n, fc.f) == n;
+    }
+    if (ok && g2_len) ok = fwrite(g2_bytes, 1, g2_len, fc.f) == g2_len;
+    if (!ok) { set_error("h2b_srs_write: short write to %s", path); return H2B_ERR_BAD_ARGUMENT; }
+    return H2B_OK;
 }
 
 // ---- quotient evaluation -----------------------------------------------------------------------

@@ -12,18 +12,48 @@ import numpy as np
 from . import _lib
 
 
+class SerdeFormat:
+    """[UP] halo2_proofs::SerdeFormat"""
+    Processed, RawBytes, RawBytesUnchecked = 0, 1, 2
+
+
 class ParamsKZG:
-    def __init__(self, k: int, g: np.ndarray, g_lagrange: np.ndarray, lib=None):
+    def __init__(self, k: int, g: np.ndarray, g_lagrange: np.ndarray, lib=None, g2_bytes: bytes = b"", _handles=None):
         self.lib = lib or _lib.load()
         if self.lib.device_count() == 0:
             self.lib.init(0)
         self.k = k
         self.n = 1 << k
-        g = np.ascontiguousarray(g, dtype=np.uint64).reshape(-1, 8)
-        g_lagrange = np.ascontiguousarray(g_lagrange, dtype=np.uint64).reshape(-1, 8)
-        assert g.shape[0] == self.n and g_lagrange.shape[0] == self.n
-        self._g = self.lib.register_bases(g)
-        self._g_lagrange = self.lib.register_bases(g_lagrange)
+        self.g = np.ascontiguousarray(g, dtype=np.uint64).reshape(-1, 8)
+        self.g_lagrange = np.ascontiguousarray(g_lagrange, dtype=np.uint64).reshape(-1, 8)
+        self.g2_bytes = g2_bytes                       # g2 | s_g2 as stored; G2 arithmetic is the verifier's (host) business
+        assert self.g.shape[0] == self.n and self.g_lagrange.shape[0] == self.n
+        if _handles:
+            self._g, self._g_lagrange = _handles
+        else:
+            self._g = self.lib.register_bases(self.g)
+            self._g_lagrange = self.lib.register_bases(self.g_lagrange)
+
+    @classmethod
+    def read_custom(cls, path: str, fmt: int, lib=None) -> "ParamsKZG":
+        """ParamsKZG::read_custom: the file is decoded on the device and both vectors stay resident there as registered
+        base sets (no second upload); the host copies are what `get_g()` and the verifier read"""
+        lib = lib or _lib.load()
+        if lib.device_count() == 0:
+            lib.init(0)
+        r = lib.srs_read(path, fmt)
+        return cls(r["k"], r["g"], r["g_lagrange"], lib, r["g2_bytes"], (r["handle_g"], r["handle_g_lagrange"]))
+
+    @classmethod
+    def read(cls, path: str, lib=None) -> "ParamsKZG":
+        """ParamsKZG::read = read_custom(reader, SerdeFormat::RawBytes)"""
+        return cls.read_custom(path, SerdeFormat.RawBytes, lib)
+
+    def write_custom(self, path: str, fmt: int):
+        self.lib.srs_write(path, fmt, self.k, self.g, self.g_lagrange, self.g2_bytes)
+
+    def write(self, path: str):
+        self.write_custom(path, SerdeFormat.RawBytes)
 
     def commit(self, poly: np.ndarray) -> np.ndarray:
         """best_multiexp(poly, g[..poly.len()]) -> G1 Jacobian"""

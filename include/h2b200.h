@@ -198,6 +198,32 @@ int h2b_evaluate_h_lookup_dev(int device, const h2b_graph* graph, const h2b_eval
 /* slots (live values per row) and micro-operations the last compiled graph of this thread needed -- diagnostics / tests */
 int h2b_evaluate_graph_info(uint32_t* slots, uint32_t* micro_ops);
 
+/* ---- SRS on-disk format ------------------------------------------------------------------
+ * [UP] halo2_proofs/src/poly/kzg/commitment.rs ParamsKZG::{read_custom, write_custom} / halo2_proofs::SerdeFormat and
+ * [UP] halo2curves 0.3.x GroupEncoding / SerdeObject for G1Affine; the reference loads params/kzg_bn254_{k}.srs at
+ * src/scaffold.rs:119,174,271.  File: k (u32 LE) | g[2^k] | g_lagrange[2^k] | g2 | s_g2. */
+enum h2b_serde_format {
+    H2B_SERDE_PROCESSED = 0,            /* compressed: 32 B = canonical LE x, (y & 1) << 7 in byte 31, all-zero = identity */
+    H2B_SERDE_RAW_BYTES = 1,            /* x | y Montgomery limbs (64 B), range- and curve-checked */
+    H2B_SERDE_RAW_BYTES_UNCHECKED = 2   /* the same bytes, unchecked */
+};
+/* n encoded points (device) -> n affine points x | y Montgomery (device; may alias the input for the raw formats).
+ * With first_invalid != NULL the call synchronises the stream, stores the index of the first invalid encoding (or
+ * UINT64_MAX) and fails with H2B_ERR_BAD_ARGUMENT if there is one (upstream unwraps / returns io::Error); with NULL it
+ * stays asynchronous and invalid points decode to the identity. */
+int h2b_g1_decode_dev(int device, const void* d_bytes, size_t n, int format, void* d_out_affine, uint64_t* first_invalid, void* stream);
+/* n affine points (device) -> n x 32 compressed bytes (device): G1Affine::to_bytes */
+int h2b_g1_encode_dev(int device, const void* d_affine, size_t n, void* d_out_bytes, void* stream);
+/* ParamsKZG::read_custom: reads the file, decodes g and g_lagrange on the device and leaves both resident as registered
+ * base sets (window tables built, every device of h2b_init) -> *handle_g, *handle_g_lagrange for
+ * h2b_msm_bn254_g1_registered (commit / commit_lagrange).  out_g / out_g_lagrange (2^k x 8 words each, may be NULL) receive
+ * the decoded points for the host-side ParamsKZG; the G2 section (g2 | s_g2, 2 x 64 B compressed or 2 x 128 B raw) is
+ * returned as bytes for the host to parse.  Either handle pointer may be NULL (that vector is then only decoded). */
+int h2b_srs_read(const char* path, int format, uint32_t* k, uint64_t* out_g, uint64_t* out_g_lagrange, uint8_t* g2_bytes, size_t g2_cap,
+                 size_t* g2_len, uint64_t* handle_g, uint64_t* handle_g_lagrange);
+/* ParamsKZG::write_custom for host arrays (Processed: compressed on the device) */
+int h2b_srs_write(const char* path, int format, uint32_t k, const uint64_t* g, const uint64_t* g_lagrange, const uint8_t* g2_bytes, size_t g2_len);
+
 /* ---- raw device memory helpers (so that non-CUDA hosts -- ctypes, Rust -- can hold device buffers) --- */
 int h2b_dev_alloc(int device, size_t bytes, void** out);
 int h2b_dev_free(int device, void* p);

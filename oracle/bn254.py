@@ -429,3 +429,83 @@ def graph_evaluate_row(constants, rotations, calcs, parts, n_intermediates, fixe
         inter[target] = v % R_MOD
         last = target
     return inter[last] if last is not None else 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SRS on-disk format ([UP] halo2_proofs/src/poly/kzg/commitment.rs ParamsKZG::{read_custom, write_custom};
+# [UP] halo2curves 0.3.x GroupEncoding / SerdeObject for G1Affine).  Points are canonical (x, y) or None.
+# File: k (u32 LE) | g[2^k] | g_lagrange[2^k] | g2 | s_g2 (the G2 section is carried as opaque bytes).
+# ---------------------------------------------------------------------------------------------------------
+SERDE_PROCESSED, SERDE_RAW_BYTES, SERDE_RAW_BYTES_UNCHECKED = 0, 1, 2
+
+
+def g1_to_bytes(P) -> bytes:
+    """G1Affine::to_bytes: canonical little-endian x, (y & 1) << 7 in byte 31; the identity is all-zero"""
+    if P is None:
+        return bytes(32)
+    b = bytearray(P[0].to_bytes(32, "little"))
+    b[31] |= (P[1] & 1) << 7
+    return bytes(b)
+
+
+def g1_from_bytes(b: bytes):
+    """G1Affine::from_bytes -> point, None for the identity; raises ValueError on an invalid encoding"""
+    assert len(b) == 32
+    ysign = b[31] >> 7
+    x = int.from_bytes(b, "little") & ((1 << 255) - 1)
+    if x >= P_MOD:
+        raise ValueError("x is not canonical")
+    if x == 0 and not ysign:
+        return None
+    rhs = (x * x * x + CURVE_B) % P_MOD
+    y = pow(rhs, (P_MOD + 1) // 4, P_MOD)          # p = 3 mod 4
+    if y * y % P_MOD != rhs:
+        raise ValueError("x^3 + 3 is not a square")
+    if (y & 1) != ysign:
+        y = (-y) % P_MOD
+    return (x, y)
+
+
+def g1_write_raw(P) -> bytes:
+    """SerdeObject::write_raw: the Montgomery limbs of x and y as they sit in memory; identity = (0, 0)"""
+    if P is None:
+        return bytes(64)
+    return to_mont(P[0], P_MOD).to_bytes(32, "little") + to_mont(P[1], P_MOD).to_bytes(32, "little")
+
+
+def g1_read_raw(b: bytes, checked: bool = True):
+    assert len(b) == 64
+    xm, ym = int.from_bytes(b[:32], "little"), int.from_bytes(b[32:], "little")
+    if checked and (xm >= P_MOD or ym >= P_MOD):
+        raise ValueError("limbs are not below the modulus")
+    if xm == 0 and ym == 0:
+        return None
+    P = (from_mont(xm, P_MOD), from_mont(ym, P_MOD))
+    if checked and not is_on_curve(P):
+        raise ValueError("not on the curve")
+    return P
+
+
+def srs_write(path, k, g, g_lagrange, g2_bytes: bytes, fmt: int = SERDE_RAW_BYTES):
+    enc = g1_to_bytes if fmt == SERDE_PROCESSED else g1_write_raw
+    with open(path, "wb") as f:
+        f.write(int(k).to_bytes(4, "little"))
+        for v in (g, g_lagrange):
+            assert len(v) == 1 << k
+            f.write(b"".join(enc(P) for P in v))
+        f.write(g2_bytes)
+
+
+def srs_read(path, fmt: int = SERDE_RAW_BYTES):
+    with open(path, "rb") as f:
+        k = int.from_bytes(f.read(4), "little")
+        n, ps = 1 << k, 32 if fmt == SERDE_PROCESSED else 64
+        out = []
+        for _ in range(2):
+            raw = f.read(n * ps)
+            assert len(raw) == n * ps
+            if fmt == SERDE_PROCESSED:
+                out.append([g1_from_bytes(raw[i * ps:(i + 1) * ps]) for i in range(n)])
+            else:
+                out.append([g1_read_raw(raw[i * ps:(i + 1) * ps], fmt == SERDE_RAW_BYTES) for i in range(n)])
+        return k, out[0], out[1], f.read()

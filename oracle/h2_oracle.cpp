@@ -550,6 +550,56 @@ void orc_evaluate_h_permutation(u64* values, uint32_t size, int32_t rot_scale, c
 }  // extern "C"
 
 extern "C" {
+// ---------------------------------------------------------------------------------
+// SRS point encodings ([UP] halo2curves 0.3.x GroupEncoding::{to_bytes, from_bytes} for G1Affine; upstream's
+// ParamsKZG::read_custom decompresses with `parallelize`, here std::thread).  Returns the index of the first invalid
+// encoding, or n.
+// ---------------------------------------------------------------------------------
+size_t orc_g1_from_bytes(const unsigned char* bytes, size_t n, int threads, u64* out_aff) {
+    static const u64 E[4] = {0x4f082305b61f3f52ULL, 0x65e05aa45a1c72a3ULL, 0x6e14116da0605617ULL, 0x0c19139cb84c680aULL};   // (p + 1) / 4
+    if (threads < 1) threads = 1;
+    std::vector<size_t> bad(threads, n);
+    std::vector<std::thread> th;
+    size_t per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        size_t lo = t * per, hi = std::min(n, lo + per);
+        if (lo >= hi) break;
+        th.emplace_back([=, &bad] {
+            const Fq three = Fq::one() + Fq::one() + Fq::one();
+            for (size_t i = lo; i < hi; ++i) {
+                Fq x; memcpy(x.l, bytes + 32 * i, 32);
+                const bool ysign = (x.l[3] >> 63) & 1;
+                x.l[3] &= ~(1ULL << 63);
+                G1Affine p; p.x = Fq::zero(); p.y = Fq::zero();
+                bool ok = !Fq::geq_mod(x.l);
+                if (ok && !(x.is_zero() && !ysign)) {
+                    Fq xm = x.to_mont();
+                    Fq rhs = xm.sqr() * xm + three;
+                    Fq y = rhs.pow(E);
+                    ok = y.sqr() == rhs;
+                    if (ok) {
+                        if (((y.from_mont().l[0] & 1) != 0) != ysign) y = y.neg();
+                        p.x = xm; p.y = y;
+                    }
+                }
+                if (!ok && bad[t] == n) bad[t] = i;
+                memcpy(out_aff + 8 * i, &p, 64);
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    size_t first = n;
+    for (size_t b : bad) first = std::min(first, b);
+    return first;
+}
+void orc_g1_to_bytes(const u64* aff, size_t n, unsigned char* out) {
+    for (size_t i = 0; i < n; ++i) {
+        Fq x, y; memcpy(x.l, aff + 8 * i, 32); memcpy(y.l, aff + 8 * i + 4, 32);
+        Fq c = Fq::zero();
+        if (!(x.is_zero() && y.is_zero())) { c = x.from_mont(); c.l[3] |= (y.from_mont().l[0] & 1) << 63; }
+        memcpy(out + 32 * i, c.l, 32);
+    }
+}
 // uniform scalars in Montgomery form: 512-bit SplitMix64 draw reduced mod r (same stream as oracle/bn254.py random_fr)
 void orc_random_fr(u64 seed, size_t n, u64* out) {
     Fr two64; two64.l[0] = 0; two64.l[1] = 1; two64.l[2] = two64.l[3] = 0; two64 = two64.to_mont();

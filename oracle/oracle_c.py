@@ -44,6 +44,9 @@ def lib():
         L.orc_fr_eval_polynomial.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_fr_kate_division.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_random_fr.argtypes = [ctypes.c_uint64, ctypes.c_size_t, u64p]
+        L.orc_g1_from_bytes.argtypes = [u64p, ctypes.c_size_t, ctypes.c_int, u64p]
+        L.orc_g1_from_bytes.restype = ctypes.c_size_t
+        L.orc_g1_to_bytes.argtypes = [u64p, ctypes.c_size_t, u64p]
         u32, i32 = ctypes.c_uint32, ctypes.c_int32
         graph = [u64p, u32, u64p, u32, u64p, u32, u64p, u32, u32]           # constants, rotations, calculations, parts, n_intermediates
         columns = [u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p]          # fixed, advice, instance, challenges, beta, gamma, theta, y
@@ -144,6 +147,22 @@ def fr_kate_division(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     if a.shape[0] > 1:
         lib().orc_fr_kate_division(_p(a), a.shape[0], _p(b), _p(q))
     return q
+
+
+# ---- SRS point encodings ([UP] halo2curves GroupEncoding for G1Affine) -------------------------------------------------
+def g1_from_bytes(b: np.ndarray, threads: int = 0):
+    """(n, 32) uint8 compressed points -> ((n, 8) uint64 affine Montgomery, index of the first invalid encoding or n)"""
+    b = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1, 32)
+    out = np.empty((b.shape[0], 8), dtype=np.uint64)
+    first = lib().orc_g1_from_bytes(b.ctypes.data, b.shape[0], threads or hardware_threads(), out.ctypes.data)
+    return out, int(first)
+
+
+def g1_to_bytes(aff: np.ndarray) -> np.ndarray:
+    aff = np.ascontiguousarray(aff, dtype=np.uint64).reshape(-1, 8)
+    out = np.empty((aff.shape[0], 32), dtype=np.uint8)
+    lib().orc_g1_to_bytes(aff.ctypes.data, aff.shape[0], out.ctypes.data)
+    return out
 
 
 # ---- quotient evaluation ([UP] halo2_proofs/src/plonk/evaluation.rs) ------------------------------------------------

@@ -374,3 +374,77 @@ def check_evaluate_h(L, oc, cases):
         want = oc.evaluate_h_lookup(tup(E.lookups[0]), fixed, advice, instance, ch, beta, gamma, theta, y, want, rot_scale, lks[0]["product_coset"],
                                     lks[0]["permuted_input_coset"], lks[0]["permuted_table_coset"], l0, l_last, l_active)
         assert (got == want).all(), ("evaluate_h", ek, k, groups, seed)
+
+
+# ---- SRS on-disk format ----------------------------------------------------------------------------------------------------
+def check_g1_codec(L, oc, n, seed=5):
+    """G1Affine::{to_bytes, from_bytes} and the raw formats against the oracle, identity and invalid encodings included"""
+    from halo2_scaffold_b200._lib import H2BError
+    P = oc.gen_points(seed, n)
+    if n > 3:
+        P[2] = 0                                                   # the identity
+    want_bytes = oc.g1_to_bytes(P)
+    assert (L.g1_encode(P) == want_bytes).all()
+    assert (L.g1_decode(want_bytes, 0) == P).all()
+    dec, first = oc.g1_from_bytes(want_bytes)
+    assert first == n and (dec == P).all()
+    raw = P.view(np.uint8).reshape(n, 64)
+    assert (L.g1_decode(raw, 1) == P).all() and (L.g1_decode(raw, 2) == P).all()
+    if n > 8:
+        # x with no square root of x^3 + 3, a non-canonical x, and a raw point off the curve -> refused at the right index
+        bad = want_bytes.copy()
+        x = 4
+        while pow(x ** 3 + 3, (o.P_MOD - 1) // 2, o.P_MOD) == 1:
+            x += 1
+        bad[5] = np.frombuffer(x.to_bytes(32, "little"), dtype=np.uint8)
+        bad[7] = np.frombuffer((o.P_MOD + 1).to_bytes(32, "little"), dtype=np.uint8)
+        assert oc.g1_from_bytes(bad)[1] == 5
+        try:
+            L.g1_decode(bad, 0)
+            raise AssertionError("invalid encoding accepted")
+        except H2BError as e:
+            assert "point 5" in str(e)
+        off = raw.copy()
+        off[6, 0] ^= 1
+        try:
+            L.g1_decode(off, 1)
+            raise AssertionError("off-curve point accepted")
+        except H2BError as e:
+            assert "point 6" in str(e)
+        assert (L.g1_decode(off, 2).view(np.uint8).reshape(n, 64) == off).all()         # unchecked: taken as is
+
+
+def check_srs_file_round_trip(L, oc, tmp_path, k, seed=3):
+    """ParamsKZG::write_custom -> read_custom in all three formats: same points, resident base sets that commit correctly;
+    and the file bytes equal the big-int writer's (oracle/bn254.py) for small k"""
+    import halo2_scaffold_b200 as h2
+    from halo2_scaffold_b200.kzg import SerdeFormat
+    n = 1 << k
+    g, gl = oc.gen_points(seed, n), oc.gen_points(seed + 1, n)
+    g2 = bytes(range(256))
+    params = h2.ParamsKZG(k, g, gl, lib=L, g2_bytes=g2)
+    scalars = oc.random_fr(seed + 2, n)
+    want_c, want_l = affine_of(oc, oc.best_multiexp(scalars, g)), affine_of(oc, oc.best_multiexp(scalars, gl))
+    for fmt in (SerdeFormat.Processed, SerdeFormat.RawBytes, SerdeFormat.RawBytesUnchecked):
+        path = str(tmp_path / ("kzg_bn254_%d_%d.srs" % (k, fmt)))
+        g2f = g2[:128] if fmt == SerdeFormat.Processed else g2
+        params.g2_bytes = g2f
+        params.write_custom(path, fmt)
+        if k <= 6:
+            def pts(w):
+                v = oc.words_to_ints(np.ascontiguousarray(w).reshape(-1, 4))
+                return [None if (v[2 * i] == 0 and v[2 * i + 1] == 0) else (o.from_mont(v[2 * i], o.P_MOD), o.from_mont(v[2 * i + 1], o.P_MOD))
+                        for i in range(len(v) // 2)]
+            ref = str(tmp_path / "ref.srs")
+            o.srs_write(ref, k, pts(g), pts(gl), g2f, fmt)
+            assert open(ref, "rb").read() == open(path, "rb").read(), fmt
+            kk, rg, rgl, rg2 = o.srs_read(path, fmt)
+            assert kk == k and rg == pts(g) and rgl == pts(gl) and rg2 == g2f
+        back = h2.ParamsKZG.read_custom(path, fmt, lib=L)
+        try:
+            assert back.k == k and (back.g == g).all() and (back.g_lagrange == gl).all() and back.g2_bytes == g2f
+            assert (affine_of(oc, back.commit(scalars)) == want_c).all(), fmt
+            assert (affine_of(oc, back.commit_lagrange(scalars)) == want_l).all(), fmt
+        finally:
+            back.close()
+    params.close()

@@ -356,3 +356,24 @@ def test_evaluate_graph_scheduling_keeps_few_values_live(emu, oc):
 
 def test_evaluate_h_all_three_loops(emu, oc):
     pc.check_evaluate_h(emu, oc, [(5, 3, 1, 1), (7, 5, 2, 2), (6, 6, 1, 3)])
+
+
+def test_g1_point_codec(emu, oc):
+    for n in (1, 2, 33, 300):
+        pc.check_g1_codec(emu, oc, n)
+
+
+def test_srs_file_round_trip(emu, oc, tmp_path):
+    pc.check_srs_file_round_trip(emu, oc, tmp_path, 4)
+    pc.check_srs_file_round_trip(emu, oc, tmp_path, 7)
+
+
+def test_srs_reader_rejects_bad_files(emu, oc, tmp_path):
+    from halo2_scaffold_b200._lib import H2BError
+    p = tmp_path / "short.srs"
+    for content in (b"", (3).to_bytes(4, "little") + bytes(100), (40).to_bytes(4, "little"), (2).to_bytes(4, "little") + bytes(2 * 4 * 64 + 10)):
+        p.write_bytes(content)
+        with pytest.raises(H2BError):
+            emu.srs_read(str(p), 1)
+    with pytest.raises((H2BError, FileNotFoundError)):
+        emu.srs_read(str(tmp_path / "missing.srs"), 1)

@@ -159,6 +159,16 @@ def test_polynomial_evaluation_and_kate_division(gpu, oc):
     pc.check_poly_eval_and_division(gpu, oc, [1, 2, 17, 256, 257, 65537, (1 << 20) - 1, 1 << 22])
 
 
+def test_g1_point_codec(gpu, oc):
+    for n in (1, 33, 5000, 1 << 16):
+        pc.check_g1_codec(gpu, oc, n)
+
+
+def test_srs_file_round_trip(gpu, oc, tmp_path):
+    pc.check_srs_file_round_trip(gpu, oc, tmp_path, 5)
+    pc.check_srs_file_round_trip(gpu, oc, tmp_path, 14)
+
+
 def test_evaluate_graph_random_programs(gpu, oc):
     cases = [(1, 1, 3, 21), (1000, 1, 40, 22), (1 << 12, 4, 150, 23), ((1 << 14) + 77, 2, 300, 24), (1 << 16, 4, 80, 25), (1 << 18, 4, 30, 26),
              (1 << 15, 8, 600, 27), (300000, 3, 50, 29)]

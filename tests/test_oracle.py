@@ -1,5 +1,6 @@
 """CPU: the oracle itself -- big-int Python vs external anchors, C++ restatement vs Python, both vs golden fixtures."""
 import numpy as np
+import pytest
 
 import bn254 as o
 
@@ -127,3 +128,28 @@ def test_graph_evaluator_restatement_matches_big_int_walk(oc):
             w = o.graph_evaluate_row(ints(g[0]), [int(r) for r in g[1]], g[2].tolist(), g[3].tolist(), g[4], ci[:2], ci[2:5], ci[5:], si[:2],
                                      si[2], si[3], si[4], si[5], vi[idx], idx, 3, size)
             assert o.from_mont(oc.words_to_ints(got[idx:idx + 1])[0], o.R_MOD) == w, (seed, idx)
+
+
+def test_g1_encoding_anchors(oc):
+    """G1Affine::to_bytes / from_bytes of the restatements on the EIP-196 anchors: G = (1, 2) and 2G"""
+    import bn254 as o
+    G = (1, 2)
+    G2 = o.g1_add(G, G)
+    assert G2 == (1368015179489954701390400359078579693043519447331113978918064868415326638035,
+                  9918110051302171585080402603319702774565515993150576347155970296011118125764)
+    assert o.g1_to_bytes(G) == bytes([1] + [0] * 31) and o.g1_to_bytes(None) == bytes(32)
+    b2 = bytearray(G2[0].to_bytes(32, "little"))
+    b2[31] |= (G2[1] & 1) << 7
+    assert o.g1_to_bytes(G2) == bytes(b2)
+    for P in (G, G2, o.g1_neg(G), o.g1_neg(G2), None, o.g1_mul(G, 0xDEADBEEF)):
+        assert o.g1_from_bytes(o.g1_to_bytes(P)) == P
+        assert o.g1_read_raw(o.g1_write_raw(P)) == P
+    # the C++ restatement agrees with the big-int one, point by point
+    pts = [o.g1_mul(G, 3 + 7 * i) for i in range(20)] + [None]
+    raw = np.frombuffer(b"".join(o.g1_write_raw(P) for P in pts), dtype=np.uint64).reshape(-1, 8)
+    enc = oc.g1_to_bytes(raw)
+    assert enc.tobytes() == b"".join(o.g1_to_bytes(P) for P in pts)
+    dec, first = oc.g1_from_bytes(enc)
+    assert first == len(pts) and (dec == raw).all()
+    with pytest.raises(ValueError):
+        o.g1_from_bytes((o.P_MOD + 5).to_bytes(32, "little"))
