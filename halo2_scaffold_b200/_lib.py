@@ -36,7 +36,7 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
-    "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write",
+    "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
 
@@ -429,6 +429,9 @@ class Lib:
                                        g2.ctypes.data, g2.size, ctypes.byref(g2_len), ctypes.byref(hg) if register else None,
                                        ctypes.byref(hl) if register else None))
         return dict(k=k.value, g=g, g_lagrange=gl, g2_bytes=bytes(g2[:g2_len.value]), handle_g=hg.value, handle_g_lagrange=hl.value)
+
+    def srs_cache_clear(self):
+        self.check(self.L.h2b_srs_cache_clear())
 
     def srs_write(self, path: str, fmt: int, k: int, g: np.ndarray, g_lagrange: np.ndarray, g2_bytes: bytes):
         g, g_lagrange = _u64(g).reshape(-1, 8), _u64(g_lagrange).reshape(-1, 8)

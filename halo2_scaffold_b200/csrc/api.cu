@@ -4,6 +4,10 @@
 #include <atomic>
 #include <memory>
 #include <thread>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/h2b200.h"
 #include "common.h"
@@ -34,12 +38,25 @@ struct BaseSet {
     uint32_t n_tables = 1;            // 1: points only;  > 1: table j = 2^(c0*j) * P (msm.cu step 0)
     uint32_t c0 = 0;
     std::vector<void*> dev;           // per device: n_tables x n x 64 bytes
+    int refs = 1;                     // h2b_unregister_bases frees the set when the last holder lets go (SRS cache + its readers)
+};
+
+// files h2b_srs_read has already decoded: the reference re-reads params/kzg_bn254_{k}.srs for every proof
+// (src/scaffold.rs:174); a second read of an unchanged file hands out the resident base sets again
+struct SrsCacheEntry {
+    std::string path;
+    int format = 0;
+    long long size = 0, mtime_ns = 0;
+    uint32_t k = 0;
+    uint64_t handle_g = 0, handle_g_lagrange = 0;
+    std::vector<unsigned char> g2;
 };
 
 struct Global {
     std::mutex mu;
     std::vector<std::unique_ptr<DeviceCtx>> devs;
     std::vector<std::unique_ptr<BaseSet>> sets;
+    std::vector<SrsCacheEntry> srs_cache;
     uint64_t next_handle = 1;
     uint64_t use_counter = 0;
     std::atomic<unsigned> rr{0};
@@ -395,6 +412,7 @@ void h2b_shutdown(void) {
     std::lock_guard<std::mutex> lk(G.mu);
     for (auto& bs : G.sets) free_set(*bs);
     G.sets.clear();
+    G.srs_cache.clear();
     for (auto& c : G.devs) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
@@ -468,6 +486,7 @@ int h2b_unregister_bases(uint64_t handle) {
     std::lock_guard<std::mutex> lk(G.mu);
     for (size_t i = 0; i < G.sets.size(); ++i) {
         if (G.sets[i]->handle == handle) {
+            if (--G.sets[i]->refs > 0) return H2B_OK;
             free_set(*G.sets[i]);
             G.sets.erase(G.sets.begin() + i);
             return H2B_OK;
@@ -727,23 +746,22 @@ int h2b_g1_encode_dev(int device, const void* d_affine, size_t n, void* d_out_by
 
 namespace {
 struct FileCloser { FILE* f; ~FileCloser() { if (f) fclose(f); } };
-}
+}  // namespace
 
 // one vector of the file: bytes -> device 0 -> decoded points; optionally downloaded and / or registered on every device
-static int srs_read_vector(FILE* f, const char* what, size_t n, int format, uint64_t* host_out, uint64_t* handle) {
+static int srs_read_vector(const unsigned char* raw, const char* what, size_t n, int format, uint64_t* host_out, uint64_t* handle) {
     const size_t ps = format == H2B_SERDE_PROCESSED ? 32 : 64;
-    std::vector<unsigned char> raw(n * ps);
-    if (fread(raw.data(), 1, raw.size(), f) != raw.size()) { set_error("h2b_srs_read: file ends inside %s", what); return H2B_ERR_BAD_ARGUMENT; }
     std::lock_guard<std::mutex> glk(G.mu);
     DeviceCtx& c = *G.devs[0];
     void* d_pts = nullptr;
     {
         std::lock_guard<std::mutex> lk(c.mu);
         H2B_CUDA(cudaSetDevice(c.device));
-        H2B_TRY(c.srs_io.reserve(raw.size()));
+        H2B_TRY(c.srs_io.reserve(n * ps));
         cudaError_t e = cudaMalloc(&d_pts, n * 64 + 64);
         if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes for %s failed: %s", n * 64, what, cudaGetErrorString(e)); return H2B_ERR_OOM; }
-        int rc = host_upload(c, c.srs_io.p, raw.data(), raw.size(), c.stream);
+        // the mapping is pageable memory: the staging threads of stage.cu pull it through the page cache in parallel
+        int rc = host_upload(c, c.srs_io.p, raw, n * ps, c.stream);
         uint64_t bad = 0;
         if (!rc) rc = g1_decode_run(c, c.srs_io.p, n, format, d_pts, &bad, c.stream);
         if (!rc && host_out) rc = host_download(c, host_out, d_pts, n * 64, c.stream);
@@ -771,35 +789,145 @@ static int srs_read_vector(FILE* f, const char* what, size_t n, int format, uint
     return H2B_OK;
 }
 
+namespace {
+struct Mapping {
+    int fd = -1;
+    void* p = MAP_FAILED;
+    size_t len = 0;
+    ~Mapping() {
+        if (p != MAP_FAILED) munmap(p, len);
+        if (fd >= 0) close(fd);
+    }
+};
+static bool srs_cache_enabled() {
+    const char* e = getenv("H2B_SRS_CACHE");
+    return !(e && e[0] == '0');
+}
+static BaseSet* find_set_locked(uint64_t handle) {
+    for (auto& up : G.sets) if (up->handle == handle) return up.get();
+    return nullptr;
+}
+}  // namespace
+
+// points of a resident set (table 0) -> host
+static int srs_download_points(uint64_t handle, size_t n, uint64_t* out) {
+    void* src = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        BaseSet* bs = find_set_locked(handle);
+        if (!bs || bs->n != n) { set_error("h2b_srs_read: cached base set vanished"); return H2B_ERR_BAD_HANDLE; }
+        src = bs->dev[0];
+    }
+    DeviceCtx& c = *G.devs[0];
+    std::lock_guard<std::mutex> lk(c.mu);
+    H2B_CUDA(cudaSetDevice(c.device));
+    H2B_TRY(host_download(c, out, src, n * 64, c.stream));
+    H2B_CUDA(cudaStreamSynchronize(c.stream));
+    return H2B_OK;
+}
+
 int h2b_srs_read(const char* path, int format, uint32_t* k, uint64_t* out_g, uint64_t* out_g_lagrange, uint8_t* g2_bytes, size_t g2_cap, size_t* g2_len,
                  uint64_t* handle_g, uint64_t* handle_g_lagrange) {
     H2B_TRY(require_init());
     if (!path || !k) { set_error("h2b_srs_read: null path / k"); return H2B_ERR_BAD_ARGUMENT; }
     if (format < H2B_SERDE_PROCESSED || format > H2B_SERDE_RAW_BYTES_UNCHECKED) { set_error("h2b_srs_read: unknown format %d", format); return H2B_ERR_BAD_ARGUMENT; }
-    FileCloser fc{fopen(path, "rb")};
-    if (!fc.f) { set_error("h2b_srs_read: cannot open %s", path); return H2B_ERR_BAD_ARGUMENT; }
-    unsigned char kb[4];
-    if (fread(kb, 1, 4, fc.f) != 4) { set_error("h2b_srs_read: %s is empty", path); return H2B_ERR_BAD_ARGUMENT; }
-    const uint32_t kk = (uint32_t)kb[0] | ((uint32_t)kb[1] << 8) | ((uint32_t)kb[2] << 16) | ((uint32_t)kb[3] << 24);
-    if (kk > 28) { set_error("h2b_srs_read: k = %u in %s (at most 28)", kk, path); return H2B_ERR_BAD_ARGUMENT; }
-    *k = kk;
-    const size_t n = (size_t)1 << kk;
-    uint64_t hg = 0;
-    H2B_TRY(srs_read_vector(fc.f, "g", n, format, out_g, handle_g ? &hg : nullptr));
-    int rc = srs_read_vector(fc.f, "g_lagrange", n, format, out_g_lagrange, handle_g_lagrange);
-    if (rc != H2B_OK) { if (handle_g) h2b_unregister_bases(hg); return rc; }
-    if (handle_g) *handle_g = hg;
-    const size_t want = format == H2B_SERDE_PROCESSED ? 128 : 256;      // g2 | s_g2
-    std::vector<unsigned char> tail(want);
-    const size_t got = fread(tail.data(), 1, want, fc.f);
-    if (got != want) {
-        if (handle_g) h2b_unregister_bases(hg);
-        if (handle_g_lagrange) h2b_unregister_bases(*handle_g_lagrange);
-        set_error("h2b_srs_read: %s ends inside the G2 section", path);
-        return H2B_ERR_BAD_ARGUMENT;
+    Mapping m;
+    m.fd = open(path, O_RDONLY);
+    struct stat sb;
+    if (m.fd < 0 || fstat(m.fd, &sb) != 0) { set_error("h2b_srs_read: cannot open %s", path); return H2B_ERR_BAD_ARGUMENT; }
+    const long long mtime_ns = (long long)sb.st_mtim.tv_sec * 1000000000ll + sb.st_mtim.tv_nsec;
+    // an unchanged file that was decoded before: hand out its resident sets again
+    if (srs_cache_enabled()) {
+        SrsCacheEntry hit;
+        bool found = false;
+        {
+            std::lock_guard<std::mutex> lk(G.mu);
+            for (const SrsCacheEntry& e : G.srs_cache) {
+                if (e.path != path || e.format != format || e.size != (long long)sb.st_size || e.mtime_ns != mtime_ns) continue;
+                BaseSet *a = find_set_locked(e.handle_g), *b = find_set_locked(e.handle_g_lagrange);
+                if (!a || !b) continue;
+                if (handle_g) ++a->refs;
+                if (handle_g_lagrange) ++b->refs;
+                hit = e;
+                found = true;
+                break;
+            }
+        }
+        if (found) {
+            const size_t n = (size_t)1 << hit.k;
+            int rc = H2B_OK;
+            if (out_g) rc = srs_download_points(hit.handle_g, n, out_g);
+            if (!rc && out_g_lagrange) rc = srs_download_points(hit.handle_g_lagrange, n, out_g_lagrange);
+            if (rc) {
+                if (handle_g) h2b_unregister_bases(hit.handle_g);
+                if (handle_g_lagrange) h2b_unregister_bases(hit.handle_g_lagrange);
+                return rc;
+            }
+            *k = hit.k;
+            if (handle_g) *handle_g = hit.handle_g;
+            if (handle_g_lagrange) *handle_g_lagrange = hit.handle_g_lagrange;
+            if (g2_len) *g2_len = hit.g2.size();
+            if (g2_bytes) memcpy(g2_bytes, hit.g2.data(), hit.g2.size() < g2_cap ? hit.g2.size() : g2_cap);
+            return H2B_OK;
+        }
     }
-    if (g2_len) *g2_len = want;
-    if (g2_bytes) memcpy(g2_bytes, tail.data(), want < g2_cap ? want : g2_cap);
+    if (sb.st_size < 4) { set_error("h2b_srs_read: %s is empty", path); return H2B_ERR_BAD_ARGUMENT; }
+    m.len = (size_t)sb.st_size;
+    m.p = mmap(nullptr, m.len, PROT_READ, MAP_PRIVATE, m.fd, 0);
+    if (m.p == MAP_FAILED) { set_error("h2b_srs_read: cannot map %s", path); return H2B_ERR_BAD_ARGUMENT; }
+    madvise(m.p, m.len, MADV_SEQUENTIAL);
+    const unsigned char* bytes = (const unsigned char*)m.p;
+    const uint32_t kk = (uint32_t)bytes[0] | ((uint32_t)bytes[1] << 8) | ((uint32_t)bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
+    if (kk > 28) { set_error("h2b_srs_read: k = %u in %s (at most 28)", kk, path); return H2B_ERR_BAD_ARGUMENT; }
+    const size_t n = (size_t)1 << kk, ps = format == H2B_SERDE_PROCESSED ? 32 : 64;
+    const size_t g2_want = format == H2B_SERDE_PROCESSED ? 128 : 256;      // g2 | s_g2
+    if (m.len < 4 + 2 * n * ps) { set_error("h2b_srs_read: %s ends inside %s", path, m.len < 4 + n * ps ? "g" : "g_lagrange"); return H2B_ERR_BAD_ARGUMENT; }
+    if (m.len < 4 + 2 * n * ps + g2_want) { set_error("h2b_srs_read: %s ends inside the G2 section", path); return H2B_ERR_BAD_ARGUMENT; }
+    // the cache keeps both vectors resident even if the caller only asked for one handle
+    const bool cache = srs_cache_enabled();
+    uint64_t hg = 0, hl = 0;
+    H2B_TRY(srs_read_vector(bytes + 4, "g", n, format, out_g, (handle_g || cache) ? &hg : nullptr));
+    int rc = srs_read_vector(bytes + 4 + n * ps, "g_lagrange", n, format, out_g_lagrange, (handle_g_lagrange || cache) ? &hl : nullptr);
+    if (rc != H2B_OK) { if (hg) h2b_unregister_bases(hg); return rc; }
+    *k = kk;
+    if (g2_len) *g2_len = g2_want;
+    if (g2_bytes) memcpy(g2_bytes, bytes + 4 + 2 * n * ps, g2_want < g2_cap ? g2_want : g2_cap);
+    if (cache) {
+        std::lock_guard<std::mutex> lk(G.mu);
+        SrsCacheEntry e;
+        e.path = path; e.format = format; e.size = (long long)sb.st_size; e.mtime_ns = mtime_ns; e.k = kk;
+        e.handle_g = hg; e.handle_g_lagrange = hl;
+        e.g2.assign(bytes + 4 + 2 * n * ps, bytes + 4 + 2 * n * ps + g2_want);
+        // the cache's own reference is the one srs_read_vector created; each caller that took a handle adds one
+        BaseSet *a = find_set_locked(hg), *b = find_set_locked(hl);
+        if (a && handle_g) ++a->refs;
+        if (b && handle_g_lagrange) ++b->refs;
+        // a stale entry for the same path (file rewritten) gives its sets back
+        for (size_t i = 0; i < G.srs_cache.size();) {
+            if (G.srs_cache[i].path == e.path && G.srs_cache[i].format == e.format) {
+                for (uint64_t h : {G.srs_cache[i].handle_g, G.srs_cache[i].handle_g_lagrange}) {
+                    for (size_t j = 0; j < G.sets.size(); ++j)
+                        if (G.sets[j]->handle == h && --G.sets[j]->refs <= 0) { free_set(*G.sets[j]); G.sets.erase(G.sets.begin() + j); break; }
+                }
+                G.srs_cache.erase(G.srs_cache.begin() + i);
+            } else ++i;
+        }
+        G.srs_cache.push_back(std::move(e));
+    }
+    if (handle_g) *handle_g = hg;
+    if (handle_g_lagrange) *handle_g_lagrange = hl;
+    return H2B_OK;
+}
+
+int h2b_srs_cache_clear(void) {
+    H2B_TRY(require_init());
+    std::vector<uint64_t> drop;
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        for (const SrsCacheEntry& e : G.srs_cache) { drop.push_back(e.handle_g); drop.push_back(e.handle_g_lagrange); }
+        G.srs_cache.clear();
+    }
+    for (uint64_t h : drop) h2b_unregister_bases(h);
     return H2B_OK;
 }
 

@@ -221,6 +221,11 @@ int h2b_g1_encode_dev(int device, const void* d_affine, size_t n, void* d_out_by
  * returned as bytes for the host to parse.  Either handle pointer may be NULL (that vector is then only decoded). */
 int h2b_srs_read(const char* path, int format, uint32_t* k, uint64_t* out_g, uint64_t* out_g_lagrange, uint8_t* g2_bytes, size_t g2_cap,
                  size_t* g2_len, uint64_t* handle_g, uint64_t* handle_g_lagrange);
+/* A file that was read before and has not changed since (same path, format, size and mtime) is NOT decoded again: the call
+ * hands out the resident base sets (reference counted -- every handle still has to be given back with
+ * h2b_unregister_bases) and, if asked, downloads the points.  The reference re-reads the SRS file for every proof
+ * (src/scaffold.rs:174).  H2B_SRS_CACHE=0 in the environment disables this; h2b_srs_cache_clear drops the cache's references. */
+int h2b_srs_cache_clear(void);
 /* ParamsKZG::write_custom for host arrays (Processed: compressed on the device) */
 int h2b_srs_write(const char* path, int format, uint32_t k, const uint64_t* g, const uint64_t* g_lagrange, const uint8_t* g2_bytes, size_t g2_len);
 

@@ -377,3 +377,38 @@ def test_srs_reader_rejects_bad_files(emu, oc, tmp_path):
             emu.srs_read(str(p), 1)
     with pytest.raises((H2BError, FileNotFoundError)):
         emu.srs_read(str(tmp_path / "missing.srs"), 1)
+
+
+def test_srs_reader_keeps_decoded_files_resident(emu, oc, tmp_path):
+    # the reference re-reads the params file for every proof (src/scaffold.rs:174): an unchanged file is not decoded twice
+    import os
+    k, n = 5, 32
+    g, gl = oc.gen_points(41, n), oc.gen_points(42, n)
+    path = str(tmp_path / "kzg_bn254_5.srs")
+    emu.srs_write(path, 0, k, g, gl, bytes(128))
+    launches = emu.launch_count()
+    a = emu.srs_read(path, 0)
+    first = emu.launch_count() - launches
+    b = emu.srs_read(path, 0)
+    assert emu.launch_count() - launches == first, "the second read decoded again"
+    assert (a["handle_g"], a["handle_g_lagrange"]) == (b["handle_g"], b["handle_g_lagrange"])
+    assert (b["g"] == g).all() and (b["g_lagrange"] == gl).all() and b["g2_bytes"] == bytes(128)
+    s = oc.random_fr(43, n)
+    want = pc.affine_of(oc, oc.best_multiexp(s, g))
+    # every reader gives its handles back; the sets stay usable until the last one (and the cache) let go
+    emu.unregister_bases(a["handle_g"]); emu.unregister_bases(a["handle_g_lagrange"])
+    assert (pc.affine_of(oc, emu.msm_registered(s, b["handle_g"], 0)) == want).all()
+    emu.unregister_bases(b["handle_g"]); emu.unregister_bases(b["handle_g_lagrange"])
+    c = emu.srs_read(path, 0, want_host=False)
+    assert c["handle_g"] == a["handle_g"]
+    emu.unregister_bases(c["handle_g"]); emu.unregister_bases(c["handle_g_lagrange"])
+    # a rewritten file is decoded afresh
+    emu.srs_write(path, 0, k, gl, g, bytes(128))
+    os.utime(path, ns=(1, 1))
+    d = emu.srs_read(path, 0)
+    assert d["handle_g"] != a["handle_g"] and (d["g"] == gl).all()
+    emu.unregister_bases(d["handle_g"]); emu.unregister_bases(d["handle_g_lagrange"])
+    emu.srs_cache_clear()
+    from halo2_scaffold_b200._lib import H2BError
+    with pytest.raises(H2BError):
+        emu.msm_registered(s, d["handle_g"], 0)
