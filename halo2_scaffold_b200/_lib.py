@@ -36,7 +36,7 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
-    "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
+    "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
 
@@ -150,6 +150,8 @@ class Lib:
         L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
         L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
+        L.h2b_permutation_product_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.h2b_lookup_product_dev.argtypes = [i32, vp, vp, vp, vp, sz, vp, vp, vp, vp]
         L.h2b_g1_decode_dev.argtypes = [i32, vp, sz, i32, vp, ctypes.POINTER(u64), vp]
         L.h2b_g1_encode_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_srs_read.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(u32), vp, vp, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(u64), ctypes.POINTER(u64)]
@@ -378,6 +380,53 @@ class Lib:
             self.dev_free(device, d)
             self.dev_free(device, d_q)
         return q
+
+    # ---- grand products (permutation / lookup z polynomials) -------------------------------------------
+    def permutation_product_dev(self, device: int, d_values, d_permutations, n: int, beta, gamma, delta, deltaomega, omega, last_z, d_z: int,
+                                stream: int = 0):
+        v, p = np.array(list(d_values), dtype=np.uint64), np.array(list(d_permutations), dtype=np.uint64)
+        assert v.shape == p.shape
+        w = [np.ascontiguousarray(x, dtype=np.uint64).reshape(4) for x in (beta, gamma, delta, deltaomega, omega, last_z)]
+        self.check(self.L.h2b_permutation_product_dev(device, v.ctypes.data, p.ctypes.data, v.shape[0], n, *[x.ctypes.data for x in w], d_z, stream))
+
+    def lookup_product_dev(self, device: int, d_compressed_input: int, d_compressed_table: int, d_permuted_input: int, d_permuted_table: int, n: int,
+                           beta, gamma, d_z: int, stream: int = 0):
+        w = [np.ascontiguousarray(x, dtype=np.uint64).reshape(4) for x in (beta, gamma)]
+        self.check(self.L.h2b_lookup_product_dev(device, d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table, n,
+                                                 w[0].ctypes.data, w[1].ctypes.data, d_z, stream))
+
+    def _columns_op(self, cols, n: int, op, device: int = 0) -> np.ndarray:
+        """upload `cols` (n x 4 each), run op(device pointers, d_out), download n x 4"""
+        held = []
+        try:
+            for c in cols:
+                d = self.dev_alloc(device, max(n, 1) * 32)
+                held.append(d)
+                if n:
+                    self.h2d(device, d, _u64(c).reshape(-1, 4))
+            d_out = self.dev_alloc(device, max(n, 1) * 32)
+            held.append(d_out)
+            op(held[:-1], d_out)
+            self.dev_sync(device)
+            out = np.empty((n, 4), dtype=np.uint64)
+            if n:
+                self.d2h(device, out, d_out)
+            return out
+        finally:
+            for d in held:
+                self.dev_free(device, d)
+
+    def permutation_product(self, values, permutations, beta, gamma, delta, deltaomega, omega, last_z, device: int = 0) -> np.ndarray:
+        """permutation::Argument::commit for one set, host arrays in and out (z without the blinding rows)"""
+        m, n = len(values), _u64(values[0]).size // 4
+        return self._columns_op(list(values) + list(permutations), n,
+                                lambda d, d_z: self.permutation_product_dev(device, d[:m], d[m:], n, beta, gamma, delta, deltaomega, omega, last_z, d_z),
+                                device)
+
+    def lookup_product(self, compressed_input, compressed_table, permuted_input, permuted_table, beta, gamma, device: int = 0) -> np.ndarray:
+        n = _u64(compressed_input).size // 4
+        return self._columns_op([compressed_input, compressed_table, permuted_input, permuted_table], n,
+                                lambda d, d_z: self.lookup_product_dev(device, d[0], d[1], d[2], d[3], n, beta, gamma, d_z), device)
 
     # ---- SRS on-disk format ---------------------------------------------------------------------------
     def g1_decode(self, data: np.ndarray, fmt: int, device: int = 0) -> np.ndarray:

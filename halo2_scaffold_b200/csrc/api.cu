@@ -729,6 +729,23 @@ int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64
     return fr_kate_division_run(*c, d_a, n, b, d_q, (cudaStream_t)stream);
 }
 
+int h2b_permutation_product_dev(int device, const void* const* d_values, const void* const* d_permutations, uint32_t n_columns, size_t n,
+                                const uint64_t beta[4], const uint64_t gamma[4], const uint64_t delta[4], const uint64_t deltaomega[4], const uint64_t omega[4],
+                                const uint64_t last_z[4], void* d_z, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return permutation_product_run(*c, d_values, d_permutations, n_columns, n, beta, gamma, delta, deltaomega, omega, last_z, d_z, (cudaStream_t)stream);
+}
+
+int h2b_lookup_product_dev(int device, const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input,
+                           const void* d_permuted_table, size_t n, const uint64_t beta[4], const uint64_t gamma[4], void* d_z, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return lookup_product_run(*c, d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table, n, beta, gamma, d_z, (cudaStream_t)stream);
+}
+
 // ---- SRS on-disk format -----------------------------------------------------------------------------
 int h2b_g1_decode_dev(int device, const void* d_bytes, size_t n, int format, void* d_out_affine, uint64_t* first_invalid, void* stream) {
     DeviceCtx* c = nullptr;

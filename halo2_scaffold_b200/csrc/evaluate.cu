@@ -480,21 +480,11 @@ struct PermParams {
     Fr beta, gamma, y, delta, zeta, omega;
 };
 
-__device__ __noinline__ Fr fr_pow_u32(Fr base, uint32_t e) {
-    Fr r = fp_one<FR>();
-    while (e) {
-        if (e & 1) r = fp_mul(r, base);
-        base = fp_sqr(base);
-        e >>= 1;
-    }
-    return r;
-}
-
 __global__ void __launch_bounds__(128) evaluate_h_permutation_kernel(PermParams p, uint4* __restrict__ values) {
     const uint32_t stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.size) return;
-    Fr beta_term = fr_pow_u32(p.omega, t);                  // extended_omega^idx
-    const Fr omega_step = fr_pow_u32(p.omega, stride);
+    Fr beta_term = fp_pow_u32<FR>(p.omega, t);                  // extended_omega^idx
+    const Fr omega_step = fp_pow_u32<FR>(p.omega, stride);
     const Fr delta_start = fp_mul(p.beta, p.zeta);
     const uint4* z_first = (const uint4*)p.product[0];
     const uint4* z_last = (const uint4*)p.product[p.n_sets - 1];

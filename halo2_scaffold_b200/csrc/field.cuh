@@ -220,4 +220,15 @@ template <int F> __device__ __noinline__ Fp<F> fp_inv(const Fp<F>& a) {
     return r;
 }
 
+// base^e for a small exponent (row indices: omega^i), square-and-multiply from the low bit
+template <int F> __device__ __noinline__ Fp<F> fp_pow_u32(Fp<F> base, uint32_t e) {
+    Fp<F> r = fp_one<F>();
+    while (e) {
+        if (e & 1) r = fp_mul(r, base);
+        base = fp_sqr(base);
+        e >>= 1;
+    }
+    return r;
+}
+
 }  // namespace h2b

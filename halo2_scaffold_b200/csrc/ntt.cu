@@ -507,23 +507,30 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
     return H2B_OK;
 }
 
-// a[i] *= factors[i % count]   (count in {1, 3}: the 1/n of lagrange_to_coeff / extended_to_coeff and the
-// zeta-coset pattern of coeff_to_extended, [UP] halo2_proofs/src/poly/domain.rs)
-struct ScaleParams { uint32_t f[3][8]; uint32_t count; };
+// a[i] *= factors[i % count]   (count 1 / 3: the 1/n of lagrange_to_coeff / extended_to_coeff and the zeta-coset pattern
+// of coeff_to_extended; count 2^(extended_k - k) <= 8: the t_evaluations of divide_by_vanishing_poly --
+// [UP] halo2_proofs/src/poly/domain.rs)
+struct ScaleParams { uint32_t f[8][8]; uint32_t count; };
 __global__ void __launch_bounds__(256) ntt_scale_kernel(uint4* a, size_t n, ScaleParams s) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t k = s.count == 1 ? 0u : (uint32_t)(i % 3);
     Fr f;
+    if (s.count <= 3) {
+        uint32_t k = s.count == 1 ? 0u : (uint32_t)(i % s.count);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f.l[j] = k == 0 ? s.f[0][j] : (k == 1 ? s.f[1][j] : s.f[2][j]);
+        for (int j = 0; j < 8; ++j) f.l[j] = k == 0 ? s.f[0][j] : (k == 1 ? s.f[1][j] : s.f[2][j]);
+    } else {
+        const uint32_t k = (uint32_t)(i % s.count);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f.l[j] = s.f[k][j];
+    }
     Fr v = fp_load<FR>(a + 2 * i);
     fp_store<FR>(a + 2 * i, fp_mul(v, f));
 }
 
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors, int count, cudaStream_t stream) {
     (void)ctx;
-    if (count != 1 && count != 3) { set_error("scale: count must be 1 or 3"); return H2B_ERR_BAD_ARGUMENT; }
+    if (count < 1 || count > 8) { set_error("scale: count must be in [1, 8]"); return H2B_ERR_BAD_ARGUMENT; }
     if (n == 0) return H2B_OK;
     ScaleParams s;
     memset(&s, 0, sizeof(s));

@@ -239,4 +239,117 @@ int fr_kate_division_run(DeviceCtx& ctx, const void* d_a, size_t n, const uint64
     return H2B_OK;
 }
 
+// ---- the grand products themselves --------------------------------------------------------------------------------------
+// [UP] halo2_proofs/src/plonk/permutation/prover.rs `Argument::commit` (one call per chunk of columns = one set) and
+// [UP] halo2_proofs/src/plonk/lookup/prover.rs `Permuted::commit_product`: both build
+//     z[0] = start,  z[i + 1] = z[i] * numerator[i] / denominator[i]
+// with the denominators inverted in one batch.  On the device: one elementwise kernel for the denominators, the batch
+// inversion, one elementwise kernel for the numerators, the exclusive prefix product, and the scaling by `start`
+// (last_z of the previous set).  The blinding rows at the end of z are the caller's (they are random).
+static const uint32_t PERM_MAX_COLUMNS = 16;        // a set holds cs.degree() - 2 columns
+
+struct PermProductParams {
+    const uint4* values[PERM_MAX_COLUMNS];
+    const uint4* sigma[PERM_MAX_COLUMNS];
+    uint32_t m;
+    Fr beta, gamma, delta, deltaomega, omega;
+};
+
+// out[i] = prod_j (beta * sigma_j[i] + gamma + v_j[i])
+__global__ void __launch_bounds__(128) perm_denominator_kernel(PermProductParams p, size_t n, uint4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr acc = fp_one<FR>();
+    for (uint32_t j = 0; j < p.m; ++j) {
+        const Fr t = fp_add(fp_add(fp_mul(p.beta, fp_load<FR>(p.sigma[j] + 2 * i)), p.gamma), fp_load<FR>(p.values[j] + 2 * i));
+        acc = j ? fp_mul(acc, t) : t;
+    }
+    fp_store<FR>(out + 2 * i, acc);
+}
+
+// out[i] *= prod_j (deltaomega * delta^j * omega^i * beta + gamma + v_j[i])
+__global__ void __launch_bounds__(128) perm_numerator_kernel(PermProductParams p, size_t n, uint4* __restrict__ out) {
+    const uint32_t stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    Fr w = fp_mul(fp_mul(p.deltaomega, p.beta), fp_pow_u32<FR>(p.omega, t));      // deltaomega * beta * omega^i
+    const Fr step = fp_pow_u32<FR>(p.omega, stride);
+    for (size_t i = t; i < n; i += stride) {
+        Fr acc = fp_load<FR>(out + 2 * i);
+        Fr d = w;
+        for (uint32_t j = 0; j < p.m; ++j) {
+            acc = fp_mul(acc, fp_add(fp_add(d, p.gamma), fp_load<FR>(p.values[j] + 2 * i)));
+            d = fp_mul(d, p.delta);
+        }
+        fp_store<FR>(out + 2 * i, acc);
+        w = fp_mul(w, step);
+    }
+}
+
+static bool is_montgomery_one(const uint64_t* w) {
+    Fr one;
+    for (int i = 0; i < 8; ++i) one.l[i] = FpParams<FR>::ONE(i);
+    return memcmp(w, one.l, 32) == 0;
+}
+
+int permutation_product_run(DeviceCtx& ctx, const void* const* d_values, const void* const* d_sigma, uint32_t m, size_t n, const uint64_t* beta,
+                            const uint64_t* gamma, const uint64_t* delta, const uint64_t* deltaomega, const uint64_t* omega, const uint64_t* last_z,
+                            void* d_z, cudaStream_t stream) {
+    if (!d_z || !beta || !gamma || !delta || !deltaomega || !omega || !last_z || (m && (!d_values || !d_sigma))) {
+        set_error("permutation_product: null pointer");
+        return H2B_ERR_BAD_ARGUMENT;
+    }
+    if (m == 0 || m > PERM_MAX_COLUMNS) { set_error("permutation_product: 1 .. %u columns per set", PERM_MAX_COLUMNS); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) return H2B_OK;
+    if (n > ((size_t)1 << 31)) { set_error("permutation_product: at most 2^31 rows"); return H2B_ERR_BAD_ARGUMENT; }
+    PermProductParams p;
+    memset(&p, 0, sizeof(p));
+    p.m = m;
+    for (uint32_t j = 0; j < m; ++j) {
+        if (!d_values[j] || !d_sigma[j]) { set_error("permutation_product: null column"); return H2B_ERR_BAD_ARGUMENT; }
+        p.values[j] = (const uint4*)d_values[j];
+        p.sigma[j] = (const uint4*)d_sigma[j];
+    }
+    memcpy(p.beta.l, beta, 32); memcpy(p.gamma.l, gamma, 32); memcpy(p.delta.l, delta, 32);
+    memcpy(p.deltaomega.l, deltaomega, 32); memcpy(p.omega.l, omega, 32);
+    H2B_LAUNCH(perm_denominator_kernel, (unsigned)((n + 127) / 128), 128, 0, stream, p, n, (uint4*)d_z);
+    H2B_TRY(fr_batch_invert_run(ctx, d_z, n, stream));
+    const size_t want = (n + 127) / 128, cap = (size_t)ctx.sm_count * 8;
+    H2B_LAUNCH(perm_numerator_kernel, (unsigned)(want < cap ? want : cap), 128, 0, stream, p, n, (uint4*)d_z);
+    H2B_TRY(fr_prefix_product_run(ctx, d_z, d_z, n, stream));
+    if (!is_montgomery_one(last_z)) H2B_TRY(ntt_scale_run(ctx, d_z, n, last_z, 1, stream));
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
+// out[i] = (a'[i] + beta) * (s'[i] + gamma)        (denominators)
+// out[i] *= (a[i] + beta) * (s[i] + gamma)         (numerators; a, s = the theta-compressed input / table expressions)
+struct LookupProductParams { Fr beta, gamma; };
+__global__ void __launch_bounds__(128) lookup_product_terms_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, LookupProductParams p, size_t n,
+                                                                 uint4* __restrict__ out, int multiply) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr t = fp_mul(fp_add(fp_load<FR>(x + 2 * i), p.beta), fp_add(fp_load<FR>(y + 2 * i), p.gamma));
+    if (multiply) t = fp_mul(t, fp_load<FR>(out + 2 * i));
+    fp_store<FR>(out + 2 * i, t);
+}
+
+int lookup_product_run(DeviceCtx& ctx, const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input,
+                       const void* d_permuted_table, size_t n, const uint64_t* beta, const uint64_t* gamma, void* d_z, cudaStream_t stream) {
+    if (!beta || !gamma || (n && (!d_compressed_input || !d_compressed_table || !d_permuted_input || !d_permuted_table || !d_z))) {
+        set_error("lookup_product: null pointer");
+        return H2B_ERR_BAD_ARGUMENT;
+    }
+    if (n == 0) return H2B_OK;
+    if (n > ((size_t)1 << 31)) { set_error("lookup_product: at most 2^31 rows"); return H2B_ERR_BAD_ARGUMENT; }
+    LookupProductParams p;
+    memcpy(p.beta.l, beta, 32); memcpy(p.gamma.l, gamma, 32);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    H2B_LAUNCH(lookup_product_terms_kernel, grid, 128, 0, stream, (const uint4*)d_permuted_input, (const uint4*)d_permuted_table, p, n, (uint4*)d_z, 0);
+    H2B_TRY(fr_batch_invert_run(ctx, d_z, n, stream));
+    H2B_LAUNCH(lookup_product_terms_kernel, grid, 128, 0, stream, (const uint4*)d_compressed_input, (const uint4*)d_compressed_table, p, n, (uint4*)d_z, 1);
+    H2B_TRY(fr_prefix_product_run(ctx, d_z, d_z, n, stream));
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
 }  // namespace h2b

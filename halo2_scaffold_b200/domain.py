@@ -53,6 +53,16 @@ class EvaluationDomain:
         self.extended_ifft_divisor = pow(1 << ek, -1, FR_MODULUS)
         self.g_coset = FR_ZETA
         self.g_coset_inv = FR_ZETA * FR_ZETA % FR_MODULUS
+        # t_evaluations[i] = 1 / t(zeta * extended_omega^i), t(X) = X^n - 1: it repeats with period 2^(extended_k - k)
+        orig, step = pow(FR_ZETA, self.n, FR_MODULUS), pow(self.extended_omega, self.n, FR_MODULUS)
+        cur, t = orig, []
+        while True:
+            t.append(cur)
+            cur = cur * step % FR_MODULUS
+            if cur == orig:
+                break
+        assert len(t) == 1 << (ek - k)
+        self.t_evaluations = [pow(v - 1, -1, FR_MODULUS) for v in t]
 
     # -- helpers ----------------------------------------------------------------------------------
     def _run(self, a: np.ndarray, out_len: int, work_len: int, steps, alloc_len: int | None = None):
@@ -105,3 +115,11 @@ class EvaluationDomain:
         return self._run(a, self.n * self.quotient_poly_degree, en, [
             lambda d: L.extended_to_coeff_dev(dev, d, self.extended_k, fr_to_words(self.extended_omega_inv), zs),
         ])
+
+    def divide_by_vanishing_poly(self, a: np.ndarray) -> np.ndarray:
+        """a[i] *= t_evaluations[i % len]: the extended-coset evaluations of h(X) = (gate combination) / (X^n - 1)"""
+        en = 1 << self.extended_k
+        assert a.size == 4 * en
+        L, dev = self.lib, self.device
+        t = np.stack([fr_to_words(v) for v in self.t_evaluations])
+        return self._run(a, en, en, [lambda d: L.fr_scale_dev(dev, d, en, t)])

@@ -107,8 +107,9 @@ int h2b_msm_bn254_g1_dev_registered(int device, const void* d_scalars, uint64_t 
 int h2b_msm_fold_partials(int device, const uint64_t* host_blocks /* count x 28 u64 */, size_t count, uint64_t out_jac[12]);
 /* same, blocks and result in device memory, asynchronous on `stream` */
 int h2b_msm_fold_partials_dev(int device, const void* d_blocks, size_t count, void* d_out_jac /* 96 B */, void* stream);
-/* a[i] *= factors[i % count], count in {1, 3}: the 1/n scaling of lagrange_to_coeff / extended_to_coeff and
- * the (1, zeta, zeta^2) coset pattern of coeff_to_extended ([UP] halo2_proofs/src/poly/domain.rs). */
+/* a[i] *= factors[i % count], 1 <= count <= 8: the 1/n scaling of lagrange_to_coeff / extended_to_coeff (count 1), the
+ * (1, zeta, zeta^2) coset pattern of coeff_to_extended (count 3) and EvaluationDomain::divide_by_vanishing_poly, whose
+ * t_evaluations repeat with period 2^(extended_k - k) ([UP] halo2_proofs/src/poly/domain.rs). */
 int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, int count, void* stream);
 
 /* EvaluationDomain's three conversions on a device-resident column ([UP] halo2_proofs/src/poly/domain.rs, SURVEY.md row
@@ -134,6 +135,22 @@ int h2b_fr_prefix_product_dev(int device, const void* d_in, void* d_out, size_t 
  * [UP] halo2_proofs::arithmetic::kate_division(a, b): the n - 1 coefficients of a(X) / (X - b) -> d_q (must not alias d_a) */
 int h2b_fr_eval_polynomial_dev(int device, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, void* stream);
 int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream);
+
+/* The grand products themselves, on device-resident Lagrange-basis columns of n = 2^k rows:
+ *   [UP] plonk/permutation/prover.rs Argument::commit, one call per set (chunk of cs.degree() - 2 columns, at most 16):
+ *        z[0] = last_z,  z[i+1] = z[i] * prod_j (v_j[i] + deltaomega * delta^j * omega^i * beta + gamma)
+ *                                      / prod_j (v_j[i] + beta * s_j[i] + gamma)
+ *        d_values[j] / d_permutations[j]: the j-th column of the set and its permutation column s_j; deltaomega = delta^(index of
+ *        the set's first column in the whole argument); last_z = one for the first set, z[n - (blinding_factors + 1)] of the
+ *        previous set afterwards.  All n entries of d_z are written; the caller overwrites the blinding rows.
+ *   [UP] plonk/lookup/prover.rs Permuted::commit_product:
+ *        z[0] = 1,  z[i+1] = z[i] * (a[i] + beta) (s[i] + gamma) / ((a'[i] + beta) (s'[i] + gamma))
+ *        a, s: theta-compressed input / table expressions; a', s': their permuted versions. */
+int h2b_permutation_product_dev(int device, const void* const* d_values, const void* const* d_permutations, uint32_t n_columns, size_t n,
+                                const uint64_t beta[4], const uint64_t gamma[4], const uint64_t delta[4], const uint64_t deltaomega[4], const uint64_t omega[4],
+                                const uint64_t last_z[4], void* d_z, void* stream);
+int h2b_lookup_product_dev(int device, const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input,
+                           const void* d_permuted_table, size_t n, const uint64_t beta[4], const uint64_t gamma[4], void* d_z, void* stream);
 
 /* ---- quotient evaluation: evaluate_h on device-resident extended-coset columns ----------
  * [UP] halo2_proofs/src/plonk/evaluation.rs.  A GraphEvaluator is passed in the vocabulary upstream builds it in

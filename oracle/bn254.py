@@ -326,6 +326,18 @@ class EvaluationDomain:
         self.extended_ifft_divisor = pow(1 << ek, -1, R_MOD)
         self.g_coset = FR_ZETA
         self.g_coset_inv = FR_ZETA * FR_ZETA % R_MOD
+        # [UP] domain.rs: evaluations of t(X) = X^n - 1 over the zeta coset, one period, inverted
+        orig, step = pow(FR_ZETA, self.n, R_MOD), pow(self.extended_omega, self.n, R_MOD)
+        cur, t = orig, []
+        while True:
+            t.append(cur)
+            cur = cur * step % R_MOD
+            if cur == orig:
+                break
+        self.t_evaluations = [pow(v - 1, -1, R_MOD) for v in t]
+
+    def divide_by_vanishing_poly(self, a):
+        return [x * self.t_evaluations[i % len(self.t_evaluations)] % R_MOD for i, x in enumerate(a)]
 
     def lagrange_to_coeff(self, a):
         a = list(a)

@@ -550,6 +550,38 @@ void orc_evaluate_h_permutation(u64* values, uint32_t size, int32_t rot_scale, c
 }  // extern "C"
 
 extern "C" {
+// [UP] plonk/permutation/prover.rs Argument::commit, one set: modified_values = prod_j (beta s_j + gamma + v_j); batch_invert;
+// *= prod_j (deltaomega beta + gamma + v_j) with deltaomega running over omega^i and delta^j; z[0] = last_z, z[row] = z[row-1] * modified[row-1]
+void orc_permutation_product(const u64* const* values, const u64* const* sigma, uint32_t m, size_t n, const u64* beta_w, const u64* gamma_w,
+                             const u64* delta_w, const u64* deltaomega_w, const u64* omega_w, const u64* last_z_w, u64* z) {
+    const Fr beta = fr_at(beta_w, 0), gamma = fr_at(gamma_w, 0), delta = fr_at(delta_w, 0), omega = fr_at(omega_w, 0);
+    std::vector<Fr> modified(n, Fr::one());
+    for (uint32_t j = 0; j < m; ++j)
+        for (size_t i = 0; i < n; ++i) modified[i] = modified[i] * (beta * fr_at(sigma[j], i) + gamma + fr_at(values[j], i));
+    if (n) orc_fr_batch_invert((u64*)modified.data(), n);
+    Fr deltaomega_col = fr_at(deltaomega_w, 0);
+    for (uint32_t j = 0; j < m; ++j) {
+        Fr deltaomega = deltaomega_col;
+        for (size_t i = 0; i < n; ++i) {
+            modified[i] = modified[i] * (deltaomega * beta + gamma + fr_at(values[j], i));
+            deltaomega = deltaomega * omega;
+        }
+        deltaomega_col = deltaomega_col * delta;
+    }
+    Fr run = fr_at(last_z_w, 0);
+    for (size_t row = 0; row < n; ++row) { memcpy(z + 4 * row, run.l, 32); run = run * modified[row]; }
+}
+// [UP] plonk/lookup/prover.rs Permuted::commit_product
+void orc_lookup_product(const u64* compressed_input, const u64* compressed_table, const u64* permuted_input, const u64* permuted_table, size_t n,
+                        const u64* beta_w, const u64* gamma_w, u64* z) {
+    const Fr beta = fr_at(beta_w, 0), gamma = fr_at(gamma_w, 0);
+    std::vector<Fr> lookup_product(n);
+    for (size_t i = 0; i < n; ++i) lookup_product[i] = (fr_at(permuted_input, i) + beta) * (fr_at(permuted_table, i) + gamma);
+    if (n) orc_fr_batch_invert((u64*)lookup_product.data(), n);
+    for (size_t i = 0; i < n; ++i) lookup_product[i] = lookup_product[i] * ((fr_at(compressed_input, i) + beta) * (fr_at(compressed_table, i) + gamma));
+    Fr run = Fr::one();
+    for (size_t i = 0; i < n; ++i) { memcpy(z + 4 * i, run.l, 32); run = run * lookup_product[i]; }
+}
 // ---------------------------------------------------------------------------------
 // SRS point encodings ([UP] halo2curves 0.3.x GroupEncoding::{to_bytes, from_bytes} for G1Affine; upstream's
 // ParamsKZG::read_custom decompresses with `parallelize`, here std::thread).  Returns the index of the first invalid

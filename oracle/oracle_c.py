@@ -44,6 +44,8 @@ def lib():
         L.orc_fr_eval_polynomial.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_fr_kate_division.argtypes = [u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_random_fr.argtypes = [ctypes.c_uint64, ctypes.c_size_t, u64p]
+        L.orc_permutation_product.argtypes = [u64p, u64p, ctypes.c_uint32, ctypes.c_size_t] + [u64p] * 7
+        L.orc_lookup_product.argtypes = [u64p] * 4 + [ctypes.c_size_t] + [u64p] * 3
         L.orc_g1_from_bytes.argtypes = [u64p, ctypes.c_size_t, ctypes.c_int, u64p]
         L.orc_g1_from_bytes.restype = ctypes.c_size_t
         L.orc_g1_to_bytes.argtypes = [u64p, ctypes.c_size_t, u64p]
@@ -224,6 +226,26 @@ def evaluate_h_permutation(values, rot_scale: int, product_cosets, columns, perm
     lib().orc_evaluate_h_permutation(values.ctypes.data, values.shape[0], rot_scale, pp.ctypes.data, len(kp), pc.ctypes.data, ps.ctypes.data, len(kc),
                                      chunk_len, last_rotation, *[v.ctypes.data for v in extra])
     return values
+
+
+def permutation_product(values, sigma, beta, gamma, delta, deltaomega, omega, last_z) -> np.ndarray:
+    """[UP] permutation::Argument::commit for one set of columns -> z (n x 4), blinding rows not applied"""
+    kv, pv = _ptrs(values)
+    ks, ps = _ptrs(sigma)
+    n = kv[0].shape[0]
+    z = np.empty((n, 4), dtype=np.uint64)
+    sc = [_col(v) for v in (beta, gamma, delta, deltaomega, omega, last_z)]
+    lib().orc_permutation_product(pv.ctypes.data, ps.ctypes.data, len(kv), n, *[v.ctypes.data for v in sc], z.ctypes.data)
+    return z
+
+
+def lookup_product(compressed_input, compressed_table, permuted_input, permuted_table, beta, gamma) -> np.ndarray:
+    cols = [_col(v) for v in (compressed_input, compressed_table, permuted_input, permuted_table)]
+    n = cols[0].shape[0]
+    z = np.empty((n, 4), dtype=np.uint64)
+    sc = [_col(v) for v in (beta, gamma)]
+    lib().orc_lookup_product(*[c.ctypes.data for c in cols], n, *[v.ctypes.data for v in sc], z.ctypes.data)
+    return z
 
 
 def field_op(field: str, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:

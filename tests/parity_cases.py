@@ -448,3 +448,62 @@ def check_srs_file_round_trip(L, oc, tmp_path, k, seed=3):
         finally:
             back.close()
     params.close()
+
+
+def check_vanishing_division(L, oc, cases):
+    """EvaluationDomain::divide_by_vanishing_poly through the mirror: against the big-int domain, and the identity
+    h = q * (X^n - 1)  =>  extended_to_coeff(divide_by_vanishing_poly(coset evaluations of h)) = q.   cases: (j, k)"""
+    import halo2_scaffold_b200 as h2
+    for j, k in cases:
+        dom, ref = h2.EvaluationDomain(j, k, lib=L), o.EvaluationDomain(j, k)
+        n, en = 1 << k, 1 << ref.extended_k
+        assert len(dom.t_evaluations) == 1 << (ref.extended_k - k) and dom.t_evaluations == ref.t_evaluations
+        a = oc.random_fr(0xF000 + 16 * j + k, en)
+        ai = [o.from_mont(v, o.R_MOD) for v in oc.words_to_ints(a)]
+        want = oc.ints_to_words([o.to_mont(v, o.R_MOD) for v in ref.divide_by_vanishing_poly(ai)])
+        assert (dom.divide_by_vanishing_poly(a) == want).all(), (j, k)
+        # q of degree < n (j - 2); h = q X^n - q has n (j - 1) coefficients
+        qn = n * (j - 2)
+        q = [o.from_mont(v, o.R_MOD) for v in oc.words_to_ints(oc.random_fr(0xF100 + 16 * j + k, qn))]
+        h = [0] * (n * (j - 1))
+        for i, c in enumerate(q):
+            h[i] = (h[i] - c) % o.R_MOD
+            h[i + n] = (h[i + n] + c) % o.R_MOD
+        z = [1, ref.g_coset, ref.g_coset_inv]
+        hz = [c * z[i % 3] % o.R_MOD for i, c in enumerate(h)] + [0] * (en - len(h))
+        h_ext = oc.ints_to_words([o.to_mont(v, o.R_MOD) for v in o.best_fft(hz, ref.extended_omega, ref.extended_k)])
+        back = dom.extended_to_coeff(dom.divide_by_vanishing_poly(h_ext))
+        want_q = oc.ints_to_words([o.to_mont(v, o.R_MOD) for v in q + [0] * (n * (j - 1) - qn)])
+        assert (back == want_q).all(), ("quotient identity", j, k)
+
+
+def check_grand_products(L, oc, sizes):
+    """permutation::Argument::commit (per set, chained through last_z and delta^j) and lookup commit_product against the oracle;
+    plus the argument's own telescoping property: with sigma = identity permutation (s_j = delta^j omega^i) every factor is 1"""
+    from halo2_scaffold_b200.domain import fr_to_words
+    DELTA = pow(7, 1 << 28, o.R_MOD)                  # Fr::DELTA = GENERATOR^(2^S)
+    for n in sizes:
+        k = max(1, (n - 1).bit_length())
+        omega = fr_to_words(o.omega_for(k))
+        sc = oc.random_fr(0x9000 + n, 3)
+        beta, gamma, last_z = sc
+        one = fr_to_words(1)
+        for m, first_col in ((1, 0), (3, 0), (2, 3), (16, 5)):
+            vals = [oc.random_fr(0x9100 + 17 * n + j, n) for j in range(m)]
+            sig = [oc.random_fr(0x9200 + 17 * n + j, n) for j in range(m)]
+            dw = fr_to_words(pow(DELTA, first_col, o.R_MOD))
+            lz = one if first_col == 0 else last_z
+            want = oc.permutation_product(vals, sig, beta, gamma, fr_to_words(DELTA), dw, omega, lz)
+            got = L.permutation_product(vals, sig, beta, gamma, fr_to_words(DELTA), dw, omega, lz)
+            assert (got == want).all(), ("permutation_product", n, m, first_col)
+        # identity permutation: sigma_j[i] = delta^j omega^i  =>  z stays at last_z on every row
+        m = 3
+        vals = [oc.random_fr(0x9300 + n + j, n) for j in range(m)]
+        w = o.omega_for(k)
+        sig = [oc.ints_to_words([o.to_mont(pow(DELTA, j, o.R_MOD) * pow(w, i, o.R_MOD) % o.R_MOD, o.R_MOD) for i in range(n)]) for j in range(m)]
+        got = L.permutation_product(vals, sig, beta, gamma, fr_to_words(DELTA), one, omega, last_z)
+        assert (got == last_z).all(), ("identity permutation", n)
+        cols = [oc.random_fr(0x9400 + 5 * n + j, n) for j in range(4)]
+        assert (L.lookup_product(*cols, beta, gamma) == oc.lookup_product(*cols, beta, gamma)).all(), ("lookup_product", n)
+        # a' = a and s' = s: the product telescopes to one
+        assert (L.lookup_product(cols[0], cols[1], cols[0], cols[1], beta, gamma) == one).all(), ("lookup identity", n)

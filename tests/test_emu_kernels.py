@@ -412,3 +412,11 @@ def test_srs_reader_keeps_decoded_files_resident(emu, oc, tmp_path):
     from halo2_scaffold_b200._lib import H2BError
     with pytest.raises(H2BError):
         emu.msm_registered(s, d["handle_g"], 0)
+
+
+def test_divide_by_vanishing_poly(emu, oc):
+    pc.check_vanishing_division(emu, oc, [(3, 3), (4, 4), (5, 5), (9, 4)])
+
+
+def test_permutation_and_lookup_grand_products(emu, oc):
+    pc.check_grand_products(emu, oc, [1, 2, 8, 64, 100, 1024, 5000])

@@ -159,6 +159,14 @@ def test_polynomial_evaluation_and_kate_division(gpu, oc):
     pc.check_poly_eval_and_division(gpu, oc, [1, 2, 17, 256, 257, 65537, (1 << 20) - 1, 1 << 22])
 
 
+def test_permutation_and_lookup_grand_products(gpu, oc):
+    pc.check_grand_products(gpu, oc, [1, 64, 4096, 1 << 16, (1 << 18) + 5])
+
+
+def test_divide_by_vanishing_poly(gpu, oc):
+    pc.check_vanishing_division(gpu, oc, [(3, 5), (4, 8), (5, 9), (9, 6)])
+
+
 def test_g1_point_codec(gpu, oc):
     for n in (1, 33, 5000, 1 << 16):
         pc.check_g1_codec(gpu, oc, n)

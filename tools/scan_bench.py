@@ -33,4 +33,23 @@ for k in [int(a) for a in (sys.argv[1:] or ["20", "22", "24"])]:
         out[name + "_ms"] = round(ms, 4)
         out[name + "_elements_per_s"] = n / ms * 1e3
         out[name + "_algorithmic_gb_s"] = round(64.0 * n / ms / 1e6, 1)
+    # the grand products themselves: one permutation set of 3 columns (cs.degree() = 5), one lookup argument
+    cols = [torch.empty(n * 4, dtype=torch.int64, device=dev) for _ in range(6)]
+    for j, c in enumerate(cols):
+        L.gen_scalars_dev(0, 100 + j, n, 0, c.data_ptr(), st)
+    sc = L.gen_scalars(5, 6)
+    for name, fn in (("permutation_product_3_columns", lambda: L.permutation_product_dev(0, [c.data_ptr() for c in cols[:3]], [c.data_ptr() for c in cols[3:]], n, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], d_q.data_ptr(), st)),
+                     ("lookup_product", lambda: L.lookup_product_dev(0, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(), cols[3].data_ptr(), n, sc[0], sc[1], d_q.data_ptr(), st))):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name + "_ms"] = round(ms, 4)
+        out[name + "_rows_per_s"] = n / ms * 1e3
+    del cols
     print(json.dumps(out), flush=True)
