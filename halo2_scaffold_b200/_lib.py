@@ -36,7 +36,7 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
-    "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
+    "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
 
@@ -150,6 +150,7 @@ class Lib:
         L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
         L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
+        L.h2b_fr_lincomb_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp]
         L.h2b_permutation_product_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_lookup_product_dev.argtypes = [i32, vp, vp, vp, vp, sz, vp, vp, vp, vp]
         L.h2b_g1_decode_dev.argtypes = [i32, vp, sz, i32, vp, ctypes.POINTER(u64), vp]
@@ -394,6 +395,17 @@ class Lib:
         w = [np.ascontiguousarray(x, dtype=np.uint64).reshape(4) for x in (beta, gamma)]
         self.check(self.L.h2b_lookup_product_dev(device, d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table, n,
                                                  w[0].ctypes.data, w[1].ctypes.data, d_z, stream))
+
+    def fr_lincomb_dev(self, device: int, d_cols, coeffs, n: int, d_out: int, stream: int = 0):
+        p = np.array(list(d_cols), dtype=np.uint64)
+        c = _u64(coeffs).reshape(-1, 4)
+        assert c.shape[0] == p.shape[0]
+        self.check(self.L.h2b_fr_lincomb_dev(device, p.ctypes.data if p.size else None, c.ctypes.data if c.size else None, p.shape[0], n, d_out, stream))
+
+    def fr_lincomb(self, cols, coeffs, device: int = 0) -> np.ndarray:
+        """sum_j coeffs[j] * cols[j], host arrays in and out"""
+        n = _u64(cols[0]).size // 4
+        return self._columns_op(list(cols), n, lambda d, d_out: self.fr_lincomb_dev(device, d, coeffs, n, d_out), device)
 
     def _columns_op(self, cols, n: int, op, device: int = 0) -> np.ndarray:
         """upload `cols` (n x 4 each), run op(device pointers, d_out), download n x 4"""

@@ -729,6 +729,12 @@ int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64
     return fr_kate_division_run(*c, d_a, n, b, d_q, (cudaStream_t)stream);
 }
 
+int h2b_fr_lincomb_dev(int device, const void* const* d_cols, const uint64_t* coeffs, uint32_t m, size_t n, void* d_out, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    return fr_lincomb_run(*c, d_cols, coeffs, m, n, d_out, (cudaStream_t)stream);
+}
+
 int h2b_permutation_product_dev(int device, const void* const* d_values, const void* const* d_permutations, uint32_t n_columns, size_t n,
                                 const uint64_t beta[4], const uint64_t gamma[4], const uint64_t delta[4], const uint64_t deltaomega[4], const uint64_t omega[4],
                                 const uint64_t last_z[4], void* d_z, void* stream) {

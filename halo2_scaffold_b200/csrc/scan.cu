@@ -352,4 +352,44 @@ int lookup_product_run(DeviceCtx& ctx, const void* d_compressed_input, const voi
     return H2B_OK;
 }
 
+// ---- linear combination of columns -------------------------------------------------------------------------------------
+// out[i] (+)= sum_j coeffs[j] * cols[j][i]: the y- and v-weighted sums of committed polynomials in the multi-open argument
+// ([UP] halo2_proofs/src/poly/kzg/multiopen/shplonk/prover.rs) and the theta-compression of lookup expressions
+// ([UP] plonk/lookup/prover.rs `compress_expressions`).  One pass: every column is read once, out is written once.
+static const uint32_t LINCOMB_MAX = 32;
+struct LincombParams {
+    const uint4* cols[LINCOMB_MAX];
+    Fr coeffs[LINCOMB_MAX];
+    uint32_t m;
+    uint32_t accumulate;
+};
+__global__ void __launch_bounds__(128) fr_lincomb_kernel(LincombParams p, size_t n, uint4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr acc = p.accumulate ? fp_load<FR>(out + 2 * i) : fp_zero<FR>();
+    for (uint32_t j = 0; j < p.m; ++j) acc = fp_add(acc, fp_mul(p.coeffs[j], fp_load<FR>(p.cols[j] + 2 * i)));
+    fp_store<FR>(out + 2 * i, acc);
+}
+
+int fr_lincomb_run(DeviceCtx& ctx, const void* const* d_cols, const uint64_t* coeffs, uint32_t m, size_t n, void* d_out, cudaStream_t stream) {
+    (void)ctx;
+    if (!d_out || (m && (!d_cols || !coeffs))) { set_error("lincomb: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) return H2B_OK;
+    if (m == 0) { H2B_CUDA(cudaMemsetAsync(d_out, 0, n * 32, stream)); return H2B_OK; }
+    for (uint32_t lo = 0; lo < m; lo += LINCOMB_MAX) {
+        LincombParams p;
+        memset(&p, 0, sizeof(p));
+        p.m = m - lo < LINCOMB_MAX ? m - lo : LINCOMB_MAX;
+        p.accumulate = lo ? 1u : 0u;
+        for (uint32_t j = 0; j < p.m; ++j) {
+            if (!d_cols[lo + j]) { set_error("lincomb: null column"); return H2B_ERR_BAD_ARGUMENT; }
+            p.cols[j] = (const uint4*)d_cols[lo + j];
+            memcpy(p.coeffs[j].l, coeffs + 4 * (size_t)(lo + j), 32);
+        }
+        H2B_LAUNCH(fr_lincomb_kernel, (unsigned)((n + 127) / 128), 128, 0, stream, p, n, (uint4*)d_out);
+    }
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
 }  // namespace h2b

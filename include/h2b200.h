@@ -136,6 +136,10 @@ int h2b_fr_prefix_product_dev(int device, const void* d_in, void* d_out, size_t 
 int h2b_fr_eval_polynomial_dev(int device, const void* d_coeffs, size_t n, const uint64_t x[4], void* d_out, void* stream);
 int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64_t b[4], void* d_q, void* stream);
 
+/* out[i] = sum_j coeffs[j] * cols[j][i] (m columns of n elements; out may alias none of them): the y- / v-weighted sums of
+ * the multi-open argument ([UP] poly/kzg/multiopen/shplonk/prover.rs) and the theta-compression of lookup expressions
+ * ([UP] plonk/lookup/prover.rs compress_expressions) */
+int h2b_fr_lincomb_dev(int device, const void* const* d_cols, const uint64_t* coeffs /* m x 4 */, uint32_t m, size_t n, void* d_out, void* stream);
 /* The grand products themselves, on device-resident Lagrange-basis columns of n = 2^k rows:
  *   [UP] plonk/permutation/prover.rs Argument::commit, one call per set (chunk of cs.degree() - 2 columns, at most 16):
  *        z[0] = last_z,  z[i+1] = z[i] * prod_j (v_j[i] + deltaomega * delta^j * omega^i * beta + gamma)

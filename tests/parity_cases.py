@@ -507,3 +507,16 @@ def check_grand_products(L, oc, sizes):
         assert (L.lookup_product(*cols, beta, gamma) == oc.lookup_product(*cols, beta, gamma)).all(), ("lookup_product", n)
         # a' = a and s' = s: the product telescopes to one
         assert (L.lookup_product(cols[0], cols[1], cols[0], cols[1], beta, gamma) == one).all(), ("lookup identity", n)
+
+
+def check_lincomb(L, oc, cases):
+    """sum_j c_j * col_j against field operations of the oracle.  cases: (n, m)"""
+    for n, m in cases:
+        cols = [oc.random_fr(0xA100 + 3 * n + j, n) for j in range(m)]
+        coeffs = oc.random_fr(0xA200 + n + m, m)
+        if m > 2:
+            coeffs[1] = 0
+        want = np.zeros((n, 4), dtype=np.uint64)
+        for j in range(m):
+            want = oc.field_op("fr", "add", want, oc.field_op("fr", "mul", cols[j], np.repeat(coeffs[j:j + 1], n, axis=0)))
+        assert (L.fr_lincomb(cols, coeffs) == want).all(), (n, m)

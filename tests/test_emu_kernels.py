@@ -420,3 +420,7 @@ def test_divide_by_vanishing_poly(emu, oc):
 
 def test_permutation_and_lookup_grand_products(emu, oc):
     pc.check_grand_products(emu, oc, [1, 2, 8, 64, 100, 1024, 5000])
+
+
+def test_linear_combination_of_columns(emu, oc):
+    pc.check_lincomb(emu, oc, [(1, 1), (7, 3), (200, 32), (130, 33), (64, 70)])

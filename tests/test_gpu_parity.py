@@ -163,6 +163,10 @@ def test_permutation_and_lookup_grand_products(gpu, oc):
     pc.check_grand_products(gpu, oc, [1, 64, 4096, 1 << 16, (1 << 18) + 5])
 
 
+def test_linear_combination_of_columns(gpu, oc):
+    pc.check_lincomb(gpu, oc, [(1, 1), (5000, 3), (1 << 16, 32), (3001, 45)])
+
+
 def test_divide_by_vanishing_poly(gpu, oc):
     pc.check_vanishing_division(gpu, oc, [(3, 5), (4, 8), (5, 9), (9, 6)])
 
