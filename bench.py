@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--scalars", default="uniform", choices=["uniform", "witness"])
     ap.add_argument("--sweep", action="store_true", help="also print a k=16..26 sweep (extra JSON lines on stderr)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-widened", action="store_true", help="skip the evaluate_h / SRS extras (SURVEY.md 8f) that ride along at N = 1")
     ap.add_argument("--plain", action="store_true", help="do not use the precomputed window tables of the registered SRS")
     return ap.parse_args()
 
@@ -400,6 +401,37 @@ def run_ours(args):
                 "traffic": ncu.get("ntt_pass_kernel"),
             },
         }
+        # ---- the widened rows ride along at N = 1: quotient evaluation and SRS point decompression -----------
+        # guarded: whatever happens here cannot touch the headline numbers above
+        widened = None
+        if world == 1 and not args.no_widened:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import evaluate_h_bench
+                torch.cuda.empty_cache()
+                eh = evaluate_h_bench.measure(L, 20, 22, 8, 2, reps=3, cpu_rows=(1 << 14) if not args.no_cpu_baseline else 0)
+                m = 1 << 22
+                d_pts = torch.empty(m * 8, dtype=torch.int64, device=dev)
+                d_enc = torch.empty(m * 4, dtype=torch.int64, device=dev)
+                L.gen_points_dev(0, 5, m, d_pts.data_ptr(), st)
+                L.check(L.L.h2b_g1_encode_dev(0, d_pts.data_ptr(), m, d_enc.data_ptr(), st))
+                L.check(L.L.h2b_g1_decode_dev(0, d_enc.data_ptr(), m, 0, d_pts.data_ptr(), None, st))
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(3):
+                    L.check(L.L.h2b_g1_decode_dev(0, d_enc.data_ptr(), m, 0, d_pts.data_ptr(), None, st))
+                e1.record()
+                torch.cuda.synchronize()
+                dec_ms = e0.elapsed_time(e1) / 3
+                del d_pts, d_enc
+                widened = {"evaluate_h": {"rows": 1 << 22, "columns": eh["device_columns"], "ms": eh["evaluate_h_ms"], "rows_per_s": eh["rows_per_s"],
+                                          "custom_gates_ms": eh["custom_gates_ms"], "permutation_ms": eh["permutation_ms"], "lookups_ms": eh["lookups_ms"],
+                                          "fr_mul_frac_of_peak": [eh["custom_gates_fr_mul_frac_of_peak"], eh["permutation_fr_mul_frac_of_peak"],
+                                                                  eh["lookups_fr_mul_frac_of_peak"]],
+                                          "parity_sample": eh.get("parity"), "cpu_rows_per_s_1_thread": eh.get("cpu_restatement_rows_per_s_1_thread")},
+                           "srs_decompress": {"points": m, "ms": dec_ms, "points_per_s": m / dec_ms * 1e3}}
+            except Exception as ex:        # noqa: BLE001
+                widened = {"error": repr(ex)[:300]}
         line = {
             "metric": "bn254_g1_msm_points_per_s", "value": msm_value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": msm_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -410,6 +442,8 @@ def run_ours(args):
             "srs": dict(set_info, registration_ms=reg_ms, plain=bool(args.plain)),
             "result_x_limb0": int(result_host[0]),
         }
+        if widened:
+            line["widened_rows"] = widened
         if witness:
             line["witness_like"] = witness
         if cpu_baseline:

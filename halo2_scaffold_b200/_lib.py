@@ -30,7 +30,7 @@ _EXPORTS = [
     "h2b_is_emulator", "h2b_msm_bn254_g1", "h2b_ntt_bn254_fr", "h2b_register_bases", "h2b_unregister_bases",
     "h2b_msm_bn254_g1_registered", "h2b_ntt_bn254_fr_dev", "h2b_msm_bn254_g1_dev",
     "h2b_msm_bn254_g1_dev_partial", "h2b_msm_fold_partials", "h2b_msm_fold_partials_dev", "h2b_fr_scale_dev",
-    "h2b_dev_alloc", "h2b_dev_free", "h2b_memcpy_h2d", "h2b_memcpy_d2h", "h2b_dev_sync", "h2b_gen_points_dev",
+    "h2b_dev_alloc", "h2b_dev_free", "h2b_memcpy_h2d", "h2b_memcpy_d2h", "h2b_memcpy_h2d_async", "h2b_dev_sync", "h2b_gen_points_dev",
     "h2b_gen_scalars_dev", "h2b_field_op", "h2b_ec_op", "h2b_imad_bench", "h2b_set_msm_window",
     "h2b_launch_count", "h2b_profile_enable", "h2b_profile_read", "h2b_msm_bn254_g1_dev_registered",
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
@@ -165,6 +165,7 @@ class Lib:
         L.h2b_dev_free.argtypes = [i32, vp]
         L.h2b_memcpy_h2d.argtypes = [i32, vp, vp, sz]
         L.h2b_memcpy_d2h.argtypes = [i32, vp, vp, sz]
+        L.h2b_memcpy_h2d_async.argtypes = [i32, vp, vp, sz, vp]
         L.h2b_dev_sync.argtypes = [i32]
         L.h2b_gen_points_dev.argtypes = [i32, u64, sz, vp, vp]
         L.h2b_gen_scalars_dev.argtypes = [i32, u64, sz, i32, vp, vp]
@@ -538,6 +539,11 @@ class Lib:
     def h2d(self, device: int, d_dst: int, src: np.ndarray):
         src = np.ascontiguousarray(src)
         self.check(self.L.h2b_memcpy_h2d(device, d_dst, src.ctypes.data, src.nbytes))
+
+    def h2d_async(self, device: int, d_dst: int, src: np.ndarray, stream: int = 0):
+        """upload into a buffer nothing in flight touches, without draining the device first; `src` must be contiguous"""
+        assert src.flags["C_CONTIGUOUS"]
+        self.check(self.L.h2b_memcpy_h2d_async(device, d_dst, src.ctypes.data, src.nbytes, stream))
 
     def d2h(self, device: int, dst: np.ndarray, d_src: int):
         assert dst.flags["C_CONTIGUOUS"]

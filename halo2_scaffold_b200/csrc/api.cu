@@ -1041,6 +1041,16 @@ int h2b_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes) {
     H2B_CUDA(cudaStreamSynchronize(c->stream));
     return H2B_OK;
 }
+// Upload that does not wait for the device: d_dst must not be in use by anything in flight.  Work queued on `stream` after the
+// call sees the data; the host buffer may be reused on return (pageable sources are consumed by the staging threads, pinned
+// ones must stay valid until the stream reaches the copy, as with cudaMemcpyAsync).
+int h2b_memcpy_h2d_async(int device, void* d_dst, const void* h_src, size_t bytes, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (bytes && (!d_dst || !h_src)) { set_error("h2b_memcpy_h2d_async: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return host_upload(*c, d_dst, h_src, bytes, (cudaStream_t)stream, false);
+}
 int h2b_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes) {
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));

@@ -255,6 +255,10 @@ int h2b_dev_alloc(int device, size_t bytes, void** out);
 int h2b_dev_free(int device, void* p);
 int h2b_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes);
 int h2b_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes);
+/* Upload a fresh column while the device keeps working: nothing in flight may touch d_dst; work queued on `stream` after the
+ * call sees the data.  Pageable sources are consumed before the call returns (pinned staging threads), pinned sources must
+ * stay valid until the stream reaches the copy. */
+int h2b_memcpy_h2d_async(int device, void* d_dst, const void* h_src, size_t bytes, void* stream);
 int h2b_dev_sync(int device);
 
 /* ---- synthetic workload + diagnostics ---------------------------------------------------------------- */

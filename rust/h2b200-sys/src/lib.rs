@@ -83,6 +83,7 @@ extern "C" {
     pub fn h2b_dev_alloc(device: c_int, bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn h2b_dev_free(device: c_int, p: *mut c_void) -> c_int;
     pub fn h2b_memcpy_h2d(device: c_int, d_dst: *mut c_void, h_src: *const c_void, bytes: usize) -> c_int;
+    pub fn h2b_memcpy_h2d_async(device: c_int, d_dst: *mut c_void, h_src: *const c_void, bytes: usize, stream: *mut c_void) -> c_int;
     pub fn h2b_memcpy_d2h(device: c_int, h_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
     pub fn h2b_dev_sync(device: c_int) -> c_int;
 }

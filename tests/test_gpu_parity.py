@@ -353,3 +353,24 @@ def test_msm_window_independence_at_2_22(gpu, oc):
     assert (res[0] == res[1]).all() and (res[0] == res[2]).all()
     # and against the oracle on the witness-like column (mostly 0 / 1 / small: fast on the CPU too)
     assert (res[0] == pc.affine_of(oc, oc.best_multiexp(s, P))).all()
+
+
+def test_async_upload_overlaps_and_delivers(gpu, oc):
+    # a pageable column uploaded with h2b_memcpy_h2d_async while an NTT is in flight on the same stream: later work sees the data
+    n = 1 << 18
+    a, b = oc.random_fr(0xAB1, n), oc.random_fr(0xAB2, n)
+    w = pc.omega_words(oc, 18)
+    d_a, d_b = gpu.dev_alloc(0, n * 32), gpu.dev_alloc(0, n * 32)
+    try:
+        gpu.h2d(0, d_a, a)
+        gpu.ntt_dev(0, d_a, w, 18)
+        gpu.h2d_async(0, d_b, b)
+        gpu.ntt_dev(0, d_b, w, 18)
+        gpu.dev_sync(0)
+        out_a, out_b = np.empty_like(a), np.empty_like(b)
+        gpu.d2h(0, out_a, d_a)
+        gpu.d2h(0, out_b, d_b)
+        assert (out_a == oc.best_fft(a, w, 18)).all() and (out_b == oc.best_fft(b, w, 18)).all()
+    finally:
+        gpu.dev_free(0, d_a)
+        gpu.dev_free(0, d_b)

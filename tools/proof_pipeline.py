@@ -111,13 +111,13 @@ def main():
                 t_prev[0] = t
             # instance -> coefficient form
             d_inst = torch.empty(n * 4, dtype=torch.int64, device=dev)
-            L.h2d(0, d_inst.data_ptr(), host_inst)
+            L.h2d_async(0, d_inst.data_ptr(), host_inst, st)
             inst_c = to_coeff(d_inst)
             # advice: upload, commit_lagrange
             adv = []
             for j in range(n_adv):
                 t = torch.empty(n * 4, dtype=torch.int64, device=dev)
-                L.h2d(0, t.data_ptr(), host_adv[j])
+                L.h2d_async(0, t.data_ptr(), host_adv[j], st)
                 commit(t, h_gl)
                 adv.append(t)
             mark("advice_upload_commit")
@@ -125,7 +125,7 @@ def main():
             perm_l = []
             for j in range(LK):
                 a, s_ = torch.empty(n * 4, dtype=torch.int64, device=dev), torch.empty(n * 4, dtype=torch.int64, device=dev)
-                L.h2d(0, a.data_ptr(), host_perm[j][0]); L.h2d(0, s_.data_ptr(), host_perm[j][1])
+                L.h2d_async(0, a.data_ptr(), host_perm[j][0], st); L.h2d_async(0, s_.data_ptr(), host_perm[j][1], st)
                 commit(a, h_gl); commit(s_, h_gl)
                 perm_l.append((a, s_))
             mark("lookup_permuted_commit")
