@@ -36,7 +36,7 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
-    "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
+    "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
 
@@ -153,6 +153,7 @@ class Lib:
         L.h2b_fr_lincomb_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp]
         L.h2b_permutation_product_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_lookup_product_dev.argtypes = [i32, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+        L.h2b_lookup_permute_dev.argtypes = [i32, vp, vp, u32, vp, vp, vp]
         L.h2b_g1_decode_dev.argtypes = [i32, vp, sz, i32, vp, ctypes.POINTER(u64), vp]
         L.h2b_g1_encode_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_srs_read.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(u32), vp, vp, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(u64), ctypes.POINTER(u64)]
@@ -407,6 +408,28 @@ class Lib:
         """sum_j coeffs[j] * cols[j], host arrays in and out"""
         n = _u64(cols[0]).size // 4
         return self._columns_op(list(cols), n, lambda d, d_out: self.fr_lincomb_dev(device, d, coeffs, n, d_out), device)
+
+    def lookup_permute_dev(self, device: int, d_input: int, d_table: int, usable_rows: int, d_permuted_input: int, d_permuted_table: int, stream: int = 0):
+        self.check(self.L.h2b_lookup_permute_dev(device, d_input, d_table, usable_rows, d_permuted_input, d_permuted_table, stream))
+
+    def lookup_permute(self, input_expression, table_expression, usable_rows: int, device: int = 0):
+        """permute_expression_pair on host arrays -> (permuted_input, permuted_table), usable_rows x 4 each"""
+        a, t = _u64(input_expression).reshape(-1, 4), _u64(table_expression).reshape(-1, 4)
+        n = a.shape[0]
+        assert t.shape[0] == n and usable_rows <= n
+        d = [self.dev_alloc(device, max(n, 1) * 32) for _ in range(4)]
+        try:
+            self.h2d(device, d[0], a)
+            self.h2d(device, d[1], t)
+            self.lookup_permute_dev(device, d[0], d[1], usable_rows, d[2], d[3])
+            pa, pt = np.empty((usable_rows, 4), dtype=np.uint64), np.empty((usable_rows, 4), dtype=np.uint64)
+            if usable_rows:
+                self.d2h(device, pa, d[2])
+                self.d2h(device, pt, d[3])
+            return pa, pt
+        finally:
+            for p in d:
+                self.dev_free(device, p)
 
     def _columns_op(self, cols, n: int, op, device: int = 0) -> np.ndarray:
         """upload `cols` (n x 4 each), run op(device pointers, d_out), download n x 4"""

@@ -424,6 +424,7 @@ void h2b_shutdown(void) {
         c->scan_scratch.release();
         evaluate_release(*c);
         c->srs_status.release();
+        c->lookup_scratch.release();
         c->srs_io.release();
         for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
         c->copy_events.clear();
@@ -750,6 +751,14 @@ int h2b_lookup_product_dev(int device, const void* d_compressed_input, const voi
     H2B_TRY(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     return lookup_product_run(*c, d_compressed_input, d_compressed_table, d_permuted_input, d_permuted_table, n, beta, gamma, d_z, (cudaStream_t)stream);
+}
+
+int h2b_lookup_permute_dev(int device, const void* d_input, const void* d_table, uint32_t usable_rows, void* d_permuted_input, void* d_permuted_table,
+                           void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return lookup_permute_run(*c, d_input, d_table, usable_rows, d_permuted_input, d_permuted_table, (cudaStream_t)stream);
 }
 
 // ---- SRS on-disk format -----------------------------------------------------------------------------

@@ -156,6 +156,16 @@ int h2b_permutation_product_dev(int device, const void* const* d_values, const v
 int h2b_lookup_product_dev(int device, const void* d_compressed_input, const void* d_compressed_table, const void* d_permuted_input,
                            const void* d_permuted_table, size_t n, const uint64_t beta[4], const uint64_t gamma[4], void* d_z, void* stream);
 
+/* [UP] plonk/lookup/prover.rs permute_expression_pair on the first usable_rows = n - (blinding_factors + 1) rows of the
+ * theta-compressed input and table columns (device, Montgomery): permuted_input = the input sorted by canonical value;
+ * permuted_table: every first occurrence of a value in permuted_input has that value at the same row, the remaining rows
+ * receive the leftover table values exactly as upstream assigns them (ascending leftovers onto the repeated rows taken from
+ * the end).  The outputs may alias the inputs; rows from usable_rows on (the blinding rows) are not touched.  The call
+ * synchronises the stream: an input value that the table does not hold fails with H2B_ERR_BAD_ARGUMENT, as upstream returns
+ * Error::ConstraintSystemFailure. */
+int h2b_lookup_permute_dev(int device, const void* d_input, const void* d_table, uint32_t usable_rows, void* d_permuted_input, void* d_permuted_table,
+                           void* stream);
+
 /* ---- quotient evaluation: evaluate_h on device-resident extended-coset columns ----------
  * [UP] halo2_proofs/src/plonk/evaluation.rs.  A GraphEvaluator is passed in the vocabulary upstream builds it in
  * (ValueSource / Calculation / CalculationInfo), flattened into plain arrays; the Rust shim fills these structs from

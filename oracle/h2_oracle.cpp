@@ -22,6 +22,7 @@
 #include <cmath>
 #include <thread>
 #include <vector>
+#include <map>
 #include <algorithm>
 
 typedef uint64_t u64;
@@ -581,6 +582,39 @@ void orc_lookup_product(const u64* compressed_input, const u64* compressed_table
     for (size_t i = 0; i < n; ++i) lookup_product[i] = lookup_product[i] * ((fr_at(compressed_input, i) + beta) * (fr_at(compressed_table, i) + gamma));
     Fr run = Fr::one();
     for (size_t i = 0; i < n; ++i) { memcpy(z + 4 * i, run.l, 32); run = run * lookup_product[i]; }
+}
+// [UP] plonk/lookup/prover.rs permute_expression_pair on the first `usable` rows.  Fr's Ord compares canonical integers.
+// Returns 0, or 1 when an input value is not in the table (upstream: Err(ConstraintSystemFailure)).
+int orc_lookup_permute(const u64* input, const u64* table, size_t usable, u64* permuted_input, u64* permuted_table) {
+    struct Canon {
+        u64 l[4];
+        bool operator<(const Canon& o) const { for (int i = 3; i >= 0; --i) if (l[i] != o.l[i]) return l[i] < o.l[i]; return false; }
+        bool operator==(const Canon& o) const { return l[0] == o.l[0] && l[1] == o.l[1] && l[2] == o.l[2] && l[3] == o.l[3]; }
+    };
+    auto canon = [](const u64* col, size_t i) { Fr x = fr_at(col, i).from_mont(); Canon c; memcpy(c.l, x.l, 32); return c; };
+    auto store = [](u64* col, size_t i, const Canon& c) { Fr x; memcpy(x.l, c.l, 32); x = x.to_mont(); memcpy(col + 4 * i, x.l, 32); };
+    std::vector<Canon> permuted_input_expression(usable);
+    for (size_t i = 0; i < usable; ++i) permuted_input_expression[i] = canon(input, i);
+    std::sort(permuted_input_expression.begin(), permuted_input_expression.end());
+    std::map<Canon, uint32_t> leftover_table_map;
+    for (size_t i = 0; i < usable; ++i) leftover_table_map[canon(table, i)] += 1;
+    std::vector<Canon> permuted_table_coeffs(usable, Canon{{0, 0, 0, 0}});
+    std::vector<size_t> repeated_input_rows;
+    for (size_t row = 0; row < usable; ++row) {
+        const Canon& input_value = permuted_input_expression[row];
+        if (row == 0 || !(input_value == permuted_input_expression[row - 1])) {
+            permuted_table_coeffs[row] = input_value;
+            auto it = leftover_table_map.find(input_value);
+            if (it == leftover_table_map.end() || it->second == 0) return 1;
+            it->second -= 1;
+        } else {
+            repeated_input_rows.push_back(row);
+        }
+    }
+    for (auto& kv : leftover_table_map)
+        for (uint32_t c = 0; c < kv.second; ++c) { permuted_table_coeffs[repeated_input_rows.back()] = kv.first; repeated_input_rows.pop_back(); }
+    for (size_t i = 0; i < usable; ++i) { store(permuted_input, i, permuted_input_expression[i]); store(permuted_table, i, permuted_table_coeffs[i]); }
+    return 0;
 }
 // ---------------------------------------------------------------------------------
 // SRS point encodings ([UP] halo2curves 0.3.x GroupEncoding::{to_bytes, from_bytes} for G1Affine; upstream's

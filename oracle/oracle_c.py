@@ -46,6 +46,7 @@ def lib():
         L.orc_random_fr.argtypes = [ctypes.c_uint64, ctypes.c_size_t, u64p]
         L.orc_permutation_product.argtypes = [u64p, u64p, ctypes.c_uint32, ctypes.c_size_t] + [u64p] * 7
         L.orc_lookup_product.argtypes = [u64p] * 4 + [ctypes.c_size_t] + [u64p] * 3
+        L.orc_lookup_permute.argtypes = [u64p, u64p, ctypes.c_size_t, u64p, u64p]
         L.orc_g1_from_bytes.argtypes = [u64p, ctypes.c_size_t, ctypes.c_int, u64p]
         L.orc_g1_from_bytes.restype = ctypes.c_size_t
         L.orc_g1_to_bytes.argtypes = [u64p, ctypes.c_size_t, u64p]
@@ -246,6 +247,16 @@ def lookup_product(compressed_input, compressed_table, permuted_input, permuted_
     sc = [_col(v) for v in (beta, gamma)]
     lib().orc_lookup_product(*[c.ctypes.data for c in cols], n, *[v.ctypes.data for v in sc], z.ctypes.data)
     return z
+
+
+def lookup_permute(input_expression, table_expression, usable_rows: int):
+    """[UP] permute_expression_pair -> (permuted_input, permuted_table) of usable_rows rows; raises ValueError when an input value
+    is not in the table"""
+    a, t = _col(input_expression), _col(table_expression)
+    pa, pt = np.empty((usable_rows, 4), dtype=np.uint64), np.empty((usable_rows, 4), dtype=np.uint64)
+    if lib().orc_lookup_permute(a.ctypes.data, t.ctypes.data, usable_rows, pa.ctypes.data, pt.ctypes.data):
+        raise ValueError("ConstraintSystemFailure: input value not in the table")
+    return pa, pt
 
 
 def field_op(field: str, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -17,7 +17,7 @@ fn main() {
         return;
     }
 
-    let sources = ["api.cu", "ntt.cu", "msm.cu", "testgen.cu", "stage.cu", "scan.cu", "evaluate.cu", "srs.cu"];
+    let sources = ["api.cu", "ntt.cu", "msm.cu", "testgen.cu", "stage.cu", "scan.cu", "evaluate.cu", "srs.cu", "lookup.cu"];
     let mut objects = Vec::new();
     for src in sources {
         let obj = out.join(src.replace(".cu", ".o"));

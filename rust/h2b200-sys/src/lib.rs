@@ -60,6 +60,8 @@ extern "C" {
     pub fn h2b_permutation_product_dev(device: c_int, d_values: *const *const c_void, d_permutations: *const *const c_void, n_columns: u32, n: usize,
                                        beta: *const u64, gamma: *const u64, delta: *const u64, deltaomega: *const u64, omega: *const u64,
                                        last_z: *const u64, d_z: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_lookup_permute_dev(device: c_int, d_input: *const c_void, d_table: *const c_void, usable_rows: u32, d_permuted_input: *mut c_void,
+                                  d_permuted_table: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn h2b_lookup_product_dev(device: c_int, d_compressed_input: *const c_void, d_compressed_table: *const c_void, d_permuted_input: *const c_void,
                                   d_permuted_table: *const c_void, n: usize, beta: *const u64, gamma: *const u64, d_z: *mut c_void, stream: *mut c_void) -> c_int;
     // plonk::evaluation (evaluate_h)

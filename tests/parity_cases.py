@@ -520,3 +520,43 @@ def check_lincomb(L, oc, cases):
         for j in range(m):
             want = oc.field_op("fr", "add", want, oc.field_op("fr", "mul", cols[j], np.repeat(coeffs[j:j + 1], n, axis=0)))
         assert (L.fr_lincomb(cols, coeffs) == want).all(), (n, m)
+
+
+def check_lookup_permute(L, oc, cases):
+    """permute_expression_pair against the oracle's restatement (sort + BTreeMap walk), and the argument's invariants: A' is a
+    sorted permutation of A, S' a permutation of S, and every row has A'[r] == S'[r] or A'[r] == A'[r-1].
+    cases: (n, usable_rows, table_size, kind)"""
+    from halo2_scaffold_b200._lib import H2BError
+    for n, usable, table_size, kind, seed in cases:
+        rng = np.random.default_rng(seed)
+        pool = oc.random_fr(0xC000 + seed, table_size)             # distinct table values (random 254-bit: full-width keys)
+        if kind == "small":                                        # a range table 0 .. table_size - 1, as halo2-lib's lookup table
+            pool = oc.fr_to_mont(np.array([[v, 0, 0, 0] for v in range(table_size)], dtype=np.uint64))
+        # the table column: every pool value at least once (while rows last), the rest repeats; the input draws from the pool
+        t_idx = np.concatenate([np.arange(min(table_size, n)), rng.integers(0, table_size, size=max(0, n - table_size))])
+        rng.shuffle(t_idx)
+        table = pool[t_idx]
+        present = np.unique(t_idx[:usable])
+        a_idx = present[rng.integers(0, len(present), size=n)] if usable else np.zeros(n, dtype=np.int64)
+        if kind == "skewed" and usable:
+            a_idx[: (3 * n) // 4] = present[0]                      # one value on most rows
+        inp = pool[a_idx]
+        want_a, want_t = oc.lookup_permute(inp, table, usable)
+        got_a, got_t = L.lookup_permute(inp, table, usable)
+        assert (got_a == want_a).all(), ("permuted input", n, usable, kind)
+        assert (got_t == want_t).all(), ("permuted table", n, usable, kind)
+        if usable:
+            key = lambda w: sorted(map(tuple, w.tolist()))
+            assert key(got_a) == key(inp[:usable]) and key(got_t) == key(table[:usable])
+            same_as_table = (got_a == got_t).all(axis=1)
+            same_as_prev = np.concatenate([[False], (got_a[1:] == got_a[:-1]).all(axis=1)])
+            assert (same_as_table | same_as_prev).all()
+        # an input value outside the table is refused
+        if usable > 2 and kind != "small":
+            bad = inp.copy()
+            bad[1] = oc.random_fr(0xDEAD + seed, 1)[0]
+            try:
+                L.lookup_permute(bad, table, usable)
+                raise AssertionError("missing table value accepted")
+            except H2BError as e:
+                assert "ConstraintSystemFailure" in str(e)

@@ -51,5 +51,33 @@ for k in [int(a) for a in (sys.argv[1:] or ["20", "22", "24"])]:
         ms = e0.elapsed_time(e1) / 5
         out[name + "_ms"] = round(ms, 4)
         out[name + "_rows_per_s"] = n / ms * 1e3
+    # permute_expression_pair: range-table lookup (values < 2^16, as LOOKUP_BITS-sized tables) and full-width random values
+    usable = n - 6
+    for name, bits in (("lookup_permute_range_table", 16), ("lookup_permute_full_width", 0)):
+        if bits:
+            import numpy as _np
+            tab = torch.arange(n, device=dev, dtype=torch.int64) % (1 << bits)
+            inp = (torch.arange(n, device=dev, dtype=torch.int64) * 2654435761) % (1 << bits)
+            def to_cols(v):
+                c = torch.zeros(n * 4, dtype=torch.int64, device=dev)
+                c[0::4] = v
+                # canonical small integers -> Montgomery form on the device: multiply by R^2 through the NTT-free scale entry point
+                L.fr_scale_dev(0, c.data_ptr(), n, L.field_op("fr", "to_mont", _np.array([[1, 0, 0, 0]], dtype=_np.uint64)), st)   # x * mont(1) = x (stays canonical)
+                return c
+            a_col, t_col = to_cols(inp), to_cols(tab)
+        else:
+            t_col = cols[0]
+            a_col = cols[0].view(-1, 4).flip(0).contiguous().view(-1)     # a permutation of the table column
+        for _ in range(2):
+            L.lookup_permute_dev(0, a_col.data_ptr(), t_col.data_ptr(), usable, cols[4].data_ptr(), cols[5].data_ptr(), st)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            L.lookup_permute_dev(0, a_col.data_ptr(), t_col.data_ptr(), usable, cols[4].data_ptr(), cols[5].data_ptr(), st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[name + "_ms"] = round(ms, 4)
+        out[name + "_rows_per_s"] = n / ms * 1e3
     del cols
     print(json.dumps(out), flush=True)
