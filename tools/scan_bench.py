@@ -61,8 +61,9 @@ for k in [int(a) for a in (sys.argv[1:] or ["20", "22", "24"])]:
             def to_cols(v):
                 c = torch.zeros(n * 4, dtype=torch.int64, device=dev)
                 c[0::4] = v
-                # canonical small integers -> Montgomery form on the device: multiply by R^2 through the NTT-free scale entry point
-                L.fr_scale_dev(0, c.data_ptr(), n, L.field_op("fr", "to_mont", _np.array([[1, 0, 0, 0]], dtype=_np.uint64)), st)   # x * mont(1) = x (stays canonical)
+                # canonical small integers -> Montgomery form on the device: a Montgomery product with the raw limbs of R^2 mod r
+                r2 = L.field_op("fr", "to_mont", L.field_op("fr", "to_mont", _np.array([[1, 0, 0, 0]], dtype=_np.uint64)))
+                L.fr_scale_dev(0, c.data_ptr(), n, r2, st)
                 return c
             a_col, t_col = to_cols(inp), to_cols(tab)
         else:
