@@ -56,8 +56,9 @@ for k in [int(a) for a in (sys.argv[1:] or ["20", "22", "24"])]:
     for name, bits in (("lookup_permute_range_table", 16), ("lookup_permute_full_width", 0)):
         if bits:
             import numpy as _np
-            tab = torch.arange(n, device=dev, dtype=torch.int64) % (1 << bits)
-            inp = (torch.arange(n, device=dev, dtype=torch.int64) * 2654435761) % (1 << bits)
+            rng_ = min(1 << bits, usable)
+            tab = torch.arange(n, device=dev, dtype=torch.int64) % rng_
+            inp = (torch.arange(n, device=dev, dtype=torch.int64) * 2654435761) % rng_
             def to_cols(v):
                 c = torch.zeros(n * 4, dtype=torch.int64, device=dev)
                 c[0::4] = v
