@@ -69,7 +69,8 @@ for k in [int(a) for a in (sys.argv[1:] or ["20", "22", "24"])]:
             a_col, t_col = to_cols(inp), to_cols(tab)
         else:
             t_col = cols[0]
-            a_col = cols[0].view(-1, 4).flip(0).contiguous().view(-1)     # a permutation of the table column
+            a_col = cols[0].clone()
+            a_col.view(-1, 4)[:usable] = cols[0].view(-1, 4)[:usable].flip(0)     # a permutation of the table's usable rows
         for _ in range(2):
             L.lookup_permute_dev(0, a_col.data_ptr(), t_col.data_ptr(), usable, cols[4].data_ptr(), cols[5].data_ptr(), st)
         torch.cuda.synchronize()
