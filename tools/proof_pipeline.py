@@ -5,8 +5,7 @@ of halo2_proofs' plonk/prover.rs: witness columns are up
 else -- commitments, (i)NTTs, grand products, the quotient evaluation, the evaluations at x and the opening quotients -- runs
 through the device-pointer entry points and only 96-byte commitments / 32-byte evaluations come back.
 
-Not included (host work of the prover that stays on the host): witness generation, transcript hashing, the lookup argument's
-permute_expression_pair (a sort; synthetic permuted columns stand in), blinding-row randomness.  Proving-key columns (fixed,
+Not included (host work of the prover that stays on the host): witness generation, transcript hashing, blinding-row randomness.  Proving-key columns (fixed,
 sigma, l_0 / l_last / l_active cosets) and the SRS tables are resident before the timed region, as after keygen.
 The reference's own create_proof cannot be run here; column counts are the estimates of SURVEY.md section 3.3 / appendix.
 usage: python tools/proof_pipeline.py [cfg ...]      one JSON line per configuration
@@ -59,7 +58,9 @@ def main():
         h_g, h_gl = L.register_bases(hp), L.register_bases(hp[::-1].copy())
         del hp
         fixed_ext = [dcol(en) for _ in range(A + 1)]           # one selector per gate column + the lookup table column
-        table_lagrange = dcol(n)
+        host_table = L.gen_scalars(450 + k, n, 0)
+        table_lagrange = torch.from_numpy(host_table.view(np.int64).reshape(-1)).to(dev)
+        usable = n - 6                                          # blinding_factors + 1 = 6 rows at the end
         sigma_lagrange = [dcol(n) for _ in range(n_adv)]
         sigma_ext = [dcol(en) for _ in range(n_adv)]
         l0, l_last, l_active = dcol(en), dcol(en), dcol(en)
@@ -75,8 +76,10 @@ def main():
         tev = np.stack([W(t) for t in dom.t_evaluations])
         # the witness as the host holds it: pageable arrays
         host_adv = [L.gen_scalars(300 + j, n, 1) for j in range(n_adv)]
+        for j in range(LK):                                     # lookup-advice columns hold table values (a permutation of the usable rows)
+            host_adv[A + j] = host_table.copy()
+            host_adv[A + j][:usable] = host_table[:usable][::-1]
         host_inst = L.gen_scalars(400, n, 1)
-        host_perm = [(L.gen_scalars(500 + 2 * j, n, 1), L.gen_scalars(501 + 2 * j, n, 1)) for j in range(LK)]     # a', s' from the host-side sort
         weights = L.gen_scalars(900, 64)                         # powers of y / v of the multi-open argument (host scalars)
         blocks = torch.empty(64 * 28, dtype=torch.int64, device=dev)
         evals = torch.empty(256 * 4, dtype=torch.int64, device=dev)
@@ -121,11 +124,11 @@ def main():
                 commit(t, h_gl)
                 adv.append(t)
             mark("advice_upload_commit")
-            # lookups: permuted input / table come from the host-side sort; commit + coefficient form
+            # lookups: permute_expression_pair on the device (sort + table matching), commit both permuted columns
             perm_l = []
             for j in range(LK):
-                a, s_ = torch.empty(n * 4, dtype=torch.int64, device=dev), torch.empty(n * 4, dtype=torch.int64, device=dev)
-                L.h2d_async(0, a.data_ptr(), host_perm[j][0], st); L.h2d_async(0, s_.data_ptr(), host_perm[j][1], st)
+                a, s_ = adv[A + j].clone(), table_lagrange.clone()                 # rows >= usable: the blinding rows (host randomness)
+                L.lookup_permute_dev(0, adv[A + j].data_ptr(), table_lagrange.data_ptr(), usable, a.data_ptr(), s_.data_ptr(), st)
                 commit(a, h_gl); commit(s_, h_gl)
                 perm_l.append((a, s_))
             mark("lookup_permuted_commit")
@@ -225,8 +228,8 @@ def main():
         total_ms = (time.perf_counter() - t0) * 1e3
         print(json.dumps({"config": name, "k": k, "extended_k": ek, "gate_advice": A, "lookup_advice": LK, "degree": d, "permutation_sets": sets,
                           "device_resident_hot_path_ms": round(total_ms, 2), "phases_ms": phase, "calls": dict(counts),
-                          "h2d_bytes": (n_adv + 1 + 2 * LK) * n * 32, "note": "1 x B200; witness columns uploaded from pageable host arrays; host-side prover work "
-                          "(witness generation, transcript, permute_expression_pair, blinding) not included; column counts are estimates"}), flush=True)
+                          "h2d_bytes": (n_adv + 1) * n * 32, "note": "1 x B200; witness columns uploaded from pageable host arrays; host-side prover work "
+                          "(witness generation, transcript, blinding) not included; column counts are estimates"}), flush=True)
         L.unregister_bases(h_g); L.unregister_bases(h_gl)
         del fixed_ext, sigma_ext, sigma_lagrange
         torch.cuda.empty_cache()
