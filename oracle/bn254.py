@@ -521,3 +521,57 @@ def srs_read(path, fmt: int = SERDE_RAW_BYTES):
             else:
                 out.append([g1_read_raw(raw[i * ps:(i + 1) * ps], fmt == SERDE_RAW_BYTES) for i in range(n)])
         return k, out[0], out[1], f.read()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Grand products and the lookup permutation on canonical integers -- the independent check of h2_oracle.cpp's
+# restatements ([UP] plonk/permutation/prover.rs Argument::commit, plonk/lookup/prover.rs commit_product and
+# permute_expression_pair).  Written from the formulas of the arguments, not from the C++ code.
+# ---------------------------------------------------------------------------------------------------------
+FR_DELTA = pow(FR_GENERATOR, 1 << FR_S, R_MOD)
+
+
+def permutation_product(values, sigma, beta, gamma, deltaomega, omega, last_z):
+    """z[0] = last_z; z[i+1] = z[i] * prod_j (v_j[i] + deltaomega delta^j omega^i beta + gamma) / prod_j (v_j[i] + beta s_j[i] + gamma)"""
+    n = len(values[0])
+    z, run = [], last_z % R_MOD
+    for i in range(n):
+        z.append(run)
+        num = den = 1
+        for j, (v, s) in enumerate(zip(values, sigma)):
+            num = num * (v[i] + deltaomega * pow(FR_DELTA, j, R_MOD) * pow(omega, i, R_MOD) * beta + gamma) % R_MOD
+            den = den * (v[i] + beta * s[i] + gamma) % R_MOD
+        run = run * num % R_MOD * (pow(den, -1, R_MOD) if den else 0) % R_MOD
+    return z
+
+
+def lookup_product(a, s, a_perm, s_perm, beta, gamma):
+    """z[0] = 1; z[i+1] = z[i] (a[i] + beta)(s[i] + gamma) / ((a'[i] + beta)(s'[i] + gamma))"""
+    z, run = [], 1
+    for i in range(len(a)):
+        z.append(run)
+        den = (a_perm[i] + beta) * (s_perm[i] + gamma) % R_MOD
+        run = run * (a[i] + beta) % R_MOD * (s[i] + gamma) % R_MOD * (pow(den, -1, R_MOD) if den else 0) % R_MOD
+    return z
+
+
+def permute_expression_pair(a, s, usable_rows):
+    """-> (A', S') over the first usable_rows rows; raises ValueError if an input value is missing from the table"""
+    from collections import Counter
+    a_sorted = sorted(a[:usable_rows])
+    leftover = Counter(s[:usable_rows])
+    s_perm = [None] * usable_rows
+    repeated = []
+    for row, v in enumerate(a_sorted):
+        if row == 0 or v != a_sorted[row - 1]:
+            if leftover[v] <= 0:
+                raise ValueError("ConstraintSystemFailure")
+            leftover[v] -= 1
+            s_perm[row] = v
+        else:
+            repeated.append(row)
+    for v in sorted(leftover):                      # BTreeMap order
+        for _ in range(leftover[v]):
+            s_perm[repeated.pop()] = v
+    assert not repeated
+    return a_sorted, s_perm

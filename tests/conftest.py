@@ -46,4 +46,4 @@ def gpu():
 @pytest.fixture(scope="session")
 def golden():
     d = os.path.join(ROOT, "tests", "golden")
-    return {name: np.load(os.path.join(d, name + "_golden.npz")) for name in ("ntt", "msm", "domain")}
+    return {name: np.load(os.path.join(d, name + "_golden.npz")) for name in ("ntt", "msm", "domain", "prover")}

@@ -104,8 +104,75 @@ def make_domain():
                         extended=words(ext, o.R_MOD), back=words(back, o.R_MOD))
 
 
+def make_prover():
+    """Fixtures of the widened rows, all from the big-int code of oracle/bn254.py: GraphEvaluator walk, permutation and
+    lookup grand products, permute_expression_pair, divide_by_vanishing_poly, the G1 point encodings."""
+    data = {}
+    n = 16
+    # a small GraphEvaluator: q * (a + b[next] * c - d[prev]) combined with y into the previous value, via every op kind
+    consts = [0, 1, 2, 0x1234567]
+    rotations = [0, 1, -1]
+    calcs = [[7, 0, 2, 0, 0, 0, 0, 0, 0, 0],          # t0 = fixed0
+             [2, 1, 3, 1, 1, 3, 2, 0, 0, 0],          # t1 = advice1[next] * advice2
+             [0, 2, 3, 0, 0, 1, 1, 0, 0, 0],          # t2 = advice0 + t1
+             [1, 3, 1, 2, 0, 3, 0, 2, 0, 0],          # t3 = t2 - advice0[prev]
+             [2, 4, 1, 0, 0, 1, 3, 0, 0, 0],          # t4 = t0 * t3
+             [3, 5, 1, 4, 0, 0, 0, 0, 0, 0],          # t5 = t4^2
+             [4, 6, 4, 0, 0, 0, 0, 0, 0, 0],          # t6 = 2 * instance0
+             [5, 7, 5, 0, 0, 0, 0, 0, 0, 0],          # t7 = -challenge0
+             [0, 8, 0, 3, 0, 6, 0, 0, 0, 0],          # t8 = const3 + beta      (dead)
+             [6, 9, 10, 0, 0, 9, 0, 0, 0, 4]]         # t9 = Horner(previous, [t4, t5, t6, t7], y)
+    parts = [[1, 4, 0], [1, 5, 0], [1, 6, 0], [1, 7, 0]]
+    cols = [o.random_fr(0x900D2000 + j, n) for j in range(5)]          # fixed0, advice0..2, instance0
+    sc = o.random_fr(0x900D2100, 6)                                     # challenge0, beta, gamma, theta, y + spare
+    prev = o.random_fr(0x900D2200, n)
+    out = [o.graph_evaluate_row(consts, rotations, calcs, parts, 10, cols[:1], cols[1:4], cols[4:], sc[:1], sc[1], sc[2], sc[3], sc[4], prev[i], i, 2, n)
+           for i in range(n)]
+    data["graph_constants"] = words(consts, o.R_MOD)
+    data["graph_rotations"] = np.array(rotations, dtype=np.int32)
+    data["graph_calcs"] = np.array(calcs, dtype=np.uint32)
+    data["graph_parts"] = np.array(parts, dtype=np.uint32)
+    data["graph_cols"] = np.stack([words(c, o.R_MOD) for c in cols])
+    data["graph_scalars"] = words(sc, o.R_MOD)
+    data["graph_prev"] = words(prev, o.R_MOD)
+    data["graph_out"] = words(out, o.R_MOD)
+    # grand products
+    k = 4
+    w = o.omega_for(k)
+    vals = [o.random_fr(0x900D3000 + j, n) for j in range(3)]
+    sig = [o.random_fr(0x900D3100 + j, n) for j in range(3)]
+    beta, gamma, last_z = o.random_fr(0x900D3200, 3)
+    dw = pow(o.FR_DELTA, 2, o.R_MOD)
+    data["perm_values"] = np.stack([words(v, o.R_MOD) for v in vals])
+    data["perm_sigma"] = np.stack([words(v, o.R_MOD) for v in sig])
+    data["perm_scalars"] = words([beta, gamma, o.FR_DELTA, dw, w, last_z], o.R_MOD)
+    data["perm_z"] = words(o.permutation_product(vals, sig, beta, gamma, dw, w, last_z), o.R_MOD)
+    lk = [o.random_fr(0x900D3300 + j, n) for j in range(4)]
+    data["lookup_cols"] = np.stack([words(v, o.R_MOD) for v in lk])
+    data["lookup_z"] = words(o.lookup_product(*lk, beta, gamma), o.R_MOD)
+    # permute_expression_pair: 13 usable rows, table with duplicates, input with repeats, a negative value
+    table = [5, 0, 3, 3, o.R_MOD - 1, 9, 2**200 + 7, 1, 4, 5, 5, 8, 6, 77, 78, 79]
+    inp = [3, 5, 5, o.R_MOD - 1, 0, 0, 0, 2**200 + 7, 9, 3, 1, 5, 8, 111, 112, 113]
+    pa, pt = o.permute_expression_pair(inp, table, 13)
+    data["permute_input"] = words(inp, o.R_MOD)
+    data["permute_table"] = words(table, o.R_MOD)
+    data["permute_out_input"] = words(pa, o.R_MOD)
+    data["permute_out_table"] = words(pt, o.R_MOD)
+    # divide_by_vanishing_poly for j = 4, k = 3 (period 4)
+    dom = o.EvaluationDomain(4, 3)
+    a = o.random_fr(0x900D3400, 1 << dom.extended_k)
+    data["vanishing_in"] = words(a, o.R_MOD)
+    data["vanishing_out"] = words(dom.divide_by_vanishing_poly(a), o.R_MOD)
+    # point encodings: generator, its double, a negation, the identity, larger multiples
+    pts = [o.G1_GEN, o.g1_add(o.G1_GEN, o.G1_GEN), o.g1_neg(o.G1_GEN), None] + [o.g1_mul(o.G1_GEN, 0xABCDEF + 977 * i) for i in range(12)]
+    data["codec_points"] = affine_words(pts)
+    data["codec_bytes"] = np.frombuffer(b"".join(o.g1_to_bytes(P) for P in pts), dtype=np.uint8).reshape(-1, 32).copy()
+    np.savez_compressed(os.path.join(HERE, "prover_golden.npz"), **data)
+
+
 if __name__ == "__main__":
     make_ntt()
     make_msm()
     make_domain()
+    make_prover()
     print("golden fixtures written to", HERE)

@@ -560,3 +560,38 @@ def check_lookup_permute(L, oc, cases):
                 raise AssertionError("missing table value accepted")
             except H2BError as e:
                 assert "ConstraintSystemFailure" in str(e)
+
+
+def check_golden_prover_oracle(oc, g):
+    """the C++ restatements reproduce the big-int fixture of the widened rows (tests/golden/prover_golden.npz)"""
+    c, sc = g["graph_cols"], g["graph_scalars"]
+    graph = (g["graph_constants"], g["graph_rotations"], g["graph_calcs"], g["graph_parts"], 10)
+    assert (oc.evaluate_graph(graph, c[:1], c[1:4], c[4:], sc[:1], sc[1], sc[2], sc[3], sc[4], g["graph_prev"], 2) == g["graph_out"]).all()
+    ps = g["perm_scalars"]
+    assert (oc.permutation_product(list(g["perm_values"]), list(g["perm_sigma"]), ps[0], ps[1], ps[2], ps[3], ps[4], ps[5]) == g["perm_z"]).all()
+    lk = g["lookup_cols"]
+    assert (oc.lookup_product(lk[0], lk[1], lk[2], lk[3], ps[0], ps[1]) == g["lookup_z"]).all()
+    pa, pt = oc.lookup_permute(g["permute_input"], g["permute_table"], 13)
+    assert (pa == g["permute_out_input"]).all() and (pt == g["permute_out_table"]).all()
+    dec, first = oc.g1_from_bytes(g["codec_bytes"])
+    assert first == len(g["codec_bytes"]) and (dec == g["codec_points"]).all()
+    assert (oc.g1_to_bytes(g["codec_points"]) == g["codec_bytes"]).all()
+
+
+def check_golden_prover(L, g):
+    """the kernels (emulated or on the GPU) reproduce the same fixture through the C ABI"""
+    import halo2_scaffold_b200 as h2
+    from halo2_scaffold_b200 import evaluation as ev
+    from halo2_scaffold_b200._lib import GraphArrays
+    c, sc = g["graph_cols"], g["graph_scalars"]
+    ga = GraphArrays(g["graph_constants"], g["graph_rotations"], g["graph_calcs"], g["graph_parts"], 10)
+    assert (ev.evaluate_graph(L, ga, c[:1], c[1:4], c[4:], sc[:1], sc[1], sc[2], sc[3], sc[4], g["graph_prev"], 2) == g["graph_out"]).all()
+    ps = g["perm_scalars"]
+    assert (L.permutation_product(list(g["perm_values"]), list(g["perm_sigma"]), ps[0], ps[1], ps[2], ps[3], ps[4], ps[5]) == g["perm_z"]).all()
+    lk = g["lookup_cols"]
+    assert (L.lookup_product(lk[0], lk[1], lk[2], lk[3], ps[0], ps[1]) == g["lookup_z"]).all()
+    pa, pt = L.lookup_permute(g["permute_input"], g["permute_table"], 13)
+    assert (pa == g["permute_out_input"]).all() and (pt == g["permute_out_table"]).all()
+    assert (h2.EvaluationDomain(4, 3, lib=L).divide_by_vanishing_poly(g["vanishing_in"]) == g["vanishing_out"]).all()
+    assert (L.g1_decode(g["codec_bytes"], 0) == g["codec_points"]).all()
+    assert (L.g1_encode(g["codec_points"]) == g["codec_bytes"]).all()

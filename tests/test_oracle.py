@@ -153,3 +153,8 @@ def test_g1_encoding_anchors(oc):
     assert first == len(pts) and (dec == raw).all()
     with pytest.raises(ValueError):
         o.g1_from_bytes((o.P_MOD + 5).to_bytes(32, "little"))
+
+
+def test_prover_rows_golden(oc, golden):
+    import parity_cases as pc
+    pc.check_golden_prover_oracle(oc, golden["prover"])
