@@ -6,7 +6,10 @@
 //   h2b200::arithmetic::best_multiexp   <- [UP] halo2_proofs::arithmetic::best_multiexp   
 //   h2b200::arithmetic::best_fft        <- [UP] halo2_proofs::arithmetic::best_fft        (row a3)
 //   h2b200::poly::EvaluationDomain      <- [UP] halo2_proofs::poly::EvaluationDomain      (row a6, Appendix B)
-//   h2b200::poly::kzg::ParamsKZG        <- [UP] halo2_proofs::poly::kzg::commitment::ParamsKZG::{commit, commit_lagrange} (row a7)
+//   h2b200::poly::kzg::ParamsKZG        <- [UP] halo2_proofs::poly::kzg::commitment::ParamsKZG::{commit, commit_lagrange,
+//                                          read_custom, write_custom} (rows a7, f4)
+//   h2b200::plonk::evaluation::GraphEvaluator, h2b200::plonk::{permutation, lookup}::*
+//                                       <- [UP] halo2_proofs::plonk::evaluation / permutation::prover / lookup::prover (rows f2, f3)
 //
 // Rust `assert!`/`panic!` become h2b200::Panic (a std::logic_error); a non-zero return of the C ABI becomes
 // h2b200::Panic carrying h2b_last_error(), exactly what the Rust shim of INTEGRATION.md does.
@@ -15,6 +18,8 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -105,6 +110,12 @@ inline Fr from_u64(uint64_t v) {
     return from_canonical(c);
 }
 inline Fr one() { return from_u64(1); }
+inline Fr sub(const Fr& a, const Fr& b) {
+    Fr r; u128 bw = 0;
+    for (int i = 0; i < 4; ++i) { u128 d = (u128)a.l[i] - b.l[i] - (uint64_t)bw; r.l[i] = (uint64_t)d; bw = (d >> 64) & 1; }
+    if (bw) { u128 c = 0; for (int i = 0; i < 4; ++i) { c += (u128)r.l[i] + MODULUS[i]; r.l[i] = (uint64_t)c; c >>= 64; } }
+    return r;
+}
 inline Fr square(const Fr& a) { return mul(a, a); }
 inline Fr pow(const Fr& a, const uint64_t e[4]) {
     Fr r = one();
@@ -190,6 +201,15 @@ class EvaluationDomain {
         extended_ifft_divisor_ = fr::invert(fr::from_u64((uint64_t)1 << extended_k_));
         g_coset_ = fr::zeta();
         g_coset_inv_ = fr::square(g_coset_);
+        // t_evaluations: 1 / (X^n - 1) on the zeta coset repeats with period 2^(extended_k - k)
+        const uint64_t e[4] = {n_, 0, 0, 0};
+        const Fr orig = fr::pow(g_coset_, e), step = fr::pow(extended_omega_, e);
+        Fr cur = orig;
+        do {
+            t_evaluations_.push_back(fr::invert(fr::sub(cur, fr::one())));
+            cur = fr::mul(cur, step);
+        } while (!(cur == orig));
+        if (t_evaluations_.size() != ((size_t)1 << (extended_k_ - k_)) || t_evaluations_.size() > 8) throw Panic("EvaluationDomain::new: unexpected t_evaluations period");
     }
     uint32_t k() const { return k_; }
     uint32_t extended_k() const { return extended_k_; }
@@ -224,6 +244,14 @@ class EvaluationDomain {
         });
     }
 
+    // pub fn divide_by_vanishing_poly(&self, a: Polynomial<_, ExtendedLagrangeCoeff>) -> Polynomial<_, ExtendedLagrangeCoeff>
+    std::vector<Fr> divide_by_vanishing_poly(const std::vector<Fr>& a) const {
+        if (a.size() != extended_len()) throw Panic("assertion failed: a.len() == self.extended_len()");
+        return run(a, extended_len(), extended_len(), extended_len(), [&](void* d) {
+            check(h2b_fr_scale_dev(device_, d, extended_len(), t_evaluations_[0].l, (int)t_evaluations_.size(), nullptr), "divide_by_vanishing_poly");
+        });
+    }
+
   private:
     // upload `upload_len` elements of `a` into a device buffer of `alloc_len`, run `steps`, download `out_len`
     template <class F>
@@ -240,20 +268,51 @@ class EvaluationDomain {
     uint32_t k_, extended_k_;
     uint64_t n_, quotient_poly_degree_;
     Fr omega_, omega_inv_, extended_omega_, extended_omega_inv_, ifft_divisor_, extended_ifft_divisor_, g_coset_, g_coset_inv_;
+    std::vector<Fr> t_evaluations_;
 };
 
 namespace kzg {
 
 // pub struct ParamsKZG<E: Engine> { k, n, g: Vec<G1Affine>, g_lagrange: Vec<G1Affine>, ... }
 // Both SRS vectors are registered once (device resident, window tables precomputed).
+// pub enum SerdeFormat { Processed, RawBytes, RawBytesUnchecked }
+enum class SerdeFormat : int { Processed = H2B_SERDE_PROCESSED, RawBytes = H2B_SERDE_RAW_BYTES, RawBytesUnchecked = H2B_SERDE_RAW_BYTES_UNCHECKED };
+
 class ParamsKZG {
   public:
-    ParamsKZG(uint32_t k, const std::vector<G1Affine>& g, const std::vector<G1Affine>& g_lagrange) : k_(k), n_((uint64_t)1 << k) {
+    ParamsKZG(uint32_t k, const std::vector<G1Affine>& g, const std::vector<G1Affine>& g_lagrange, std::vector<uint8_t> g2_bytes = {})
+        : k_(k), n_((uint64_t)1 << k), host_g_(g), host_g_lagrange_(g_lagrange), g2_bytes_(std::move(g2_bytes)) {
         ensure_init();
         if (g.size() != n_ || g_lagrange.size() != n_) throw Panic("ParamsKZG: g and g_lagrange must hold 2^k points");
         check(h2b_register_bases(reinterpret_cast<const uint64_t*>(g.data()), g.size(), &g_), "register g");
         check(h2b_register_bases(reinterpret_cast<const uint64_t*>(g_lagrange.data()), g_lagrange.size(), &g_lagrange_), "register g_lagrange");
     }
+    // pub fn read_custom<R: io::Read>(reader, format) -> io::Result<Self>: decoded on the device, both vectors stay resident there
+    ParamsKZG(const std::string& path, SerdeFormat format) {
+        ensure_init();
+        FILE* f = fopen(path.c_str(), "rb");
+        unsigned char kb[4];
+        if (!f || fread(kb, 1, 4, f) != 4) { if (f) fclose(f); throw Panic("ParamsKZG::read_custom: cannot read " + path); }
+        fclose(f);
+        k_ = (uint32_t)kb[0] | ((uint32_t)kb[1] << 8) | ((uint32_t)kb[2] << 16) | ((uint32_t)kb[3] << 24);
+        if (k_ > 28) throw Panic("ParamsKZG::read_custom: k out of range");
+        n_ = (uint64_t)1 << k_;
+        host_g_.resize(n_); host_g_lagrange_.resize(n_);
+        g2_bytes_.resize(256);
+        size_t g2_len = 0;
+        uint32_t k = 0;
+        check(h2b_srs_read(path.c_str(), (int)format, &k, reinterpret_cast<uint64_t*>(host_g_.data()), reinterpret_cast<uint64_t*>(host_g_lagrange_.data()),
+                           g2_bytes_.data(), g2_bytes_.size(), &g2_len, &g_, &g_lagrange_), "ParamsKZG::read_custom");
+        g2_bytes_.resize(g2_len);
+    }
+    // pub fn write_custom<W: io::Write>(&self, writer, format)
+    void write_custom(const std::string& path, SerdeFormat format) const {
+        check(h2b_srs_write(path.c_str(), (int)format, k_, reinterpret_cast<const uint64_t*>(host_g_.data()), reinterpret_cast<const uint64_t*>(host_g_lagrange_.data()),
+                            g2_bytes_.data(), g2_bytes_.size()), "ParamsKZG::write_custom");
+    }
+    const std::vector<G1Affine>& get_g() const { return host_g_; }
+    const std::vector<G1Affine>& get_g_lagrange() const { return host_g_lagrange_; }
+    const std::vector<uint8_t>& g2_bytes() const { return g2_bytes_; }
     ~ParamsKZG() {
         if (g_) h2b_unregister_bases(g_);
         if (g_lagrange_) h2b_unregister_bases(g_lagrange_);
@@ -274,11 +333,179 @@ class ParamsKZG {
         check(h2b_msm_bn254_g1_registered(reinterpret_cast<const uint64_t*>(poly.data()), handle, 0, poly.size(), reinterpret_cast<uint64_t*>(&out)), "commit");
         return out;
     }
-    uint32_t k_;
-    uint64_t n_;
+    uint32_t k_ = 0;
+    uint64_t n_ = 0;
+    std::vector<G1Affine> host_g_, host_g_lagrange_;
+    std::vector<uint8_t> g2_bytes_;           // g2 | s_g2 as stored: G2 arithmetic is the verifier's (host) business
     uint64_t g_ = 0, g_lagrange_ = 0;
 };
 
 }  // namespace kzg
 }  // namespace poly
+
+// ---- plonk: quotient evaluation, grand products, lookup permutation -----------------------
+namespace plonk {
+
+// host columns of equal length, uploaded for the duration of one call
+class DeviceColumns {
+  public:
+    DeviceColumns(int device, size_t rows) : device_(device), rows_(rows) {}
+    const void* upload(const std::vector<Fr>& col) {
+        if (col.size() != rows_) throw Panic("column length mismatch");
+        bufs_.emplace_back(new DeviceBuffer(device_, (rows_ ? rows_ : 1) * sizeof(Fr)));
+        if (rows_) check(h2b_memcpy_h2d(device_, bufs_.back()->get(), col.data(), rows_ * sizeof(Fr)), "h2d");
+        return bufs_.back()->get();
+    }
+    void* scratch() {
+        bufs_.emplace_back(new DeviceBuffer(device_, (rows_ ? rows_ : 1) * sizeof(Fr)));
+        return bufs_.back()->get();
+    }
+    std::vector<Fr> download(const void* d, size_t rows) const {
+        std::vector<Fr> out(rows);
+        check(h2b_dev_sync(device_), "sync");
+        if (rows) check(h2b_memcpy_d2h(device_, out.data(), d, rows * sizeof(Fr)), "d2h");
+        return out;
+    }
+  private:
+    int device_;
+    size_t rows_;
+    std::vector<std::unique_ptr<DeviceBuffer>> bufs_;
+};
+
+namespace evaluation {
+
+// pub enum ValueSource / pub enum Calculation, as include/h2b200.h flattens them
+struct ValueSource : h2b_value_source {
+    static ValueSource make(uint32_t kind, uint32_t index = 0, uint32_t rotation = 0) { ValueSource v; v.kind = kind; v.index = index; v.rotation = rotation; return v; }
+    static ValueSource Constant(uint32_t i) { return make(H2B_VS_CONSTANT, i); }
+    static ValueSource Intermediate(uint32_t i) { return make(H2B_VS_INTERMEDIATE, i); }
+    static ValueSource Fixed(uint32_t c, uint32_t r) { return make(H2B_VS_FIXED, c, r); }
+    static ValueSource Advice(uint32_t c, uint32_t r) { return make(H2B_VS_ADVICE, c, r); }
+    static ValueSource Instance(uint32_t c, uint32_t r) { return make(H2B_VS_INSTANCE, c, r); }
+    static ValueSource Challenge(uint32_t i) { return make(H2B_VS_CHALLENGE, i); }
+    static ValueSource Beta() { return make(H2B_VS_BETA); }
+    static ValueSource Gamma() { return make(H2B_VS_GAMMA); }
+    static ValueSource Theta() { return make(H2B_VS_THETA); }
+    static ValueSource Y() { return make(H2B_VS_Y); }
+    static ValueSource PreviousValue() { return make(H2B_VS_PREVIOUS_VALUE); }
+    bool operator==(const ValueSource& o) const { return kind == o.kind && index == o.index && rotation == o.rotation; }
+};
+
+// pub struct GraphEvaluator<C> { constants, rotations, calculations, num_intermediates }  (Default: constants 0, 1, 2)
+class GraphEvaluator {
+  public:
+    GraphEvaluator() : constants_{fr::from_u64(0), fr::one(), fr::from_u64(2)} {}
+    // fn add_rotation(&mut self, rotation: &Rotation) -> usize
+    uint32_t add_rotation(int32_t rotation) {
+        for (size_t i = 0; i < rotations_.size(); ++i) if (rotations_[i] == rotation) return (uint32_t)i;
+        rotations_.push_back(rotation);
+        return (uint32_t)rotations_.size() - 1;
+    }
+    // fn add_constant(&mut self, constant: &C::ScalarExt) -> ValueSource
+    ValueSource add_constant(const Fr& c) {
+        for (size_t i = 0; i < constants_.size(); ++i) if (constants_[i] == c) return ValueSource::Constant((uint32_t)i);
+        constants_.push_back(c);
+        return ValueSource::Constant((uint32_t)constants_.size() - 1);
+    }
+    // fn add_calculation(&mut self, calculation: Calculation) -> ValueSource   (an existing identical calculation is reused)
+    ValueSource add_calculation(uint32_t op, const ValueSource& a, const ValueSource& b = ValueSource::Constant(0), const std::vector<ValueSource>& parts = {}) {
+        for (size_t i = 0; i < calcs_.size(); ++i) {
+            const h2b_calculation& c = calcs_[i];
+            if (c.op != op || !(ValueSource::make(c.a.kind, c.a.index, c.a.rotation) == a) || !(ValueSource::make(c.b.kind, c.b.index, c.b.rotation) == b) ||
+                c.parts_len != parts.size()) continue;
+            bool same = true;
+            for (size_t j = 0; j < parts.size() && same; ++j) same = static_cast<const ValueSource&>(parts_[c.parts_offset + j]) == parts[j];
+            if (same) return ValueSource::Intermediate(c.target);
+        }
+        h2b_calculation c;
+        c.op = op; c.target = num_intermediates_++; c.a = a; c.b = b;
+        c.parts_offset = (uint32_t)parts_.size(); c.parts_len = (uint32_t)parts.size();
+        for (const ValueSource& p : parts) parts_.push_back(p);
+        calcs_.push_back(c);
+        return ValueSource::Intermediate(c.target);
+    }
+    // pub fn evaluate(..) for every row idx < isize: values[idx] = evaluate(.., previous_value = values[idx], idx, rot_scale, isize)
+    std::vector<Fr> evaluate(const std::vector<std::vector<Fr>>& fixed, const std::vector<std::vector<Fr>>& advice, const std::vector<std::vector<Fr>>& instance,
+                             const std::vector<Fr>& challenges, const Fr& beta, const Fr& gamma, const Fr& theta, const Fr& y, const std::vector<Fr>& values,
+                             int32_t rot_scale, int device = 0) const {
+        ensure_init();
+        const size_t size = values.size();
+        DeviceColumns dev(device, size);
+        std::vector<const void*> f, a, i;
+        for (auto& c : fixed) f.push_back(dev.upload(c));
+        for (auto& c : advice) a.push_back(dev.upload(c));
+        for (auto& c : instance) i.push_back(dev.upload(c));
+        void* d_values = const_cast<void*>(dev.upload(values));
+        h2b_graph g;
+        g.constants = reinterpret_cast<const uint64_t*>(constants_.data()); g.n_constants = (uint32_t)constants_.size();
+        g.rotations = rotations_.data(); g.n_rotations = (uint32_t)rotations_.size();
+        g.calculations = calcs_.data(); g.n_calculations = (uint32_t)calcs_.size();
+        g.parts = parts_.data(); g.n_parts = (uint32_t)parts_.size();
+        g.n_intermediates = num_intermediates_;
+        h2b_eval_columns c;
+        c.fixed = f.data(); c.n_fixed = (uint32_t)f.size();
+        c.advice = a.data(); c.n_advice = (uint32_t)a.size();
+        c.instance = i.data(); c.n_instance = (uint32_t)i.size();
+        c.challenges = reinterpret_cast<const uint64_t*>(challenges.data()); c.n_challenges = (uint32_t)challenges.size();
+        c.beta = beta.l; c.gamma = gamma.l; c.theta = theta.l; c.y = y.l;
+        check(h2b_evaluate_graph_dev(device, &g, &c, d_values, (uint32_t)size, rot_scale, nullptr), "GraphEvaluator::evaluate");
+        return dev.download(d_values, size);
+    }
+    uint32_t num_intermediates() const { return num_intermediates_; }
+
+  private:
+    std::vector<Fr> constants_;
+    std::vector<int32_t> rotations_;
+    std::vector<h2b_calculation> calcs_;
+    std::vector<h2b_value_source> parts_;
+    uint32_t num_intermediates_ = 0;
+};
+
+}  // namespace evaluation
+
+namespace permutation {
+// permutation::Argument::commit for one set of columns: z[0] = last_z, z[i+1] = z[i] * numerator_i / denominator_i
+inline std::vector<Fr> commit_product(const std::vector<std::vector<Fr>>& values, const std::vector<std::vector<Fr>>& permutations, const Fr& beta, const Fr& gamma,
+                                      const Fr& delta, const Fr& deltaomega, const Fr& omega, const Fr& last_z, int device = 0) {
+    ensure_init();
+    if (values.empty() || values.size() != permutations.size()) throw Panic("permutation::commit: column / permutation count mismatch");
+    const size_t n = values[0].size();
+    DeviceColumns dev(device, n);
+    std::vector<const void*> v, p;
+    for (auto& c : values) v.push_back(dev.upload(c));
+    for (auto& c : permutations) p.push_back(dev.upload(c));
+    void* z = dev.scratch();
+    check(h2b_permutation_product_dev(device, v.data(), p.data(), (uint32_t)v.size(), n, beta.l, gamma.l, delta.l, deltaomega.l, omega.l, last_z.l, z, nullptr),
+          "permutation::commit");
+    return dev.download(z, n);
+}
+}  // namespace permutation
+
+namespace lookup {
+// fn permute_expression_pair(..) -> Result<(Vec<F>, Vec<F>), Error>: the first usable_rows rows of (A', S')
+inline std::pair<std::vector<Fr>, std::vector<Fr>> permute_expression_pair(const std::vector<Fr>& input_expression, const std::vector<Fr>& table_expression,
+                                                                            size_t usable_rows, int device = 0) {
+    ensure_init();
+    if (input_expression.size() != table_expression.size() || usable_rows > input_expression.size()) throw Panic("permute_expression_pair: bad lengths");
+    DeviceColumns dev(device, input_expression.size());
+    const void* a = dev.upload(input_expression);
+    const void* t = dev.upload(table_expression);
+    void* pa = dev.scratch();
+    void* pt = dev.scratch();
+    check(h2b_lookup_permute_dev(device, a, t, (uint32_t)usable_rows, pa, pt, nullptr), "Error::ConstraintSystemFailure");
+    return {dev.download(pa, usable_rows), dev.download(pt, usable_rows)};
+}
+// Permuted::commit_product: z[0] = 1, z[i+1] = z[i] (a + beta)(s + gamma) / ((a' + beta)(s' + gamma))
+inline std::vector<Fr> commit_product(const std::vector<Fr>& compressed_input, const std::vector<Fr>& compressed_table, const std::vector<Fr>& permuted_input,
+                                      const std::vector<Fr>& permuted_table, const Fr& beta, const Fr& gamma, int device = 0) {
+    ensure_init();
+    const size_t n = compressed_input.size();
+    DeviceColumns dev(device, n);
+    const void* c[4] = {dev.upload(compressed_input), dev.upload(compressed_table), dev.upload(permuted_input), dev.upload(permuted_table)};
+    void* z = dev.scratch();
+    check(h2b_lookup_product_dev(device, c[0], c[1], c[2], c[3], n, beta.l, gamma.l, z, nullptr), "lookup::commit_product");
+    return dev.download(z, n);
+}
+}  // namespace lookup
+}  // namespace plonk
 }  // namespace h2b200

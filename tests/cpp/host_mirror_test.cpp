@@ -68,6 +68,67 @@ int main(int argc, char** argv) {
             G1 c[2] = {params.commit(scalars), params.commit_lagrange(std::vector<Fr>(scalars.begin(), scalars.begin() + scalars.size() / 2))};
             write_all(dir + "/commit.bin", c, 2);
         }
+        // ---- the widened rows: vanishing division, SRS file round trip, GraphEvaluator, grand products, lookup permutation
+        auto divided = dom.divide_by_vanishing_poly(ext);
+        write_all(dir + "/divided.bin", divided.data(), divided.size());
+        if (bases.size() == ((size_t)1 << k)) {
+            std::vector<uint8_t> g2(128);
+            for (size_t i = 0; i < g2.size(); ++i) g2[i] = (uint8_t)(i * 7 + 1);
+            std::vector<G1Affine> reversed(bases.rbegin(), bases.rend());
+            poly::kzg::ParamsKZG params(k, bases, reversed, g2);
+            params.write_custom(dir + "/params.srs", poly::kzg::SerdeFormat::Processed);
+            poly::kzg::ParamsKZG back2(dir + "/params.srs", poly::kzg::SerdeFormat::Processed);
+            if (back2.k() != k || std::memcmp(back2.get_g().data(), bases.data(), bases.size() * sizeof(G1Affine)) != 0 ||
+                std::memcmp(back2.get_g_lagrange().data(), reversed.data(), reversed.size() * sizeof(G1Affine)) != 0 || back2.g2_bytes() != g2) {
+                fprintf(stderr, "SRS round trip differs\n");
+                return 1;
+            }
+            G1 c2 = back2.commit(scalars);
+            write_all(dir + "/commit_after_read.bin", &c2, 1);
+        }
+        {
+            using namespace plonk::evaluation;
+            // q * (a + b[next] * c - a[prev]) folded into the previous value with y, built the way Evaluator::new builds it
+            GraphEvaluator ge;
+            const uint32_t r0 = ge.add_rotation(0), r1 = ge.add_rotation(1), rm = ge.add_rotation(-1);
+            ValueSource q = ge.add_calculation(H2B_CALC_STORE, ValueSource::Fixed(0, r0));
+            ValueSource bc = ge.add_calculation(H2B_CALC_MUL, ValueSource::Advice(1, r1), ValueSource::Advice(2, r0));
+            ValueSource sum = ge.add_calculation(H2B_CALC_ADD, ValueSource::Advice(0, r0), bc);
+            ValueSource diff = ge.add_calculation(H2B_CALC_SUB, sum, ValueSource::Advice(0, rm));
+            ValueSource gate = ge.add_calculation(H2B_CALC_MUL, q, diff);
+            ValueSource again = ge.add_calculation(H2B_CALC_MUL, q, diff);              // identical calculation: reused
+            if (!(again == gate)) { fprintf(stderr, "add_calculation did not reuse an identical calculation\n"); return 1; }
+            ValueSource sq = ge.add_calculation(H2B_CALC_SQUARE, gate);
+            ValueSource cst = ge.add_constant(fr::from_u64(0x1234567));
+            ValueSource scaled = ge.add_calculation(H2B_CALC_MUL, ValueSource::Instance(0, r0), cst);
+            ge.add_calculation(H2B_CALC_HORNER, ValueSource::PreviousValue(), ValueSource::Y(), {gate, sq, scaled, ValueSource::Challenge(0)});
+            auto cols = read_all<Fr>(dir + "/eval_cols.bin");          // fixed0 | advice0..2 | instance0 | previous values, `rows` each
+            auto sc = read_all<Fr>(dir + "/eval_scalars.bin");         // challenge0, beta, gamma, theta, y, delta, deltaomega, last_z
+            const size_t rows = cols.size() / 6;
+            auto col = [&](size_t j) { return std::vector<Fr>(cols.begin() + j * rows, cols.begin() + (j + 1) * rows); };
+            auto out = ge.evaluate({col(0)}, {col(1), col(2), col(3)}, {col(4)}, {sc[0]}, sc[1], sc[2], sc[3], sc[4], col(5), 2);
+            write_all(dir + "/eval_out.bin", out.data(), out.size());
+            // grand products over the same columns (rows is a power of two here; omega of that size)
+            uint32_t kr = 0;
+            while (((size_t)1 << kr) < rows) ++kr;
+            poly::EvaluationDomain dr(3, kr);
+            auto z = plonk::permutation::commit_product({col(1), col(2)}, {col(3), col(4)}, sc[1], sc[2], sc[5], sc[6], dr.get_omega(), sc[7]);
+            write_all(dir + "/perm_z.bin", z.data(), z.size());
+            auto zl = plonk::lookup::commit_product(col(1), col(2), col(3), col(4), sc[1], sc[2]);
+            write_all(dir + "/lookup_z.bin", zl.data(), zl.size());
+            // permute_expression_pair: input / table files hold a satisfiable pair; a foreign input value must fail
+            auto lin = read_all<Fr>(dir + "/lookup_input.bin");
+            auto ltab = read_all<Fr>(dir + "/lookup_table.bin");
+            auto pr = plonk::lookup::permute_expression_pair(lin, ltab, lin.size() - 6);
+            write_all(dir + "/permuted_input.bin", pr.first.data(), pr.first.size());
+            write_all(dir + "/permuted_table.bin", pr.second.data(), pr.second.size());
+            panicked = false;
+            try {
+                lin[0] = sc[3];
+                plonk::lookup::permute_expression_pair(lin, ltab, lin.size() - 6);
+            } catch (const Panic&) { panicked = true; }
+            if (!panicked) { fprintf(stderr, "missing table value did not fail\n"); return 1; }
+        }
     } catch (const Panic& e) {
         fprintf(stderr, "panic: %s\n", e.what());
         return 1;
