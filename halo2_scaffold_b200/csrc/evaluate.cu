@@ -13,6 +13,7 @@
 //     coalesced 32-byte-per-lane access); the slots live in per-thread local memory (hardware-interleaved, L1-resident).
 // The kernels are bound by the Fr multiplication rate (IMAD), like everything else on this path.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -380,6 +381,16 @@ struct EvalScratch {
 
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
+// resident CTAs (of 128 threads) per SM for the grid-stride row kernels; H2B_EVAL_CTAS_PER_SM overrides (tuning)
+static uint32_t eval_ctas_per_sm() {
+    static const uint32_t v = [] {
+        const char* e = getenv("H2B_EVAL_CTAS_PER_SM");
+        const int x = e ? atoi(e) : 0;
+        return (uint32_t)(x >= 1 && x <= 32 ? x : 8);
+    }();
+    return v;
+}
+
 static int upload_program(DeviceCtx& ctx, const Compiled& c, uint32_t size, cudaStream_t stream, EvalProgram& dev, ProgramBuf** used) {
     if (!ctx.eval) ctx.eval = new EvalScratch();
     ProgramBuf& pb = ctx.eval->ring[ctx.eval->next++ & 3];
@@ -408,7 +419,7 @@ static int upload_program(DeviceCtx& ctx, const Compiled& c, uint32_t size, cuda
 
 template <int MODE>
 static int launch_graph(DeviceCtx& ctx, const EvalProgram& p, uint32_t n_slots, void* d_values, const LookupTerms& lk, cudaStream_t stream) {
-    const uint32_t want = (p.size + 127) / 128, cap = (uint32_t)ctx.sm_count * 8;
+    const uint32_t want = (p.size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm();
     const uint32_t grid = want < cap ? want : cap;
     if (n_slots <= 8) H2B_LAUNCH((evaluate_graph_kernel<8, MODE>), grid, 128, 0, stream, p, (uint4*)d_values, lk);
     else if (n_slots <= 16) H2B_LAUNCH((evaluate_graph_kernel<16, MODE>), grid, 128, 0, stream, p, (uint4*)d_values, lk);
@@ -566,7 +577,7 @@ int evaluate_h_permutation_run(DeviceCtx& ctx, void* d_values, uint32_t size, in
     p.off_next = rem_euclid_u32((int64_t)rot_scale, size);
     p.off_last = rem_euclid_u32((int64_t)last_rotation * rot_scale, size);
     load_fr(p.beta, beta); load_fr(p.gamma, gamma); load_fr(p.y, y); load_fr(p.delta, delta); load_fr(p.zeta, zeta); load_fr(p.omega, extended_omega);
-    const uint32_t want = (size + 127) / 128, cap = (uint32_t)ctx.sm_count * 8;
+    const uint32_t want = (size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm();
     H2B_LAUNCH(evaluate_h_permutation_kernel, want < cap ? want : cap, 128, 0, stream, p, (uint4*)d_values);
     H2B_CUDA(cudaGetLastError());
     H2B_CUDA(cudaEventRecord(pb.done, stream));

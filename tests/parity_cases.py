@@ -595,3 +595,28 @@ def check_golden_prover(L, g):
     assert (h2.EvaluationDomain(4, 3, lib=L).divide_by_vanishing_poly(g["vanishing_in"]) == g["vanishing_out"]).all()
     assert (L.g1_decode(g["codec_bytes"], 0) == g["codec_points"]).all()
     assert (L.g1_encode(g["codec_points"]) == g["codec_bytes"]).all()
+
+
+def check_evaluate_graph_property(L, oc, examples, max_rows, max_calcs):
+    """Property test over the GraphEvaluator compiler: random program length, column counts, rotation scale, row count and target re-use --
+    the re-scheduled, slot-allocated, register-forwarded program always gives the bits of upstream's sequential walk."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from halo2_scaffold_b200 import evaluation as ev
+
+    @settings(max_examples=examples, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(size=st.integers(1, max_rows), rot_scale=st.sampled_from([1, 2, 4, 8, 3]), n_calcs=st.integers(1, max_calcs), seed=st.integers(0, 10 ** 6),
+           reuse=st.booleans(), nf=st.integers(0, 3), na=st.integers(1, 5), ni=st.integers(0, 2), nch=st.integers(0, 2))
+    def run(size, rot_scale, n_calcs, seed, reuse, nf, na, ni, nch):
+        rng = np.random.default_rng(seed)
+        graph, n_const = random_graph(rng, nf, na, ni, nch, n_calcs, reuse_targets=reuse)
+        g, ga = _graph_pair(oc, graph, n_const, seed)
+        cols = [oc.random_fr(seed * 131 + j, size) for j in range(nf + na + ni)]
+        fixed, advice, instance = cols[:nf], cols[nf:nf + na], cols[nf + na:]
+        sc = oc.random_fr(seed * 7 + 1, nch + 4)
+        challenges, (beta, gamma, theta, y) = sc[:nch], sc[nch:]
+        values = oc.random_fr(seed * 7 + 2, size)
+        want = oc.evaluate_graph(g, fixed, advice, instance, challenges, beta, gamma, theta, y, values, rot_scale)
+        got = ev.evaluate_graph(L, ga, fixed, advice, instance, challenges, beta, gamma, theta, y, values, rot_scale)
+        assert (got == want).all(), (size, rot_scale, n_calcs, seed, reuse, nf, na, ni, nch)
+
+    run()

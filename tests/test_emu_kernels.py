@@ -433,3 +433,7 @@ def test_lookup_permute_expression_pair(emu, oc):
 
 def test_prover_rows_golden(emu, golden):
     pc.check_golden_prover(emu, golden["prover"])
+
+
+def test_evaluate_graph_property(emu, oc):
+    pc.check_evaluate_graph_property(emu, oc, examples=80, max_rows=70, max_calcs=160)

@@ -209,6 +209,10 @@ def test_evaluate_graph_many_live_values(gpu, oc):
         assert (ev.evaluate_graph(gpu, ga, [], adv, [], none, *sc, vals, 1) == oc.evaluate_graph(g, [], adv, [], none, *sc, vals, 1)).all(), n_live
 
 
+def test_evaluate_graph_property(gpu, oc):
+    pc.check_evaluate_graph_property(gpu, oc, examples=40, max_rows=20000, max_calcs=400)
+
+
 def test_evaluate_h_all_three_loops(gpu, oc):
     pc.check_evaluate_h(gpu, oc, [(5, 3, 1, 1), (12, 10, 2, 2), (16, 14, 3, 3), (18, 16, 1, 4)])
 
