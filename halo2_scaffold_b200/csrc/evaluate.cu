@@ -382,13 +382,15 @@ struct EvalScratch {
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 // resident CTAs (of 128 threads) per SM for the grid-stride row kernels; H2B_EVAL_CTAS_PER_SM overrides (tuning)
-static uint32_t eval_ctas_per_sm() {
-    static const uint32_t v = [] {
+// (measured at 2^22 rows, profiles/r01_evaluate_h.jsonl: the 48-register interpreter gains 8 % from 16 over 8, the 128-register
+// permutation kernel is best at 8)
+static uint32_t eval_ctas_per_sm(uint32_t dflt) {
+    static const int forced = [] {
         const char* e = getenv("H2B_EVAL_CTAS_PER_SM");
         const int x = e ? atoi(e) : 0;
-        return (uint32_t)(x >= 1 && x <= 32 ? x : 8);
+        return x >= 1 && x <= 32 ? x : 0;
     }();
-    return v;
+    return forced ? (uint32_t)forced : dflt;
 }
 
 static int upload_program(DeviceCtx& ctx, const Compiled& c, uint32_t size, cudaStream_t stream, EvalProgram& dev, ProgramBuf** used) {
@@ -419,7 +421,7 @@ static int upload_program(DeviceCtx& ctx, const Compiled& c, uint32_t size, cuda
 
 template <int MODE>
 static int launch_graph(DeviceCtx& ctx, const EvalProgram& p, uint32_t n_slots, void* d_values, const LookupTerms& lk, cudaStream_t stream) {
-    const uint32_t want = (p.size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm();
+    const uint32_t want = (p.size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm(16);
     const uint32_t grid = want < cap ? want : cap;
     if (n_slots <= 8) H2B_LAUNCH((evaluate_graph_kernel<8, MODE>), grid, 128, 0, stream, p, (uint4*)d_values, lk);
     else if (n_slots <= 16) H2B_LAUNCH((evaluate_graph_kernel<16, MODE>), grid, 128, 0, stream, p, (uint4*)d_values, lk);
@@ -577,7 +579,7 @@ int evaluate_h_permutation_run(DeviceCtx& ctx, void* d_values, uint32_t size, in
     p.off_next = rem_euclid_u32((int64_t)rot_scale, size);
     p.off_last = rem_euclid_u32((int64_t)last_rotation * rot_scale, size);
     load_fr(p.beta, beta); load_fr(p.gamma, gamma); load_fr(p.y, y); load_fr(p.delta, delta); load_fr(p.zeta, zeta); load_fr(p.omega, extended_omega);
-    const uint32_t want = (size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm();
+    const uint32_t want = (size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm(8);
     H2B_LAUNCH(evaluate_h_permutation_kernel, want < cap ? want : cap, 128, 0, stream, p, (uint4*)d_values);
     H2B_CUDA(cudaGetLastError());
     H2B_CUDA(cudaEventRecord(pb.done, stream));
