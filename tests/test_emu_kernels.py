@@ -437,3 +437,30 @@ def test_prover_rows_golden(emu, golden):
 
 def test_evaluate_graph_property(emu, oc):
     pc.check_evaluate_graph_property(emu, oc, examples=80, max_rows=70, max_calcs=160)
+
+
+def test_msm_pair_pre_reduction(emu, oc):
+    # the batched-affine pair stage only switches on for long lists; H2B_MSM_PAIR_LEVELS forces it at CPU-friendly sizes
+    # (fresh library instance per setting: the knob is read once per process).  Golden vectors (identity bases, duplicate points,
+    # P and -P in one bucket), random shapes with forced windows and table spacings, and witness-like columns.
+    import os, subprocess, sys
+    root = pc.__file__.rsplit('/tests/', 1)[0]
+    code = (
+        "import sys; sys.path[:0]=[%r,%r,%r]\n"
+        "import numpy as np, oracle_c as oc, parity_cases as pc\n"
+        "from halo2_scaffold_b200._lib import Lib\n"
+        "L=Lib(%r, allow_emulator=True); L.init(1)\n"
+        "g=np.load(%r)\n"
+        "pc.check_golden_msm(L, oc, g)\n"
+        "pc.check_msm_random(L, oc, examples=14, max_n=600, spacings=(-1, 4, 6, 8), windows=(0, 2, 3, 4, 6))\n"
+        "for n, kind in ((3000, 1), (2500, 0)):\n"
+        "    s, P = L.gen_scalars(n, n, kind), oc.gen_points(n + 1, n)\n"
+        "    P[5] = P[4]; P[7] = 0; P[9, :4] = P[8, :4]; P[9, 4:] = oc.field_op('fq', 'sub', np.zeros((1, 4), dtype=np.uint64), P[8:9, 4:])[0]; s[9] = s[8]\n"
+        "    h = L.register_bases(P)\n"
+        "    assert (pc.affine_of(oc, L.msm_registered(s, h, 0)) == pc.affine_of(oc, oc.best_multiexp(s, P))).all(), (n, kind)\n"
+        "    assert (pc.affine_of(oc, L.msm(s, P)) == pc.affine_of(oc, oc.best_multiexp(s, P))).all(), (n, kind, 'plain')\n"
+        "print('ok')\n") % (root, root + '/oracle', root + '/tests', emu.path, root + '/tests/golden/msm_golden.npz')
+    for levels in ("1", "2", "3"):
+        env = dict(os.environ, H2B_MSM_PAIR_LEVELS=levels)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and "ok" in out.stdout, (levels, out.stderr[-3000:])
