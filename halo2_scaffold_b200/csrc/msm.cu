@@ -388,11 +388,14 @@ __global__ void __launch_bounds__(128) msm_pair_reduce_kernel(uint32_t B, const 
     } else {
         p0.x = fp_zero<FQ>(); p0.y = p0.x; p1 = p0;
     }
+    Fq pre = prefix[q1 - 1 - q0];
     for (uint32_t q = q1; q-- > q0;) {
         const bool two_c = two;
         const uint32_t e0c = e0, e1c = e1;
         Affine c0 = p0, c1 = p1;
+        const Fq pre_c = pre;
         if (q > q0) {
+            pre = prefix[q - 1 - q0];              // lives in local memory (L2 / HBM by now): fetched one position ahead like the points
             src = cur.backward(q - 1, offsets, new_offsets);
             two = src + 1 < cur.src_end;
             e0 = sorted[src];
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(128) msm_pair_reduce_kernel(uint32_t B, const 
         if (mode == 4) {
             r.x = fp_zero<FQ>(); r.y = fp_zero<FQ>();
         } else {
-            const Fq inv_d = fp_mul(inv, prefix[q - q0]);
+            const Fq inv_d = fp_mul(inv, pre_c);
             inv = fp_mul(inv, d);
             Fq lambda;
             if (mode == 0) lambda = fp_mul(fp_sub(c1.y, c0.y), inv_d);
