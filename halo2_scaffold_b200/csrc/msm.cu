@@ -270,30 +270,13 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(MsmPlan pl, const uint
 // division: a lone last entry, an identity operand, P + (-P)), inverts once, and walks back writing the pair sums into
 // the pair buffer and entries that name them (PAIR_BIT) into the next list.  Lone entries and identity cases are passed
 // through by entry, so they cost no point write.  The accumulation then runs over a list 2^levels shorter.
-// a random 64-byte gather: no L1 allocation (no reuse), 64-byte L2 fetch granularity (the neighbouring sectors are other points)
-__device__ __forceinline__ uint4 gather_load(const uint4* p) {
-#ifdef H2B_EMU
-    return *p;
-#else
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-#endif
-}
-__device__ __forceinline__ Fq gather_fq(const uint4* p) {
-    const uint4 a = gather_load(p), b = gather_load(p + 1);
-    Fq r;
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-    return r;
-}
-__device__ __forceinline__ const uint4* msm_entry_ptr(const uint4* __restrict__ tables, const uint4* __restrict__ pair_pts, uint32_t e) {
-    return (e & PAIR_BIT) ? pair_pts + 4 * (size_t)(e & ~(SIGN_BIT | PAIR_BIT)) : tables + 4 * (size_t)(e & ~SIGN_BIT);
-}
 __device__ __forceinline__ Affine msm_entry_point(const uint4* __restrict__ tables, const uint4* __restrict__ pair_pts, uint32_t e) {
-    return affine_load(msm_entry_ptr(tables, pair_pts, e));
+    return (e & PAIR_BIT) ? affine_load(pair_pts + 4 * (size_t)(e & ~(SIGN_BIT | PAIR_BIT))) : affine_load(tables + 4 * (size_t)(e & ~SIGN_BIT));
 }
-__device__ __forceinline__ Fq signed_y(const Fq& x, const Fq& y, uint32_t e) {       // the identity (0, 0) has no sign
-    return ((e & SIGN_BIT) && !(fp_is_zero(x) && fp_is_zero(y))) ? fp_neg(y) : y;
+__device__ __forceinline__ Affine msm_entry_point_signed(const uint4* __restrict__ tables, const uint4* __restrict__ pair_pts, uint32_t e) {
+    Affine p = msm_entry_point(tables, pair_pts, e);
+    if ((e & SIGN_BIT) && !affine_is_identity(p)) p.y = fp_neg(p.y);
+    return p;
 }
 
 __global__ void __launch_bounds__(256) msm_pair_counts_kernel(const uint32_t* __restrict__ offsets, uint32_t B, uint32_t* __restrict__ counts2) {
@@ -301,39 +284,20 @@ __global__ void __launch_bounds__(256) msm_pair_counts_kernel(const uint32_t* __
     if (b < B) counts2[b] = (offsets[b + 1] - offsets[b] + 1) >> 1;
 }
 
-// what the addition of the pair (p0, p1) needs: 0 = a division by d = x1 - x0, 1 = a doubling (d = 2 y), 2 = p0 is the identity
-// (result p1), 3 = p1 is the identity (result p0), 4 = p1 = -p0 (result: identity).  Only the x coordinates are needed unless they
-// coincide or vanish; y0 / y1 are fetched through the callbacks in those rare cases.
-template <class Y0, class Y1>
-__device__ __forceinline__ int msm_pair_mode(const Fq& x0, const Fq& x1, Y0 y0, Y1 y1, Fq& d) {
-    if (fp_is_zero(x0) && fp_is_zero(y0())) return 2;
-    if (fp_is_zero(x1) && fp_is_zero(y1())) return 3;
-    d = fp_sub(x1, x0);
+// what the addition of the pair (p0, p1) needs: 0 = a division by d, 1 = a doubling (d = 2 y), 2 = p0 is the identity (result p1),
+// 3 = p1 is the identity (result p0), 4 = p1 = -p0 (result: identity)
+__device__ __forceinline__ int msm_pair_mode(const Affine& p0, const Affine& p1, Fq& d) {
+    if (affine_is_identity(p0)) return 2;
+    if (affine_is_identity(p1)) return 3;
+    d = fp_sub(p1.x, p0.x);
     if (!fp_is_zero(d)) return 0;
-    const Fq a = y0(), b = y1();
-    if (!fp_eq(a, b)) return 4;
-    d = fp_dbl(a);
+    if (!fp_eq(p0.y, p1.y)) return 4;
+    d = fp_dbl(p0.y);
     return 1;
 }
 
-// position -> (first source entry, whether a second one exists), walking forward / backward through the buckets
-struct PairCursor {
-    uint32_t b, base2, next2, src0, src_end;
-    __device__ __forceinline__ void load(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ new_offsets) {
-        base2 = new_offsets[b]; next2 = new_offsets[b + 1]; src0 = offsets[b]; src_end = offsets[b + 1];
-    }
-    __device__ __forceinline__ uint32_t forward(uint32_t q, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ new_offsets) {
-        while (q >= next2) { ++b; load(offsets, new_offsets); }
-        return src0 + 2 * (q - base2);
-    }
-    __device__ __forceinline__ uint32_t backward(uint32_t q, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ new_offsets) {
-        while (q < base2) { --b; load(offsets, new_offsets); }
-        return src0 + 2 * (q - base2);
-    }
-};
-
-template <int K>
-__global__ void __launch_bounds__(128) msm_pair_reduce_kernel(uint32_t B, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
+template <int K, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_pair_reduce_kernel(uint32_t B, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
                                                             const uint32_t* __restrict__ new_offsets, uint32_t* __restrict__ new_sorted,
                                                             const uint4* __restrict__ tables, uint4* __restrict__ pair_pts, uint32_t out_base) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,82 +311,40 @@ __global__ void __launch_bounds__(128) msm_pair_reduce_kernel(uint32_t B, const 
     }
     Fq prefix[K];
     Fq run = fp_one<FQ>();
-    PairCursor cur;
-    cur.b = lo;
-    cur.load(offsets, new_offsets);
-    // forward: multiply the denominators up.  The x coordinates of the next pair are in flight while this one is processed.
-    uint32_t src = cur.forward(q0, offsets, new_offsets);
-    bool two = src + 1 < cur.src_end;
-    uint32_t e0 = sorted[src], e1 = two ? sorted[src + 1] : e0;
-    Fq x0 = gather_fq(msm_entry_ptr(tables, pair_pts, e0)), x1 = two ? gather_fq(msm_entry_ptr(tables, pair_pts, e1)) : x0;
+    uint32_t b = lo, base2 = new_offsets[b], next2 = new_offsets[b + 1], src0 = offsets[b], src_end = offsets[b + 1];
     for (uint32_t q = q0; q < q1; ++q) {
-        const bool two_c = two;
-        const uint32_t e0c = e0, e1c = e1;
-        const Fq x0c = x0, x1c = x1;
-        if (q + 1 < q1) {
-            src = cur.forward(q + 1, offsets, new_offsets);
-            two = src + 1 < cur.src_end;
-            e0 = sorted[src];
-            e1 = two ? sorted[src + 1] : e0;
-            x0 = gather_fq(msm_entry_ptr(tables, pair_pts, e0));
-            x1 = two ? gather_fq(msm_entry_ptr(tables, pair_pts, e1)) : x0;
-        }
+        while (q >= next2) { ++b; base2 = next2; next2 = new_offsets[b + 1]; src0 = offsets[b]; src_end = offsets[b + 1]; }
+        const uint32_t src = src0 + 2 * (q - base2);
         prefix[q - q0] = run;
-        if (two_c) {
+        if (src + 1 < src_end) {
+            const Affine p0 = msm_entry_point_signed(tables, pair_pts, sorted[src]), p1 = msm_entry_point_signed(tables, pair_pts, sorted[src + 1]);
             Fq d;
-            const int mode = msm_pair_mode(x0c, x1c, [&] { return signed_y(x0c, gather_fq(msm_entry_ptr(tables, pair_pts, e0c) + 2), e0c); },
-                                           [&] { return signed_y(x1c, gather_fq(msm_entry_ptr(tables, pair_pts, e1c) + 2), e1c); }, d);
-            if (mode <= 1) run = fp_mul(run, d);
+            if (msm_pair_mode(p0, p1, d) <= 1) run = fp_mul(run, d);
         }
     }
     Fq inv = fp_inv(run);
-    // backward: the full points of the previous position are in flight while this one is added
-    src = cur.backward(q1 - 1, offsets, new_offsets);
-    two = src + 1 < cur.src_end;
-    e0 = sorted[src];
-    e1 = two ? sorted[src + 1] : e0;
-    Affine p0, p1;
-    if (two) {
-        const uint4 *a0 = msm_entry_ptr(tables, pair_pts, e0), *a1 = msm_entry_ptr(tables, pair_pts, e1);
-        p0.x = gather_fq(a0); p0.y = gather_fq(a0 + 2); p1.x = gather_fq(a1); p1.y = gather_fq(a1 + 2);
-    } else {
-        p0.x = fp_zero<FQ>(); p0.y = p0.x; p1 = p0;
-    }
-    Fq pre = prefix[q1 - 1 - q0];
     for (uint32_t q = q1; q-- > q0;) {
-        const bool two_c = two;
-        const uint32_t e0c = e0, e1c = e1;
-        Affine c0 = p0, c1 = p1;
-        const Fq pre_c = pre;
-        if (q > q0) {
-            pre = prefix[q - 1 - q0];              // lives in local memory (L2 / HBM by now): fetched one position ahead like the points
-            src = cur.backward(q - 1, offsets, new_offsets);
-            two = src + 1 < cur.src_end;
-            e0 = sorted[src];
-            e1 = two ? sorted[src + 1] : e0;
-            if (two) {
-                const uint4 *a0 = msm_entry_ptr(tables, pair_pts, e0), *a1 = msm_entry_ptr(tables, pair_pts, e1);
-                p0.x = gather_fq(a0); p0.y = gather_fq(a0 + 2); p1.x = gather_fq(a1); p1.y = gather_fq(a1 + 2);
-            }
-        }
-        if (!two_c) { new_sorted[q] = e0c; continue; }      // a lone last entry of its bucket
-        c0.y = signed_y(c0.x, c0.y, e0c);
-        c1.y = signed_y(c1.x, c1.y, e1c);
+        while (q < base2) { --b; base2 = new_offsets[b]; next2 = new_offsets[b + 1]; src0 = offsets[b]; src_end = offsets[b + 1]; }
+        const uint32_t src = src0 + 2 * (q - base2);
+        const uint32_t e0 = sorted[src];
+        if (src + 1 >= src_end) { new_sorted[q] = e0; continue; }      // a lone last entry of its bucket
+        const uint32_t e1 = sorted[src + 1];
+        const Affine p0 = msm_entry_point_signed(tables, pair_pts, e0), p1 = msm_entry_point_signed(tables, pair_pts, e1);
         Fq d;
-        const int mode = msm_pair_mode(c0.x, c1.x, [&] { return c0.y; }, [&] { return c1.y; }, d);
-        if (mode == 2) { new_sorted[q] = e1c; continue; }
-        if (mode == 3) { new_sorted[q] = e0c; continue; }
+        const int mode = msm_pair_mode(p0, p1, d);
+        if (mode == 2) { new_sorted[q] = e1; continue; }
+        if (mode == 3) { new_sorted[q] = e0; continue; }
         Affine r;
         if (mode == 4) {
             r.x = fp_zero<FQ>(); r.y = fp_zero<FQ>();
         } else {
-            const Fq inv_d = fp_mul(inv, pre_c);
+            const Fq inv_d = fp_mul(inv, prefix[q - q0]);
             inv = fp_mul(inv, d);
             Fq lambda;
-            if (mode == 0) lambda = fp_mul(fp_sub(c1.y, c0.y), inv_d);
-            else { const Fq xx = fp_sqr(c0.x); lambda = fp_mul(fp_add(fp_dbl(xx), xx), inv_d); }
-            r.x = fp_sub(fp_sub(fp_sqr(lambda), c0.x), c1.x);
-            r.y = fp_sub(fp_mul(lambda, fp_sub(c0.x, r.x)), c0.y);
+            if (mode == 0) lambda = fp_mul(fp_sub(p1.y, p0.y), inv_d);
+            else { const Fq xx = fp_sqr(p0.x); lambda = fp_mul(fp_add(fp_dbl(xx), xx), inv_d); }
+            r.x = fp_sub(fp_sub(fp_sqr(lambda), p0.x), p1.x);
+            r.y = fp_sub(fp_mul(lambda, fp_sub(p0.x, r.x)), p0.y);
         }
         affine_store(pair_pts + 4 * (size_t)(out_base + q), r);
         new_sorted[q] = PAIR_BIT | (out_base + q);
@@ -968,8 +890,17 @@ static int msm_accumulate_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl
             H2B_LAUNCH(msm_pair_counts_kernel, (pl.B + 255) / 256, 256, 0, stream, offsets, pl.B, (uint32_t*)s.pair_counts.p);
             H2B_TRY(exclusive_scan(s, (const uint32_t*)s.pair_counts.p, pl.B, offsets_l, sorted_l /* cursor copy: unused, overwritten below */, stream));
             const uint64_t threads = (cap[l] + PAIR_K - 1) / PAIR_K;
-            H2B_LAUNCH(msm_pair_reduce_kernel<PAIR_K>, (unsigned)((threads + 127) / 128), 128, 0, stream, pl.B, offsets, sorted, (const uint32_t*)offsets_l, sorted_l,
-                       (const uint4*)tables, (uint4*)s.pair_pts.p, (uint32_t)base[l]);
+            static int env_occ = -1;
+            if (env_occ < 0) env_occ = env_int("H2B_MSM_PAIR_OCC", 5);
+            if (env_occ >= 8)
+                H2B_LAUNCH((msm_pair_reduce_kernel<PAIR_K, 8>), (unsigned)((threads + 127) / 128), 128, 0, stream, pl.B, offsets, sorted, (const uint32_t*)offsets_l,
+                           sorted_l, (const uint4*)tables, (uint4*)s.pair_pts.p, (uint32_t)base[l]);
+            else if (env_occ >= 6)
+                H2B_LAUNCH((msm_pair_reduce_kernel<PAIR_K, 6>), (unsigned)((threads + 127) / 128), 128, 0, stream, pl.B, offsets, sorted, (const uint32_t*)offsets_l,
+                           sorted_l, (const uint4*)tables, (uint4*)s.pair_pts.p, (uint32_t)base[l]);
+            else
+                H2B_LAUNCH((msm_pair_reduce_kernel<PAIR_K, 4>), (unsigned)((threads + 127) / 128), 128, 0, stream, pl.B, offsets, sorted, (const uint32_t*)offsets_l,
+                           sorted_l, (const uint4*)tables, (uint4*)s.pair_pts.p, (uint32_t)base[l]);
             offsets = offsets_l;
             sorted = sorted_l;
         }
