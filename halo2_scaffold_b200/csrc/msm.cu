@@ -861,16 +861,18 @@ static int msm_accumulate_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl
     uint4* target = (uint4*)(pl.add_into ? s.bucket_tmp.p : s.bucket_acc.p);
     H2B_CUDA(cudaMemsetAsync(ctrl, 0, 16, stream));
     ctx.prof.mark(PROF_BEGIN, stream);
-    // pair pre-reduction: worth it when buckets hold many entries and the list is long enough to hide the per-thread inversion
-    // (341 dependent multiplications).  Entries must leave bit 30 free for PAIR_BIT.
+    // pair pre-reduction (batched affine additions, section 2b): OFF by default.  Measured at 2^24 points (profiles/r01_msm_pair_stage.jsonl):
+    // every level halves the accumulation exactly as modelled (34.8 -> 17.5 -> 8.8 -> 4.4 ms), but one level costs 23.8 ms instead of the
+    // 10.3 ms its multiplications need -- its two passes gather every point twice, and the kernel runs at the random 64-byte access rate
+    // of HBM (~18 G gathers/s; more resident warps, software prefetch and 64-byte fetch hints change nothing), where the XYZZ
+    // accumulation hides ONE gather behind ten multiplications.  41.5 ms without, 48.0 / 48.8 / 50.1 ms with 1 / 2 / 3 levels.
+    // H2B_MSM_PAIR_LEVELS=1..3 turns it on (tests run it on the emulator).  Entries must leave bit 30 free for PAIR_BIT.
     const uint64_t upper = (uint64_t)pl.n * pl.W;
     uint32_t levels = 0;
     {
         static int env_levels = -2;
-        if (env_levels == -2) env_levels = env_int("H2B_MSM_PAIR_LEVELS", -1);
-        const uint64_t per_bucket = upper / pl.B;
-        if (upper >= ((uint64_t)1 << 24) && per_bucket >= 16) levels = per_bucket >= 64 ? 2 : 1;
-        if (env_levels >= 0) levels = env_levels > 3 ? 3u : (uint32_t)env_levels;
+        if (env_levels == -2) env_levels = env_int("H2B_MSM_PAIR_LEVELS", 0);
+        if (env_levels > 0) levels = env_levels > 3 ? 3u : (uint32_t)env_levels;
         const uint64_t table_rows = pl.stride ? (uint64_t)pl.stride * ((pl.W + pl.m - 1) / pl.m) : pl.n;
         if (table_rows >= PAIR_BIT || upper + 3 * (uint64_t)pl.B >= PAIR_BIT) levels = 0;
     }
