@@ -207,7 +207,8 @@ typedef struct h2b_eval_columns {        /* host arrays of device pointers + the
     const uint64_t* beta; const uint64_t* gamma; const uint64_t* theta; const uint64_t* y;   /* 4 words each */
 } h2b_eval_columns;
 /* values[idx] = graph.evaluate(.., previous_value = values[idx], idx, rot_scale, isize = size) for every idx < size: the
- * "Custom gates" loop of evaluate_h.  A graph without calculations writes zero, as upstream does.  The rotated row is
+ * "Custom gates" loop of evaluate_h.  The same call on Lagrange-basis columns (size = 2^k, rot_scale = 1) is the lookup argument's
+ * compress_expressions ([UP] plonk/lookup/prover.rs).  A graph without calculations writes zero, as upstream does.  The rotated row is
  * get_rotation_idx(idx, rot, rot_scale, isize) = (idx + rot * rot_scale).rem_euclid(isize). */
 int h2b_evaluate_graph_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
                            void* stream);
