@@ -620,3 +620,83 @@ def check_evaluate_graph_property(L, oc, examples, max_rows, max_calcs):
         assert (got == want).all(), (size, rot_scale, n_calcs, seed, reuse, nf, na, ni, nch)
 
     run()
+
+
+def check_quotient_is_a_polynomial(L, oc, k=4, seed=1, break_it=None):
+    """The algebra the verifier relies on, end to end through the device entry points: for a SATISFIED toy circuit -- one
+    multiplication gate, copy constraints between three advice columns (two permutation sets), one lookup -- the combination that
+    evaluate_h computes vanishes on the whole domain, so (evaluate_h / (X^n - 1)) interpolates to a polynomial of degree < 3n: the top
+    quarter of its 4n coefficients is zero.  A wrong rotation, sign, delta / omega bookkeeping or fill order anywhere in evaluate_h,
+    the grand products or the lookup permutation breaks exactly this.  `break_it` perturbs one ingredient and must make it fail.
+    Uses nothing recalled from upstream beyond the PLONK / halo2 argument itself."""
+    import halo2_scaffold_b200 as h2
+    from halo2_scaffold_b200 import evaluation as ev
+    from halo2_scaffold_b200.domain import fr_to_words, FR_MODULUS as R
+    rng = np.random.default_rng(seed)
+    n, bf = 1 << k, 5
+    u = n - (bf + 1)                                   # usable rows; row u carries l_last, rows u+1.. are blinding rows
+    dom = h2.EvaluationDomain(4, k, lib=L)
+    en, rot_scale = 1 << dom.extended_k, 1 << (dom.extended_k - k)
+    W = lambda vals: np.stack([fr_to_words(int(v)) for v in vals])
+    rnd = lambda: int(rng.integers(1, 1 << 62)) * int(rng.integers(1, 1 << 62)) % R
+    DELTA = pow(7, 1 << 28, R)
+    # ---- witness: c = a * b on the gated rows; copies a[i+1] = c[i] on even usable rows; a stays inside the lookup table
+    table = [int(v) for v in rng.integers(0, 50, size=n)]
+    q = [1 if (i < u and i % 2 == 0) else 0 for i in range(n)]
+    a, b, c = [0] * n, [0] * n, [0] * n
+    for i in range(n):
+        a[i], b[i], c[i] = rnd(), rnd(), rnd()
+    lk = [table[int(rng.integers(0, u))] for _ in range(n)]                  # lookup-advice column: values of the table's usable rows
+    copies = []
+    for i in range(0, u - 1, 2):
+        c[i] = a[i] * b[i] % R
+        a[i + 1] = c[i]                                                        # copy constraint (column 0, row i+1) == (column 2, row i)
+        copies.append(((0, i + 1), (2, i)))
+    cols_perm = [a, b, c]
+    omega = dom.omega
+    # sigma: identity delta^j omega^i with the two cells of every copy swapped
+    sigma = [[pow(DELTA, j, R) * pow(omega, i, R) % R for i in range(n)] for j in range(3)]
+    for (j0, i0), (j1, i1) in copies:
+        sigma[j0][i0], sigma[j1][i1] = sigma[j1][i1], sigma[j0][i0]
+    sc = [rnd() for _ in range(4)]
+    beta, gamma, theta, y = sc
+    if break_it == "witness":
+        c[2] = (c[2] + 1) % R
+    # ---- grand products and the lookup permutation on the device
+    chunk_len = 2
+    sets = [(0, 2), (2, 3)]
+    z_cols, last_z = [], 1
+    for lo, hi in sets:
+        z = L.permutation_product([W(cols_perm[j]) for j in range(lo, hi)], [W(sigma[j]) for j in range(lo, hi)], fr_to_words(beta), fr_to_words(gamma),
+                                  fr_to_words(DELTA), fr_to_words(pow(DELTA, lo, R)), fr_to_words(omega), fr_to_words(last_z))
+        z_int = [o.from_mont(v, R) for v in oc.words_to_ints(z)]
+        last_z = z_int[u]
+        z_cols.append(z_int)
+    assert z_cols[-1][u] == 1 or break_it, "the permutation product does not close"
+    pa, pt = L.lookup_permute(W(lk), W(table), u)
+    a_perm = [o.from_mont(v, R) for v in oc.words_to_ints(pa)] + [rnd() for _ in range(n - u)]
+    s_perm = [o.from_mont(v, R) for v in oc.words_to_ints(pt)] + [rnd() for _ in range(n - u)]
+    if break_it == "fill":
+        a_perm[0], a_perm[u - 1] = a_perm[u - 1], a_perm[0]
+    zl = L.lookup_product(W(lk), W(table), W(a_perm), W(s_perm), fr_to_words(beta), fr_to_words(gamma))
+    zl_int = [o.from_mont(v, R) for v in oc.words_to_ints(zl)]
+    assert zl_int[u] == 1 or break_it, "the lookup product does not close"
+    # ---- everything to the extended coset
+    ext = lambda vals: dom.coeff_to_extended(dom.lagrange_to_coeff(W(vals)))
+    l0 = [1] + [0] * (n - 1)
+    l_last = [1 if i == u else 0 for i in range(n)]
+    l_active = [1 if i < u else 0 for i in range(n)]
+    polys = [ev.Product(ev.Fixed(0), ev.Sum(ev.Product(ev.Advice(0), ev.Advice(1)), ev.Negated(ev.Advice(2))))]
+    E = ev.Evaluator(polys, [([ev.Advice(3)], [ev.Fixed(1)])])
+    sig_for_eval = sigma if break_it != "sigma" else [sigma[1], sigma[0], sigma[2]]
+    h_ext = E.evaluate_h(size=en, rot_scale=rot_scale, fixed=[ext(q), ext(table)], advice=[ext(a), ext(b), ext(c), ext(lk)], instance=[],
+                         challenges=np.zeros((0, 4), dtype=np.uint64), y=fr_to_words(y), beta=fr_to_words(beta), gamma=fr_to_words(gamma),
+                         theta=fr_to_words(theta), l0=ext(l0), l_last=ext(l_last), l_active_row=ext(l_active),
+                         permutation=dict(product_cosets=[ext(z) for z in z_cols], columns=[("advice", 0), ("advice", 1), ("advice", 2)],
+                                          cosets=[ext(s) for s in sig_for_eval], chunk_len=chunk_len, last_rotation=-(bf + 1), delta=fr_to_words(DELTA),
+                                          zeta=fr_to_words(dom.g_coset), extended_omega=fr_to_words(dom.extended_omega)),
+                         lookups=[dict(product_coset=ext(zl_int), permuted_input_coset=ext(a_perm), permuted_table_coset=ext(s_perm))], lib=L)
+    quotient = dom.divide_by_vanishing_poly(h_ext)
+    coeffs = L.ntt(np.ascontiguousarray(quotient), fr_to_words(dom.extended_omega_inv), dom.extended_k)      # scaling / coset factors keep zeros zero
+    top = coeffs[3 * n:]
+    return not top.any(), h_ext

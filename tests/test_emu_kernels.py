@@ -464,3 +464,12 @@ def test_msm_pair_pre_reduction(emu, oc):
         env = dict(os.environ, H2B_MSM_PAIR_LEVELS=levels)
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
         assert out.returncode == 0 and "ok" in out.stdout, (levels, out.stderr[-3000:])
+
+
+def test_quotient_of_a_satisfied_circuit_is_a_polynomial(emu, oc):
+    ok, h = pc.check_quotient_is_a_polynomial(emu, oc, k=4, seed=1)
+    assert ok and h.any()
+    assert pc.check_quotient_is_a_polynomial(emu, oc, k=5, seed=2)[0]
+    # and the property is sharp: an unsatisfied gate, a wrong sigma column or a disturbed fill order all break it
+    for what in ("witness", "sigma", "fill"):
+        assert not pc.check_quotient_is_a_polynomial(emu, oc, k=4, seed=3, break_it=what)[0], what

@@ -165,6 +165,11 @@ def test_permutation_and_lookup_grand_products(gpu, oc):
     pc.check_grand_products(gpu, oc, [1, 64, 4096, 1 << 16, (1 << 18) + 5])
 
 
+def test_quotient_of_a_satisfied_circuit_is_a_polynomial(gpu, oc):
+    assert pc.check_quotient_is_a_polynomial(gpu, oc, k=6, seed=4)[0]
+    assert not pc.check_quotient_is_a_polynomial(gpu, oc, k=6, seed=5, break_it="sigma")[0]
+
+
 def test_prover_rows_golden(gpu, golden):
     pc.check_golden_prover(gpu, golden["prover"])
 
