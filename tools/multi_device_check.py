@@ -64,4 +64,38 @@ for t in ths:
 for t in ths:
     t.join()
 assert not errs, errs
+
+# SRS file -> base sets resident on EVERY device (decoded on device 0, peer-copied, tables built per device); a sharded MSM over them
+import tempfile
+from halo2_scaffold_b200 import evaluation as ev
+k = 18
+g, gl = P[: 1 << k], P[1 << k: 2 << k] if n >= (2 << k) else P[: 1 << k][::-1].copy()
+path = os.path.join(tempfile.mkdtemp(prefix="h2b_md_"), "kzg_bn254_%d.srs" % k)
+L.srs_write(path, 0, k, g, gl, bytes(128))
+r = L.srs_read(path, 0)
+assert (r["g"] == g).all() and (r["g_lagrange"] == gl).all()
+sk = s[: 1 << k]
+assert (pc.affine_of(oc, L.msm_registered(sk, r["handle_g"])) == pc.affine_of(oc, oc.best_multiexp(sk, g))).all()
+assert (pc.affine_of(oc, L.msm_registered(sk, r["handle_g_lagrange"])) == pc.affine_of(oc, oc.best_multiexp(sk, gl))).all()
+L.unregister_bases(r["handle_g"]); L.unregister_bases(r["handle_g_lagrange"])
+L.srs_cache_clear()
+# the widened rows on the LAST device of the process: quotient evaluation, grand product, lookup permutation
+dev = nd - 1
+rng = np.random.default_rng(7)
+graph, n_const = pc.random_graph(rng, 2, 3, 1, 1, 120)
+gq, ga = pc._graph_pair(oc, graph, n_const, 7)
+rows = 5000
+cols = [oc.random_fr(900 + j, rows) for j in range(6)]
+scq = oc.random_fr(950, 5)
+vals = oc.random_fr(951, rows)
+want_v = oc.evaluate_graph(gq, cols[:2], cols[2:5], cols[5:], scq[:1], scq[1], scq[2], scq[3], scq[4], vals, 2)
+assert (ev.evaluate_graph(L, ga, cols[:2], cols[2:5], cols[5:], scq[:1], scq[1], scq[2], scq[3], scq[4], vals, 2, device=dev) == want_v).all()
+w13 = pc.omega_words(oc, 13)
+assert (L.permutation_product(cols[:2], cols[2:4], scq[0], scq[1], scq[2], scq[3], w13, scq[4], device=dev) ==
+        oc.permutation_product(cols[:2], cols[2:4], scq[0], scq[1], scq[2], scq[3], w13, scq[4])).all()
+tab = cols[0]
+inp = tab[:rows - 6][rng.integers(0, rows - 6, size=rows)]
+got_a, got_t = L.lookup_permute(inp, tab, rows - 6, device=dev)
+want_a, want_t = oc.lookup_permute(inp, tab, rows - 6)
+assert (got_a == want_a).all() and (got_t == want_t).all()
 print("MULTI_DEVICE_OK", nd)
