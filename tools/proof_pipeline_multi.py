@@ -1,0 +1,265 @@
+#!/usr/bin/env python3
+"""
+tools/proof_pipeline.py across the D GPUs of one process (BASELINE.json configs[4]: "many advice columns; commits sharded across 8
+GPUs"): the SRS (with window tables) is resident on every device; column j lives on device j mod D, where it is
+uploaded (pinned host arrays, one PCIe link per GPU), committed, brought to coefficient form and to the extended coset; every
+permutation set and every lookup argument runs on one device (the set's columns are peer-copied there); the extended columns are then
+gathered on device 0 over NVLink for evaluate_h; the quotient pieces, the evaluations at x and the per-column work of the opening
+go back to one device per polynomial.  No collective: only peer copies of whole columns.
+The wall time is taken on the host around the whole sequence with every device synchronised at the end.
+usage: python tools/proof_pipeline_multi.py [cfg ...]        (uses every visible GPU)
+"""
+import json, math, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT]
+import numpy as np
+import torch
+import halo2_scaffold_b200 as h2
+from halo2_scaffold_b200 import _lib, evaluation as ev
+from halo2_scaffold_b200.domain import EvaluationDomain, fr_to_words, FR_MODULUS
+
+SHAPES = {
+    "linear_regression_k20": dict(k=20, A=2, LK=1, d=4),
+    "logistic_regression_k22": dict(k=22, A=6, LK=2, d=4),
+    "logistic_regression_k22_wide": dict(k=22, A=14, LK=2, d=4),
+}
+DELTA = pow(7, 1 << 28, FR_MODULUS)
+
+
+def main():
+    L = h2.load(); L.init(0)
+    D = L.device_count()
+    devs = [torch.device("cuda", i) for i in range(D)]
+    st = [torch.cuda.current_stream(i).cuda_stream for i in range(D)]
+    W = fr_to_words
+    for name in (sys.argv[1:] or ["logistic_regression_k22"]):
+        s = SHAPES[name]
+        k, A, LK, d = s["k"], s["A"], s["LK"], s["d"]
+        n = 1 << k
+        dom = EvaluationDomain(d, k, lib=L)
+        ek, en, rot_scale = dom.extended_k, 1 << dom.extended_k, 1 << (dom.extended_k - k)
+        chunk, n_adv, usable = d - 2, A + LK, n - 6
+        sets = math.ceil(n_adv / chunk)
+        seed = [7000 * k]
+
+        def dcol(dv, rows):
+            with torch.cuda.device(dv):
+                t = torch.empty(rows * 4, dtype=torch.int64, device=devs[dv])
+                seed[0] += 1
+                L.gen_scalars_dev(dv, seed[0], rows, 0, t.data_ptr(), st[dv])
+            return t
+        # ---- resident before the proof ---------------------------------------------------------------------------------------
+        with torch.cuda.device(0):
+            pts = torch.empty(n * 8, dtype=torch.int64, device=devs[0])
+            L.gen_points_dev(0, 99 + k, n, pts.data_ptr(), st[0])
+            torch.cuda.synchronize(0)
+            hp = pts.cpu().numpy().view(np.uint64).reshape(n, 8)
+            del pts
+        h_g, h_gl = L.register_bases(hp), L.register_bases(hp[::-1].copy())          # every device gets the points and its own tables
+        del hp
+        fixed_ext = [dcol(0, en) for _ in range(A + 1)]
+        sigma_ext = [dcol(0, en) for _ in range(n_adv)]
+        l0, l_last, l_active = dcol(0, en), dcol(0, en), dcol(0, en)
+        host_table = L.gen_scalars(450 + k, n, 0)
+        table_lagrange = [torch.from_numpy(host_table.view(np.int64).reshape(-1)).to(devs[i]) for i in range(D)]      # proving-key data, replicated
+        set_dev = [si % D for si in range(sets)]
+        sigma_lagrange = [dcol(set_dev[c // chunk], n) for c in range(n_adv)]
+        polys = [ev.Product(ev.Fixed(c), ev.Sum(ev.Sum(ev.Advice(c, 0), ev.Product(ev.Advice(c, 1), ev.Advice(c, 2))), ev.Negated(ev.Advice(c, 3))))
+                 for c in range(A)]
+        E = ev.Evaluator(polys, [([ev.Advice(A + j)], [ev.Fixed(A)]) for j in range(LK)])
+        g_gates, g_lk = E.custom_gates.arrays(), [g.arrays() for g in E.lookups]
+        sc = L.gen_scalars(5, 8)
+        theta, beta, gamma, y, x, v = sc[:6]
+        one = W(1)
+        zs = np.stack([W(1), W(dom.g_coset), W(dom.g_coset_inv)])
+        e2c = np.stack([W(dom.extended_ifft_divisor), W(dom.extended_ifft_divisor * dom.g_coset_inv), W(dom.extended_ifft_divisor * dom.g_coset)])
+        tev = np.stack([W(t) for t in dom.t_evaluations])
+        weights = L.gen_scalars(900, 64)
+        # the witness in PINNED host memory (one DMA per column, each GPU over its own PCIe link)
+        host_adv = []
+        for j in range(n_adv):
+            a = L.gen_scalars(300 + j, n, 1) if j < A else host_table.copy()
+            if j >= A:
+                a[:usable] = host_table[:usable][::-1]
+            host_adv.append(torch.from_numpy(a.view(np.int64).reshape(-1)).pin_memory())
+        host_inst = torch.from_numpy(L.gen_scalars(400, n, 1).view(np.int64).reshape(-1)).pin_memory()
+        blocks = [torch.empty(64 * 28, dtype=torch.int64, device=devs[i]) for i in range(D)]
+        evals = [torch.empty(256 * 4, dtype=torch.int64, device=devs[i]) for i in range(D)]
+        n_msm = [0] * D
+        n_eval = [0] * D
+        torch.cuda.synchronize()
+
+        def on(t):
+            return t.device.index
+
+        def commit(t, handle):
+            dv = on(t)
+            with torch.cuda.device(dv):
+                L.msm_dev_registered(dv, t.data_ptr(), handle, 0, n, blocks[dv].data_ptr() + 224 * (n_msm[dv] % 64), st[dv])
+            n_msm[dv] += 1
+
+        def to_coeff(t):
+            dv = on(t)
+            with torch.cuda.device(dv):
+                c = t.clone()
+                L.lagrange_to_coeff_dev(dv, c.data_ptr(), k, W(dom.omega_inv), W(dom.ifft_divisor), st[dv])
+            return c
+
+        def to_ext(c):
+            dv = on(c)
+            with torch.cuda.device(dv):
+                e = torch.empty(en * 4, dtype=torch.int64, device=devs[dv])
+                e[: n * 4] = c
+                L.coeff_to_extended_dev(dv, e.data_ptr(), k, ek, W(dom.extended_omega), zs, st[dv])
+            return e
+
+        def move(t, dv):
+            return t if on(t) == dv else t.to(devs[dv], non_blocking=True)
+
+        def run():
+            for i in range(D):
+                n_msm[i] = n_eval[i] = 0
+            phase, t_prev = {}, [time.perf_counter()]
+
+            def mark(label):
+                for i in range(D):
+                    torch.cuda.synchronize(i)
+                t = time.perf_counter()
+                phase[label] = round((t - t_prev[0]) * 1e3, 3)
+                t_prev[0] = t
+            # columns: upload, commit_lagrange, coefficient form, extended coset -- column j on device j mod D
+            adv, adv_c, adv_e = [], [], []
+            for j in range(n_adv):
+                dv = j % D
+                with torch.cuda.device(dv):
+                    t = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
+                    t.copy_(host_adv[j], non_blocking=True)
+                commit(t, h_gl)
+                adv.append(t)
+            with torch.cuda.device(0):
+                d_inst = torch.empty(n * 4, dtype=torch.int64, device=devs[0])
+                d_inst.copy_(host_inst, non_blocking=True)
+            inst_c = to_coeff(d_inst)
+            for t in adv:
+                adv_c.append(to_coeff(t))
+            for c in adv_c:
+                adv_e.append(to_ext(c))
+            inst_e = to_ext(inst_c)
+            # permutation sets: the set's columns are copied to the set's device; z, commit, coefficient + extended form
+            z_l, last_z = [], one
+            for si in range(sets):
+                dv = set_dev[si]
+                cols = list(range(si * chunk, min((si + 1) * chunk, n_adv)))
+                with torch.cuda.device(dv):
+                    local = [move(adv[c], dv) for c in cols]
+                    z = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
+                    L.permutation_product_dev(dv, [t.data_ptr() for t in local], [sigma_lagrange[c].data_ptr() for c in cols], n, beta, gamma, W(DELTA),
+                                              W(pow(DELTA, cols[0], FR_MODULUS)), W(dom.omega), last_z, z.data_ptr(), st[dv])
+                commit(z, h_gl)
+                z_l.append(z)
+                last_z = gamma                                  # stands in for z[n - (blinding_factors + 1)] of the previous set (a 32-byte read-back)
+            z_c = [to_coeff(t) for t in z_l]
+            z_e = [to_ext(c) for c in z_c]
+            mark("columns_and_permutation")
+            # lookups (the permutation call checks the table membership and therefore synchronises its device): on the column's device
+            perm_l, zl_l = [], []
+            for j in range(LK):
+                dv = on(adv[A + j])
+                with torch.cuda.device(dv):
+                    a, s_ = adv[A + j].clone(), table_lagrange[dv].clone()
+                    L.lookup_permute_dev(dv, adv[A + j].data_ptr(), table_lagrange[dv].data_ptr(), usable, a.data_ptr(), s_.data_ptr(), st[dv])
+                    z = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
+                    L.lookup_product_dev(dv, adv[A + j].data_ptr(), table_lagrange[dv].data_ptr(), a.data_ptr(), s_.data_ptr(), n, beta, gamma, z.data_ptr(), st[dv])
+                commit(a, h_gl); commit(s_, h_gl); commit(z, h_gl)
+                perm_l.append((a, s_)); zl_l.append(z)
+            zl_c = [to_coeff(t) for t in zl_l]
+            perm_c = [(to_coeff(a), to_coeff(s_)) for a, s_ in perm_l]
+            lk_e = [(to_ext(zc), to_ext(pc[0]), to_ext(pc[1])) for zc, pc in zip(zl_c, perm_c)]
+            with torch.cuda.device(D - 1):
+                rnd = dcol(D - 1, n)
+            commit(rnd, h_g)
+            mark("lookups")
+            # evaluate_h on device 0: every extended column arrives over NVLink
+            with torch.cuda.device(0):
+                g_adv_e = [move(t, 0) for t in adv_e]
+                g_z_e = [move(t, 0) for t in z_e]
+                g_lk_e = [tuple(move(t, 0) for t in tr) for tr in lk_e]
+                values = torch.zeros(en * 4, dtype=torch.int64, device=devs[0])
+                mark("gather_extended_columns")
+                cols = _lib.EvalColumns([t.data_ptr() for t in fixed_ext], [t.data_ptr() for t in g_adv_e], [inst_e.data_ptr()], np.zeros((0, 4), dtype=np.uint64),
+                                        beta, gamma, theta, y)
+                L.evaluate_graph_dev(0, g_gates, cols, values.data_ptr(), en, rot_scale, st[0])
+                L.evaluate_h_permutation_dev(0, values.data_ptr(), en, rot_scale, [t.data_ptr() for t in g_z_e], [t.data_ptr() for t in g_adv_e],
+                                             [t.data_ptr() for t in sigma_ext], chunk, -6, l0.data_ptr(), l_last.data_ptr(), l_active.data_ptr(), beta, gamma, y,
+                                             W(DELTA), W(dom.g_coset), W(dom.extended_omega), st[0])
+                for g, (ze, ae, se) in zip(g_lk, g_lk_e):
+                    L.evaluate_h_lookup_dev(0, g, cols, values.data_ptr(), en, rot_scale, ze.data_ptr(), ae.data_ptr(), se.data_ptr(), l0.data_ptr(),
+                                            l_last.data_ptr(), l_active.data_ptr(), st[0])
+                L.fr_scale_dev(0, values.data_ptr(), en, tev, st[0])
+                L.extended_to_coeff_dev(0, values.data_ptr(), ek, W(dom.extended_omega_inv), e2c, st[0])
+                pieces = [values[p * n * 4:(p + 1) * n * 4] for p in range(d - 1)]
+            mark("evaluate_h_and_quotient")
+            # quotient pieces: one device each
+            h_pieces = []
+            for p, t in enumerate(pieces):
+                dv = p % D
+                with torch.cuda.device(dv):
+                    t2 = move(t, dv) if dv else t
+                h_pieces.append(t2)
+                commit(t2, h_g)
+            # evaluations at x: on the device that holds the coefficients
+            queried = [(c, 4) for c in adv_c] + [(c, 3) for c in z_c] + [(c, 2) for c in zl_c] + [(p_, 1) for pc in perm_c for p_ in pc] + \
+                      [(t, 1) for t in h_pieces] + [(rnd, 1)]
+            for c, rotations in queried:
+                dv = on(c)
+                with torch.cuda.device(dv):
+                    for r in range(rotations):
+                        L.check(L.L.h2b_fr_eval_polynomial_dev(dv, c.data_ptr(), n, x.ctypes.data, evals[dv].data_ptr() + 32 * (n_eval[dv] % 256), st[dv]))
+                        n_eval[dv] += 1
+            mark("quotient_commit_and_evaluations")
+            # SHPLONK: each rotation set on its own device (its polynomials are copied there), the final quotient on device 0
+            rot_sets = [(npts, [c for c, r in queried if r == npts]) for npts in (4, 3, 2, 1)]
+            quot = []
+            for qi, (npts, members) in enumerate(rot_sets):
+                if not members:
+                    continue
+                dv = qi % D
+                with torch.cuda.device(dv):
+                    local = [move(m_, dv) for m_ in members]
+                    comb = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
+                    L.fr_lincomb_dev(dv, [m_.data_ptr() for m_ in local], weights[:len(local)], n, comb.data_ptr(), st[dv])
+                    q = comb
+                    for _ in range(npts):
+                        nxt = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
+                        L.check(L.L.h2b_fr_kate_division_dev(dv, q.data_ptr(), n, x.ctypes.data, nxt.data_ptr(), st[dv]))
+                        q = nxt
+                quot.append(q)
+            with torch.cuda.device(0):
+                quot0 = [move(q, 0) for q in quot]
+                hq = torch.empty(n * 4, dtype=torch.int64, device=devs[0])
+                L.fr_lincomb_dev(0, [q.data_ptr() for q in quot0], weights[:len(quot0)], n, hq.data_ptr(), st[0])
+                commit(hq, h_g)
+                fin = torch.empty(n * 4, dtype=torch.int64, device=devs[0])
+                L.check(L.L.h2b_fr_kate_division_dev(0, hq.data_ptr(), n, v.ctypes.data, fin.data_ptr(), st[0]))
+                commit(fin, h_g)
+            out = [b.cpu() for b in blocks] + [e.cpu() for e in evals]
+            mark("multiopen")
+            return phase
+
+        run()
+        for i in range(D):
+            torch.cuda.synchronize(i)
+        t0 = time.perf_counter()
+        phase = run()
+        total_ms = (time.perf_counter() - t0) * 1e3
+        print(json.dumps({"config": name, "devices": D, "k": k, "extended_k": ek, "gate_advice": A, "lookup_advice": LK, "permutation_sets": sets,
+                          "device_resident_hot_path_ms": round(total_ms, 2), "phases_ms": phase, "msm_per_device": list(n_msm),
+                          "note": "one process, %d x B200; witness in pinned host memory; columns round-robin over the devices, evaluate_h on device 0 "
+                                  "(extended columns gathered over NVLink); host-side prover work not included; column counts are estimates" % D}), flush=True)
+        L.unregister_bases(h_g); L.unregister_bases(h_gl)
+        del fixed_ext, sigma_ext, sigma_lagrange, table_lagrange
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
