@@ -36,7 +36,7 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
-    "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
+    "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
 
@@ -154,6 +154,7 @@ class Lib:
         L.h2b_permutation_product_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_lookup_product_dev.argtypes = [i32, vp, vp, vp, vp, sz, vp, vp, vp, vp]
         L.h2b_lookup_permute_dev.argtypes = [i32, vp, vp, u32, vp, vp, vp]
+        L.h2b_lookup_permute_async_dev.argtypes = [i32, vp, vp, u32, vp, vp, vp, vp]
         L.h2b_g1_decode_dev.argtypes = [i32, vp, sz, i32, vp, ctypes.POINTER(u64), vp]
         L.h2b_g1_encode_dev.argtypes = [i32, vp, sz, vp, vp]
         L.h2b_srs_read.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(u32), vp, vp, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(u64), ctypes.POINTER(u64)]
@@ -411,6 +412,10 @@ class Lib:
 
     def lookup_permute_dev(self, device: int, d_input: int, d_table: int, usable_rows: int, d_permuted_input: int, d_permuted_table: int, stream: int = 0):
         self.check(self.L.h2b_lookup_permute_dev(device, d_input, d_table, usable_rows, d_permuted_input, d_permuted_table, stream))
+
+    def lookup_permute_async_dev(self, device: int, d_input: int, d_table: int, usable_rows: int, d_permuted_input: int, d_permuted_table: int,
+                                 d_status: int, stream: int = 0):
+        self.check(self.L.h2b_lookup_permute_async_dev(device, d_input, d_table, usable_rows, d_permuted_input, d_permuted_table, d_status, stream))
 
     def lookup_permute(self, input_expression, table_expression, usable_rows: int, device: int = 0):
         """permute_expression_pair on host arrays -> (permuted_input, permuted_table), usable_rows x 4 each"""

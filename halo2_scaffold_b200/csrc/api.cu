@@ -758,7 +758,16 @@ int h2b_lookup_permute_dev(int device, const void* d_input, const void* d_table,
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
-    return lookup_permute_run(*c, d_input, d_table, usable_rows, d_permuted_input, d_permuted_table, (cudaStream_t)stream);
+    return lookup_permute_run(*c, d_input, d_table, usable_rows, d_permuted_input, d_permuted_table, nullptr, (cudaStream_t)stream);
+}
+
+int h2b_lookup_permute_async_dev(int device, const void* d_input, const void* d_table, uint32_t usable_rows, void* d_permuted_input, void* d_permuted_table,
+                                 void* d_status, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_status) { set_error("h2b_lookup_permute_async_dev: null status word"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return lookup_permute_run(*c, d_input, d_table, usable_rows, d_permuted_input, d_permuted_table, d_status, (cudaStream_t)stream);
 }
 
 // ---- SRS on-disk format -----------------------------------------------------------------------------

@@ -125,7 +125,7 @@ int lookup_product_run(DeviceCtx& ctx, const void* d_compressed_input, const voi
                        const void* d_permuted_table, size_t n, const uint64_t* beta, const uint64_t* gamma, void* d_z, cudaStream_t stream);
 // ---- lookup.cu ----
 int lookup_permute_run(DeviceCtx& ctx, const void* d_input, const void* d_table, uint32_t usable_rows, void* d_permuted_input, void* d_permuted_table,
-                       cudaStream_t stream);
+                       void* d_status, cudaStream_t stream);
 // ---- srs.cu ----
 int g1_decode_run(DeviceCtx& ctx, const void* d_bytes, size_t n, int format, void* d_out, uint64_t* first_invalid, cudaStream_t stream);
 int g1_encode_run(DeviceCtx& ctx, const void* d_affine, size_t n, void* d_out_bytes, cudaStream_t stream);

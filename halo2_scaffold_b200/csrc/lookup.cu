@@ -231,8 +231,11 @@ __global__ void __launch_bounds__(256) lookup_fill_kernel(const uint4* __restric
 }
 
 int lookup_permute_run(DeviceCtx& ctx, const void* d_input, const void* d_table, uint32_t usable_rows, void* d_permuted_input, void* d_permuted_table,
-                       cudaStream_t stream) {
-    if (usable_rows == 0) return H2B_OK;
+                       void* d_status, cudaStream_t stream) {
+    if (usable_rows == 0) {
+        if (d_status) H2B_CUDA(cudaMemsetAsync(d_status, 0, 4, stream));
+        return H2B_OK;
+    }
     if (!d_input || !d_table || !d_permuted_input || !d_permuted_table) { set_error("lookup_permute: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
     if (usable_rows > (1u << 28)) { set_error("lookup_permute: at most 2^28 rows"); return H2B_ERR_BAD_ARGUMENT; }
     uint32_t padded = SORT_TILE;
@@ -266,7 +269,13 @@ int lookup_permute_run(DeviceCtx& ctx, const void* d_input, const void* d_table,
     H2B_LAUNCH(lookup_fill_kernel, gu, 256, 0, stream, (const uint4*)ka, (const uint4*)kt, usable_rows, (const uint32_t*)repeated, (const uint32_t*)rank_r,
                (const uint32_t*)unused, (const uint32_t*)rank_l, (const uint32_t*)rows_of_rank, (uint4*)d_permuted_input, (uint4*)d_permuted_table);
     H2B_CUDA(cudaGetLastError());
-    // upstream returns Err(ConstraintSystemFailure) for an input value the table does not hold: the call is synchronous
+    // upstream returns Err(ConstraintSystemFailure) for an input value the table does not hold.  With a status word the verdict is left
+    // on the device (0 = satisfied, otherwise 1 + the sorted row of a missing value) and the call stays asynchronous; without one
+    // the call synchronises and fails
+    if (d_status) {
+        H2B_CUDA(cudaMemcpyAsync(d_status, missing, 4, cudaMemcpyDeviceToDevice, stream));
+        return H2B_OK;
+    }
     uint32_t miss = 0;
     H2B_CUDA(cudaMemcpyAsync(&miss, missing, 4, cudaMemcpyDeviceToHost, stream));
     H2B_CUDA(cudaStreamSynchronize(stream));

@@ -165,6 +165,11 @@ int h2b_lookup_product_dev(int device, const void* d_compressed_input, const voi
  * Error::ConstraintSystemFailure. */
 int h2b_lookup_permute_dev(int device, const void* d_input, const void* d_table, uint32_t usable_rows, void* d_permuted_input, void* d_permuted_table,
                            void* stream);
+/* The same without the synchronisation: the verdict is written to the 32-bit device word d_status on `stream` (0 = every input value
+ * is in the table, otherwise 1 + the sorted row of one that is not -- the outputs are then meaningless); the caller reads it when it
+ * next synchronises.  Lets several devices permute their lookups concurrently. */
+int h2b_lookup_permute_async_dev(int device, const void* d_input, const void* d_table, uint32_t usable_rows, void* d_permuted_input,
+                                 void* d_permuted_table, void* d_status, void* stream);
 
 /* ---- quotient evaluation: evaluate_h on device-resident extended-coset columns ----------
  * [UP] halo2_proofs/src/plonk/evaluation.rs.  A GraphEvaluator is passed in the vocabulary upstream builds it in

@@ -62,6 +62,8 @@ extern "C" {
                                        last_z: *const u64, d_z: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn h2b_lookup_permute_dev(device: c_int, d_input: *const c_void, d_table: *const c_void, usable_rows: u32, d_permuted_input: *mut c_void,
                                   d_permuted_table: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_lookup_permute_async_dev(device: c_int, d_input: *const c_void, d_table: *const c_void, usable_rows: u32, d_permuted_input: *mut c_void,
+                                        d_permuted_table: *mut c_void, d_status: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn h2b_lookup_product_dev(device: c_int, d_compressed_input: *const c_void, d_compressed_table: *const c_void, d_permuted_input: *const c_void,
                                   d_permuted_table: *const c_void, n: usize, beta: *const u64, gamma: *const u64, d_z: *mut c_void, stream: *mut c_void) -> c_int;
     // plonk::evaluation (evaluate_h)

@@ -700,3 +700,33 @@ def check_quotient_is_a_polynomial(L, oc, k=4, seed=1, break_it=None):
     coeffs = L.ntt(np.ascontiguousarray(quotient), fr_to_words(dom.extended_omega_inv), dom.extended_k)      # scaling / coset factors keep zeros zero
     top = coeffs[3 * n:]
     return not top.any(), h_ext
+
+
+def check_lookup_permute_async(L, oc):
+    """the asynchronous variant leaves the verdict in a device word: 0 for a satisfiable pair, 1 + a sorted row otherwise"""
+    n, usable = 200, 194
+    pool = oc.random_fr(0xC900, 30)
+    rng = np.random.default_rng(9)
+    table = pool[np.concatenate([np.arange(30), rng.integers(0, 30, size=n - 30)])]
+    inp = table[:usable][rng.integers(0, usable, size=n)]
+    for bad in (False, True):
+        a = inp.copy()
+        if bad:
+            a[3] = oc.random_fr(0xC901, 1)[0]
+        d = [L.dev_alloc(0, n * 32) for _ in range(4)] + [L.dev_alloc(0, 4)]
+        try:
+            L.h2d(0, d[0], a)
+            L.h2d(0, d[1], table)
+            L.lookup_permute_async_dev(0, d[0], d[1], usable, d[2], d[3], d[4])
+            L.dev_sync(0)
+            status = np.zeros(1, dtype=np.uint32)
+            L.d2h(0, status, d[4])
+            assert (status[0] != 0) == bad
+            if not bad:
+                pa, pt = np.empty((usable, 4), dtype=np.uint64), np.empty((usable, 4), dtype=np.uint64)
+                L.d2h(0, pa, d[2]); L.d2h(0, pt, d[3])
+                wa, wt = oc.lookup_permute(a, table, usable)
+                assert (pa == wa).all() and (pt == wt).all()
+        finally:
+            for p in d:
+                L.dev_free(0, p)

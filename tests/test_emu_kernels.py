@@ -426,6 +426,10 @@ def test_linear_combination_of_columns(emu, oc):
     pc.check_lincomb(emu, oc, [(1, 1), (7, 3), (200, 32), (130, 33), (64, 70)])
 
 
+def test_lookup_permute_async_status(emu, oc):
+    pc.check_lookup_permute_async(emu, oc)
+
+
 def test_lookup_permute_expression_pair(emu, oc):
     pc.check_lookup_permute(emu, oc, [(8, 8, 3, "random", 1), (64, 58, 10, "random", 2), (1024, 1018, 1000, "random", 3), (1024, 1018, 16, "small", 4),
                                       (2048, 2042, 700, "skewed", 5), (3000, 2994, 256, "small", 6), (4096, 4090, 5000, "random", 7), (16, 0, 4, "random", 8)])

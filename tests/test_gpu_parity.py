@@ -174,6 +174,10 @@ def test_prover_rows_golden(gpu, golden):
     pc.check_golden_prover(gpu, golden["prover"])
 
 
+def test_lookup_permute_async_status(gpu, oc):
+    pc.check_lookup_permute_async(gpu, oc)
+
+
 def test_lookup_permute_expression_pair(gpu, oc):
     pc.check_lookup_permute(gpu, oc, [(64, 58, 10, "random", 2), (1 << 12, (1 << 12) - 6, 1000, "random", 3), (1 << 16, (1 << 16) - 6, 1 << 10, "small", 4),
                                       (1 << 17, (1 << 17) - 6, 70000, "skewed", 5), ((1 << 18) + 100, (1 << 18) + 94, 1 << 19, "random", 6)])

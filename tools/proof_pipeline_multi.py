@@ -161,13 +161,15 @@ def main():
             z_c = [to_coeff(t) for t in z_l]
             z_e = [to_ext(c) for c in z_c]
             mark("columns_and_permutation")
-            # lookups (the permutation call checks the table membership and therefore synchronises its device): on the column's device
-            perm_l, zl_l = [], []
+            # lookups on the column's device; the table-membership verdict of each permutation is read at the end (asynchronous variant)
+            perm_l, zl_l, status = [], [], []
             for j in range(LK):
                 dv = on(adv[A + j])
                 with torch.cuda.device(dv):
                     a, s_ = adv[A + j].clone(), table_lagrange[dv].clone()
-                    L.lookup_permute_dev(dv, adv[A + j].data_ptr(), table_lagrange[dv].data_ptr(), usable, a.data_ptr(), s_.data_ptr(), st[dv])
+                    status.append(torch.zeros(1, dtype=torch.int32, device=devs[dv]))
+                    L.lookup_permute_async_dev(dv, adv[A + j].data_ptr(), table_lagrange[dv].data_ptr(), usable, a.data_ptr(), s_.data_ptr(),
+                                               status[-1].data_ptr(), st[dv])
                     z = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
                     L.lookup_product_dev(dv, adv[A + j].data_ptr(), table_lagrange[dv].data_ptr(), a.data_ptr(), s_.data_ptr(), n, beta, gamma, z.data_ptr(), st[dv])
                 commit(a, h_gl); commit(s_, h_gl); commit(z, h_gl)
@@ -243,6 +245,7 @@ def main():
                 L.check(L.L.h2b_fr_kate_division_dev(0, hq.data_ptr(), n, v.ctypes.data, fin.data_ptr(), st[0]))
                 commit(fin, h_g)
             out = [b.cpu() for b in blocks] + [e.cpu() for e in evals]
+            assert all(int(w.cpu()[0]) == 0 for w in status), "a lookup input value is not in the table"
             mark("multiopen")
             return phase
 
