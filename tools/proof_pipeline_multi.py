@@ -163,6 +163,7 @@ def main():
             mark("columns_and_permutation")
             # lookups on the column's device; the table-membership verdict of each permutation is read at the end (asynchronous variant)
             perm_l, zl_l, status = [], [], []
+            spare = [(2 * j + 1) % D for j in range(2 * LK)]             # where the permuted columns of each lookup are committed and transformed
             for j in range(LK):
                 dv = on(adv[A + j])
                 with torch.cuda.device(dv):
@@ -172,8 +173,14 @@ def main():
                                                status[-1].data_ptr(), st[dv])
                     z = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
                     L.lookup_product_dev(dv, adv[A + j].data_ptr(), table_lagrange[dv].data_ptr(), a.data_ptr(), s_.data_ptr(), n, beta, gamma, z.data_ptr(), st[dv])
-                commit(a, h_gl); commit(s_, h_gl); commit(z, h_gl)
-                perm_l.append((a, s_)); zl_l.append(z)
+                commit(z, h_gl)
+                # the two permuted columns leave for other devices: only z stays on the lookup's critical path
+                with torch.cuda.device(spare[2 * j]):
+                    a2 = move(a, spare[2 * j])
+                with torch.cuda.device(spare[2 * j + 1]):
+                    s2 = move(s_, spare[2 * j + 1])
+                commit(a2, h_gl); commit(s2, h_gl)
+                perm_l.append((a2, s2)); zl_l.append(z)
             zl_c = [to_coeff(t) for t in zl_l]
             perm_c = [(to_coeff(a), to_coeff(s_)) for a, s_ in perm_l]
             lk_e = [(to_ext(zc), to_ext(pc[0]), to_ext(pc[1])) for zc, pc in zip(zl_c, perm_c)]
@@ -240,10 +247,14 @@ def main():
                 quot0 = [move(q, 0) for q in quot]
                 hq = torch.empty(n * 4, dtype=torch.int64, device=devs[0])
                 L.fr_lincomb_dev(0, [q.data_ptr() for q in quot0], weights[:len(quot0)], n, hq.data_ptr(), st[0])
-                commit(hq, h_g)
                 fin = torch.empty(n * 4, dtype=torch.int64, device=devs[0])
                 L.check(L.L.h2b_fr_kate_division_dev(0, hq.data_ptr(), n, v.ctypes.data, fin.data_ptr(), st[0]))
-                commit(fin, h_g)
+                commit(hq, h_g)
+            with torch.cuda.device(D - 1):                               # the two opening commitments on two devices
+                fin2 = move(fin, D - 1)
+            commit(fin2, h_g)
+            with torch.cuda.device(0):
+                pass
             out = [b.cpu() for b in blocks] + [e.cpu() for e in evals]
             assert all(int(w.cpu()[0]) == 0 for w in status), "a lookup input value is not in the table"
             mark("multiopen")
