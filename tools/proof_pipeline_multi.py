@@ -163,7 +163,9 @@ def main():
             mark("columns_and_permutation")
             # lookups on the column's device; the table-membership verdict of each permutation is read at the end (asynchronous variant)
             perm_l, zl_l, status = [], [], []
-            spare = [(2 * j + 1) % D for j in range(2 * LK)]             # where the permuted columns of each lookup are committed and transformed
+            busy = {(A + j) % D for j in range(LK)} | {0}
+            idle = [i for i in range(D) if i not in busy] or list(range(D))
+            spare = [idle[i % len(idle)] for i in range(2 * LK + 1)]     # where the permuted columns of each lookup are committed and transformed
             for j in range(LK):
                 dv = on(adv[A + j])
                 with torch.cuda.device(dv):
@@ -184,8 +186,8 @@ def main():
             zl_c = [to_coeff(t) for t in zl_l]
             perm_c = [(to_coeff(a), to_coeff(s_)) for a, s_ in perm_l]
             lk_e = [(to_ext(zc), to_ext(pc[0]), to_ext(pc[1])) for zc, pc in zip(zl_c, perm_c)]
-            with torch.cuda.device(D - 1):
-                rnd = dcol(D - 1, n)
+            with torch.cuda.device(spare[2 * LK]):
+                rnd = dcol(spare[2 * LK], n)
             commit(rnd, h_g)
             mark("lookups")
             # evaluate_h on device 0: every extended column arrives over NVLink
