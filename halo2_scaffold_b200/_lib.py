@@ -37,7 +37,7 @@ _EXPORTS = [
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
     "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
-    "h2b_evaluate_graph_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
+    "h2b_evaluate_graph_dev", "h2b_evaluate_graph_shard_dev", "h2b_evaluate_h_permutation_shard_dev", "h2b_evaluate_h_lookup_shard_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
 ]
 
 
@@ -65,6 +65,10 @@ class EvalColumnsStruct(ctypes.Structure):
                 ("instance", ctypes.c_void_p), ("n_instance", ctypes.c_uint32),
                 ("challenges", ctypes.c_void_p), ("n_challenges", ctypes.c_uint32),
                 ("beta", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("theta", ctypes.c_void_p), ("y", ctypes.c_void_p)]
+
+
+class ShardStruct(ctypes.Structure):
+    _fields_ = [("row0", ctypes.c_uint32), ("rows", ctypes.c_uint32), ("halo", ctypes.c_uint32)]
 
 
 assert ctypes.sizeof(CalculationStruct) == 40
@@ -162,6 +166,9 @@ class Lib:
         L.h2b_evaluate_graph_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp]
         L.h2b_evaluate_h_permutation_dev.argtypes = [i32, vp, u32, i32, vp, u32, vp, vp, u32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_evaluate_h_lookup_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.h2b_evaluate_graph_shard_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp, vp]
+        L.h2b_evaluate_h_permutation_shard_dev.argtypes = [i32, vp, u32, i32, vp, u32, vp, vp, u32, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.h2b_evaluate_h_lookup_shard_dev.argtypes = [i32, vp, vp, vp, u32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_evaluate_graph_info.argtypes = [ctypes.POINTER(u32), ctypes.POINTER(u32)]
         L.h2b_dev_alloc.argtypes = [i32, sz, ctypes.POINTER(vp)]
         L.h2b_dev_free.argtypes = [i32, vp]
@@ -530,25 +537,41 @@ class Lib:
         self.check(self.L.h2b_srs_write(path.encode(), fmt, k, g.ctypes.data, g_lagrange.ctypes.data, buf.ctypes.data if buf.size else None, buf.size))
 
     # ---- quotient evaluation (evaluate_h) on device-resident extended-coset columns ------------------
-    def evaluate_graph_dev(self, device: int, graph: GraphArrays, cols: EvalColumns, d_values: int, size: int, rot_scale: int, stream: int = 0):
+    def evaluate_graph_dev(self, device: int, graph: GraphArrays, cols: EvalColumns, d_values: int, size: int, rot_scale: int, stream: int = 0,
+                           shard=None):
+        """shard = (row0, rows, halo): the row-sharded variant (column pointers are slices with halo, d_values the halo-free slice)"""
         g, c = graph.struct(), cols.struct()
-        self.check(self.L.h2b_evaluate_graph_dev(device, ctypes.addressof(g), ctypes.addressof(c), d_values, size, rot_scale, stream))
+        if shard is None:
+            self.check(self.L.h2b_evaluate_graph_dev(device, ctypes.addressof(g), ctypes.addressof(c), d_values, size, rot_scale, stream))
+        else:
+            sh = ShardStruct(*shard)
+            self.check(self.L.h2b_evaluate_graph_shard_dev(device, ctypes.addressof(g), ctypes.addressof(c), d_values, size, rot_scale,
+                                                           ctypes.addressof(sh), stream))
 
     def evaluate_h_permutation_dev(self, device: int, d_values: int, size: int, rot_scale: int, product_cosets, columns, perm_cosets, chunk_len: int,
                                    last_rotation: int, d_l0: int, d_l_last: int, d_l_active_row: int, beta, gamma, y, delta, zeta, extended_omega,
-                                   stream: int = 0):
+                                   stream: int = 0, shard=None):
         pc, co, pe = (np.array(list(v), dtype=np.uint64) for v in (product_cosets, columns, perm_cosets))
         assert co.shape[0] == pe.shape[0]
         w = [np.ascontiguousarray(v, dtype=np.uint64).reshape(4) for v in (beta, gamma, y, delta, zeta, extended_omega)]
-        self.check(self.L.h2b_evaluate_h_permutation_dev(device, d_values, size, rot_scale, pc.ctypes.data, pc.shape[0], co.ctypes.data, pe.ctypes.data,
-                                                         co.shape[0], chunk_len, last_rotation, d_l0, d_l_last, d_l_active_row,
-                                                         *[v.ctypes.data for v in w], stream))
+        args = [device, d_values, size, rot_scale, pc.ctypes.data, pc.shape[0], co.ctypes.data, pe.ctypes.data, co.shape[0], chunk_len, last_rotation, d_l0,
+                d_l_last, d_l_active_row, *[v.ctypes.data for v in w]]
+        if shard is None:
+            self.check(self.L.h2b_evaluate_h_permutation_dev(*args, stream))
+        else:
+            sh = ShardStruct(*shard)
+            self.check(self.L.h2b_evaluate_h_permutation_shard_dev(*args, ctypes.addressof(sh), stream))
 
     def evaluate_h_lookup_dev(self, device: int, graph: GraphArrays, cols: EvalColumns, d_values: int, size: int, rot_scale: int, d_product: int,
-                              d_permuted_input: int, d_permuted_table: int, d_l0: int, d_l_last: int, d_l_active_row: int, stream: int = 0):
+                              d_permuted_input: int, d_permuted_table: int, d_l0: int, d_l_last: int, d_l_active_row: int, stream: int = 0, shard=None):
         g, c = graph.struct(), cols.struct()
-        self.check(self.L.h2b_evaluate_h_lookup_dev(device, ctypes.addressof(g), ctypes.addressof(c), d_values, size, rot_scale, d_product,
-                                                    d_permuted_input, d_permuted_table, d_l0, d_l_last, d_l_active_row, stream))
+        args = [device, ctypes.addressof(g), ctypes.addressof(c), d_values, size, rot_scale, d_product, d_permuted_input, d_permuted_table, d_l0, d_l_last,
+                d_l_active_row]
+        if shard is None:
+            self.check(self.L.h2b_evaluate_h_lookup_dev(*args, stream))
+        else:
+            sh = ShardStruct(*shard)
+            self.check(self.L.h2b_evaluate_h_lookup_shard_dev(*args, ctypes.addressof(sh), stream))
 
     def evaluate_graph_info(self):
         """-> (live-value slots, micro-operations) of the graph this thread compiled last"""

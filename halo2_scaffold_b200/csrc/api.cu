@@ -1005,7 +1005,15 @@ int h2b_evaluate_graph_dev(int device, const h2b_graph* graph, const h2b_eval_co
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
-    return evaluate_graph_run(*c, graph, cols, d_values, size, rot_scale, (cudaStream_t)stream);
+    return evaluate_graph_run(*c, graph, cols, d_values, size, rot_scale, nullptr, (cudaStream_t)stream);
+}
+int h2b_evaluate_graph_shard_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                                 const h2b_eval_shard* shard, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!shard) { set_error("h2b_evaluate_graph_shard_dev: null shard"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return evaluate_graph_run(*c, graph, cols, d_values, size, rot_scale, shard, (cudaStream_t)stream);
 }
 
 int h2b_evaluate_h_permutation_dev(int device, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
@@ -1017,7 +1025,19 @@ int h2b_evaluate_h_permutation_dev(int device, void* d_values, uint32_t size, in
     H2B_TRY(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     return evaluate_h_permutation_run(*c, d_values, size, rot_scale, d_product_cosets, n_sets, d_columns, d_perm_cosets, n_columns, chunk_len, last_rotation,
-                                      d_l0, d_l_last, d_l_active_row, beta, gamma, y, delta, zeta, extended_omega, (cudaStream_t)stream);
+                                      d_l0, d_l_last, d_l_active_row, beta, gamma, y, delta, zeta, extended_omega, nullptr, (cudaStream_t)stream);
+}
+int h2b_evaluate_h_permutation_shard_dev(int device, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
+                                         const void* const* d_columns, const void* const* d_perm_cosets, uint32_t n_columns, uint32_t chunk_len,
+                                         int32_t last_rotation, const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t beta[4],
+                                         const uint64_t gamma[4], const uint64_t y[4], const uint64_t delta[4], const uint64_t zeta[4],
+                                         const uint64_t extended_omega[4], const h2b_eval_shard* shard, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!shard) { set_error("h2b_evaluate_h_permutation_shard_dev: null shard"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return evaluate_h_permutation_run(*c, d_values, size, rot_scale, d_product_cosets, n_sets, d_columns, d_perm_cosets, n_columns, chunk_len, last_rotation,
+                                      d_l0, d_l_last, d_l_active_row, beta, gamma, y, delta, zeta, extended_omega, shard, (cudaStream_t)stream);
 }
 
 int h2b_evaluate_h_lookup_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
@@ -1027,7 +1047,17 @@ int h2b_evaluate_h_lookup_dev(int device, const h2b_graph* graph, const h2b_eval
     H2B_TRY(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     return evaluate_h_lookup_run(*c, graph, cols, d_values, size, rot_scale, d_product_coset, d_permuted_input_coset, d_permuted_table_coset, d_l0, d_l_last,
-                                 d_l_active_row, (cudaStream_t)stream);
+                                 d_l_active_row, nullptr, (cudaStream_t)stream);
+}
+int h2b_evaluate_h_lookup_shard_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                                    const void* d_product_coset, const void* d_permuted_input_coset, const void* d_permuted_table_coset, const void* d_l0,
+                                    const void* d_l_last, const void* d_l_active_row, const h2b_eval_shard* shard, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!shard) { set_error("h2b_evaluate_h_lookup_shard_dev: null shard"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return evaluate_h_lookup_run(*c, graph, cols, d_values, size, rot_scale, d_product_coset, d_permuted_input_coset, d_permuted_table_coset, d_l0, d_l_last,
+                                 d_l_active_row, shard, (cudaStream_t)stream);
 }
 
 int h2b_evaluate_graph_info(uint32_t* slots, uint32_t* micro_ops) {

@@ -130,14 +130,16 @@ int lookup_permute_run(DeviceCtx& ctx, const void* d_input, const void* d_table,
 int g1_decode_run(DeviceCtx& ctx, const void* d_bytes, size_t n, int format, void* d_out, uint64_t* first_invalid, cudaStream_t stream);
 int g1_encode_run(DeviceCtx& ctx, const void* d_affine, size_t n, void* d_out_bytes, cudaStream_t stream);
 // ---- evaluate.cu ----
-int evaluate_graph_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale, cudaStream_t stream);
+int evaluate_graph_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                       const h2b_eval_shard* shard, cudaStream_t stream);
 int evaluate_h_lookup_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
                           const void* d_product, const void* d_permuted_input, const void* d_permuted_table, const void* d_l0, const void* d_l_last,
-                          const void* d_l_active_row, cudaStream_t stream);
+                          const void* d_l_active_row, const h2b_eval_shard* shard, cudaStream_t stream);
 int evaluate_h_permutation_run(DeviceCtx& ctx, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
                                const void* const* d_columns, const void* const* d_perm_cosets, uint32_t n_columns, uint32_t chunk_len, int32_t last_rotation,
                                const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t* beta, const uint64_t* gamma,
-                               const uint64_t* y, const uint64_t* delta, const uint64_t* zeta, const uint64_t* extended_omega, cudaStream_t stream);
+                               const uint64_t* y, const uint64_t* delta, const uint64_t* zeta, const uint64_t* extended_omega, const h2b_eval_shard* shard,
+                               cudaStream_t stream);
 void evaluate_graph_last_info(uint32_t* slots, uint32_t* micro_ops);
 void evaluate_release(DeviceCtx& ctx);
 // ---- ntt.cu ----

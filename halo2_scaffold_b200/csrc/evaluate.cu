@@ -32,7 +32,12 @@ struct EvalProgram {            // device view of a compiled graph
     const void* const* cols;    // fixed..., advice..., instance..., values
     uint32_t n_ops;
     uint32_t size;
+    // row shard: this launch evaluates rows [row0, row0 + rows) of the domain; every column pointer is a slice that starts at global row
+    // `base` = row0 - halo (mod size) and holds rows + 2 * halo rows.  The whole domain is row0 = base = 0, rows = size.
+    uint32_t row0, rows, base;
 };
+
+__device__ __forceinline__ uint32_t shard_local(uint32_t row, uint32_t base, uint32_t size) { return row >= base ? row - base : row + (size - base); }
 
 struct LookupTerms {            // the lookup argument's extra columns
     const uint4 *product, *permuted_input, *permuted_table, *l0, *l_last, *l_active_row;
@@ -47,6 +52,7 @@ __device__ __forceinline__ Fr eval_fetch(const EvalProgram& p, uint32_t enc, uin
     if (kind == OPK_CONST) return fp_load<FR>(p.consts + 2 * (size_t)v);
     uint32_t row = idx + __ldg(p.rot_off + (v & (MAX_ROT - 1)));
     if (row >= p.size) row -= p.size;
+    row = shard_local(row, p.base, p.size);
     const uint4* col = reinterpret_cast<const uint4*>(__ldg(reinterpret_cast<const unsigned long long*>(p.cols) + (v >> 10)));
     return fp_load<FR>(col + 2 * (size_t)row);
 }
@@ -88,23 +94,27 @@ template <int S, int MODE>
 __global__ void __launch_bounds__(128) evaluate_graph_kernel(EvalProgram p, uint4* __restrict__ values, LookupTerms lk) {
     Fr slots[S];
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < p.size; idx += stride) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.rows; i += stride) {
+        const uint32_t idx = p.row0 + i;                           // global row; `i` indexes the (halo-free) values slice
+        const uint32_t li = shard_local(idx, p.base, p.size);        // the same row inside the column slices
         Fr g = eval_row<S>(p, idx, slots);
         if (MODE == 0) {
-            fp_store<FR>(values + 2 * (size_t)idx, g);
+            fp_store<FR>(values + 2 * (size_t)i, g);
         } else {
             const Fr beta = fp_load<FR>(p.consts + 2 * (size_t)lk.beta), gamma = fp_load<FR>(p.consts + 2 * (size_t)lk.gamma);
             const Fr y = fp_load<FR>(p.consts + 2 * (size_t)lk.y);
             uint32_t r_next = idx + lk.off_next, r_prev = idx + lk.off_prev;
             if (r_next >= p.size) r_next -= p.size;
             if (r_prev >= p.size) r_prev -= p.size;
-            const Fr z = fp_load<FR>(lk.product + 2 * (size_t)idx), z_next = fp_load<FR>(lk.product + 2 * (size_t)r_next);
-            const Fr a = fp_load<FR>(lk.permuted_input + 2 * (size_t)idx), a_prev = fp_load<FR>(lk.permuted_input + 2 * (size_t)r_prev);
-            const Fr s = fp_load<FR>(lk.permuted_table + 2 * (size_t)idx);
-            const Fr l0 = fp_load<FR>(lk.l0 + 2 * (size_t)idx), l_last = fp_load<FR>(lk.l_last + 2 * (size_t)idx);
-            const Fr l_active = fp_load<FR>(lk.l_active_row + 2 * (size_t)idx);
+            r_next = shard_local(r_next, p.base, p.size);
+            r_prev = shard_local(r_prev, p.base, p.size);
+            const Fr z = fp_load<FR>(lk.product + 2 * (size_t)li), z_next = fp_load<FR>(lk.product + 2 * (size_t)r_next);
+            const Fr a = fp_load<FR>(lk.permuted_input + 2 * (size_t)li), a_prev = fp_load<FR>(lk.permuted_input + 2 * (size_t)r_prev);
+            const Fr s = fp_load<FR>(lk.permuted_table + 2 * (size_t)li);
+            const Fr l0 = fp_load<FR>(lk.l0 + 2 * (size_t)li), l_last = fp_load<FR>(lk.l_last + 2 * (size_t)li);
+            const Fr l_active = fp_load<FR>(lk.l_active_row + 2 * (size_t)li);
             const Fr a_minus_s = fp_sub(a, s);
-            Fr v = fp_load<FR>(values + 2 * (size_t)idx);
+            Fr v = fp_load<FR>(values + 2 * (size_t)i);
             // l_0(X) * (1 - z(X)) = 0
             v = fp_add(fp_mul(v, y), fp_mul(fp_sub(fp_one<FR>(), z), l0));
             // l_last(X) * (z(X)^2 - z(X)) = 0
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(128) evaluate_graph_kernel(EvalProgram p, uint
             v = fp_add(fp_mul(v, y), fp_mul(a_minus_s, l0));
             // (1 - (l_last + l_blind)) * (a' - s') * (a' - a'(w^-1 X)) = 0
             v = fp_add(fp_mul(v, y), fp_mul(fp_mul(a_minus_s, fp_sub(a, a_prev)), l_active));
-            fp_store<FR>(values + 2 * (size_t)idx, v);
+            fp_store<FR>(values + 2 * (size_t)i, v);
         }
     }
 }
@@ -140,6 +150,24 @@ struct Compiled {
 
 thread_local uint32_t t_last_slots = 0, t_last_ops = 0;
 
+struct Shard { uint32_t row0, rows, halo, base; };
+// whole domain when `sh` is null; otherwise rows [row0, row0 + rows) with `halo` rows of every column on both sides
+static int make_shard(const h2b_eval_shard* sh, uint32_t size, Shard& out) {
+    if (!sh) { out = Shard{0, size, 0, 0}; return H2B_OK; }
+    if (sh->rows == 0 || sh->row0 >= size || sh->rows > size - sh->row0 || (uint64_t)sh->rows + 2ull * sh->halo > size) {
+        set_error("evaluate: shard [%u, %u) + halo %u does not fit a domain of %u rows", sh->row0, sh->row0 + sh->rows, sh->halo, size);
+        return H2B_ERR_BAD_ARGUMENT;
+    }
+    out.row0 = sh->row0; out.rows = sh->rows; out.halo = sh->halo;
+    out.base = sh->row0 >= sh->halo ? sh->row0 - sh->halo : size - (sh->halo - sh->row0);
+    return H2B_OK;
+}
+// a rotated read at offset `off` (already reduced mod size) must stay inside the halo
+static bool offset_within_halo(uint32_t off, uint32_t size, const Shard& sh) {
+    if (sh.rows == size && sh.halo == 0) return true;
+    return off <= sh.halo || size - off <= sh.halo;
+}
+
 static uint32_t rem_euclid_u32(int64_t v, uint32_t size) {
     int64_t m = v % (int64_t)size;
     if (m < 0) m += size;
@@ -147,7 +175,7 @@ static uint32_t rem_euclid_u32(int64_t v, uint32_t size) {
 }
 
 static int compile_graph(const h2b_graph* g, const h2b_eval_columns* cols, const void* d_values, uint32_t size, int32_t rot_scale, bool previous_is_zero,
-                         Compiled& out) {
+                         const Shard& shard, Compiled& out) {
     if (!g || !cols) { set_error("evaluate: null graph / columns"); return H2B_ERR_BAD_ARGUMENT; }
     if (size == 0 || size > (1u << 30)) { set_error("evaluate: size must be in [1, 2^30]"); return H2B_ERR_BAD_ARGUMENT; }
     if ((g->n_constants && !g->constants) || (g->n_rotations && !g->rotations) || (g->n_calculations && !g->calculations) || (g->n_parts && !g->parts) ||
@@ -178,7 +206,10 @@ static int compile_graph(const h2b_graph* g, const h2b_eval_columns* cols, const
     for (uint32_t i = 0; i < cols->n_fixed; ++i) out.cols.push_back(cols->fixed[i]);
     for (uint32_t i = 0; i < cols->n_advice; ++i) out.cols.push_back(cols->advice[i]);
     for (uint32_t i = 0; i < cols->n_instance; ++i) out.cols.push_back(cols->instance[i]);
-    out.cols.push_back(d_values);
+    for (uint32_t i = 0; i < g->n_rotations; ++i)
+        if (!offset_within_halo(out.rot_off[i], size, shard)) { set_error("evaluate: rotation %d x %d exceeds the shard's halo of %u rows", g->rotations[i], rot_scale, shard.halo); return H2B_ERR_BAD_ARGUMENT; }
+    // the values slice carries no halo: shifting its pointer back by `halo` rows makes the column indexing (row - base) land on it
+    out.cols.push_back((const char*)d_values - (size_t)shard.halo * 32);
     for (const void* p : out.cols) if (!p) { set_error("evaluate: null column pointer"); return H2B_ERR_BAD_ARGUMENT; }
     const uint32_t values_col = (uint32_t)out.cols.size() - 1;
 
@@ -393,7 +424,7 @@ static uint32_t eval_ctas_per_sm(uint32_t dflt) {
     return forced ? (uint32_t)forced : dflt;
 }
 
-static int upload_program(DeviceCtx& ctx, const Compiled& c, uint32_t size, cudaStream_t stream, EvalProgram& dev, ProgramBuf** used) {
+static int upload_program(DeviceCtx& ctx, const Compiled& c, uint32_t size, const Shard& shard, cudaStream_t stream, EvalProgram& dev, ProgramBuf** used) {
     if (!ctx.eval) ctx.eval = new EvalScratch();
     ProgramBuf& pb = ctx.eval->ring[ctx.eval->next++ & 3];
     const size_t o_ops = 0, o_consts = align16(o_ops + c.ops.size() * 16), o_rot = align16(o_consts + c.consts.size() * 8),
@@ -415,13 +446,14 @@ static int upload_program(DeviceCtx& ctx, const Compiled& c, uint32_t size, cuda
     dev.cols = (const void* const*)(d + o_cols);
     dev.n_ops = (uint32_t)c.ops.size();
     dev.size = size;
+    dev.row0 = shard.row0; dev.rows = shard.rows; dev.base = shard.base;
     *used = &pb;
     return H2B_OK;
 }
 
 template <int MODE>
 static int launch_graph(DeviceCtx& ctx, const EvalProgram& p, uint32_t n_slots, void* d_values, const LookupTerms& lk, cudaStream_t stream) {
-    const uint32_t want = (p.size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm(16);
+    const uint32_t want = (p.rows + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm(16);
     const uint32_t grid = want < cap ? want : cap;
     if (n_slots <= 8) H2B_LAUNCH((evaluate_graph_kernel<8, MODE>), grid, 128, 0, stream, p, (uint4*)d_values, lk);
     else if (n_slots <= 16) H2B_LAUNCH((evaluate_graph_kernel<16, MODE>), grid, 128, 0, stream, p, (uint4*)d_values, lk);
@@ -432,19 +464,22 @@ static int launch_graph(DeviceCtx& ctx, const EvalProgram& p, uint32_t n_slots, 
 }
 
 int evaluate_graph_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
-                       cudaStream_t stream) {
+                       const h2b_eval_shard* sh, cudaStream_t stream) {
     if (!d_values) { set_error("evaluate_graph: null values"); return H2B_ERR_BAD_ARGUMENT; }
+    if (size == 0 || size > (1u << 30)) { set_error("evaluate: size must be in [1, 2^30]"); return H2B_ERR_BAD_ARGUMENT; }
+    Shard shard;
+    H2B_TRY(make_shard(sh, size, shard));
     Compiled c;
-    H2B_TRY(compile_graph(g, cols, d_values, size, rot_scale, false, c));
+    H2B_TRY(compile_graph(g, cols, d_values, size, rot_scale, false, shard, c));
     t_last_slots = c.n_slots;
     t_last_ops = (uint32_t)c.ops.size();
     if (c.ops.empty()) {        // no calculations: upstream returns zero for every row
-        H2B_CUDA(cudaMemsetAsync(d_values, 0, (size_t)size * 32, stream));
+        H2B_CUDA(cudaMemsetAsync(d_values, 0, (size_t)shard.rows * 32, stream));
         return H2B_OK;
     }
     EvalProgram p;
     ProgramBuf* pb = nullptr;
-    H2B_TRY(upload_program(ctx, c, size, stream, p, &pb));
+    H2B_TRY(upload_program(ctx, c, size, shard, stream, p, &pb));
     LookupTerms lk;
     memset(&lk, 0, sizeof(lk));
     H2B_TRY(launch_graph<0>(ctx, p, c.n_slots, d_values, lk, stream));
@@ -454,19 +489,23 @@ int evaluate_graph_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_column
 
 int evaluate_h_lookup_run(DeviceCtx& ctx, const h2b_graph* g, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
                           const void* d_product, const void* d_permuted_input, const void* d_permuted_table, const void* d_l0, const void* d_l_last,
-                          const void* d_l_active_row, cudaStream_t stream) {
+                          const void* d_l_active_row, const h2b_eval_shard* sh, cudaStream_t stream) {
     if (!d_values || !d_product || !d_permuted_input || !d_permuted_table || !d_l0 || !d_l_last || !d_l_active_row) {
         set_error("evaluate_h_lookup: null pointer");
         return H2B_ERR_BAD_ARGUMENT;
     }
+    if (size == 0 || size > (1u << 30)) { set_error("evaluate: size must be in [1, 2^30]"); return H2B_ERR_BAD_ARGUMENT; }
+    Shard shard;
+    H2B_TRY(make_shard(sh, size, shard));
+    if (!offset_within_halo(rem_euclid_u32((int64_t)rot_scale, size), size, shard)) { set_error("evaluate_h_lookup: rot_scale exceeds the shard's halo"); return H2B_ERR_BAD_ARGUMENT; }
     Compiled c;
-    H2B_TRY(compile_graph(g, cols, d_values, size, rot_scale, true, c));
+    H2B_TRY(compile_graph(g, cols, d_values, size, rot_scale, true, shard, c));
     if (c.ops.empty()) c.ops.push_back(make_uint4(MOP_MOV | MOP_NOSTORE, OPK_CONST | c.c_zero, 0, 0));      // table_value = 0
     t_last_slots = c.n_slots;
     t_last_ops = (uint32_t)c.ops.size();
     EvalProgram p;
     ProgramBuf* pb = nullptr;
-    H2B_TRY(upload_program(ctx, c, size, stream, p, &pb));
+    H2B_TRY(upload_program(ctx, c, size, shard, stream, p, &pb));
     LookupTerms lk;
     lk.product = (const uint4*)d_product; lk.permuted_input = (const uint4*)d_permuted_input; lk.permuted_table = (const uint4*)d_permuted_table;
     lk.l0 = (const uint4*)d_l0; lk.l_last = (const uint4*)d_l_last; lk.l_active_row = (const uint4*)d_l_active_row;
@@ -489,35 +528,38 @@ struct PermParams {
     const void* const* columns;     // n_columns
     const void* const* cosets;      // n_columns
     const uint4 *l0, *l_last, *l_active_row;
-    uint32_t n_sets, n_columns, chunk_len, size, off_next, off_last;
+    uint32_t n_sets, n_columns, chunk_len, size, off_next, off_last, row0, rows, base;
     Fr beta, gamma, y, delta, zeta, omega;
 };
 
 __global__ void __launch_bounds__(128) evaluate_h_permutation_kernel(PermParams p, uint4* __restrict__ values) {
     const uint32_t stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.size) return;
-    Fr beta_term = fp_pow_u32<FR>(p.omega, t);                  // extended_omega^idx
+    if (t >= p.rows) return;
+    Fr beta_term = fp_pow_u32<FR>(p.omega, p.row0 + t);         // extended_omega^idx
     const Fr omega_step = fp_pow_u32<FR>(p.omega, stride);
     const Fr delta_start = fp_mul(p.beta, p.zeta);
     const uint4* z_first = (const uint4*)p.product[0];
     const uint4* z_last = (const uint4*)p.product[p.n_sets - 1];
-    for (uint32_t idx = t; idx < p.size; idx += stride) {
+    for (uint32_t i = t; i < p.rows; i += stride) {
+        const uint32_t idx = p.row0 + i, li = shard_local(idx, p.base, p.size);
         uint32_t r_next = idx + p.off_next, r_last = idx + p.off_last;
         if (r_next >= p.size) r_next -= p.size;
         if (r_last >= p.size) r_last -= p.size;
-        const Fr l0 = fp_load<FR>(p.l0 + 2 * (size_t)idx), l_last = fp_load<FR>(p.l_last + 2 * (size_t)idx);
-        const Fr l_active = fp_load<FR>(p.l_active_row + 2 * (size_t)idx);
-        Fr v = fp_load<FR>(values + 2 * (size_t)idx);
+        r_next = shard_local(r_next, p.base, p.size);
+        r_last = shard_local(r_last, p.base, p.size);
+        const Fr l0 = fp_load<FR>(p.l0 + 2 * (size_t)li), l_last = fp_load<FR>(p.l_last + 2 * (size_t)li);
+        const Fr l_active = fp_load<FR>(p.l_active_row + 2 * (size_t)li);
+        Fr v = fp_load<FR>(values + 2 * (size_t)i);
         // l_0(X) * (1 - z_0(X)) = 0
-        v = fp_add(fp_mul(v, p.y), fp_mul(fp_sub(fp_one<FR>(), fp_load<FR>(z_first + 2 * (size_t)idx)), l0));
+        v = fp_add(fp_mul(v, p.y), fp_mul(fp_sub(fp_one<FR>(), fp_load<FR>(z_first + 2 * (size_t)li)), l0));
         // l_last(X) * (z_l(X)^2 - z_l(X)) = 0
         {
-            const Fr z = fp_load<FR>(z_last + 2 * (size_t)idx);
+            const Fr z = fp_load<FR>(z_last + 2 * (size_t)li);
             v = fp_add(fp_mul(v, p.y), fp_mul(fp_sub(fp_sqr(z), z), l_last));
         }
         // l_0(X) * (z_i(X) - z_{i-1}(w^(last) X)) = 0
         for (uint32_t s = 1; s < p.n_sets; ++s) {
-            const Fr zi = fp_load<FR>((const uint4*)p.product[s] + 2 * (size_t)idx);
+            const Fr zi = fp_load<FR>((const uint4*)p.product[s] + 2 * (size_t)li);
             const Fr zp = fp_load<FR>((const uint4*)p.product[s - 1] + 2 * (size_t)r_last);
             v = fp_add(fp_mul(v, p.y), fp_mul(fp_sub(zi, zp), l0));
         }
@@ -526,17 +568,17 @@ __global__ void __launch_bounds__(128) evaluate_h_permutation_kernel(PermParams 
         for (uint32_t s = 0, c0 = 0; s < p.n_sets && c0 < p.n_columns; ++s, c0 += p.chunk_len) {
             const uint32_t c1 = c0 + p.chunk_len < p.n_columns ? c0 + p.chunk_len : p.n_columns;
             const uint4* z = (const uint4*)p.product[s];
-            Fr left = fp_load<FR>(z + 2 * (size_t)r_next), right = fp_load<FR>(z + 2 * (size_t)idx);
+            Fr left = fp_load<FR>(z + 2 * (size_t)r_next), right = fp_load<FR>(z + 2 * (size_t)li);
             for (uint32_t c = c0; c < c1; ++c) {
-                const Fr val = fp_load<FR>((const uint4*)p.columns[c] + 2 * (size_t)idx);
-                const Fr perm = fp_load<FR>((const uint4*)p.cosets[c] + 2 * (size_t)idx);
+                const Fr val = fp_load<FR>((const uint4*)p.columns[c] + 2 * (size_t)li);
+                const Fr perm = fp_load<FR>((const uint4*)p.cosets[c] + 2 * (size_t)li);
                 left = fp_mul(left, fp_add(fp_add(val, fp_mul(p.beta, perm)), p.gamma));
                 right = fp_mul(right, fp_add(fp_add(val, current_delta), p.gamma));
                 current_delta = fp_mul(current_delta, p.delta);
             }
             v = fp_add(fp_mul(v, p.y), fp_mul(fp_sub(left, right), l_active));
         }
-        fp_store<FR>(values + 2 * (size_t)idx, v);
+        fp_store<FR>(values + 2 * (size_t)i, v);
         beta_term = fp_mul(beta_term, omega_step);
     }
 }
@@ -546,7 +588,8 @@ static void load_fr(Fr& dst, const uint64_t* w) { memcpy(dst.l, w, 32); }
 int evaluate_h_permutation_run(DeviceCtx& ctx, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
                                const void* const* d_columns, const void* const* d_perm_cosets, uint32_t n_columns, uint32_t chunk_len, int32_t last_rotation,
                                const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t* beta, const uint64_t* gamma,
-                               const uint64_t* y, const uint64_t* delta, const uint64_t* zeta, const uint64_t* extended_omega, cudaStream_t stream) {
+                               const uint64_t* y, const uint64_t* delta, const uint64_t* zeta, const uint64_t* extended_omega, const h2b_eval_shard* sh,
+                               cudaStream_t stream) {
     if (n_sets == 0) return H2B_OK;                         // upstream: `if !sets.is_empty()`
     if (!d_values || !d_product_cosets || (n_columns && (!d_columns || !d_perm_cosets)) || !d_l0 || !d_l_last || !d_l_active_row || !beta || !gamma || !y ||
         !delta || !zeta || !extended_omega) {
@@ -578,8 +621,15 @@ int evaluate_h_permutation_run(DeviceCtx& ctx, void* d_values, uint32_t size, in
     p.n_sets = n_sets; p.n_columns = n_columns; p.chunk_len = chunk_len; p.size = size;
     p.off_next = rem_euclid_u32((int64_t)rot_scale, size);
     p.off_last = rem_euclid_u32((int64_t)last_rotation * rot_scale, size);
+    Shard shard;
+    H2B_TRY(make_shard(sh, size, shard));
+    if (!offset_within_halo(p.off_next, size, shard) || !offset_within_halo(p.off_last, size, shard)) {
+        set_error("evaluate_h_permutation: rot_scale / last_rotation exceed the shard's halo of %u rows", shard.halo);
+        return H2B_ERR_BAD_ARGUMENT;
+    }
+    p.row0 = shard.row0; p.rows = shard.rows; p.base = shard.base;
     load_fr(p.beta, beta); load_fr(p.gamma, gamma); load_fr(p.y, y); load_fr(p.delta, delta); load_fr(p.zeta, zeta); load_fr(p.omega, extended_omega);
-    const uint32_t want = (size + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm(8);
+    const uint32_t want = (shard.rows + 127) / 128, cap = (uint32_t)ctx.sm_count * eval_ctas_per_sm(8);
     H2B_LAUNCH(evaluate_h_permutation_kernel, want < cap ? want : cap, 128, 0, stream, p, (uint4*)d_values);
     H2B_CUDA(cudaGetLastError());
     H2B_CUDA(cudaEventRecord(pb.done, stream));

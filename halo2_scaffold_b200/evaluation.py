@@ -270,13 +270,17 @@ class Evaluator:
 
     def evaluate_h(self, *, size: int, rot_scale: int, fixed, advice, instance, challenges, y, beta, gamma, theta, l0, l_last, l_active_row,
                    permutation: dict | None = None, lookups: Sequence[dict] = (), values: np.ndarray | None = None, lib=None,
-                   device: int = 0) -> np.ndarray:
+                   device: int = 0, shard: tuple | None = None) -> np.ndarray:
         """One proof's pass of evaluate_h.  Columns are host arrays (size x 4 u64, Montgomery) of extended-coset
         evaluations; they are uploaded once and all three loops run on the device.
         permutation = dict(product_cosets=[..], columns=[("advice"|"fixed"|"instance", index), ..], cosets=[..], chunk_len=,
                            last_rotation=, delta=, zeta=, extended_omega=)       (words: 4 x u64 Montgomery)
         lookups[n]  = dict(product_coset=, permuted_input_coset=, permuted_table_coset=)"""
         L = lib or _lib.load()
+        if shard is not None:
+            return self._evaluate_h_shard(L, device, shard, size=size, rot_scale=rot_scale, fixed=fixed, advice=advice, instance=instance,
+                                          challenges=challenges, y=y, beta=beta, gamma=gamma, theta=theta, l0=l0, l_last=l_last, l_active_row=l_active_row,
+                                          permutation=permutation, lookups=lookups, values=values)
         with _Device(L, device, size) as dev:
             up = dev.up
             d_fixed, d_advice, d_instance = [up(c) for c in fixed], [up(c) for c in advice], [up(c) for c in instance]
@@ -298,3 +302,31 @@ class Evaluator:
                 L.evaluate_h_lookup_dev(device, graph.arrays(), cols, d_values, size, rot_scale, up(lk["product_coset"]),
                                         up(lk["permuted_input_coset"]), up(lk["permuted_table_coset"]), d_l0, d_l_last, d_l_active)
             return dev.down(d_values)
+
+    def _evaluate_h_shard(self, L, device, shard, *, size, rot_scale, fixed, advice, instance, challenges, y, beta, gamma, theta, l0, l_last, l_active_row,
+                          permutation, lookups, values):
+        """rows [row0, row0 + rows) only: every column is cut to its slice with `halo` rows on both sides (wrap-around included) before it is
+        uploaded -- what each device of a row-sharded evaluate_h holds.  -> the `rows` values of the shard"""
+        row0, rows, halo = shard
+        take = (np.arange(row0 - halo, row0 + rows + halo) % size)
+
+        def cut(a):
+            return np.ascontiguousarray(np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)[take])
+        with _Device(L, device, rows + 2 * halo) as dev, _Device(L, device, rows) as vdev:
+            up = lambda a: dev.up(cut(a))
+            d_fixed, d_advice, d_instance = [up(c) for c in fixed], [up(c) for c in advice], [up(c) for c in instance]
+            d_l0, d_l_last, d_l_active = up(l0), up(l_last), up(l_active_row)
+            v0 = np.zeros((rows, 4), dtype=np.uint64) if values is None else np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)[row0:row0 + rows]
+            d_values = vdev.up(v0)
+            cols = _lib.EvalColumns(d_fixed, d_advice, d_instance, challenges, beta, gamma, theta, y)
+            L.evaluate_graph_dev(device, self.custom_gates.arrays(), cols, d_values, size, rot_scale, shard=shard)
+            if permutation is not None and permutation["product_cosets"]:
+                by_type = {"advice": d_advice, "fixed": d_fixed, "instance": d_instance}
+                L.evaluate_h_permutation_dev(device, d_values, size, rot_scale, [up(c) for c in permutation["product_cosets"]],
+                                             [by_type[t][i] for t, i in permutation["columns"]], [up(c) for c in permutation["cosets"]],
+                                             permutation["chunk_len"], permutation["last_rotation"], d_l0, d_l_last, d_l_active, beta, gamma, y,
+                                             permutation["delta"], permutation["zeta"], permutation["extended_omega"], shard=shard)
+            for graph, lk in zip(self.lookups, lookups):
+                L.evaluate_h_lookup_dev(device, graph.arrays(), cols, d_values, size, rot_scale, up(lk["product_coset"]),
+                                        up(lk["permuted_input_coset"]), up(lk["permuted_table_coset"]), d_l0, d_l_last, d_l_active, shard=shard)
+            return vdev.down(d_values)

@@ -232,6 +232,22 @@ int h2b_evaluate_h_permutation_dev(int device, void* d_values, uint32_t size, in
 int h2b_evaluate_h_lookup_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
                               const void* d_product_coset, const void* d_permuted_input_coset, const void* d_permuted_table_coset, const void* d_l0,
                               const void* d_l_last, const void* d_l_active_row, void* stream);
+/* Row-sharded variants (evaluate_h across devices): this call produces rows [row0, row0 + rows) of the domain.  Every column pointer
+ * (fixed / advice / instance, product / permuted / sigma cosets, l_0, l_last, l_active) is then a SLICE of rows + 2 * halo rows that
+ * starts at global row (row0 - halo) mod size -- wrap-around included -- and d_values is the halo-free slice of `rows` rows.  halo must
+ * cover the largest rotated read: max |rotation| * rot_scale of the graph, rot_scale for lookups, max(1, |last_rotation|) * rot_scale
+ * for the permutation argument; otherwise the call is refused.  Row values do not depend on the sharding. */
+typedef struct h2b_eval_shard { uint32_t row0, rows, halo; } h2b_eval_shard;
+int h2b_evaluate_graph_shard_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                                 const h2b_eval_shard* shard, void* stream);
+int h2b_evaluate_h_permutation_shard_dev(int device, void* d_values, uint32_t size, int32_t rot_scale, const void* const* d_product_cosets, uint32_t n_sets,
+                                         const void* const* d_columns, const void* const* d_perm_cosets, uint32_t n_columns, uint32_t chunk_len,
+                                         int32_t last_rotation, const void* d_l0, const void* d_l_last, const void* d_l_active_row, const uint64_t beta[4],
+                                         const uint64_t gamma[4], const uint64_t y[4], const uint64_t delta[4], const uint64_t zeta[4],
+                                         const uint64_t extended_omega[4], const h2b_eval_shard* shard, void* stream);
+int h2b_evaluate_h_lookup_shard_dev(int device, const h2b_graph* graph, const h2b_eval_columns* cols, void* d_values, uint32_t size, int32_t rot_scale,
+                                    const void* d_product_coset, const void* d_permuted_input_coset, const void* d_permuted_table_coset, const void* d_l0,
+                                    const void* d_l_last, const void* d_l_active_row, const h2b_eval_shard* shard, void* stream);
 /* slots (live values per row) and micro-operations the last compiled graph of this thread needed -- diagnostics / tests */
 int h2b_evaluate_graph_info(uint32_t* slots, uint32_t* micro_ops);
 

@@ -730,3 +730,37 @@ def check_lookup_permute_async(L, oc):
         finally:
             for p in d:
                 L.dev_free(0, p)
+
+
+def check_evaluate_h_sharded(L, oc, ek=7, k=5, groups=2, seed=6, shards=((0, 40, 24), (40, 50, 24), (90, 38, 30))):
+    """row-sharded evaluate_h: every shard sees only its slice (+ halo, wrap-around included) of every column, and the concatenation of the
+    shards equals the unsharded evaluation; a halo that is too small is refused"""
+    from halo2_scaffold_b200 import evaluation as ev
+    from halo2_scaffold_b200._lib import H2BError
+    from halo2_scaffold_b200.domain import fr_to_words
+    size, rot_scale = 1 << ek, 1 << (ek - k)
+    polys, lookup_exprs, nf, na = standard_plonk_like(groups)
+    E = ev.Evaluator(polys, lookup_exprs)
+    fixed = [oc.random_fr(seed * 1000 + j, size) for j in range(nf)]
+    advice = [oc.random_fr(seed * 1000 + 100 + j, size) for j in range(na)]
+    instance = [oc.random_fr(seed * 1000 + 200, size)]
+    beta, gamma, theta, y, delta, zeta = oc.random_fr(seed * 1000 + 300, 6)
+    l0, l_last, l_active = (oc.random_fr(seed * 1000 + 400 + j, size) for j in range(3))
+    perm_cols = [("advice", j) for j in range(na)] + [("fixed", 0)]
+    n_sets = (len(perm_cols) + 1) // 2
+    kw = dict(size=size, rot_scale=rot_scale, fixed=fixed, advice=advice, instance=instance, challenges=np.zeros((0, 4), dtype=np.uint64), y=y, beta=beta,
+              gamma=gamma, theta=theta, l0=l0, l_last=l_last, l_active_row=l_active,
+              permutation=dict(product_cosets=[oc.random_fr(seed * 1000 + 500 + j, size) for j in range(n_sets)], columns=perm_cols,
+                               cosets=[oc.random_fr(seed * 1000 + 600 + j, size) for j in range(len(perm_cols))], chunk_len=2, last_rotation=-6, delta=delta,
+                               zeta=zeta, extended_omega=fr_to_words(o.omega_for(ek))),
+              lookups=[dict(product_coset=oc.random_fr(seed * 1000 + 700, size), permuted_input_coset=oc.random_fr(seed * 1000 + 701, size),
+                            permuted_table_coset=oc.random_fr(seed * 1000 + 702, size))], lib=L)
+    whole = E.evaluate_h(**kw)
+    assert sum(r for _, r, _ in shards) == size
+    parts = [E.evaluate_h(shard=sh, **kw) for sh in shards]
+    assert (np.concatenate(parts) == whole).all()
+    try:
+        E.evaluate_h(shard=(shards[0][0], shards[0][1], 6 * rot_scale - 1), **kw)          # last_rotation = -6 needs 6 * rot_scale rows of halo
+        raise AssertionError("a halo that is too small was accepted")
+    except H2BError as e:
+        assert "halo" in str(e)

@@ -477,3 +477,7 @@ def test_quotient_of_a_satisfied_circuit_is_a_polynomial(emu, oc):
     # and the property is sharp: an unsatisfied gate, a wrong sigma column or a disturbed fill order all break it
     for what in ("witness", "sigma", "fill"):
         assert not pc.check_quotient_is_a_polynomial(emu, oc, k=4, seed=3, break_it=what)[0], what
+
+
+def test_evaluate_h_row_shards(emu, oc):
+    pc.check_evaluate_h_sharded(emu, oc)

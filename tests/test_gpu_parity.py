@@ -224,6 +224,10 @@ def test_evaluate_graph_property(gpu, oc):
     pc.check_evaluate_graph_property(gpu, oc, examples=40, max_rows=20000, max_calcs=400)
 
 
+def test_evaluate_h_row_shards(gpu, oc):
+    pc.check_evaluate_h_sharded(gpu, oc, ek=14, k=12, groups=2, seed=8, shards=((0, 5000, 24), (5000, 6000, 40), (11000, 5384, 24)))
+
+
 def test_evaluate_h_all_three_loops(gpu, oc):
     pc.check_evaluate_h(gpu, oc, [(5, 3, 1, 1), (12, 10, 2, 2), (16, 14, 3, 3), (18, 16, 1, 4)])
 

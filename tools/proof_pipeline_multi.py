@@ -3,8 +3,8 @@
 tools/proof_pipeline.py across the D GPUs of one process (BASELINE.json configs[4]: "many advice columns; commits sharded across 8
 GPUs"): the SRS (with window tables) is resident on every device; column j lives on device j mod D, where it is
 uploaded (pinned host arrays, one PCIe link per GPU), committed, brought to coefficient form and to the extended coset; every
-permutation set and every lookup argument runs on one device (the set's columns are peer-copied there); the extended columns are then
-gathered on device 0 over NVLink for evaluate_h; the quotient pieces, the evaluations at x and the per-column work of the opening
+permutation set and every lookup argument runs on one device (the set's columns are peer-copied there); evaluate_h is sharded by rows: every device receives its
+row slice (+ halo) of each extended column over NVLink; the quotient pieces, the evaluations at x and the per-column work of the opening
 go back to one device per polynomial.  No collective: only peer copies of whole columns.
 The wall time is taken on the host around the whole sequence with every device synchronised at the end.
 usage: python tools/proof_pipeline_multi.py [cfg ...]        (uses every visible GPU)
@@ -60,6 +60,24 @@ def main():
         fixed_ext = [dcol(0, en) for _ in range(A + 1)]
         sigma_ext = [dcol(0, en) for _ in range(n_adv)]
         l0, l_last, l_active = dcol(0, en), dcol(0, en), dcol(0, en)
+        halo = 6 * rot_scale if D > 1 else 0                       # |last_rotation| * rot_scale covers every rotated read of evaluate_h
+        rows_d = en // D
+
+        def slice_to(t, dv):
+            """rows [dv * rows_d - halo, (dv + 1) * rows_d + halo) of an extended column (wrap-around included) as a tensor on device dv"""
+            v = t.view(-1, 4)
+            lo, hi = dv * rows_d - halo, (dv + 1) * rows_d + halo
+            with torch.cuda.device(dv):
+                if D == 1:
+                    return t
+                if lo < 0:
+                    return torch.cat([v[lo + en:].to(devs[dv], non_blocking=True), v[:hi].to(devs[dv], non_blocking=True)]).view(-1)
+                if hi > en:
+                    return torch.cat([v[lo:].to(devs[dv], non_blocking=True), v[:hi - en].to(devs[dv], non_blocking=True)]).view(-1)
+                return v[lo:hi].to(devs[dv], non_blocking=True).contiguous().view(-1)
+        # proving-key columns of evaluate_h: every device keeps its row slice (with halo) from keygen on
+        pk_slices = [dict(fixed=[slice_to(t, dv) for t in fixed_ext], sigma=[slice_to(t, dv) for t in sigma_ext], l0=slice_to(l0, dv),
+                          l_last=slice_to(l_last, dv), l_active=slice_to(l_active, dv)) for dv in range(D)]
         host_table = L.gen_scalars(450 + k, n, 0)
         table_lagrange = [torch.from_numpy(host_table.view(np.int64).reshape(-1)).to(devs[i]) for i in range(D)]      # proving-key data, replicated
         set_dev = [si % D for si in range(sets)]
@@ -190,26 +208,35 @@ def main():
                 rnd = dcol(spare[2 * LK], n)
             commit(rnd, h_g)
             mark("lookups")
-            # evaluate_h on device 0: every extended column arrives over NVLink
+            # evaluate_h sharded by rows: device dv evaluates rows [dv * en / D, (dv + 1) * en / D); it receives that slice (+ halo) of every
+            # witness-dependent extended column over NVLink and already holds its slice of the proving-key columns
+            shard_vals = []
+            for dv in range(D):
+                with torch.cuda.device(dv):
+                    s_adv = [slice_to(t, dv) for t in adv_e]
+                    s_inst = slice_to(inst_e, dv)
+                    s_z = [slice_to(t, dv) for t in z_e]
+                    s_lk = [tuple(slice_to(t, dv) for t in tr) for tr in lk_e]
+                    vals = torch.zeros(rows_d * 4, dtype=torch.int64, device=devs[dv])
+                    pk = pk_slices[dv]
+                    shard = (dv * rows_d, rows_d, halo)
+                    cols = _lib.EvalColumns([t.data_ptr() for t in pk["fixed"]], [t.data_ptr() for t in s_adv], [s_inst.data_ptr()],
+                                            np.zeros((0, 4), dtype=np.uint64), beta, gamma, theta, y)
+                    L.evaluate_graph_dev(dv, g_gates, cols, vals.data_ptr(), en, rot_scale, st[dv], shard=shard)
+                    L.evaluate_h_permutation_dev(dv, vals.data_ptr(), en, rot_scale, [t.data_ptr() for t in s_z], [t.data_ptr() for t in s_adv],
+                                                 [t.data_ptr() for t in pk["sigma"]], chunk, -6, pk["l0"].data_ptr(), pk["l_last"].data_ptr(),
+                                                 pk["l_active"].data_ptr(), beta, gamma, y, W(DELTA), W(dom.g_coset), W(dom.extended_omega), st[dv], shard=shard)
+                    for g, (ze, ae, se) in zip(g_lk, s_lk):
+                        L.evaluate_h_lookup_dev(dv, g, cols, vals.data_ptr(), en, rot_scale, ze.data_ptr(), ae.data_ptr(), se.data_ptr(), pk["l0"].data_ptr(),
+                                                pk["l_last"].data_ptr(), pk["l_active"].data_ptr(), st[dv], shard=shard)
+                    shard_vals.append((vals, s_adv, s_inst, s_z, s_lk))          # keep the slices alive until the kernels have run
+            mark("evaluate_h_row_sharded")
             with torch.cuda.device(0):
-                g_adv_e = [move(t, 0) for t in adv_e]
-                g_z_e = [move(t, 0) for t in z_e]
-                g_lk_e = [tuple(move(t, 0) for t in tr) for tr in lk_e]
-                values = torch.zeros(en * 4, dtype=torch.int64, device=devs[0])
-                mark("gather_extended_columns")
-                cols = _lib.EvalColumns([t.data_ptr() for t in fixed_ext], [t.data_ptr() for t in g_adv_e], [inst_e.data_ptr()], np.zeros((0, 4), dtype=np.uint64),
-                                        beta, gamma, theta, y)
-                L.evaluate_graph_dev(0, g_gates, cols, values.data_ptr(), en, rot_scale, st[0])
-                L.evaluate_h_permutation_dev(0, values.data_ptr(), en, rot_scale, [t.data_ptr() for t in g_z_e], [t.data_ptr() for t in g_adv_e],
-                                             [t.data_ptr() for t in sigma_ext], chunk, -6, l0.data_ptr(), l_last.data_ptr(), l_active.data_ptr(), beta, gamma, y,
-                                             W(DELTA), W(dom.g_coset), W(dom.extended_omega), st[0])
-                for g, (ze, ae, se) in zip(g_lk, g_lk_e):
-                    L.evaluate_h_lookup_dev(0, g, cols, values.data_ptr(), en, rot_scale, ze.data_ptr(), ae.data_ptr(), se.data_ptr(), l0.data_ptr(),
-                                            l_last.data_ptr(), l_active.data_ptr(), st[0])
+                values = torch.cat([move(v[0], 0) for v in shard_vals])
                 L.fr_scale_dev(0, values.data_ptr(), en, tev, st[0])
                 L.extended_to_coeff_dev(0, values.data_ptr(), ek, W(dom.extended_omega_inv), e2c, st[0])
                 pieces = [values[p * n * 4:(p + 1) * n * 4] for p in range(d - 1)]
-            mark("evaluate_h_and_quotient")
+            mark("gather_values_and_quotient")
             # quotient pieces: one device each
             h_pieces = []
             for p, t in enumerate(pieces):
@@ -270,8 +297,8 @@ def main():
         total_ms = (time.perf_counter() - t0) * 1e3
         print(json.dumps({"config": name, "devices": D, "k": k, "extended_k": ek, "gate_advice": A, "lookup_advice": LK, "permutation_sets": sets,
                           "device_resident_hot_path_ms": round(total_ms, 2), "phases_ms": phase, "msm_per_device": list(n_msm),
-                          "note": "one process, %d x B200; witness in pinned host memory; columns round-robin over the devices, evaluate_h on device 0 "
-                                  "(extended columns gathered over NVLink); host-side prover work not included; column counts are estimates" % D}), flush=True)
+                          "note": "one process, %d x B200; witness in pinned host memory; columns round-robin over the devices, evaluate_h sharded by rows over the devices "
+                                  "(slices + halo exchanged over NVLink); host-side prover work not included; column counts are estimates" % D}), flush=True)
         L.unregister_bases(h_g); L.unregister_bases(h_gl)
         del fixed_ext, sigma_ext, sigma_lagrange, table_lagrange
         torch.cuda.empty_cache()
