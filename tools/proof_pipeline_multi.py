@@ -210,13 +210,18 @@ def main():
             mark("lookups")
             # evaluate_h sharded by rows: device dv evaluates rows [dv * en / D, (dv + 1) * en / D); it receives that slice (+ halo) of every
             # witness-dependent extended column over NVLink and already holds its slice of the proving-key columns
+            # all slice exchanges are queued before any evaluation kernel: a peer copy orders the destination stream after everything already
+            # queued on the source stream, so an evaluation queued on device 0 first would hold back every copy out of device 0
+            slices = []
+            for dv in range(D):
+                with torch.cuda.device(dv):
+                    slices.append(([slice_to(t, dv) for t in adv_e], slice_to(inst_e, dv), [slice_to(t, dv) for t in z_e],
+                                   [tuple(slice_to(t, dv) for t in tr) for tr in lk_e]))
+            mark("exchange_row_slices")
             shard_vals = []
             for dv in range(D):
                 with torch.cuda.device(dv):
-                    s_adv = [slice_to(t, dv) for t in adv_e]
-                    s_inst = slice_to(inst_e, dv)
-                    s_z = [slice_to(t, dv) for t in z_e]
-                    s_lk = [tuple(slice_to(t, dv) for t in tr) for tr in lk_e]
+                    s_adv, s_inst, s_z, s_lk = slices[dv]
                     vals = torch.zeros(rows_d * 4, dtype=torch.int64, device=devs[dv])
                     pk = pk_slices[dv]
                     shard = (dv * rows_d, rows_d, halo)
@@ -229,7 +234,7 @@ def main():
                     for g, (ze, ae, se) in zip(g_lk, s_lk):
                         L.evaluate_h_lookup_dev(dv, g, cols, vals.data_ptr(), en, rot_scale, ze.data_ptr(), ae.data_ptr(), se.data_ptr(), pk["l0"].data_ptr(),
                                                 pk["l_last"].data_ptr(), pk["l_active"].data_ptr(), st[dv], shard=shard)
-                    shard_vals.append((vals, s_adv, s_inst, s_z, s_lk))          # keep the slices alive until the kernels have run
+                    shard_vals.append((vals,))
             mark("evaluate_h_row_sharded")
             with torch.cuda.device(0):
                 values = torch.cat([move(v[0], 0) for v in shard_vals])
