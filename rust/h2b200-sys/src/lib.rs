@@ -7,6 +7,10 @@
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
 
+/// Row range of a sharded `evaluate_h` call (include/h2b200.h `h2b_eval_shard`).
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct h2b_eval_shard { pub row0: u32, pub rows: u32, pub halo: u32 }
 /// `enum ValueSource` of halo2_proofs/src/plonk/evaluation.rs, flattened: kind = variant index in declaration order
 /// (Constant, Intermediate, Fixed, Advice, Instance, Challenge, Beta, Gamma, Theta, Y, PreviousValue).
 #[repr(C)]
@@ -77,6 +81,17 @@ extern "C" {
     pub fn h2b_evaluate_h_lookup_dev(device: c_int, graph: *const h2b_graph, cols: *const h2b_eval_columns, d_values: *mut c_void, size: u32, rot_scale: i32,
                                      d_product_coset: *const c_void, d_permuted_input_coset: *const c_void, d_permuted_table_coset: *const c_void,
                                      d_l0: *const c_void, d_l_last: *const c_void, d_l_active_row: *const c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_evaluate_graph_shard_dev(device: c_int, graph: *const h2b_graph, cols: *const h2b_eval_columns, d_values: *mut c_void, size: u32, rot_scale: i32,
+                                        shard: *const h2b_eval_shard, stream: *mut c_void) -> c_int;
+    pub fn h2b_evaluate_h_permutation_shard_dev(device: c_int, d_values: *mut c_void, size: u32, rot_scale: i32, d_product_cosets: *const *const c_void,
+                                                n_sets: u32, d_columns: *const *const c_void, d_perm_cosets: *const *const c_void, n_columns: u32, chunk_len: u32,
+                                                last_rotation: i32, d_l0: *const c_void, d_l_last: *const c_void, d_l_active_row: *const c_void,
+                                                beta: *const u64, gamma: *const u64, y: *const u64, delta: *const u64, zeta: *const u64,
+                                                extended_omega: *const u64, shard: *const h2b_eval_shard, stream: *mut c_void) -> c_int;
+    pub fn h2b_evaluate_h_lookup_shard_dev(device: c_int, graph: *const h2b_graph, cols: *const h2b_eval_columns, d_values: *mut c_void, size: u32,
+                                           rot_scale: i32, d_product_coset: *const c_void, d_permuted_input_coset: *const c_void,
+                                           d_permuted_table_coset: *const c_void, d_l0: *const c_void, d_l_last: *const c_void,
+                                           d_l_active_row: *const c_void, shard: *const h2b_eval_shard, stream: *mut c_void) -> c_int;
     // SRS file -> resident base sets (ParamsKZG::read_custom / write_custom)
     pub fn h2b_g1_decode_dev(device: c_int, d_bytes: *const c_void, n: usize, format: c_int, d_out_affine: *mut c_void, first_invalid: *mut u64, stream: *mut c_void) -> c_int;
     pub fn h2b_g1_encode_dev(device: c_int, d_affine: *const c_void, n: usize, d_out_bytes: *mut c_void, stream: *mut c_void) -> c_int;
