@@ -391,6 +391,27 @@ struct ValueSource : h2b_value_source {
     bool operator==(const ValueSource& o) const { return kind == o.kind && index == o.index && rotation == o.rotation; }
 };
 
+// pub enum Expression<F> (plonk/circuit.rs) -- the variants the evaluator sees (selectors are replaced before it is built)
+struct Expression {
+    enum Kind { Constant, Fixed, Advice, Instance, Challenge, Negated, Sum, Product, Scaled } kind;
+    Fr scalar{};                              // Constant / Scaled
+    uint32_t index = 0;                       // column or challenge index
+    int32_t rotation = 0;
+    std::shared_ptr<Expression> a, b;
+    static std::shared_ptr<Expression> make(Kind k) { auto e = std::make_shared<Expression>(); e->kind = k; return e; }
+};
+typedef std::shared_ptr<Expression> Expr;
+inline Expr constant(const Fr& c) { Expr e = Expression::make(Expression::Constant); e->scalar = c; return e; }
+inline Expr column(Expression::Kind k, uint32_t index, int32_t rotation = 0) { Expr e = Expression::make(k); e->index = index; e->rotation = rotation; return e; }
+inline Expr fixed(uint32_t i, int32_t r = 0) { return column(Expression::Fixed, i, r); }
+inline Expr advice(uint32_t i, int32_t r = 0) { return column(Expression::Advice, i, r); }
+inline Expr instance(uint32_t i, int32_t r = 0) { return column(Expression::Instance, i, r); }
+inline Expr challenge(uint32_t i) { return column(Expression::Challenge, i); }
+inline Expr negated(Expr a) { Expr e = Expression::make(Expression::Negated); e->a = std::move(a); return e; }
+inline Expr sum(Expr a, Expr b) { Expr e = Expression::make(Expression::Sum); e->a = std::move(a); e->b = std::move(b); return e; }
+inline Expr product(Expr a, Expr b) { Expr e = Expression::make(Expression::Product); e->a = std::move(a); e->b = std::move(b); return e; }
+inline Expr scaled(Expr a, const Fr& f) { Expr e = Expression::make(Expression::Scaled); e->a = std::move(a); e->scalar = f; return e; }
+
 // pub struct GraphEvaluator<C> { constants, rotations, calculations, num_intermediates }  (Default: constants 0, 1, 2)
 class GraphEvaluator {
   public:
@@ -423,6 +444,56 @@ class GraphEvaluator {
         for (const ValueSource& p : parts) parts_.push_back(p);
         calcs_.push_back(c);
         return ValueSource::Intermediate(c.target);
+    }
+    // fn add_expression(&mut self, expr: &Expression<C::ScalarExt>) -> ValueSource
+    ValueSource add_expression(const Expr& expr) {
+        const ValueSource zero = ValueSource::Constant(0), one = ValueSource::Constant(1), two = ValueSource::Constant(2);
+        auto ordered = [&](uint32_t op, const ValueSource& x, const ValueSource& y) {     // derived PartialOrd: variant, then fields
+            const bool le = x.kind != y.kind ? x.kind < y.kind : (x.index != y.index ? x.index < y.index : x.rotation <= y.rotation);
+            return le ? add_calculation(op, x, y) : add_calculation(op, y, x);
+        };
+        switch (expr->kind) {
+            case Expression::Constant: return add_constant(expr->scalar);
+            case Expression::Fixed: return add_calculation(H2B_CALC_STORE, ValueSource::Fixed(expr->index, add_rotation(expr->rotation)));
+            case Expression::Advice: return add_calculation(H2B_CALC_STORE, ValueSource::Advice(expr->index, add_rotation(expr->rotation)));
+            case Expression::Instance: return add_calculation(H2B_CALC_STORE, ValueSource::Instance(expr->index, add_rotation(expr->rotation)));
+            case Expression::Challenge: return add_calculation(H2B_CALC_STORE, ValueSource::Challenge(expr->index));
+            case Expression::Negated: {
+                if (expr->a->kind == Expression::Constant) return add_constant(fr::sub(fr::from_u64(0), expr->a->scalar));
+                const ValueSource ra = add_expression(expr->a);
+                return ra == zero ? ra : add_calculation(H2B_CALC_NEGATE, ra);
+            }
+            case Expression::Sum: {
+                if (expr->b->kind == Expression::Negated) {                 // a + (-b) is stored back as a subtraction
+                    const ValueSource ra = add_expression(expr->a), rb = add_expression(expr->b->a);
+                    if (ra == zero) return add_calculation(H2B_CALC_NEGATE, rb);
+                    if (rb == zero) return ra;
+                    return add_calculation(H2B_CALC_SUB, ra, rb);
+                }
+                const ValueSource ra = add_expression(expr->a), rb = add_expression(expr->b);
+                if (ra == zero) return rb;
+                if (rb == zero) return ra;
+                return ordered(H2B_CALC_ADD, ra, rb);
+            }
+            case Expression::Product: {
+                const ValueSource ra = add_expression(expr->a), rb = add_expression(expr->b);
+                if (ra == zero || rb == zero) return zero;
+                if (ra == one) return rb;
+                if (rb == one) return ra;
+                if (ra == two) return add_calculation(H2B_CALC_DOUBLE, rb);
+                if (rb == two) return add_calculation(H2B_CALC_DOUBLE, ra);
+                if (ra == rb) return add_calculation(H2B_CALC_SQUARE, ra);
+                return ordered(H2B_CALC_MUL, ra, rb);
+            }
+            case Expression::Scaled: {
+                if (expr->scalar == fr::from_u64(0)) return zero;
+                if (expr->scalar == fr::one()) return add_expression(expr->a);
+                const ValueSource cst = add_constant(expr->scalar);
+                const ValueSource ra = add_expression(expr->a);
+                return add_calculation(H2B_CALC_MUL, ra, cst);
+            }
+        }
+        throw Panic("unreachable: Expression::Selector");
     }
     // pub fn evaluate(..) for every row idx < isize: values[idx] = evaluate(.., previous_value = values[idx], idx, rot_scale, isize)
     std::vector<Fr> evaluate(const std::vector<std::vector<Fr>>& fixed, const std::vector<std::vector<Fr>>& advice, const std::vector<std::vector<Fr>>& instance,
@@ -460,6 +531,15 @@ class GraphEvaluator {
     std::vector<h2b_value_source> parts_;
     uint32_t num_intermediates_ = 0;
 };
+
+// Evaluator::new(cs), custom gates: every gate polynomial through add_expression, combined by one Horner in y over the previous value
+inline GraphEvaluator custom_gates_evaluator(const std::vector<Expr>& gate_polynomials) {
+    GraphEvaluator g;
+    std::vector<ValueSource> parts;
+    for (const Expr& poly : gate_polynomials) parts.push_back(g.add_expression(poly));
+    g.add_calculation(H2B_CALC_HORNER, ValueSource::PreviousValue(), ValueSource::Y(), parts);
+    return g;
+}
 
 }  // namespace evaluation
 

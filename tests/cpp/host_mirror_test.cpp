@@ -108,6 +108,15 @@ int main(int argc, char** argv) {
             auto col = [&](size_t j) { return std::vector<Fr>(cols.begin() + j * rows, cols.begin() + (j + 1) * rows); };
             auto out = ge.evaluate({col(0)}, {col(1), col(2), col(3)}, {col(4)}, {sc[0]}, sc[1], sc[2], sc[3], sc[4], col(5), 2);
             write_all(dir + "/eval_out.bin", out.data(), out.size());
+            // the same gate built from Expressions through add_expression / Evaluator::new: q * (a + b[next] * c - a[prev]), its square, 0x1234567 * instance
+            {
+                namespace E = plonk::evaluation;          // (the driver's locals `sum` and `scaled` shadow the builders)
+                E::Expr gate_e = E::product(E::fixed(0), E::sum(E::sum(E::advice(0), E::product(E::advice(1, 1), E::advice(2))), E::negated(E::advice(0, -1))));
+                GraphEvaluator from_expr = custom_gates_evaluator({gate_e, E::product(gate_e, gate_e), E::scaled(E::instance(0), fr::from_u64(0x1234567)),
+                                                                  E::challenge(0)});
+                auto out2 = from_expr.evaluate({col(0)}, {col(1), col(2), col(3)}, {col(4)}, {sc[0]}, sc[1], sc[2], sc[3], sc[4], col(5), 2);
+                if (std::memcmp(out2.data(), out.data(), out.size() * sizeof(Fr)) != 0) { fprintf(stderr, "add_expression graph differs from the hand-built one\n"); return 1; }
+            }
             // grand products over the same columns (rows is a power of two here; omega of that size)
             uint32_t kr = 0;
             while (((size_t)1 << kr) < rows) ++kr;
