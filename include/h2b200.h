@@ -95,7 +95,11 @@ int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omeg
 
 /* ---- device-resident entry points (device pointers on `device`, caller's CUDA stream) ------------- */
 /* Asynchronous with respect to the host: work is enqueued on `stream` (a cudaStream_t; NULL = the
- * legacy default stream).  `device` is an index into the devices given to h2b_init. */
+ * legacy default stream).  `device` is an index into the devices given to h2b_init.
+ * Stream contract: the *_dev entry points of one device share that device's grow-only scratch buffers (sort lists, NTT work
+ * buffer, scan / lookup scratch), so calls on the SAME device must be ordered with respect to each other -- issue them on one
+ * stream (what a prover thread does), or order the streams with events.  Different devices are independent.  (The compiled
+ * programs of evaluate_h are the exception: they rotate through a small ring guarded by events.) */
 int h2b_ntt_bn254_fr_dev(int device, void* d_a, const uint64_t omega[4], uint32_t log_n, void* stream);
 int h2b_msm_bn254_g1_dev(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_jac /* 96 B */, void* stream);
 /* Point-range sharding across processes (one process per GPU): each rank computes a partial
