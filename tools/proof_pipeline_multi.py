@@ -5,7 +5,8 @@ GPUs"): the SRS (with window tables) is resident on every 
 uploaded (pinned host arrays, one PCIe link per GPU), committed, brought to coefficient form and to the extended coset; every
 permutation set and every lookup argument runs on one device (the set's columns are peer-copied there); evaluate_h is sharded by rows: every device receives its
 row slice (+ halo) of each extended column over NVLink; the quotient pieces, the evaluations at x and the per-column work of the opening
-go back to one device per polynomial.  No collective: only peer copies of whole columns.
+go back to one device per polynomial.  Commitments that sit alone on a dependency chain (a lookup's z, the quotient pieces, the
+opening) are split by point range over all devices and their partial sums folded on device 0.  No collective: only peer copies.
 The wall time is taken on the host around the whole sequence with every device synchronised at the end.
 usage: python tools/proof_pipeline_multi.py [cfg ...]        (uses every visible GPU)
 """
@@ -116,6 +117,55 @@ def main():
                 L.msm_dev_registered(dv, t.data_ptr(), handle, 0, n, blocks[dv].data_ptr() + 224 * (n_msm[dv] % 64), st[dv])
             n_msm[dv] += 1
 
+        folded = [torch.empty(12, dtype=torch.int64, device=devs[0]) for _ in range(16)]
+        n_sharded = [0]
+
+        def commit_sharded(t, handle):
+            """ONE commitment split by point range over all devices: device dv gets scalars [dv n / D, (dv + 1) n / D) over NVLink, runs a
+            partial MSM over the matching rows of its resident tables, and the D partial sums (224-byte blocks) are folded on device 0.  For the
+            commitments that sit alone on a dependency chain (a lookup's z, the quotient pieces, the opening)."""
+            if D == 1:
+                return commit(t, handle)
+            v = t.view(-1, 4)
+            per = n // D
+            parts = []
+            for dv in range(D):
+                with torch.cuda.device(dv):
+                    sl = v[dv * per:(dv + 1) * per]
+                    sl = sl if on(t) == dv else sl.to(devs[dv], non_blocking=True)
+                    blk = torch.empty(28, dtype=torch.int64, device=devs[dv])
+                    L.msm_dev_registered(dv, sl.data_ptr(), handle, dv * per, per, blk.data_ptr(), st[dv])
+                    n_msm[dv] += 1
+                    parts.append((sl, blk))
+            with torch.cuda.device(0):
+                allb = torch.cat([move(b, 0) for _, b in parts])
+                L.msm_fold_partials_dev(0, allb.data_ptr(), D, folded[n_sharded[0] % 16].data_ptr(), st[0])
+            n_sharded[0] += 1
+            return parts, allb
+
+        P_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+
+        def affine_of_jacobian(words):
+            """x | y | z Montgomery limbs (12 x u64) -> canonical affine (x, y) or None; host big-int arithmetic, for the self-check only"""
+            w = [int(v) & 0xFFFFFFFFFFFFFFFF for v in words]
+            val = lambda i: sum(w[4 * i + j] << (64 * j) for j in range(4)) * pow(1 << 256, -1, P_MOD) % P_MOD
+            X, Y, Z = val(0), val(1), val(2)
+            if Z == 0:
+                return None
+            zi = pow(Z, -1, P_MOD)
+            return (X * zi * zi % P_MOD, Y * zi * zi * zi % P_MOD)
+
+        def self_check():
+            """a sharded commitment equals the same commitment on one device"""
+            t = dcol(0, n)
+            commit(t, h_g)
+            commit_sharded(t, h_g)
+            for i in range(D):
+                torch.cuda.synchronize(i)
+            one_dev = blocks[0][((n_msm[0] - 2 if D > 1 else n_msm[0] - 2) % 64) * 28:][:12].cpu().numpy()
+            shard = folded[(n_sharded[0] - 1) % 16].cpu().numpy() if D > 1 else blocks[0][((n_msm[0] - 1) % 64) * 28:][:12].cpu().numpy()
+            assert affine_of_jacobian(one_dev) == affine_of_jacobian(shard), "sharded commitment differs"
+
         def to_coeff(t):
             dv = on(t)
             with torch.cuda.device(dv):
@@ -137,6 +187,7 @@ def main():
         def run():
             for i in range(D):
                 n_msm[i] = n_eval[i] = 0
+            keep = []                                           # slices and partial blocks of the sharded commitments stay alive until the end
             phase, t_prev = {}, [time.perf_counter()]
 
             def mark(label):
@@ -193,7 +244,7 @@ def main():
                                                status[-1].data_ptr(), st[dv])
                     z = torch.empty(n * 4, dtype=torch.int64, device=devs[dv])
                     L.lookup_product_dev(dv, adv[A + j].data_ptr(), table_lagrange[dv].data_ptr(), a.data_ptr(), s_.data_ptr(), n, beta, gamma, z.data_ptr(), st[dv])
-                commit(z, h_gl)
+                keep.append(commit_sharded(z, h_gl))
                 # the two permuted columns leave for other devices: only z stays on the lookup's critical path
                 with torch.cuda.device(spare[2 * j]):
                     a2 = move(a, spare[2 * j])
@@ -206,7 +257,7 @@ def main():
             lk_e = [(to_ext(zc), to_ext(pc[0]), to_ext(pc[1])) for zc, pc in zip(zl_c, perm_c)]
             with torch.cuda.device(spare[2 * LK]):
                 rnd = dcol(spare[2 * LK], n)
-            commit(rnd, h_g)
+            keep.append(commit_sharded(rnd, h_g))
             mark("lookups")
             # evaluate_h sharded by rows: device dv evaluates rows [dv * en / D, (dv + 1) * en / D); it receives that slice (+ halo) of every
             # witness-dependent extended column over NVLink and already holds its slice of the proving-key columns
@@ -249,7 +300,7 @@ def main():
                 with torch.cuda.device(dv):
                     t2 = move(t, dv) if dv else t
                 h_pieces.append(t2)
-                commit(t2, h_g)
+                keep.append(commit_sharded(t2, h_g))
             # evaluations at x: on the device that holds the coefficients
             queried = [(c, 4) for c in adv_c] + [(c, 3) for c in z_c] + [(c, 2) for c in zl_c] + [(p_, 1) for pc in perm_c for p_ in pc] + \
                       [(t, 1) for t in h_pieces] + [(rnd, 1)]
@@ -283,17 +334,16 @@ def main():
                 L.fr_lincomb_dev(0, [q.data_ptr() for q in quot0], weights[:len(quot0)], n, hq.data_ptr(), st[0])
                 fin = torch.empty(n * 4, dtype=torch.int64, device=devs[0])
                 L.check(L.L.h2b_fr_kate_division_dev(0, hq.data_ptr(), n, v.ctypes.data, fin.data_ptr(), st[0]))
-                commit(hq, h_g)
+                keep.append(commit_sharded(hq, h_g))
             with torch.cuda.device(D - 1):                               # the two opening commitments on two devices
                 fin2 = move(fin, D - 1)
-            commit(fin2, h_g)
-            with torch.cuda.device(0):
-                pass
+            keep.append(commit_sharded(fin2, h_g))
             out = [b.cpu() for b in blocks] + [e.cpu() for e in evals]
             assert all(int(w.cpu()[0]) == 0 for w in status), "a lookup input value is not in the table"
             mark("multiopen")
             return phase
 
+        self_check()
         run()
         for i in range(D):
             torch.cuda.synchronize(i)
