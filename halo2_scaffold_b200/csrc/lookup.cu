@@ -8,7 +8,7 @@
 // Here:
 //   * both columns leave Montgomery form and are sorted by a bitonic network on the 8-limb canonical keys.  Equal keys are
 //     indistinguishable, so no stability is needed; compare-exchange distances below the tile run in shared memory
-//     (limb-major layout), larger ones as streaming passes.  Padding up to a power of two is the all-ones key;
+//     (limb-major layout), larger ones as streaming passes, two distances per pass.  Padding up to a power of two is the all-ones key;
 //   * first occurrences, the match of every distinct input value to the first equal table entry (binary search in the
 //     sorted table), the ranks of the repeated rows and of the unmatched table entries (two exclusive scans) and the fill
 //     are elementwise kernels.  The order of the fill is exactly upstream's: the i-th smallest leftover value goes to the
@@ -70,6 +70,23 @@ __global__ void __launch_bounds__(256) bitonic_global_kernel(uint4* __restrict__
     }
 }
 
+// two consecutive passes (distances j and j / 2, both >= SORT_TILE) in one sweep over memory: a thread owns the four keys of one
+// two-level butterfly, so every key is read and written once for two levels of the network
+__device__ __forceinline__ void key_cmpx(Key& a, Key& b, bool up) {
+    if (key_less(b, a) == up) { const Key t = a; a = b; b = t; }
+}
+__global__ void __launch_bounds__(256) bitonic_global2_kernel(uint4* __restrict__ keys, uint32_t quarter, uint32_t j, uint32_t k) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= quarter) return;
+    const uint32_t h = j >> 1;
+    const uint32_t i00 = ((t & ~(h - 1)) << 2) | (t & (h - 1)), i01 = i00 | h, i10 = i00 | j, i11 = i10 | h;
+    const bool up = (i00 & k) == 0;                    // j < k: the four keys lie in the same run of length k
+    Key a = key_load(keys, i00), b = key_load(keys, i01), c = key_load(keys, i10), d = key_load(keys, i11);
+    key_cmpx(a, c, up); key_cmpx(b, d, up);            // distance j
+    key_cmpx(a, b, up); key_cmpx(c, d, up);            // distance j / 2
+    key_store(keys, i00, a); key_store(keys, i01, b); key_store(keys, i10, c); key_store(keys, i11, d);
+}
+
 // all passes with distance < SORT_TILE of one tile in shared memory.  k_lo == 0: the whole network up to runs of SORT_TILE
 // (the first phase); otherwise the tail j = min(k_lo, SORT_TILE) / 2 ... 1 of the stage with run length k_lo.
 __global__ void __launch_bounds__(512) bitonic_shared_kernel(uint4* __restrict__ keys, uint32_t count, uint32_t k_lo) {
@@ -119,8 +136,10 @@ static int bitonic_sort(uint4* keys, uint32_t padded, cudaStream_t stream) {    
     const uint32_t tiles = (padded + SORT_TILE - 1) / SORT_TILE;
     H2B_LAUNCH(bitonic_shared_kernel, tiles, 512, 0, stream, keys, padded, 0u);
     for (uint32_t k = SORT_TILE << 1; k != 0 && k <= padded; k <<= 1) {
-        for (uint32_t j = k >> 1; j >= SORT_TILE; j >>= 1)
-            H2B_LAUNCH(bitonic_global_kernel, (padded / 2 + 255) / 256, 256, 0, stream, keys, padded / 2, j, k);
+        uint32_t j = k >> 1;
+        for (; j >= 2 * SORT_TILE; j >>= 2)             // two distances per sweep while both are >= SORT_TILE
+            H2B_LAUNCH(bitonic_global2_kernel, (padded / 4 + 255) / 256, 256, 0, stream, keys, padded / 4, j, k);
+        if (j >= SORT_TILE) H2B_LAUNCH(bitonic_global_kernel, (padded / 2 + 255) / 256, 256, 0, stream, keys, padded / 2, j, k);
         H2B_LAUNCH(bitonic_shared_kernel, tiles, 512, 0, stream, keys, padded, k);
     }
     H2B_CUDA(cudaGetLastError());

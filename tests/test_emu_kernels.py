@@ -432,7 +432,8 @@ def test_lookup_permute_async_status(emu, oc):
 
 def test_lookup_permute_expression_pair(emu, oc):
     pc.check_lookup_permute(emu, oc, [(8, 8, 3, "random", 1), (64, 58, 10, "random", 2), (1024, 1018, 1000, "random", 3), (1024, 1018, 16, "small", 4),
-                                      (2048, 2042, 700, "skewed", 5), (3000, 2994, 256, "small", 6), (4096, 4090, 5000, "random", 7), (16, 0, 4, "random", 8)])
+                                      (2048, 2042, 700, "skewed", 5), (3000, 2994, 256, "small", 6), (4096, 4090, 5000, "random", 7), (16, 0, 4, "random", 8),
+                                      (1 << 14, (1 << 14) - 6, 3000, "random", 9), (8192 + 77, 8192 + 71, 64, "small", 10)])
 
 
 def test_prover_rows_golden(emu, golden):
