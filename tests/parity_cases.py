@@ -662,24 +662,23 @@ def check_quotient_is_a_polynomial(L, oc, k=4, seed=1, break_it=None):
     beta, gamma, theta, y = sc
     if break_it == "witness":
         c[2] = (c[2] + 1) % R
-    # ---- grand products and the lookup permutation on the device
+    # ---- grand products and the lookup permutation on the device, through the host mirrors of the two argument provers (blinding rows included)
+    from halo2_scaffold_b200 import prover
     chunk_len = 2
-    sets = [(0, 2), (2, 3)]
-    z_cols, last_z = [], 1
-    for lo, hi in sets:
-        z = L.permutation_product([W(cols_perm[j]) for j in range(lo, hi)], [W(sigma[j]) for j in range(lo, hi)], fr_to_words(beta), fr_to_words(gamma),
-                                  fr_to_words(DELTA), fr_to_words(pow(DELTA, lo, R)), fr_to_words(omega), fr_to_words(last_z))
-        z_int = [o.from_mont(v, R) for v in oc.words_to_ints(z)]
-        last_z = z_int[u]
-        z_cols.append(z_int)
+    blind = lambda count: W([rnd() for _ in range(count)])
+    ints = lambda w: [o.from_mont(v, R) for v in oc.words_to_ints(np.ascontiguousarray(w))]
+    zs, _ = prover.permutation_commit([W(cc) for cc in cols_perm], [W(sg) for sg in sigma], chunk_len=chunk_len, blinding_factors=bf, beta=fr_to_words(beta),
+                                      gamma=fr_to_words(gamma), omega=fr_to_words(omega), blind=blind, lib=L)
+    z_cols = [ints(z) for z in zs]
+    assert len(z_cols) == 2 and z_cols[1][0] == z_cols[0][u], "the second set does not start at the first set's last_z"
     assert z_cols[-1][u] == 1 or break_it, "the permutation product does not close"
-    pa, pt = L.lookup_permute(W(lk), W(table), u)
-    a_perm = [o.from_mont(v, R) for v in oc.words_to_ints(pa)] + [rnd() for _ in range(n - u)]
-    s_perm = [o.from_mont(v, R) for v in oc.words_to_ints(pt)] + [rnd() for _ in range(n - u)]
+    pa, pt, _ = prover.lookup_commit_permuted(W(lk), W(table), blinding_factors=bf, blind=blind, lib=L)
+    a_perm, s_perm = ints(pa), ints(pt)
     if break_it == "fill":
         a_perm[0], a_perm[u - 1] = a_perm[u - 1], a_perm[0]
-    zl = L.lookup_product(W(lk), W(table), W(a_perm), W(s_perm), fr_to_words(beta), fr_to_words(gamma))
-    zl_int = [o.from_mont(v, R) for v in oc.words_to_ints(zl)]
+    zl, _ = prover.lookup_commit_product(W(lk), W(table), W(a_perm), W(s_perm), blinding_factors=bf, beta=fr_to_words(beta), gamma=fr_to_words(gamma),
+                                         blind=blind, lib=L)
+    zl_int = ints(zl)
     assert zl_int[u] == 1 or break_it, "the lookup product does not close"
     # ---- everything to the extended coset
     ext = lambda vals: dom.coeff_to_extended(dom.lagrange_to_coeff(W(vals)))

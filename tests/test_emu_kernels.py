@@ -482,3 +482,34 @@ def test_quotient_of_a_satisfied_circuit_is_a_polynomial(emu, oc):
 
 def test_evaluate_h_row_shards(emu, oc):
     pc.check_evaluate_h_sharded(emu, oc)
+
+
+def test_argument_prover_mirrors_commit(emu, oc):
+    # permutation::Argument::commit / lookup commit_permuted + commit_product through halo2_scaffold_b200.prover with a ParamsKZG:
+    # the commitments are commit_lagrange of exactly the columns that are returned
+    import halo2_scaffold_b200 as h2
+    from halo2_scaffold_b200 import prover
+    from halo2_scaffold_b200.domain import fr_to_words
+    k, n, bf = 5, 32, 5
+    params = h2.ParamsKZG(k, oc.gen_points(61, n), oc.gen_points(62, n), lib=emu)
+    try:
+        cols = [oc.random_fr(70 + j, n) for j in range(3)]
+        sig = [oc.random_fr(80 + j, n) for j in range(3)]
+        beta, gamma = oc.random_fr(90, 2)
+        blind = lambda count: oc.random_fr(91 + count, count)
+        zs, coms = prover.permutation_commit(cols, sig, chunk_len=2, blinding_factors=bf, beta=beta, gamma=gamma, omega=pc.omega_words(oc, k), blind=blind,
+                                             params=params, lib=emu)
+        assert len(zs) == 2 and (zs[1][0] == zs[0][n - bf - 1]).all()
+        for z, c in zip(zs, coms):
+            assert (z[n - bf:] == blind(bf)).all()
+            assert (pc.affine_of(oc, c) == pc.affine_of(oc, oc.best_multiexp(z, params.g_lagrange))).all()
+        table = oc.random_fr(95, n)
+        inp = table[: n - bf - 1][np.random.default_rng(3).integers(0, n - bf - 1, size=n)]
+        pa, pt, (ca, ct) = prover.lookup_commit_permuted(inp, table, blinding_factors=bf, blind=blind, params=params, lib=emu)
+        assert pa.shape == (n, 4) and (pa[n - bf - 1:] == blind(bf + 1)).all()
+        assert (pc.affine_of(oc, ca) == pc.affine_of(oc, oc.best_multiexp(pa, params.g_lagrange))).all()
+        z, cz = prover.lookup_commit_product(inp, table, pa, pt, blinding_factors=bf, beta=beta, gamma=gamma, blind=blind, params=params, lib=emu)
+        assert (z[0] == fr_to_words(1)).all() and (z[n - bf - 1] == fr_to_words(1)).all()          # the product closes on the last usable row
+        assert (pc.affine_of(oc, cz) == pc.affine_of(oc, oc.best_multiexp(z, params.g_lagrange))).all()
+    finally:
+        params.close()
