@@ -46,6 +46,21 @@ def permutation_commit(columns: Sequence[np.ndarray], permutations: Sequence[np.
     return zs, commitments
 
 
+def lookup_compress_expressions(expressions: Sequence, *, fixed, advice, instance, challenges, theta, lib=None, device: int = 0) -> np.ndarray:
+    """lookup::Argument::commit_permuted's `compress_expressions`: theta^(m-1) e_0 + ... + e_(m-1) over the n Lagrange rows, every expression
+    evaluated at the row (rotations wrap inside the n rows, rot_scale = 1).  The expressions go through GraphEvaluator::add_expression and
+    one Horner in theta -- the same graph Evaluator::new builds for the extended-coset side -- and run on the device."""
+    from . import evaluation as ev
+    L = lib or _lib.load()
+    g = ev.GraphEvaluator()
+    parts = [g.add_expression(e) for e in expressions]
+    g.add_calculation(ev.HORNER, ev.ValueSource(ev.CONSTANT, 0), ev.ValueSource(ev.THETA), parts)
+    n = _rows((list(fixed) + list(advice) + list(instance))[0]).shape[0]
+    zero = fr_to_words(0)
+    return ev.evaluate_graph(L, g.arrays(), fixed, advice, instance, challenges, zero, zero, theta, zero, np.zeros((n, 4), dtype=np.uint64), 1,
+                             device=device)
+
+
 def lookup_commit_permuted(compressed_input: np.ndarray, compressed_table: np.ndarray, *, blinding_factors: int, blind: Callable[[int], np.ndarray],
                            params=None, lib=None, device: int = 0):
     """lookup::Argument::commit_permuted after compress_expressions: permute_expression_pair on the usable rows, blinding rows appended.

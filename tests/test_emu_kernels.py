@@ -513,3 +513,21 @@ def test_argument_prover_mirrors_commit(emu, oc):
         assert (pc.affine_of(oc, cz) == pc.affine_of(oc, oc.best_multiexp(z, params.g_lagrange))).all()
     finally:
         params.close()
+
+
+def test_lookup_compress_expressions(emu, oc):
+    # theta-compression of lookup expressions over the Lagrange rows against field arithmetic of the oracle (rotation wraps inside n)
+    from halo2_scaffold_b200 import evaluation as ev, prover
+    n = 50
+    adv = [oc.random_fr(31 + j, n) for j in range(2)]
+    fix = [oc.random_fr(41, n)]
+    theta = oc.random_fr(51, 1)[0]
+    exprs = [ev.Product(ev.Fixed(0), ev.Advice(0)), ev.Advice(1, 1), ev.Sum(ev.Advice(0, -1), ev.Constant(5))]
+    got = prover.lookup_compress_expressions(exprs, fixed=fix, advice=adv, instance=[], challenges=np.zeros((0, 4), dtype=np.uint64), theta=theta, lib=emu)
+    mul = lambda a, b: oc.field_op("fr", "mul", a, b)
+    add = lambda a, b: oc.field_op("fr", "add", a, b)
+    five = np.repeat(oc.fr_to_mont(np.array([[5, 0, 0, 0]], dtype=np.uint64)), n, axis=0)
+    th = np.repeat(theta.reshape(1, 4), n, axis=0)
+    e0, e1, e2 = mul(fix[0], adv[0]), np.roll(adv[1], -1, axis=0), add(np.roll(adv[0], 1, axis=0), five)
+    want = add(mul(add(mul(e0, th), e1), th), e2)
+    assert (got == want).all()
