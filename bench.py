@@ -13,9 +13,12 @@ are all-gathered over NCCL and folded on the device.  After the MSM region the s
 times the Fr NTT at 2^k per GPU; its numbers ride along in the "ntt" object of the same JSON line.
 
 `value`  : whole-job MSM throughput, inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : the same metric through the reference-facing call best_multiexp(coeffs, bases) with HOST buffers
-           (pinned): every step uploads the scalars, runs, downloads the 96-byte result.  Bases are the SRS:
-           registered once outside the timed region, exactly like ParamsKZG holds `g` / `g_lagrange`.
+`e2e`    : the same metric through the reference-facing drop-in best_multiexp(coeffs, bases) = h2b_msm_bn254_g1 with
+           PAGEABLE host arrays (what Rust Vecs are): every step uploads the scalars, re-verifies the digest of the
+           caller's bases array against the resident copy (implicit SRS cache), runs, downloads the 96-byte result.
+           `e2e_registered_pinned` is the friendlier variant (pinned scalars, explicitly registered SRS) for comparison.
+`verified`: after the timed loops the device-timed result, the e2e result and the O(n) checksum [sum s_i z_i] G
+           (field arithmetic only: h2b_msm_checksum_dev + one big-int scalar multiplication) must agree -- at every N.
 `roofline`: dominant kernel (msm_accumulate_kernel) against the measured integer-pipe peak.
 `cpu_baseline`: the C++ restatement of halo2_proofs' best_multiexp/best_fft (oracle/) on the host cores.
 """
@@ -47,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-widened", action="store_true", help="skip the evaluate_h / SRS extras (SURVEY.md 8f) that ride along at N = 1")
     ap.add_argument("--plain", action="store_true", help="do not use the precomputed window tables of the registered SRS")
+    ap.add_argument("--no-inprocess", action="store_true", help="N > 1: skip the in-process h2b_init(N) parity + strong-scaling leg (tools/multi_gpu_inprocess.py)")
+    ap.add_argument("--strong-k", type=int, nargs="*", default=[24, 26], help="total sizes 2^k of the strong-scaling leg at N > 1")
     return ap.parse_args()
 
 
@@ -126,7 +131,7 @@ def run_reference(args):
     import oracle_c as oc
     oc.build()
     cores = oc.hardware_threads()
-    ks = min(args.k, 20)
+    ks = min(args.k, 22)          # the same bounded sample as the repo arm's own cpu_baseline leg
     n = 1 << ks
     scal = oc.random_fr(0xB2000000 + ks, n)
     pts = oc.gen_points(0xB2001000 + ks, n)
@@ -164,6 +169,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import halo2_scaffold_b200 as h2
+    from halo2_scaffold_b200 import verify as V
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,6 +185,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # host-side waits that must not spin a kernel on the waiting GPUs
 
     k, n = args.k, 1 << args.k
     K, W = args.steps, args.warmup
@@ -202,10 +209,25 @@ def run_ours(args):
     d_block = torch.empty(28, dtype=torch.int64, device=dev)
     d_blocks = torch.empty(28 * world, dtype=torch.int64, device=dev)
     d_out = torch.empty(12, dtype=torch.int64, device=dev)
+    d_chk = torch.empty(4, dtype=torch.int64, device=dev)
+    d_chks = torch.empty(4 * world, dtype=torch.int64, device=dev)
+    d_jac = torch.empty(12, dtype=torch.int64, device=dev)
+    d_jacs = torch.empty(12 * world, dtype=torch.int64, device=dev)
     kind = 0 if args.scalars == "uniform" else 1
+    seed_p = 0xB2001000 + k + 1000 * rank
     L.gen_scalars_dev(0, 0xB2000000 + k + 1000 * rank, n, kind, d_scal.data_ptr(), st)
-    L.gen_points_dev(0, 0xB2001000 + k + 1000 * rank, n, d_base.data_ptr(), st)
+    L.gen_points_dev(0, seed_p, n, d_base.data_ptr(), st)
     torch.cuda.synchronize()
+
+    def expected_point(d_scalars):
+        """[sum over all ranks of sum_i s_i z_i] G: the O(n) checksum of the (folded) MSM, field arithmetic only"""
+        L.msm_checksum_dev(0, d_scalars.data_ptr(), seed_p, n, d_chk.data_ptr(), stream=st)
+        if world > 1:
+            dist.all_gather_into_tensor(d_chks, d_chk)
+            cs = d_chks.cpu().numpy().view(np.uint64).reshape(world, 4)
+        else:
+            cs = d_chk.cpu().numpy().view(np.uint64).reshape(1, 4)
+        return V.scalar_mul_generator(sum(V.words_to_int(c) for c in cs) % V.FR_MODULUS)
 
     # the SRS vector is registered once (ParamsKZG holds `g` / `g_lagrange` for the life of the prover): upload +
     # window tables, outside every timed region; its cost is reported as `srs_registration_ms`
@@ -268,7 +290,9 @@ def run_ours(args):
     for tag, ms in prof:
         phase_ms[tag] = phase_ms.get(tag, 0.0) + ms / K
     msm_value = world * n * K / (msm_ms / 1e3)
-    result_host = d_out.cpu().numpy().astype(np.uint64)
+    result_host = d_out.cpu().numpy().view(np.uint64)
+    expect = expected_point(d_scal)
+    checks = {"device_resident_equals_checksum": V.jacobian_words_to_affine(result_host) == expect}
 
     # ---- the same MSM over a witness-like column (50 % zero, 20 % one, 20 % < 2^19, 10 % r - small) ---------
     witness = None
@@ -290,11 +314,47 @@ def run_ours(args):
         e1.record()
         barrier()
         wit_ms = max_over_ranks(e0.elapsed_time(e1))
+        if world > 1:
+            dist.all_gather_into_tensor(d_blocks, d_block)
+            L.msm_fold_partials_dev(0, d_blocks.data_ptr(), world, d_out.data_ptr(), st)
+        else:
+            L.msm_fold_partials_dev(0, d_block.data_ptr(), 1, d_out.data_ptr(), st)
+        wit_ok = V.jacobian_words_to_affine(d_out.cpu().numpy().view(np.uint64)) == expected_point(d_wit)
+        checks["witness_like_equals_checksum"] = wit_ok
         witness = {"value": world * n * K / (wit_ms / 1e3), "unit": "points/s", "ms_per_step": wit_ms / K,
-                   "scalars": "50% zero, 20% one, 20% uniform < 2^19, 10% r - small"}
+                   "scalars": "50% zero, 20% one, 20% uniform < 2^19, 10% r - small", "verified": bool(wit_ok)}
         del d_wit
 
     # ---- MSM, end to end through the host-pointer drop-in ---------------------------------------------------
+    # (a) the real drop-in: best_multiexp(coeffs, bases) = h2b_msm_bn254_g1 with PAGEABLE arrays, as a Rust prover holds them.
+    #     Every call re-verifies the caller's bases array against the resident copy (implicit SRS cache); warm-up = upload,
+    #     window tables, reuse.  With N ranks the N results are gathered and added on the host (north_star: "combined ... on the host").
+    scal_np = d_scal.cpu().numpy().view(np.uint64).reshape(n, 4)      # pageable
+    base_np = d_base.cpu().numpy().view(np.uint64).reshape(n, 8)      # pageable
+
+    def e2e_step():
+        r = L.msm(scal_np, base_np)
+        if world == 1:
+            return r
+        d_jac.copy_(torch.from_numpy(r.view(np.int64)))
+        dist.all_gather_into_tensor(d_jacs, d_jac)
+        acc = None
+        for j in d_jacs.cpu().numpy().view(np.uint64).reshape(world, 12):
+            acc = V.affine_add(acc, V.jacobian_words_to_affine(j))
+        return acc
+    for _ in range(max(3, W)):
+        r = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        r = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n * K / e2e_s
+    checks["e2e_equals_checksum"] = (V.jacobian_words_to_affine(r) if world == 1 else r) == expect
+    cache_stats = L.implicit_cache_stats()
+    del base_np
+    # (b) the friendlier variant of round 1: pinned scalars, explicitly registered SRS (what a patched ParamsKZG::commit does)
     h_scal = torch.empty(n * 4, dtype=torch.int64).pin_memory()
     h_scal.copy_(d_scal)
     if handle is None:
@@ -302,17 +362,19 @@ def run_ours(args):
         h_base = d_base.cpu()
         handle = L.register_bases(h_base.numpy().view(np.uint64))       # plain mode: points only
         del h_base
-    scal_np = h_scal.numpy().view(np.uint64).reshape(n, 4)
-    for _ in range(max(1, W - 1)):
-        r = L.msm_registered(scal_np, handle)
+    pin_np = h_scal.numpy().view(np.uint64).reshape(n, 4)
+    for _ in range(2):
+        r = L.msm_registered(pin_np, handle)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        r = L.msm_registered(scal_np, handle)
+        r = L.msm_registered(pin_np, handle)
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * n * K / e2e_s
+    e2e_pinned_value = world * n * K / max_over_ranks(time.perf_counter() - t0)
+    if world == 1:
+        checks["e2e_registered_pinned_equals_checksum"] = V.jacobian_words_to_affine(r) == expect
     L.unregister_bases(handle)
+    del scal_np
 
     # ---- NTT, device resident + end to end --------------------------------------------------------------------
     w_words = omega_words(k)
@@ -331,7 +393,23 @@ def run_ours(args):
     L.profile_enable(False)
     pass_ms = [ms for (tag, ms) in nprof if tag >= 16]
     ntt_value = world * n * K / (ntt_ms / 1e3)
-    a_np = h_scal.numpy().view(np.uint64).reshape(n, 4)
+    # one more (untimed) step on the state the timed loop left behind, checked at 4 spot indices: out[i] = sum_j in[j] w^(i j),
+    # evaluated by Horner on the device (h2b_fr_eval_polynomial_dev shares no code with the NTT passes)
+    d_in = d_ntt.clone()
+    L.ntt_dev(0, d_ntt.data_ptr(), w_words, k, st)
+    torch.cuda.synchronize()
+    from halo2_scaffold_b200.domain import FR_MODULUS, fr_to_words
+    w_int = sum(int(w_words[i]) << (64 * i) for i in range(4)) * pow(1 << 256, -1, FR_MODULUS) % FR_MODULUS
+    d_ev = torch.empty(4, dtype=torch.int64, device=dev)
+    ntt_ok = True
+    for idx in (0, 1, n // 2 + 3, n - 1):
+        L.check(L.L.h2b_fr_eval_polynomial_dev(0, d_in.data_ptr(), n, fr_to_words(pow(w_int, idx, FR_MODULUS)).ctypes.data, d_ev.data_ptr(), st))
+        torch.cuda.synchronize()
+        ntt_ok = ntt_ok and bool((d_ev.cpu() == d_ntt[4 * idx: 4 * idx + 4].cpu()).all())
+    checks["ntt_spot_values"] = ntt_ok
+    del d_in
+    a_np = np.empty((n, 4), dtype=np.uint64)                     # pageable, like the Vec<Fr> best_fft receives
+    a_np[:] = h_scal.numpy().view(np.uint64).reshape(n, 4)
     L.ntt(a_np, w_words, k)
     barrier()
     t0 = time.perf_counter()
@@ -364,6 +442,23 @@ def run_ours(args):
                         "sample": "one best_multiexp over the first 2^%d of the 2^%d points, %d threads (C++ restatement of halo2_proofs v2023_02_02)" % (ks, k, cores),
                         "ntt_value": cpu_ntt, "ntt_unit": "elements/s", "ntt_sample": "one best_fft at 2^%d, %d threads" % (kf, cores)}
 
+    # ---- N > 1: the modes ONE prover process uses (h2b_init(N)), outside every timed region, rank 0 only ------------------
+    # parity of the in-library point-range sharding / round-robin columns against the oracle, and strong scaling of one MSM
+    in_process = None
+    if world > 1 and not args.no_inprocess:
+        del d_scal, d_base, d_ntt
+        torch.cuda.empty_cache()
+        L.shutdown()                                   # this rank's resident sets and scratch: the subprocess owns the GPUs now
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                cmd = [sys.executable, os.path.join(ROOT, "tools", "multi_gpu_inprocess.py"), str(world)] + [str(x) for x in args.strong_k]
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+                in_process = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": out.stderr[-400:]}
+            except Exception as ex:        # noqa: BLE001
+                in_process = {"error": repr(ex)[:300]}
+        dist.barrier(group=host_group)
+
     if rank == 0:
         peaks = {}
         try:
@@ -395,6 +490,7 @@ def run_ours(args):
         passes_per_ntt = max(1, len(pass_ms) // max(1, K))
         ntt = {
             "metric": "bn254_fr_ntt_elements_per_s", "value": ntt_value, "unit": "elements/s", "k": k, "ms_per_step": ntt_ms / K,
+            "verified": bool(checks["ntt_spot_values"]), "verified_how": "one extra step after the timed loop, 4 spot outputs against Horner evaluation on the device",
             "e2e": {"value": world * n * K / ntt_e2e_s, "unit": "elements/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n},
             "roofline": {
                 "kernel": "ntt_pass_kernel", "bound": "hbm", "unit": "GB/s",
@@ -442,12 +538,24 @@ def run_ours(args):
             "metric": "bn254_g1_msm_points_per_s", "value": msm_value, "unit": "points/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": msm_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": config_for(args, world),
-            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96},
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96,
+                    "call": "h2b_msm_bn254_g1(scalars, bases): pageable host arrays, implicit SRS cache (every call re-verifies the digest of "
+                            "the caller's %d MiB bases array on host threads while the GPU runs)" % (n * 64 >> 20),
+                    "implicit_cache": cache_stats},
+            "e2e_registered_pinned": {"value": e2e_pinned_value, "unit": "points/s", "call": "h2b_msm_bn254_g1_registered, pinned scalars"},
+            "verified": bool(all(checks.values())), "checks": {kk: bool(v) for kk, v in checks.items()},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ntt": ntt,
             "msm_phase_ms": {str(t): round(v, 4) for t, v in sorted(phase_ms.items())},
             "srs": dict(set_info, registration_ms=reg_ms, plain=bool(args.plain)),
             "result_x_limb0": int(result_host[0]),
         }
+        if in_process is not None:
+            line["in_process"] = in_process
+            line["strong"] = in_process.get("strong")
+            if "parity_ok" in in_process:
+                line["checks"]["in_process_multi_gpu_parity_vs_oracle"] = bool(in_process["parity_ok"])
+                line["checks"]["strong_scaling_results_equal_checksum"] = bool(all(x.get("verified") for x in in_process.get("strong", [])))
+                line["verified"] = bool(all(line["checks"].values()))
         if widened:
             line["widened_rows"] = widened
         if witness:

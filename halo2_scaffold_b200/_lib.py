@@ -38,6 +38,7 @@ _EXPORTS = [
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
     "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_graph_shard_dev", "h2b_evaluate_h_permutation_shard_dev", "h2b_evaluate_h_lookup_shard_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
+    "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev",
 ]
 
 
@@ -135,6 +136,10 @@ class Lib:
         L.h2b_ntt_bn254_fr.argtypes = [vp, vp, u32]
         L.h2b_register_bases.argtypes = [vp, sz, ctypes.POINTER(u64)]
         L.h2b_unregister_bases.argtypes = [u64]
+        L.h2b_register_bases_sharded.argtypes = [vp, sz, ctypes.POINTER(u64)]
+        L.h2b_msm_bn254_g1_dev_batch_registered.argtypes = [i32, vp, vp, sz, u64, vp, vp]
+        L.h2b_implicit_cache_stats.argtypes = [vp]
+        L.h2b_msm_checksum_dev.argtypes = [i32, vp, u64, u64, sz, vp, vp]
         L.h2b_msm_bn254_g1_registered.argtypes = [vp, u64, sz, sz, vp]
         L.h2b_ntt_bn254_fr_dev.argtypes = [i32, vp, vp, u32, vp]
         L.h2b_msm_bn254_g1_dev.argtypes = [i32, vp, vp, sz, vp, vp]
@@ -236,6 +241,18 @@ class Lib:
         self.check(self.L.h2b_register_bases(bases.ctypes.data, bases.size // 8, ctypes.byref(h)))
         return h.value
 
+    def register_bases_sharded(self, bases: np.ndarray) -> int:
+        """Rows split over the devices (device d keeps [d n/D, (d+1) n/D) and its tables): the point-range mode."""
+        bases = _u64(bases)
+        h = ctypes.c_uint64(0)
+        self.check(self.L.h2b_register_bases_sharded(bases.ctypes.data, bases.size // 8, ctypes.byref(h)))
+        return h.value
+
+    def implicit_cache_stats(self) -> dict:
+        out = np.zeros(6, dtype=np.uint64)
+        self.check(self.L.h2b_implicit_cache_stats(out.ctypes.data))
+        return dict(zip(("uploads", "hits", "stale", "direct", "sets", "sets_with_tables"), (int(v) for v in out)))
+
     def unregister_bases(self, handle: int):
         self.check(self.L.h2b_unregister_bases(handle))
 
@@ -244,24 +261,6 @@ class Lib:
         out = np.zeros(12, dtype=np.uint64)
         self.check(self.L.h2b_msm_bn254_g1_registered(scalars.ctypes.data, handle, offset, scalars.size // 4, out.ctypes.data))
         return out
-
-    def msm_batch_registered(self, columns, handle: int) -> np.ndarray:
-        """columns: list of (n_j, 4) uint64 arrays -> (len(columns), 12) Jacobian results"""
-        cols = [_u64(c).reshape(-1, 4) for c in columns]
-        ptrs = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
-        lens = (ctypes.c_size_t * len(cols))(*[c.shape[0] for c in cols])
-        out = np.zeros((len(cols), 12), dtype=np.uint64)
-        self.check(self.L.h2b_msm_bn254_g1_batch_registered(ptrs, lens, len(cols), handle, out.ctypes.data))
-        return out
-
-    def ntt_batch(self, polys, omega: np.ndarray, log_n: int):
-        """In place on each C-contiguous uint64 (2^log_n, 4) array of the list."""
-        for a in polys:
-            assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"] and a.size == 4 << log_n
-        ptrs = (ctypes.c_void_p * len(polys))(*[a.ctypes.data for a in polys])
-        omega = _u64(omega)
-        self.check(self.L.h2b_ntt_bn254_fr_batch(ptrs, len(polys), omega.ctypes.data, log_n))
-        return polys
 
     def msm_batch_registered(self, columns, handle: int) -> np.ndarray:
         """columns: list of (n_j, 4) uint64 arrays -> (len(columns), 12) Jacobian results"""
@@ -294,6 +293,16 @@ class Lib:
 
     def msm_dev_registered(self, device: int, d_scalars: int, handle: int, offset: int, n: int, d_out_block: int, stream: int = 0):
         self.check(self.L.h2b_msm_bn254_g1_dev_registered(device, d_scalars, handle, offset, n, d_out_block, stream))
+
+    def msm_dev_batch_registered(self, device: int, d_columns, lens, handle: int, d_out_blocks: int, stream: int = 0):
+        """d_columns: device pointers, lens: scalars per column; d_out_blocks: len(d_columns) x 224 bytes on the device"""
+        ptrs = (ctypes.c_void_p * len(d_columns))(*d_columns)
+        ln = (ctypes.c_size_t * len(d_columns))(*lens)
+        self.check(self.L.h2b_msm_bn254_g1_dev_batch_registered(device, ptrs, ln, len(d_columns), handle, d_out_blocks, stream))
+
+    def msm_checksum_dev(self, device: int, d_scalars: int, seed: int, n: int, d_out: int, first: int = 0, stream: int = 0):
+        """sum_i s_i z_i mod r (canonical, 32 B at d_out) for the synthetic points P_i = [z_i]G of gen_points(seed)"""
+        self.check(self.L.h2b_msm_checksum_dev(device, d_scalars, seed, first, n, d_out, stream))
 
     def set_msm_precomp(self, spacing: int):
         self.check(self.L.h2b_set_msm_precomp(spacing))

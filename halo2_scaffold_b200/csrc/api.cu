@@ -26,20 +26,35 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return t_error.c_str(); }
 
-// A base array resident on every initialised device (full copy per device: any point range can be
-// handed to any device; 2^26 points are 4 GiB of a B200's 180 GB).
+// ---- resident point sets --------------------------------------------------------------------------------------------
+// An SRS vector (or any base array) resident in device memory, with or without its window tables (msm.cu step 0).
+//   replicated: every device holds all n rows  -> any column can run on any device (round-robin columns)
+//   sharded   : device d holds rows [lo[d], lo[d] + rows[d]) only -> one MSM split by point range (8e row 1) at 1/D of the
+//               memory and of the registration time
+// Sets are immutable once published and handed out as shared_ptr: a call keeps its set alive while it runs, whatever
+// eviction, table builds or h2b_unregister_bases do meanwhile; device memory is released when the last holder lets go.
 struct BaseSet {
     uint64_t handle = 0;
-    const void* host_ptr = nullptr;   // only for implicitly cached sets
+    bool implicit = false;            // created by h2b_msm_bn254_g1's cache (not by h2b_register_bases / h2b_srs_read)
+    const void* host_ptr = nullptr;   // implicit sets: where the caller's array was when it was uploaded (a hint only)
     size_t n = 0;
-    uint64_t samples[16][8];          // sampled points, validates pointer reuse
-    uint64_t last_use = 0;
-    uint64_t uses = 0;
-    uint32_t n_tables = 1;            // 1: points only;  > 1: table j = 2^(c0*j) * P (msm.cu step 0)
+    std::vector<uint64_t> digest;     // implicit sets: 128-bit digest of every block of digest_block() points of the uploaded array
+    uint64_t last_use = 0, uses = 0;
+    uint32_t n_tables = 1;            // 1: points only;  > 1: table j = 2^(c0*j) * P
     uint32_t c0 = 0;
-    std::vector<void*> dev;           // per device: n_tables x n x 64 bytes
-    int refs = 1;                     // h2b_unregister_bases frees the set when the last holder lets go (SRS cache + its readers)
+    bool sharded = false;
+    std::vector<int> ordinal;         // CUDA ordinal of device d
+    std::vector<void*> dev;           // per device: n_tables x rows[d] x 64 bytes
+    std::vector<size_t> lo, rows;
+    int refs = 1;                     // API references (h2b_register_bases / h2b_srs_read hand-outs); guarded by G.mu
+    ~BaseSet() {
+        for (size_t d = 0; d < dev.size(); ++d)
+            if (dev[d]) { cudaSetDevice(ordinal[d]); cudaFree(dev[d]); }
+        cudaGetLastError();
+    }
+    size_t bytes_on(size_t d) const { return dev[d] ? (size_t)n_tables * rows[d] * 64 : 0; }
 };
+typedef std::shared_ptr<BaseSet> SetRef;
 
 // files h2b_srs_read has already decoded: the reference re-reads params/kzg_bn254_{k}.srs for every proof
 // (src/scaffold.rs:174); a second read of an unchanged file hands out the resident base sets again
@@ -55,17 +70,46 @@ struct SrsCacheEntry {
 struct Global {
     std::mutex mu;
     std::vector<std::unique_ptr<DeviceCtx>> devs;
-    std::vector<std::unique_ptr<BaseSet>> sets;
+    std::vector<SetRef> sets;
     std::vector<SrsCacheEntry> srs_cache;
     uint64_t next_handle = 1;
     uint64_t use_counter = 0;
     std::atomic<unsigned> rr{0};
+    std::atomic<unsigned long long> implicit_uploads{0}, implicit_hits{0}, implicit_stale{0}, direct_calls{0};
 };
 static Global G;
 
-static const size_t IMPLICIT_CACHE_MAX_SETS = 4;
-static const size_t MULTI_DEVICE_MIN_POINTS = (size_t)1 << 18;
+static const size_t IMPLICIT_CACHE_MAX_SETS = 8;
+// MSMs below this many points stay on one device (H2B_MULTI_DEVICE_MIN_LOG lowers it: tests)
+static size_t multi_device_min_points() {
+    static size_t v = 0;
+    if (!v) { const char* e = getenv("H2B_MULTI_DEVICE_MIN_LOG"); int lg = e ? atoi(e) : 18; v = (size_t)1 << (lg < 1 || lg > 28 ? 18 : lg); }
+    return v;
+}
+#define MULTI_DEVICE_MIN_POINTS (multi_device_min_points())
 static const uint64_t IMPLICIT_TABLES_AFTER_USES = 2;   // an implicitly cached SRS vector gets its tables on the 2nd MSM
+
+static int env_int_or(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// the implicit cache works on blocks of 2^H2B_DIGEST_BLOCK_LOG points (default 1024 = 64 KiB) and only takes arrays of at
+// least 2^H2B_IMPLICIT_MIN_LOG points (default 4096) whose length is a whole number of blocks; tests lower both
+static size_t digest_block() {
+    static size_t v = 0;
+    if (!v) { int lg = env_int_or("H2B_DIGEST_BLOCK_LOG", 10); v = (size_t)1 << (lg < 2 || lg > 16 ? 10 : lg); }
+    return v;
+}
+static size_t implicit_min_points() {
+    static size_t v = 0;
+    if (!v) { int lg = env_int_or("H2B_IMPLICIT_MIN_LOG", 12); v = (size_t)1 << (lg < 2 || lg > 28 ? 12 : lg); if (v < digest_block()) v = digest_block(); }
+    return v;
+}
+static bool implicit_cache_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("H2B_IMPLICIT_CACHE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 
 // table policy: -1 never build tables, 0 automatic spacing, > 0 forced spacing (tests / tuning)
 static int g_table_policy = -2;
@@ -106,199 +150,326 @@ static int init_devices(const std::vector<int>& ordinals) {
         H2B_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         G.devs.push_back(std::move(c));
     }
+    // peer access between every pair (NVLink / NVSwitch): table all-gathers and peer copies of decoded SRS vectors go direct
+    for (size_t a = 0; a < G.devs.size(); ++a) {
+        cudaSetDevice(G.devs[a]->device);
+        for (size_t b = 0; b < G.devs.size(); ++b) {
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, G.devs[a]->device, G.devs[b]->device) == cudaSuccess && can) cudaDeviceEnablePeerAccess(G.devs[b]->device, 0);
+        }
+    }
+    cudaGetLastError();      // "already enabled" is not an error
     return H2B_OK;
 }
 
 // pick a device for a single-device call: round robin, preferring one that is idle
-static DeviceCtx* pick_device(std::unique_lock<std::mutex>& lock_out) {
+static DeviceCtx* pick_device(std::unique_lock<std::mutex>& lock_out, size_t* index = nullptr) {
     size_t nd = G.devs.size();
     unsigned start = G.rr.fetch_add(1);
     for (size_t k = 0; k < nd; ++k) {
         DeviceCtx* c = G.devs[(start + k) % nd].get();
         std::unique_lock<std::mutex> lk(c->mu, std::try_to_lock);
-        if (lk.owns_lock()) { lock_out = std::move(lk); return c; }
+        if (lk.owns_lock()) { lock_out = std::move(lk); if (index) *index = (start + k) % nd; return c; }
     }
     DeviceCtx* c = G.devs[start % nd].get();
     lock_out = std::unique_lock<std::mutex>(c->mu);
+    if (index) *index = start % nd;
     return c;
 }
 
-static void sample_points(const uint64_t* bases, size_t n, uint64_t out[16][8]) {
-    for (int k = 0; k < 16; ++k) {
-        size_t idx = n <= 1 ? 0 : (size_t)(((unsigned __int128)k * (n - 1)) / 15);
-        memcpy(out[k], bases + 8 * idx, 64);
-    }
+// ---- content digests of host arrays (implicit cache) --------------------------------------------------------------------
+// best_multiexp is a pure function of its arguments: a device copy may only be reused if the caller's array still holds exactly
+// what was uploaded.  Every block of digest_block() points gets a 128-bit digest (multiply-fold over 64-bit words, four
+// independent lanes: memory-bound on one core); a cached set is reused only after ALL blocks of the call's range matched.
+static inline uint64_t mum64(uint64_t a, uint64_t b) {
+    unsigned __int128 r = (unsigned __int128)a * b;
+    return (uint64_t)r ^ (uint64_t)(r >> 64);
 }
-
-static void free_set(BaseSet& bs) {
-    for (size_t d = 0; d < bs.dev.size(); ++d) {
-        if (bs.dev[d]) {
-            std::lock_guard<std::mutex> lk(G.devs[d]->mu);      // no MSM of this device is still reading the set
-            cudaSetDevice(G.devs[d]->device);
-            cudaFree(bs.dev[d]);
+static void digest_words(const uint64_t* p, size_t words, uint64_t out[2]) {
+    uint64_t a0 = 0xa0761d6478bd642full, a1 = 0xe7037ed1a0b428dbull, a2 = 0x8ebc6af09c88c6e3ull, a3 = 0x589965cc75374cc3ull;
+    size_t i = 0;
+    for (; i + 8 <= words; i += 8) {
+        a0 = mum64(p[i] ^ 0x2d358dccaa6c78a5ull, p[i + 1] ^ a0);
+        a1 = mum64(p[i + 2] ^ 0x8bb84b93962eacc9ull, p[i + 3] ^ a1);
+        a2 = mum64(p[i + 4] ^ 0x4b33a62ed433d4a3ull, p[i + 5] ^ a2);
+        a3 = mum64(p[i + 6] ^ 0x4d5a2da51de1aa47ull, p[i + 7] ^ a3);
+    }
+    for (; i < words; ++i) a0 = mum64(p[i] ^ 0x2d358dccaa6c78a5ull, a0 ^ (0x9e3779b97f4a7c15ull + i));
+    out[0] = mum64(a0 ^ a2 ^ (uint64_t)words, a1 ^ 0xa0761d6478bd642full) ^ a3;
+    out[1] = mum64(a1 + a3, a2 ^ 0xe7037ed1a0b428dbull) ^ mum64(a0, a3 ^ 0x589965cc75374cc3ull);
+}
+static unsigned digest_threads() {
+    static unsigned v = 0;
+    if (!v) {
+        unsigned hw = std::thread::hardware_concurrency();
+        v = hw >= 16 ? 8 : (hw >= 8 ? 4 : 2);
+        int e = env_int_or("H2B_DIGEST_THREADS", 0);
+        if (e >= 1 && e <= 64) v = (unsigned)e;
+    }
+    return v;
+}
+// blocks [b0, b1) of `bases`: mode 0 writes the digests to out, mode 1 compares them with `want` (early exit) -> all equal?
+static bool digest_blocks(const uint64_t* bases, size_t b0, size_t b1, uint64_t* out, const uint64_t* want) {
+    const size_t blk = digest_block();
+    std::atomic<bool> ok{true};
+    std::atomic<size_t> next{b0};
+    auto work = [&] {
+        for (;;) {
+            const size_t b = next.fetch_add(16);
+            if (b >= b1 || !ok.load(std::memory_order_relaxed)) return;
+            for (size_t x = b; x < b + 16 && x < b1; ++x) {
+                uint64_t d[2];
+                digest_words(bases + x * blk * 8, blk * 8, d);
+                if (want) { if (d[0] != want[2 * x] || d[1] != want[2 * x + 1]) { ok = false; return; } }
+                else { out[2 * x] = d[0]; out[2 * x + 1] = d[1]; }
+            }
         }
-    }
-    bs.dev.clear();
+    };
+    const size_t count = b1 - b0;
+    unsigned T = digest_threads();
+    if (count < 256) T = 1;                     // below 16 MiB a thread launch costs more than it saves
+    if (T <= 1) { work(); return ok; }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return ok;
 }
 
-// Replace the point array of a resident set by the table set of msm.cu step 0 (table 0 = the points themselves).
-// Best effort: when the tables do not fit in device memory the set simply stays in plain mode.
-static int build_tables(BaseSet& bs) {
+// ---- building resident sets ------------------------------------------------------------------------------------------------
+static void layout_rows(size_t n, bool sharded, std::vector<size_t>& lo, std::vector<size_t>& rows) {
+    const size_t nd = G.devs.size();
+    lo.assign(nd, 0);
+    rows.assign(nd, n);
+    if (!sharded) return;
+    for (size_t d = 0; d < nd; ++d) { lo[d] = n * d / nd; rows[d] = n * (d + 1) / nd - lo[d]; }
+}
+
+static SetRef new_set_like(const BaseSet& src) {
+    SetRef bs(new BaseSet());
+    bs->handle = src.handle; bs->implicit = src.implicit; bs->host_ptr = src.host_ptr; bs->n = src.n; bs->digest = src.digest;
+    bs->last_use = src.last_use; bs->uses = src.uses; bs->sharded = src.sharded; bs->refs = src.refs;
+    bs->lo = src.lo; bs->rows = src.rows; bs->ordinal = src.ordinal;
+    bs->dev.assign(src.dev.size(), nullptr);
+    return bs;
+}
+
+// The table set of msm.cu step 0 for a resident point set (table 0 = the points themselves) as a NEW set; the source stays
+// untouched (calls in flight keep using it).  Best effort: returns the source itself when tables are off or do not fit.
+// Work split: a sharded set's device builds the tables of its own rows; the devices of a replicated set each build 1/D of
+// the rows and all-gather the rest over NVLink (peer copies run at hundreds of GB/s, recomputation at 18 G points/s), so
+// registration time falls with the device count instead of growing with it.
+static SetRef build_tables(const SetRef& src) {
     const int policy = table_policy();
-    if (policy < 0 || bs.n_tables > 1 || bs.n == 0 || bs.n > ((size_t)1 << 26)) return H2B_OK;
+    const size_t nd = G.devs.size();
+    if (policy < 0 || src->n_tables > 1 || src->n == 0) return src;
+    size_t max_rows = 0;
+    for (size_t d = 0; d < nd; ++d) max_rows = src->rows[d] > max_rows ? src->rows[d] : max_rows;
+    if (max_rows > ((size_t)1 << 26)) return src;
+    // spacing for the MSMs this layout runs: whole-set MSMs on one device (replicated) or 1/D of the set (sharded)
     uint32_t c0 = 0;
     if (policy > 0) c0 = (uint32_t)policy;
     else {
         size_t free_b = 0, total_b = 0;
         cudaSetDevice(G.devs[0]->device);
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return H2B_OK;
-        size_t max_tables = (free_b / 3) / (bs.n * 64);
-        if ((uint64_t)bs.n * max_tables >= 0x7fffffffull) max_tables = (size_t)(0x7fffffffull / bs.n);
-        c0 = msm_pick_table_spacing(bs.n, (uint32_t)(max_tables > 128 ? 128 : max_tables));
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return src;
+        size_t max_tables = (free_b / 3) / (max_rows * 64);
+        if ((uint64_t)max_rows * max_tables >= 0x7fffffffull) max_tables = (size_t)(0x7fffffffull / max_rows);
+        c0 = msm_pick_table_spacing(max_rows, (uint32_t)(max_tables > 128 ? 128 : max_tables));
     }
-    if (c0 < 2 || c0 > 24) return H2B_OK;
+    if (c0 < 2 || c0 > 24) return src;
     const uint32_t nt = msm_tables_for(c0);
-    if ((uint64_t)bs.n * nt >= 0x7fffffffull) return H2B_OK;
-    std::vector<void*> fresh(G.devs.size(), nullptr);
+    if ((uint64_t)max_rows * nt >= 0x7fffffffull) return src;
+    SetRef out = new_set_like(*src);
+    out->n_tables = nt;
+    out->c0 = c0;
     bool ok = true;
-    // every device builds its own copy; the kernels of all devices are queued first and awaited afterwards, so the
-    // devices work concurrently (registration time does not grow with the device count)
     std::vector<std::unique_lock<std::mutex>> locks;
-    for (size_t d = 0; d < G.devs.size(); ++d) locks.emplace_back(G.devs[d]->mu);
-    for (size_t d = 0; d < G.devs.size() && ok; ++d) {
+    for (size_t d = 0; d < nd; ++d) locks.emplace_back(G.devs[d]->mu);
+    const bool gather = !src->sharded && nd > 1;
+    // phase 1: every device computes its share (kernels of all devices queued first, awaited afterwards)
+    for (size_t d = 0; d < nd && ok; ++d) {
         DeviceCtx& c = *G.devs[d];
+        const size_t R = src->rows[d];
+        if (R == 0) continue;
         cudaSetDevice(c.device);
-        if (cudaMalloc(&fresh[d], (size_t)nt * bs.n * 64 + 64) != cudaSuccess) { cudaGetLastError(); fresh[d] = nullptr; ok = false; break; }
+        if (cudaMalloc(&out->dev[d], (size_t)nt * R * 64 + 64) != cudaSuccess) { cudaGetLastError(); out->dev[d] = nullptr; ok = false; break; }
+        const size_t r0 = gather ? R * d / nd : 0, r1 = gather ? R * (d + 1) / nd : R;
         c.prof.mark(PROF_BEGIN, c.stream);
-        if (cudaMemcpyAsync(fresh[d], bs.dev[d], bs.n * 64, cudaMemcpyDeviceToDevice, c.stream) != cudaSuccess) ok = false;
-        for (uint32_t j = 1; j < nt && ok; ++j)
-            ok = msm_precompute_run(c, (const char*)fresh[d] + (size_t)(j - 1) * bs.n * 64, (char*)fresh[d] + (size_t)j * bs.n * 64, bs.n, c0, c.stream) == H2B_OK;
+        if (cudaMemcpyAsync(out->dev[d], src->dev[d], R * 64, cudaMemcpyDeviceToDevice, c.stream) != cudaSuccess) ok = false;
+        for (uint32_t j = 1; j < nt && ok && r1 > r0; ++j)
+            ok = msm_precompute_run(c, (const char*)out->dev[d] + ((size_t)(j - 1) * R + r0) * 64, (char*)out->dev[d] + ((size_t)j * R + r0) * 64, r1 - r0, c0, c.stream) == H2B_OK;
         c.prof.mark(PROF_MSM_PRECOMPUTE, c.stream);
     }
-    for (size_t d = 0; d < G.devs.size(); ++d) {
-        if (!fresh[d]) continue;
+    for (size_t d = 0; d < nd; ++d) {
+        if (!out->dev[d]) continue;
         cudaSetDevice(G.devs[d]->device);
         if (cudaStreamSynchronize(G.devs[d]->stream) != cudaSuccess) ok = false;
     }
+    // phase 2 (replicated sets on several devices): every device pulls the other devices' shares
+    if (ok && gather) {
+        const size_t R = src->n;
+        for (size_t d = 0; d < nd && ok; ++d) {
+            cudaSetDevice(G.devs[d]->device);
+            for (size_t e = 0; e < nd && ok; ++e) {
+                if (e == d) continue;
+                const size_t r0 = R * e / nd, r1 = R * (e + 1) / nd;
+                for (uint32_t j = 1; j < nt && ok && r1 > r0; ++j)
+                    ok = cudaMemcpyPeerAsync((char*)out->dev[d] + ((size_t)j * R + r0) * 64, G.devs[d]->device, (const char*)out->dev[e] + ((size_t)j * R + r0) * 64,
+                                             G.devs[e]->device, (r1 - r0) * 64, G.devs[d]->stream) == cudaSuccess;
+            }
+        }
+        for (size_t d = 0; d < nd; ++d) {
+            cudaSetDevice(G.devs[d]->device);
+            if (cudaStreamSynchronize(G.devs[d]->stream) != cudaSuccess) ok = false;
+        }
+    }
     locks.clear();
-    if (!ok) {
-        for (size_t d = 0; d < fresh.size(); ++d) if (fresh[d]) { cudaSetDevice(G.devs[d]->device); cudaFree(fresh[d]); }
-        cudaGetLastError();
-        return H2B_OK;
-    }
-    for (size_t d = 0; d < G.devs.size(); ++d) {
-        std::lock_guard<std::mutex> lk(G.devs[d]->mu);
-        cudaSetDevice(G.devs[d]->device);
-        cudaFree(bs.dev[d]);
-        bs.dev[d] = fresh[d];
-    }
-    bs.n_tables = nt;
-    bs.c0 = c0;
-    return H2B_OK;
+    if (!ok) { cudaGetLastError(); return src; }      // `out` frees whatever it allocated
+    return out;
 }
 
-static int upload_set(BaseSet& bs, const uint64_t* bases, size_t n, bool with_tables) {
-    bs.n = n;
-    bs.n_tables = 1;
-    bs.c0 = 0;
-    bs.dev.assign(G.devs.size(), nullptr);
-    for (size_t d = 0; d < G.devs.size(); ++d) {
+// upload `bases` (host) as a new resident set
+static int create_set(const uint64_t* bases, size_t n, bool sharded, bool with_tables, SetRef* out) {
+    const size_t nd = G.devs.size();
+    SetRef bs(new BaseSet());
+    bs->n = n;
+    bs->sharded = sharded && nd > 1;
+    layout_rows(n, bs->sharded, bs->lo, bs->rows);
+    bs->dev.assign(nd, nullptr);
+    for (size_t d = 0; d < nd; ++d) bs->ordinal.push_back(G.devs[d]->device);
+    for (size_t d = 0; d < nd; ++d) {
+        if (bs->rows[d] == 0) continue;
         H2B_CUDA(cudaSetDevice(G.devs[d]->device));
-        cudaError_t e = cudaMalloc(&bs.dev[d], n * 64 + 64);
-        if (e != cudaSuccess) { set_error("cudaMalloc of %zu bytes for SRS bases failed: %s", n * 64, cudaGetErrorString(e)); return H2B_ERR_OOM; }
+        cudaError_t e = cudaMalloc(&bs->dev[d], bs->rows[d] * 64 + 64);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc of %zu bytes for SRS bases failed: %s", bs->rows[d] * 64, cudaGetErrorString(e)); return H2B_ERR_OOM; }
     }
-    // one upload per device, concurrently (pageable arrays go through each device's pinned staging threads)
-    std::vector<int> rcs(G.devs.size(), 0);
-    std::vector<std::string> errs(G.devs.size());
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
     auto upload_one = [&](size_t d) {
         DeviceCtx& c = *G.devs[d];
         std::lock_guard<std::mutex> lk(c.mu);
         if (cudaSetDevice(c.device) != cudaSuccess) { rcs[d] = H2B_ERR_CUDA; return; }
-        rcs[d] = host_upload(c, bs.dev[d], bases, n * 64, c.stream);
+        rcs[d] = host_upload(c, bs->dev[d], bases + 8 * bs->lo[d], bs->rows[d] * 64, c.stream);
         if (!rcs[d] && cudaStreamSynchronize(c.stream) != cudaSuccess) { set_error("SRS upload: %s", cudaGetErrorString(cudaGetLastError())); rcs[d] = H2B_ERR_CUDA; }
         if (rcs[d]) errs[d] = get_error();
     };
-    if (G.devs.size() == 1) upload_one(0);
-    else {
+    if (bs->sharded) {
+        // disjoint slices: one upload per device, concurrently (each over its own PCIe link)
         std::vector<std::thread> th;
-        for (size_t d = 0; d < G.devs.size(); ++d) th.emplace_back(upload_one, d);
+        for (size_t d = 0; d < nd; ++d) if (bs->rows[d]) th.emplace_back(upload_one, d);
         for (auto& t : th) t.join();
+    } else {
+        // one trip over PCIe, then peer copies: D concurrent uploads of the same host array only fight for the host's memory
+        upload_one(0);
+        for (size_t d = 1; d < nd && !rcs[0]; ++d) {
+            std::lock_guard<std::mutex> lk(G.devs[d]->mu);
+            cudaError_t e = cudaSetDevice(G.devs[d]->device);
+            if (e == cudaSuccess) e = cudaMemcpyPeer(bs->dev[d], G.devs[d]->device, bs->dev[0], G.devs[0]->device, n * 64);
+            if (e != cudaSuccess) { set_error("peer copy of SRS bases: %s", cudaGetErrorString(e)); rcs[d] = H2B_ERR_CUDA; errs[d] = get_error(); }
+        }
     }
-    for (size_t d = 0; d < G.devs.size(); ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
-    if (with_tables) H2B_TRY(build_tables(bs));
+    for (size_t d = 0; d < nd; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
+    *out = with_tables ? build_tables(bs) : bs;
     return H2B_OK;
 }
 
-// find or create the implicit cache entry for (bases, n). Caller holds G.mu.
-static int implicit_set(const uint64_t* bases, size_t n, BaseSet** out) {
-    for (auto& up : G.sets) {
-        BaseSet& bs = *up;
-        if (bs.host_ptr != bases || bs.n < n) continue;
-        // validate against pointer reuse: every sampled point that lies inside the requested prefix must still
-        // match what was uploaded (only [0, n) of the caller's array may be read)
-        bool same = true;
-        for (int k = 0; k < 16 && same; ++k) {
-            size_t idx = bs.n <= 1 ? 0 : (size_t)(((unsigned __int128)k * (bs.n - 1)) / 15);
-            if (idx < n && memcmp(bases + 8 * idx, bs.samples[k], 64) != 0) same = false;
-        }
-        if (same) {
-            bs.last_use = ++G.use_counter;
-            if (++bs.uses == IMPLICIT_TABLES_AFTER_USES) H2B_TRY(build_tables(bs));
-            *out = &bs;
-            return H2B_OK;
+static SetRef find_set_locked(uint64_t handle) {
+    for (auto& sp : G.sets) if (sp->handle == handle) return sp;
+    return SetRef();
+}
+static SetRef find_set(uint64_t handle) {
+    std::lock_guard<std::mutex> lk(G.mu);
+    return find_set_locked(handle);
+}
+static void publish_locked(const SetRef& bs) {
+    for (auto& sp : G.sets) if (sp->handle == bs->handle) { sp = bs; return; }
+    G.sets.push_back(bs);
+}
+static void drop_locked(uint64_t handle) {
+    for (size_t i = 0; i < G.sets.size(); ++i) if (G.sets[i]->handle == handle) { G.sets.erase(G.sets.begin() + i); return; }
+}
+
+// ---- the implicit cache of h2b_msm_bn254_g1 ---------------------------------------------------------------------------------
+// quick filter before the (concurrent) full verification: up to 16 evenly spaced blocks of the call's range. Caller holds G.mu.
+static bool spot_check(const BaseSet& bs, const uint64_t* bases, size_t nblocks) {
+    const size_t blk = digest_block();
+    for (int k = 0; k < 16; ++k) {
+        const size_t b = nblocks <= 1 ? 0 : (size_t)(((unsigned __int128)k * (nblocks - 1)) / 15);
+        uint64_t d[2];
+        digest_words(bases + b * blk * 8, blk * 8, d);
+        if (d[0] != bs.digest[2 * b] || d[1] != bs.digest[2 * b + 1]) return false;
+    }
+    return true;
+}
+
+// a resident copy that may hold bases[0, n): same address first, then any cached array (the same SRS vector re-loaded at
+// another address: src/scaffold.rs:174 re-reads the params file for every proof).  Tables are built on the 2nd use.
+static SetRef implicit_candidate_locked(const uint64_t* bases, size_t n) {
+    const size_t nblocks = n / digest_block();
+    for (int pass = 0; pass < 2; ++pass) {
+        for (auto& sp : G.sets) {
+            if (!sp->implicit || sp->n < n || (pass == 0) != (sp->host_ptr == (const void*)bases)) continue;
+            if (!spot_check(*sp, bases, nblocks)) continue;
+            SetRef hit = sp;
+            hit->last_use = ++G.use_counter;
+            if (++hit->uses == IMPLICIT_TABLES_AFTER_USES && hit->n_tables == 1) {
+                SetRef with = build_tables(hit);
+                if (with != hit) { sp = with; hit = with; }
+            }
+            return hit;
         }
     }
-    // the same SRS vector re-loaded at another address (scaffold.rs:174 re-reads the params file for every proof):
-    // same length and all 16 sampled points identical
-    for (auto& up : G.sets) {
-        BaseSet& bs = *up;
-        if (!bs.host_ptr || bs.host_ptr == bases || bs.n != n) continue;
-        uint64_t smp[16][8];
-        sample_points(bases, n, smp);
-        if (memcmp(smp, bs.samples, sizeof(smp)) != 0) continue;
-        bs.host_ptr = bases;
-        bs.last_use = ++G.use_counter;
-        if (++bs.uses == IMPLICIT_TABLES_AFTER_USES) H2B_TRY(build_tables(bs));
-        *out = &bs;
-        return H2B_OK;
-    }
-    // miss: drop stale entries with the same pointer, evict LRU implicit entries beyond the budget
+    return SetRef();
+}
+
+static int implicit_insert_locked(const uint64_t* bases, size_t n, SetRef* out) {
+    // stale entries for this address (their contents no longer match, or they are shorter), then LRU beyond the budget
     for (size_t i = 0; i < G.sets.size();) {
-        if (G.sets[i]->host_ptr == bases) { free_set(*G.sets[i]); G.sets.erase(G.sets.begin() + i); }
+        if (G.sets[i]->implicit && G.sets[i]->host_ptr == (const void*)bases) G.sets.erase(G.sets.begin() + i);
         else ++i;
     }
+    size_t total_b = 0, free_b = 0;
+    cudaSetDevice(G.devs[0]->device);
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = (size_t)64 << 30; }
+    const size_t budget = total_b / 2;
     for (;;) {
-        size_t implicit = 0, victim = (size_t)-1;
+        size_t implicit = 0, bytes = 0, victim = (size_t)-1;
         for (size_t i = 0; i < G.sets.size(); ++i) {
-            if (!G.sets[i]->host_ptr) continue;
+            if (!G.sets[i]->implicit) continue;
             ++implicit;
+            bytes += G.sets[i]->bytes_on(0);
             if (victim == (size_t)-1 || G.sets[i]->last_use < G.sets[victim]->last_use) victim = i;
         }
-        if (implicit < IMPLICIT_CACHE_MAX_SETS) break;
-        free_set(*G.sets[victim]);
+        if (victim == (size_t)-1 || (implicit < IMPLICIT_CACHE_MAX_SETS && bytes + n * 64 * 14 <= budget)) break;
         G.sets.erase(G.sets.begin() + victim);
     }
-    std::unique_ptr<BaseSet> bs(new BaseSet());
+    SetRef bs;
+    H2B_TRY(create_set(bases, n, n >= MULTI_DEVICE_MIN_POINTS, false, &bs));
     bs->handle = G.next_handle++;
+    bs->implicit = true;
     bs->host_ptr = bases;
-    sample_points(bases, n, bs->samples);
     bs->last_use = ++G.use_counter;
     bs->uses = 1;
-    int rc = upload_set(*bs, bases, n, false);
-    if (rc != H2B_OK) { free_set(*bs); return rc; }
-    *out = bs.get();
-    G.sets.push_back(std::move(bs));
+    bs->refs = 0;
+    const size_t nblocks = n / digest_block();
+    bs->digest.resize(2 * nblocks);
+    digest_blocks(bases, 0, nblocks, bs->digest.data(), nullptr);
+    G.sets.push_back(bs);
+    G.implicit_uploads++;
+    *out = bs;
     return H2B_OK;
 }
 
-// one device: scalars (host) x bases (device) -> 224-byte result block in host memory
-static MsmBases bases_of(const BaseSet& bs, size_t d, size_t row0) {
+// ---- running an MSM over a resident set --------------------------------------------------------------------------------------
+static MsmBases bases_of(const BaseSet& bs, size_t d, size_t row /* global row of the first point */) {
     MsmBases b;
     b.tables = bs.dev[d];
     b.n_tables = bs.n_tables;
     b.c0 = bs.c0;
-    b.stride = bs.n;
-    b.row0 = row0;
+    b.stride = bs.rows[d];
+    b.row0 = row - bs.lo[d];
     return b;
 }
 
@@ -308,49 +479,93 @@ static int msm_on_device(DeviceCtx& c, const uint64_t* scalars, const MsmBases& 
     return msm_run_host(c, scalars, c.msm_scalars.p, d_bases, n, out_block);
 }
 
-static int msm_host(const uint64_t* scalars, BaseSet& bs, size_t offset, size_t n, uint64_t out_jac[12]) {
+// the devices an MSM over rows [offset, offset + n) runs on: {device, first scalar, scalars}; device == SIZE_MAX: any idle one
+struct Piece { size_t d, lo, n; };
+static std::vector<Piece> split_call(const BaseSet& bs, size_t offset, size_t n) {
     const size_t nd = G.devs.size();
-    if (nd == 1 || n < MULTI_DEVICE_MIN_POINTS) {
+    std::vector<Piece> pieces;
+    if (bs.sharded) {
+        for (size_t d = 0; d < nd; ++d) {
+            const size_t a = offset > bs.lo[d] ? offset : bs.lo[d];
+            const size_t b = offset + n < bs.lo[d] + bs.rows[d] ? offset + n : bs.lo[d] + bs.rows[d];
+            if (a < b) pieces.push_back(Piece{d, a - offset, b - a});
+        }
+    } else if (nd == 1 || n < MULTI_DEVICE_MIN_POINTS) {
+        pieces.push_back(Piece{(size_t)-1, 0, n});
+    } else {
+        for (size_t d = 0; d < nd; ++d) pieces.push_back(Piece{d, n * d / nd, n * (d + 1) / nd - n * d / nd});
+    }
+    return pieces;
+}
+
+static int msm_host(const uint64_t* scalars, const BaseSet& bs, size_t offset, size_t n, uint64_t out_jac[12]) {
+    const std::vector<Piece> pieces = split_call(bs, offset, n);
+    if (pieces.size() == 1) {
+        const Piece& p = pieces[0];
         std::unique_lock<std::mutex> lk;
-        DeviceCtx* c = pick_device(lk);
-        size_t d = 0;
-        for (size_t k = 0; k < nd; ++k) if (G.devs[k].get() == c) d = k;
+        size_t d = p.d;
+        DeviceCtx* c;
+        if (d == (size_t)-1) c = pick_device(lk, &d);
+        else { c = G.devs[d].get(); lk = std::unique_lock<std::mutex>(c->mu); }
         uint64_t block[28];
-        H2B_TRY(msm_on_device(*c, scalars, bases_of(bs, d, offset), n, block));
+        H2B_TRY(msm_on_device(*c, scalars + 4 * p.lo, bases_of(bs, d, offset + p.lo), p.n, block));
         memcpy(out_jac, block, 96);
         return H2B_OK;
     }
-    // point-range sharding: device d owns [lo_d, hi_d); partial sums are folded on device 0
-    std::vector<uint64_t> blocks(28 * nd);
-    std::vector<int> rcs(nd, 0);
-    std::vector<std::string> errs(nd);
+    // point-range sharding: every piece is a complete Pippenger on its device; the partial sums are folded on device 0
+    const size_t np = pieces.size();
+    std::vector<uint64_t> blocks(28 * np);
+    std::vector<int> rcs(np, 0);
+    std::vector<std::string> errs(np);
     std::vector<std::thread> th;
-    for (size_t d = 0; d < nd; ++d) {
-        th.emplace_back([&, d] {
-            size_t lo = n * d / nd, hi = n * (d + 1) / nd;
-            DeviceCtx& c = *G.devs[d];
+    for (size_t i = 0; i < np; ++i) {
+        th.emplace_back([&, i] {
+            const Piece& p = pieces[i];
+            DeviceCtx& c = *G.devs[p.d];
             std::lock_guard<std::mutex> lk(c.mu);
-            rcs[d] = msm_on_device(c, scalars + 4 * lo, bases_of(bs, d, offset + lo), hi - lo, &blocks[28 * d]);
-            if (rcs[d]) errs[d] = get_error();
+            rcs[i] = msm_on_device(c, scalars + 4 * p.lo, bases_of(bs, p.d, offset + p.lo), p.n, &blocks[28 * i]);
+            if (rcs[i]) errs[i] = get_error();
         });
     }
     for (auto& t : th) t.join();
-    for (size_t d = 0; d < nd; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
+    for (size_t i = 0; i < np; ++i) if (rcs[i]) { set_error("device %zu: %s", pieces[i].d, errs[i].c_str()); return rcs[i]; }
     DeviceCtx& c0 = *G.devs[0];
     std::lock_guard<std::mutex> lk(c0.mu);
     H2B_CUDA(cudaSetDevice(c0.device));
-    H2B_TRY(c0.msm_scalars.reserve(224 * nd));
+    H2B_TRY(c0.msm_scalars.reserve(224 * np));
     H2B_TRY(c0.msm_out.reserve(256));
-    H2B_CUDA(cudaMemcpyAsync(c0.msm_scalars.p, blocks.data(), 224 * nd, cudaMemcpyHostToDevice, c0.stream));
-    H2B_TRY(msm_sum_partials_run(c0, c0.msm_scalars.p, (uint32_t)nd, c0.msm_out.p, c0.stream));
+    H2B_CUDA(cudaMemcpyAsync(c0.msm_scalars.p, blocks.data(), 224 * np, cudaMemcpyHostToDevice, c0.stream));
+    H2B_TRY(msm_sum_partials_run(c0, c0.msm_scalars.p, (uint32_t)np, c0.msm_out.p, c0.stream));
     H2B_CUDA(cudaMemcpyAsync(out_jac, c0.msm_out.p, 96, cudaMemcpyDeviceToHost, c0.stream));
     H2B_CUDA(cudaStreamSynchronize(c0.stream));
     return H2B_OK;
 }
 
+// best_multiexp over an array that is NOT resident: points and scalars are uploaded for this call only (verifier MSMs of a few
+// dozen fresh points, odd-length prefixes).  No device allocation in steady state, nothing cached, nothing to go stale.
+static int msm_direct(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]) {
+    std::unique_lock<std::mutex> lk;
+    DeviceCtx* c = pick_device(lk);
+    H2B_CUDA(cudaSetDevice(c->device));
+    H2B_TRY(c->msm_bases.reserve(n * 64 + 64));
+    H2B_TRY(host_upload(*c, c->msm_bases.p, bases, n * 64, c->stream));
+    MsmBases b;
+    b.tables = c->msm_bases.p;
+    b.stride = n;
+    uint64_t block[28];
+    H2B_TRY(msm_on_device(*c, scalars, b, n, block));
+    memcpy(out_jac, block, 96);
+    G.direct_calls++;
+    return H2B_OK;
+}
+
+static void jac_identity(uint64_t out_jac[12]) {
+    memset(out_jac, 0, 96);
+    for (int i = 0; i < 4; ++i) out_jac[4 + i] = (uint64_t)FpParams<FQ>::ONE(2 * i) | ((uint64_t)FpParams<FQ>::ONE(2 * i + 1) << 32);
+}
+
 // ---- batched entry points: independent columns, round-robin over the devices ------------
-// One worker thread per device; worker d takes columns d, d + D, d + 2D, ...  Each column is a complete single-device
-// call (no sharding inside a column), so D columns are in flight at once and the SRS tables of every device are used.
+// One worker thread per device; worker d takes columns d, d + D, d + 2D, ... and hands them to `some_columns` in groups.
 template <class F>
 static int run_round_robin(size_t count, F one_column) {
     const size_t nd = G.devs.size();
@@ -410,8 +625,7 @@ int h2b_init_device(int device) {
 
 void h2b_shutdown(void) {
     std::lock_guard<std::mutex> lk(G.mu);
-    for (auto& bs : G.sets) free_set(*bs);
-    G.sets.clear();
+    G.sets.clear();      // device memory goes when the last holder lets go (now, unless a call is still in flight)
     G.srs_cache.clear();
     for (auto& c : G.devs) {
         cudaSetDevice(c->device);
@@ -421,6 +635,7 @@ void h2b_shutdown(void) {
         stager_release(*c);
         c->msm_scalars.release();
         c->msm_out.release();
+        c->msm_bases.release();
         c->scan_scratch.release();
         evaluate_release(*c);
         c->srs_status.release();
@@ -454,64 +669,87 @@ int h2b_is_emulator(void) {
 int h2b_msm_bn254_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]) {
     H2B_TRY(require_init());
     if (!out_jac || (n && (!scalars || !bases))) { set_error("h2b_msm_bn254_g1: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
-    if (n == 0) {
-        memset(out_jac, 0, 96);
-        for (int i = 0; i < 4; ++i) out_jac[4 + i] = (uint64_t)FpParams<FQ>::ONE(2 * i) | ((uint64_t)FpParams<FQ>::ONE(2 * i + 1) << 32);
-        return H2B_OK;
-    }
-    BaseSet* bs = nullptr;
-    {
+    if (n == 0) { jac_identity(out_jac); return H2B_OK; }
+    // Short arrays (verifier MSMs, openings of a few dozen points) and lengths that are not a whole number of digest blocks
+    // are never cached: both arrays are uploaded for this call.
+    if (!implicit_cache_enabled() || n < implicit_min_points() || n % digest_block() != 0) return msm_direct(scalars, bases, n, out_jac);
+    const size_t nblocks = n / digest_block();
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        SetRef set;
+        bool fresh = false;
+        {
+            std::lock_guard<std::mutex> lk(G.mu);
+            set = implicit_candidate_locked(bases, n);
+            if (!set) { H2B_TRY(implicit_insert_locked(bases, n, &set)); fresh = true; }
+        }
+        if (fresh) return msm_host(scalars, *set, 0, n, out_jac);      // digests were taken from the very bytes that were uploaded
+        // A resident copy passed the spot check.  The MSM runs on it while host threads verify EVERY block of the caller's
+        // array against the digests taken at upload time; the result is only returned if all of them match (best_multiexp is a
+        // pure function: an array mutated in place, or a freed Vec whose address was reused, must not see the old points).
+        std::atomic<int> verdict{-1};
+        std::thread verifier([&] { verdict = digest_blocks(bases, 0, nblocks, nullptr, set->digest.data()) ? 1 : 0; });
+        const int rc = msm_host(scalars, *set, 0, n, out_jac);
+        verifier.join();
+        if (verdict == 1) { if (rc == H2B_OK) G.implicit_hits++; return rc; }
+        G.implicit_stale++;
         std::lock_guard<std::mutex> lk(G.mu);
-        H2B_TRY(implicit_set(bases, n, &bs));
+        if (set->host_ptr == (const void*)bases) drop_locked(set->handle);      // that address holds something else now
+        // (a copy uploaded from another address stays: its own array may well be intact); second attempt: the spot check of the
+        // remaining candidates runs again, and a miss uploads the array
     }
-    return msm_host(scalars, *bs, 0, n, out_jac);
+    return msm_direct(scalars, bases, n, out_jac);      // unreachable in practice: the array changed twice while we looked at it
 }
 
 int h2b_register_bases(const uint64_t* bases, size_t n, uint64_t* handle) {
     H2B_TRY(require_init());
     if (!bases || !handle || n == 0) { set_error("h2b_register_bases: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
     std::lock_guard<std::mutex> lk(G.mu);
-    std::unique_ptr<BaseSet> bs(new BaseSet());
+    SetRef bs;
+    H2B_TRY(create_set(bases, n, false, true, &bs));
     bs->handle = G.next_handle++;
-    bs->host_ptr = nullptr;
     bs->last_use = ++G.use_counter;
-    int rc = upload_set(*bs, bases, n, true);
-    if (rc != H2B_OK) { free_set(*bs); return rc; }
     *handle = bs->handle;
-    G.sets.push_back(std::move(bs));
+    G.sets.push_back(bs);
+    return H2B_OK;
+}
+
+int h2b_register_bases_sharded(const uint64_t* bases, size_t n, uint64_t* handle) {
+    H2B_TRY(require_init());
+    if (!bases || !handle || n == 0) { set_error("h2b_register_bases_sharded: bad argument"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(G.mu);
+    SetRef bs;
+    H2B_TRY(create_set(bases, n, true, true, &bs));
+    bs->handle = G.next_handle++;
+    bs->last_use = ++G.use_counter;
+    *handle = bs->handle;
+    G.sets.push_back(bs);
     return H2B_OK;
 }
 
 int h2b_unregister_bases(uint64_t handle) {
     H2B_TRY(require_init());
     std::lock_guard<std::mutex> lk(G.mu);
-    for (size_t i = 0; i < G.sets.size(); ++i) {
-        if (G.sets[i]->handle == handle) {
-            if (--G.sets[i]->refs > 0) return H2B_OK;
-            free_set(*G.sets[i]);
-            G.sets.erase(G.sets.begin() + i);
-            return H2B_OK;
-        }
-    }
-    set_error("unknown base-set handle %llu", (unsigned long long)handle);
-    return H2B_ERR_BAD_HANDLE;
+    SetRef bs = find_set_locked(handle);
+    if (!bs || bs->implicit) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
+    if (--bs->refs > 0) return H2B_OK;
+    drop_locked(handle);      // calls still running on the set keep it alive until they return
+    return H2B_OK;
+}
+
+static int registered_set(const char* who, uint64_t handle, size_t offset, size_t n, SetRef* out) {
+    SetRef bs = find_set(handle);
+    if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
+    if (offset > bs->n || n > bs->n - offset) { set_error("%s: range [%zu, %zu) exceeds the registered set of %zu points", who, offset, offset + n, bs->n); return H2B_ERR_BAD_ARGUMENT; }
+    *out = bs;
+    return H2B_OK;
 }
 
 int h2b_msm_bn254_g1_registered(const uint64_t* scalars, uint64_t handle, size_t offset, size_t n, uint64_t out_jac[12]) {
     H2B_TRY(require_init());
     if (!out_jac || (n && !scalars)) { set_error("h2b_msm_bn254_g1_registered: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
-    BaseSet* bs = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(G.mu);
-        for (auto& up : G.sets) if (up->handle == handle) bs = up.get();
-    }
-    if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
-    if (offset > bs->n || n > bs->n - offset) { set_error("range [%zu, %zu) exceeds the registered set of %zu points", offset, offset + n, bs->n); return H2B_ERR_BAD_ARGUMENT; }
-    if (n == 0) {
-        memset(out_jac, 0, 96);
-        for (int i = 0; i < 4; ++i) out_jac[4 + i] = (uint64_t)FpParams<FQ>::ONE(2 * i) | ((uint64_t)FpParams<FQ>::ONE(2 * i + 1) << 32);
-        return H2B_OK;
-    }
+    SetRef bs;
+    H2B_TRY(registered_set("h2b_msm_bn254_g1_registered", handle, offset, n, &bs));
+    if (n == 0) { jac_identity(out_jac); return H2B_OK; }
     return msm_host(scalars, *bs, offset, n, out_jac);
 }
 
@@ -530,28 +768,95 @@ int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
     return host_download(*c, a, c->ntt_io.p, bytes, c->stream);
 }
 
+// columns short enough to be latency bound share one kernel sequence per device (msm_run_batch): up to MSM_BATCH_MAX columns
+// and 2^23 scalars per group; longer columns run one by one (they fill the GPU on their own)
+static const size_t BATCH_GROUP_POINTS = (size_t)1 << 23;
+static const size_t BATCH_COLUMN_MAX = (size_t)1 << 21;
+
 int h2b_msm_bn254_g1_batch_registered(const uint64_t* const* scalars, const size_t* lens, size_t count, uint64_t handle, uint64_t* out_jac) {
     H2B_TRY(require_init());
     if (count == 0) return H2B_OK;
     if (!scalars || !lens || !out_jac) { set_error("h2b_msm_bn254_g1_batch_registered: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
-    BaseSet* bs = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(G.mu);
-        for (auto& up : G.sets) if (up->handle == handle) bs = up.get();
-    }
+    SetRef bs = find_set(handle);
     if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
     for (size_t j = 0; j < count; ++j) {
         if (lens[j] > bs->n) { set_error("column %zu: %zu scalars exceed the registered set of %zu points", j, lens[j], bs->n); return H2B_ERR_BAD_ARGUMENT; }
         if (lens[j] && !scalars[j]) { set_error("column %zu: null scalars", j); return H2B_ERR_BAD_ARGUMENT; }
     }
-    return run_round_robin(count, [&](size_t j, size_t d) -> int {
-        DeviceCtx& c = *G.devs[d];
-        std::lock_guard<std::mutex> lk(c.mu);
-        uint64_t block[28];
-        H2B_TRY(msm_on_device(c, scalars[j], bases_of(*bs, d, 0), lens[j], block));
-        memcpy(out_jac + 12 * j, block, 96);
+    if (bs->sharded) {
+        // every column is split by point range over the devices that hold its rows
+        for (size_t j = 0; j < count; ++j) {
+            if (lens[j] == 0) jac_identity(out_jac + 12 * j);
+            else H2B_TRY(msm_host(scalars[j], *bs, 0, lens[j], out_jac + 12 * j));
+        }
         return H2B_OK;
-    });
+    }
+    // groups of columns; group g runs on device g mod D
+    struct Group { std::vector<size_t> cols; };
+    std::vector<Group> groups;
+    static int env_batch = -1;
+    if (env_batch < 0) env_batch = env_int_or("H2B_MSM_BATCH", 1);
+    const size_t nd = G.devs.size();
+    {
+        const size_t group_cols = env_batch ? msm_batch_max() : 1;
+        // spread the columns over the devices first, then batch what lands on one device
+        std::vector<std::vector<size_t>> per_dev(nd);
+        for (size_t j = 0; j < count; ++j) per_dev[j % nd].push_back(j);
+        for (size_t d = 0; d < nd; ++d) {
+            Group cur;
+            size_t pts = 0;
+            for (size_t j : per_dev[d]) {
+                const bool solo = lens[j] > BATCH_COLUMN_MAX;
+                if (!cur.cols.empty() && (solo || cur.cols.size() >= group_cols || pts + lens[j] > BATCH_GROUP_POINTS)) { groups.push_back(cur); cur = Group(); pts = 0; }
+                cur.cols.push_back(j);
+                pts += lens[j];
+                if (solo) { groups.push_back(cur); cur = Group(); pts = 0; }
+            }
+            if (!cur.cols.empty()) groups.push_back(cur);
+        }
+    }
+    // group -> device: the device its columns were dealt to
+    std::vector<std::vector<size_t>> dev_groups(nd);
+    for (size_t g = 0; g < groups.size(); ++g) dev_groups[groups[g].cols[0] % nd].push_back(g);
+    auto run_device = [&](size_t d) -> int {
+        DeviceCtx& c = *G.devs[d];
+        for (size_t g : dev_groups[d]) {
+            const std::vector<size_t>& cols = groups[g].cols;
+            std::lock_guard<std::mutex> lk(c.mu);
+            if (cols.size() == 1) {
+                uint64_t block[28];
+                H2B_TRY(msm_on_device(c, scalars[cols[0]], bases_of(*bs, d, 0), lens[cols[0]], block));
+                memcpy(out_jac + 12 * cols[0], block, 96);
+                continue;
+            }
+            H2B_CUDA(cudaSetDevice(c.device));
+            std::vector<const void*> hp;
+            std::vector<size_t> ln;
+            size_t total = 0;
+            for (size_t j : cols) { hp.push_back(scalars[j]); ln.push_back(lens[j]); total += lens[j]; }
+            H2B_TRY(c.msm_scalars.reserve(total * 32 + 32));
+            std::vector<uint64_t> blocks(28 * cols.size());
+            H2B_TRY(msm_run_host_batch(c, hp.data(), ln.data(), (uint32_t)cols.size(), c.msm_scalars.p, bases_of(*bs, d, 0), blocks.data()));
+            for (size_t i = 0; i < cols.size(); ++i) memcpy(out_jac + 12 * cols[i], &blocks[28 * i], 96);
+        }
+        return H2B_OK;
+    };
+    size_t busy = 0;
+    for (size_t d = 0; d < nd; ++d) busy += dev_groups[d].empty() ? 0 : 1;
+    if (busy <= 1) {
+        for (size_t d = 0; d < nd; ++d) if (!dev_groups[d].empty()) H2B_TRY(run_device(d));
+        return H2B_OK;
+    }
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; ++d) {
+        if (dev_groups[d].empty()) continue;
+        th.emplace_back([&, d] { rcs[d] = run_device(d); if (rcs[d]) errs[d] = get_error(); });
+    }
+    for (auto& t : th) t.join();
+    for (size_t d = 0; d < nd; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
+    return H2B_OK;
 }
 
 int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omega[4], uint32_t log_n) {
@@ -607,15 +912,35 @@ int h2b_msm_bn254_g1_dev_registered(int device, const void* d_scalars, uint64_t 
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
     if (!d_out_block) { set_error("h2b_msm_bn254_g1_dev_registered: null output"); return H2B_ERR_BAD_ARGUMENT; }
-    BaseSet* bs = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(G.mu);
-        for (auto& up : G.sets) if (up->handle == handle) bs = up.get();
+    SetRef bs;      // declared before the device lock: released after it
+    H2B_TRY(registered_set("h2b_msm_bn254_g1_dev_registered", handle, offset, n, &bs));
+    const size_t d = (size_t)device;
+    if (n && (offset < bs->lo[d] || offset + n > bs->lo[d] + bs->rows[d])) {
+        set_error("h2b_msm_bn254_g1_dev_registered: device %d holds rows [%zu, %zu) of this sharded set, not [%zu, %zu)", device, bs->lo[d], bs->lo[d] + bs->rows[d], offset, offset + n);
+        return H2B_ERR_BAD_ARGUMENT;
     }
-    if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
-    if (offset > bs->n || n > bs->n - offset) { set_error("range [%zu, %zu) exceeds the registered set of %zu points", offset, offset + n, bs->n); return H2B_ERR_BAD_ARGUMENT; }
     std::lock_guard<std::mutex> lk(c->mu);
-    return msm_run(*c, d_scalars, bases_of(*bs, (size_t)device, offset), n, d_out_block, true, (cudaStream_t)stream);
+    // asynchronous: the set must stay registered until the caller has synchronised `stream`
+    return msm_run(*c, d_scalars, bases_of(*bs, d, offset), n, d_out_block, true, (cudaStream_t)stream);
+}
+
+int h2b_msm_bn254_g1_dev_batch_registered(int device, const void* const* d_scalars, const size_t* lens, size_t count, uint64_t handle, void* d_out_blocks, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (count == 0) return H2B_OK;
+    if (!d_scalars || !lens || !d_out_blocks) { set_error("h2b_msm_bn254_g1_dev_batch_registered: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    SetRef bs = find_set(handle);
+    if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
+    const size_t d = (size_t)device;
+    size_t n_max = 0;
+    for (size_t j = 0; j < count; ++j) n_max = lens[j] > n_max ? lens[j] : n_max;
+    if (bs->lo[d] != 0 || n_max > bs->rows[d]) { set_error("h2b_msm_bn254_g1_dev_batch_registered: device %d does not hold rows [0, %zu) of the set", device, n_max); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (size_t j0 = 0; j0 < count; j0 += msm_batch_max()) {
+        const size_t m = count - j0 < msm_batch_max() ? count - j0 : msm_batch_max();
+        H2B_TRY(msm_run_batch(*c, d_scalars + j0, lens + j0, (uint32_t)m, bases_of(*bs, d, 0), (char*)d_out_blocks + 224 * j0, (cudaStream_t)stream));
+    }
+    return H2B_OK;
 }
 
 int h2b_set_msm_precomp(int spacing) {
@@ -626,16 +951,22 @@ int h2b_set_msm_precomp(int spacing) {
 
 int h2b_base_set_info(uint64_t handle, uint32_t* n_tables, uint32_t* spacing, uint64_t* device_bytes) {
     H2B_TRY(require_init());
+    SetRef bs = find_set(handle);
+    if (!bs) { set_error("unknown base-set handle %llu", (unsigned long long)handle); return H2B_ERR_BAD_HANDLE; }
+    if (n_tables) *n_tables = bs->n_tables;
+    if (spacing) *spacing = bs->c0;
+    if (device_bytes) { uint64_t m = 0; for (size_t d = 0; d < bs->dev.size(); ++d) m = bs->bytes_on(d) > m ? bs->bytes_on(d) : m; *device_bytes = m; }
+    return H2B_OK;
+}
+
+int h2b_implicit_cache_stats(uint64_t out[6]) {
+    H2B_TRY(require_init());
+    if (!out) { set_error("h2b_implicit_cache_stats: null output"); return H2B_ERR_BAD_ARGUMENT; }
     std::lock_guard<std::mutex> lk(G.mu);
-    for (auto& up : G.sets) {
-        if (up->handle != handle) continue;
-        if (n_tables) *n_tables = up->n_tables;
-        if (spacing) *spacing = up->c0;
-        if (device_bytes) *device_bytes = (uint64_t)up->n_tables * up->n * 64;
-        return H2B_OK;
-    }
-    set_error("unknown base-set handle %llu", (unsigned long long)handle);
-    return H2B_ERR_BAD_HANDLE;
+    uint64_t sets = 0, with_tables = 0;
+    for (auto& sp : G.sets) if (sp->implicit) { ++sets; if (sp->n_tables > 1) ++with_tables; }
+    out[0] = G.implicit_uploads; out[1] = G.implicit_hits; out[2] = G.implicit_stale; out[3] = G.direct_calls; out[4] = sets; out[5] = with_tables;
+    return H2B_OK;
 }
 
 int h2b_msm_fold_partials(int device, const uint64_t* host_blocks, size_t count, uint64_t out_jac[12]) {
@@ -809,24 +1140,24 @@ static int srs_read_vector(const unsigned char* raw, const char* what, size_t n,
         if (!rc && cudaStreamSynchronize(c.stream) != cudaSuccess) { set_error("h2b_srs_read: %s", cudaGetErrorString(cudaGetLastError())); rc = H2B_ERR_CUDA; }
         if (rc || !handle) { cudaFree(d_pts); if (rc) set_error("%s: %s", what, std::string(get_error()).c_str()); return rc; }
     }
-    std::unique_ptr<BaseSet> bs(new BaseSet());
-    bs->handle = G.next_handle++;
-    bs->host_ptr = nullptr;
+    SetRef bs(new BaseSet());
     bs->last_use = ++G.use_counter;
     bs->n = n;
+    layout_rows(n, false, bs->lo, bs->rows);
     bs->dev.assign(G.devs.size(), nullptr);
+    for (size_t d = 0; d < G.devs.size(); ++d) bs->ordinal.push_back(G.devs[d]->device);
     bs->dev[0] = d_pts;
     for (size_t d = 1; d < G.devs.size(); ++d) {        // the other devices take a peer copy of the decoded points
         std::lock_guard<std::mutex> lk(G.devs[d]->mu);
         cudaError_t e = cudaSetDevice(G.devs[d]->device);
         if (e == cudaSuccess) e = cudaMalloc(&bs->dev[d], n * 64 + 64);
         if (e == cudaSuccess) e = cudaMemcpyPeer(bs->dev[d], G.devs[d]->device, d_pts, c.device, n * 64);
-        if (e != cudaSuccess) { set_error("h2b_srs_read: copy of %s to device %zu: %s", what, d, cudaGetErrorString(e)); free_set(*bs); return H2B_ERR_CUDA; }
+        if (e != cudaSuccess) { set_error("h2b_srs_read: copy of %s to device %zu: %s", what, d, cudaGetErrorString(e)); return H2B_ERR_CUDA; }
     }
-    int rc = build_tables(*bs);
-    if (rc != H2B_OK) { free_set(*bs); return rc; }
+    bs = build_tables(bs);
+    bs->handle = G.next_handle++;
     *handle = bs->handle;
-    G.sets.push_back(std::move(bs));
+    G.sets.push_back(bs);
     return H2B_OK;
 }
 
@@ -844,21 +1175,13 @@ static bool srs_cache_enabled() {
     const char* e = getenv("H2B_SRS_CACHE");
     return !(e && e[0] == '0');
 }
-static BaseSet* find_set_locked(uint64_t handle) {
-    for (auto& up : G.sets) if (up->handle == handle) return up.get();
-    return nullptr;
-}
 }  // namespace
 
 // points of a resident set (table 0) -> host
 static int srs_download_points(uint64_t handle, size_t n, uint64_t* out) {
-    void* src = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(G.mu);
-        BaseSet* bs = find_set_locked(handle);
-        if (!bs || bs->n != n) { set_error("h2b_srs_read: cached base set vanished"); return H2B_ERR_BAD_HANDLE; }
-        src = bs->dev[0];
-    }
+    SetRef bs = find_set(handle);
+    if (!bs || bs->n != n || bs->sharded) { set_error("h2b_srs_read: cached base set vanished"); return H2B_ERR_BAD_HANDLE; }
+    const void* src = bs->dev[0];
     DeviceCtx& c = *G.devs[0];
     std::lock_guard<std::mutex> lk(c.mu);
     H2B_CUDA(cudaSetDevice(c.device));
@@ -885,7 +1208,7 @@ int h2b_srs_read(const char* path, int format, uint32_t* k, uint64_t* out_g, uin
             std::lock_guard<std::mutex> lk(G.mu);
             for (const SrsCacheEntry& e : G.srs_cache) {
                 if (e.path != path || e.format != format || e.size != (long long)sb.st_size || e.mtime_ns != mtime_ns) continue;
-                BaseSet *a = find_set_locked(e.handle_g), *b = find_set_locked(e.handle_g_lagrange);
+                SetRef a = find_set_locked(e.handle_g), b = find_set_locked(e.handle_g_lagrange);
                 if (!a || !b) continue;
                 if (handle_g) ++a->refs;
                 if (handle_g_lagrange) ++b->refs;
@@ -940,7 +1263,7 @@ int h2b_srs_read(const char* path, int format, uint32_t* k, uint64_t* out_g, uin
         e.handle_g = hg; e.handle_g_lagrange = hl;
         e.g2.assign(bytes + 4 + 2 * n * ps, bytes + 4 + 2 * n * ps + g2_want);
         // the cache's own reference is the one srs_read_vector created; each caller that took a handle adds one
-        BaseSet *a = find_set_locked(hg), *b = find_set_locked(hl);
+        SetRef a = find_set_locked(hg), b = find_set_locked(hl);
         if (a && handle_g) ++a->refs;
         if (b && handle_g_lagrange) ++b->refs;
         // a stale entry for the same path (file rewritten) gives its sets back
@@ -948,7 +1271,7 @@ int h2b_srs_read(const char* path, int format, uint32_t* k, uint64_t* out_g, uin
             if (G.srs_cache[i].path == e.path && G.srs_cache[i].format == e.format) {
                 for (uint64_t h : {G.srs_cache[i].handle_g, G.srs_cache[i].handle_g_lagrange}) {
                     for (size_t j = 0; j < G.sets.size(); ++j)
-                        if (G.sets[j]->handle == h && --G.sets[j]->refs <= 0) { free_set(*G.sets[j]); G.sets.erase(G.sets.begin() + j); break; }
+                        if (G.sets[j]->handle == h && --G.sets[j]->refs <= 0) { G.sets.erase(G.sets.begin() + j); break; }
                 }
                 G.srs_cache.erase(G.srs_cache.begin() + i);
             } else ++i;
@@ -1122,6 +1445,14 @@ int h2b_gen_scalars_dev(int device, uint64_t seed, size_t n, int kind, void* d_o
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
     return gen_scalars_run(*c, seed, n, kind, d_out, (cudaStream_t)stream);
+}
+
+int h2b_msm_checksum_dev(int device, const void* d_scalars, uint64_t seed, uint64_t first, size_t n, void* d_out, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!d_out || (n && !d_scalars)) { set_error("h2b_msm_checksum_dev: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return msm_checksum_run(*c, d_scalars, seed, first, n, d_out, (cudaStream_t)stream);
 }
 
 static int elementwise_host(int which, int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out, size_t elem_bytes) {

@@ -95,6 +95,7 @@ struct DeviceCtx {
     DevBuf ntt_io;                     // staging for the host-pointer NTT entry point
     DevBuf msm_scalars;                // staging for host-pointer MSM scalars
     DevBuf msm_out;                    // 96-byte result
+    DevBuf msm_bases;                  // points of an uncached host-pointer MSM (small / odd-length calls: uploaded per call)
     DevBuf scan_scratch;               // batch inversion / prefix product scratch (scan.cu)
     DevBuf srs_status, srs_io;         // first-invalid-point flag and encoded-bytes staging of the SRS reader (srs.cu)
     DevBuf lookup_scratch;             // sorted keys, flags and ranks of permute_expression_pair (lookup.cu)
@@ -158,6 +159,9 @@ struct MsmBases {
 };
 int msm_run(DeviceCtx& ctx, const void* d_scalars, const MsmBases& bases, size_t n, void* d_out, bool with_xyzz, cudaStream_t stream);
 int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const MsmBases& bases, size_t n, void* h_out_block);
+int msm_run_batch(DeviceCtx& ctx, const void* const* d_cols, const size_t* lens, uint32_t count, const MsmBases& bases, void* d_out_blocks, cudaStream_t stream);
+int msm_run_host_batch(DeviceCtx& ctx, const void* const* h_cols, const size_t* lens, uint32_t count, void* d_staging, const MsmBases& bases, void* h_out_blocks);
+uint32_t msm_batch_max();
 int msm_precompute_run(DeviceCtx& ctx, const void* d_src, void* d_dst, size_t n, uint32_t c0, cudaStream_t stream);
 uint32_t msm_pick_table_spacing(size_t n, uint32_t max_tables);
 uint32_t msm_tables_for(uint32_t c0);
@@ -166,6 +170,7 @@ void msm_release(DeviceCtx& ctx);
 int msm_set_window(int c);   // 0 = automatic
 // ---- testgen.cu ----
 int gen_points_run(DeviceCtx& ctx, uint64_t seed, size_t n, void* d_out_affine, cudaStream_t stream);
+int msm_checksum_run(DeviceCtx& ctx, const void* d_scalars, uint64_t seed, uint64_t first, size_t n, void* d_out, cudaStream_t stream);
 int gen_scalars_run(DeviceCtx& ctx, uint64_t seed, size_t n, int kind, void* d_out, cudaStream_t stream);
 int field_selftest_run(DeviceCtx& ctx, int field, int op, const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t stream);
 int ec_selftest_run(DeviceCtx& ctx, int op, const void* d_p, const void* d_q, size_t n, void* d_out, cudaStream_t stream);

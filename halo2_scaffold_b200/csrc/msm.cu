@@ -52,6 +52,17 @@ struct MsmPlan {
     uint32_t add_into;   // 1: chunked MSM -- each chunk's bucket sums are merged into running accumulators
     uint32_t top_bins;   // > 0: the top window only has this many digit values (few scalar bits left): its histogram and
                          //      cursor atomics are aggregated per CTA in shared memory instead of hammering 2-4 counters
+    uint32_t ncols;      // batched MSM: independent scalar columns over the same points (blockIdx.y of the sort kernels); column j owns
+                         //      bucket sets [j * m, (j + 1) * m), so B = ncols * m * Nb and everything after the sort is unchanged
+};
+
+// scalar columns of a batched MSM (one sort / accumulate / reduce sequence for all of them): the columns a proof phase commits
+// are independent MSMs over the same SRS vector ([UP] plonk/prover.rs commits advice / lookup / permutation columns one by one);
+// at k <= 20 a single column is latency bound (bucket reduction depth), a batch shares every dependent step
+static const uint32_t MSM_BATCH_MAX = 32;
+struct MsmCols {
+    const uint4* scalars[MSM_BATCH_MAX];
+    uint32_t len[MSM_BATCH_MAX];
 };
 
 static const uint32_t TOP_BINS_MAX = 1026;      // top windows of up to 10 bits (+ carry) are aggregated
@@ -82,9 +93,14 @@ __device__ __forceinline__ uint32_t limb_bits(const Fr& s, uint32_t bit, uint32_
 
 // ---- 1. decompose + histogram ------------------------------------------------------------------
 // (grid-stride over blocks of 256 scalars so that the per-CTA aggregation of a narrow top window is flushed rarely)
-__global__ void __launch_bounds__(256) msm_decompose_kernel(const uint4* __restrict__ scalars, MsmPlan pl,
+__global__ void __launch_bounds__(256) msm_decompose_kernel(MsmCols cols, MsmPlan pl,
                                                           uint32_t* __restrict__ digits, uint32_t* __restrict__ counts) {
     __shared__ uint32_t top_hist[TOP_BINS_MAX];
+    const uint32_t col = blockIdx.y;
+    const uint4* __restrict__ scalars = cols.scalars[col];
+    const uint32_t col_len = cols.len[col];
+    counts += (size_t)col * pl.m * pl.Nb;
+    digits += (size_t)col * pl.W * pl.n;
     const uint32_t top_set = (pl.W - 1) % pl.m;
     if (pl.top_bins) {
         for (uint32_t b = threadIdx.x; b < pl.top_bins; b += blockDim.x) top_hist[b] = 0;
@@ -95,7 +111,7 @@ __global__ void __launch_bounds__(256) msm_decompose_kernel(const uint4* __restr
     const uint32_t rounds = (pl.n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t round = 0; round < rounds; ++round) {
         const uint32_t i = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        const bool live = i < pl.n;
+        const bool live = i < col_len;
         Fr s = fp_zero<FR>();
         uint32_t neg = 0;
         if (live) {
@@ -211,14 +227,18 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const uint32_t* __restr
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) out[count] = block_sums[gridDim.x];
 }
 
-__global__ void __launch_bounds__(256) msm_scatter_kernel(MsmPlan pl, const uint32_t* __restrict__ digits, uint32_t* __restrict__ cursor,
+__global__ void __launch_bounds__(256) msm_scatter_kernel(MsmCols cols, MsmPlan pl, const uint32_t* __restrict__ digits, uint32_t* __restrict__ cursor,
                                                         uint32_t* __restrict__ sorted) {
     __shared__ uint32_t top_cnt[TOP_BINS_MAX];      // per-round count, then the round's base position, of each top-window digit
+    const uint32_t col = blockIdx.y;
+    const uint32_t col_len = cols.len[col];
+    cursor += (size_t)col * pl.m * pl.Nb;
+    digits += (size_t)col * pl.W * pl.n;
     const uint32_t top_set = (pl.W - 1) % pl.m;
     const uint32_t rounds = (pl.n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t round = 0; round < rounds; ++round) {
         const uint32_t i = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        const bool live = i < pl.n;
+        const bool live = i < col_len;
         uint32_t set = 0, row = pl.row0 + i;
         const uint32_t lower = pl.top_bins ? pl.W - 1 : pl.W;
         {   // window 0: one cursor update per warp and bucket (see msm_decompose_kernel)
@@ -599,9 +619,12 @@ __global__ void __launch_bounds__(512) msm_reduce_tail_kernel(const uint4* __res
     if (tid == 0) xyzz_store(out + 8 * (size_t)w, x);
 }
 
-// Horner over the set sums (S[w] = Dfinal[w], weight 2^(c*w)) and conversion to a Jacobian triple
+// Horner over the set sums (S[w] = Dfinal[w], weight 2^(c*w)) and conversion to a Jacobian triple; one block per column of a
+// batched MSM (sets [col * W, (col + 1) * W), result block col)
 __global__ void msm_final_kernel(const uint4* __restrict__ S, uint32_t W, uint32_t c, uint4* __restrict__ out_jac, uint32_t accumulate) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (threadIdx.x != 0) return;
+    S += 8 * (size_t)blockIdx.x * W;
+    out_jac += 14 * (size_t)blockIdx.x;
     XYZZ acc = xyzz_load(S + 8 * (size_t)(W - 1));
     for (uint32_t w = W - 1; w-- > 0;) {
         for (uint32_t k = 0; k < c; ++k) acc = xyzz_double(acc);
@@ -678,6 +701,7 @@ struct MsmScratch {
     cudaEvent_t ev_start = nullptr, ev_sorted[2] = {nullptr, nullptr}, ev_accumulated[2] = {nullptr, nullptr};
     DevBuf digits, counts, offsets, offsets2, cursor, block_sums, sorted, sorted2, ctrl, split_list, heavy, chunk_desc, chunk_out, bucket_acc, bucket_tmp, head_partial, redA, redB, redC, redD, result;
     DevBuf pair_pts, pair_counts, pair_offsets[3], pair_sorted[3];      // pair pre-reduction (batched affine additions)
+    DevBuf batch_out;                                                   // result blocks of a batched host-pointer call
 };
 
 static int g_forced_c = 0;
@@ -766,7 +790,7 @@ static int exclusive_scan(MsmScratch& s, const uint32_t* in, uint32_t count, uin
 }
 
 // ---- an MSM = plan + one or more chunks of scalars accumulated into the same buckets + one bucket reduction ----
-static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t n_total, bool chunked, cudaStream_t stream, MsmPlan& pl) {
+static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t n_total, bool chunked, cudaStream_t stream, MsmPlan& pl, uint32_t ncols = 1) {
     (void)ctx;
     const bool tables = bases.n_tables > 1;
     memset(&pl, 0, sizeof(pl));
@@ -774,7 +798,9 @@ static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t
     pl.W = windows_for(pl.c);
     pl.m = tables ? bases.c0 / pl.c : pl.W;
     pl.Nb = 1u << (pl.c - 1);
-    pl.B = pl.m * pl.Nb;
+    pl.ncols = ncols;
+    if ((uint64_t)ncols * pl.m * pl.Nb >= 0x40000000ull) { set_error("msm: %u columns x %u sets x 2^%u buckets exceed the bucket index", ncols, pl.m, pl.c - 1); return H2B_ERR_BAD_ARGUMENT; }
+    pl.B = ncols * pl.m * pl.Nb;
     pl.stride = tables ? (uint32_t)bases.stride : 0u;
     pl.add_into = chunked ? 1u : 0u;
     {   // scalar bits left for the top window (the recoded scalar is < 2^253) -> number of digit values it can take
@@ -809,8 +835,8 @@ static void chunk_points(const MsmBases& bases, size_t done, const void** tables
 static int msm_size_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan& pl, size_t row0, uint32_t n, int b) {
     pl.n = n;
     pl.row0 = (uint32_t)row0;
-    const uint64_t upper = (uint64_t)n * pl.W;          // sorted entries, at most
-    if (upper >= 0xffffffffull) { set_error("msm: %u points x %u windows exceed the 32-bit sort index", n, pl.W); return H2B_ERR_BAD_ARGUMENT; }
+    const uint64_t upper = (uint64_t)n * pl.W * pl.ncols;          // sorted entries, at most
+    if (upper >= 0xffffffffull) { set_error("msm: %u columns x %u points x %u windows exceed the 32-bit sort index", pl.ncols, n, pl.W); return H2B_ERR_BAD_ARGUMENT; }
     // slices: about 256 entries each once the GPU is full; below one full wave they shrink down to SLICE_MIN entries
     // (a small MSM is latency bound, and a slice is a serial chain of mixed additions)
     const uint64_t resident = (uint64_t)ctx.sm_count * 512;
@@ -833,7 +859,7 @@ static int msm_size_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan& pl, size_t row
 }
 
 // stage 1 of a chunk: digits, histogram, scan, counting-sort scatter -> offsets[b], sorted[b]
-static int msm_sort_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, const void* d_scalars, int b, cudaStream_t stream) {
+static int msm_sort_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, const MsmCols& cols, int b, cudaStream_t stream) {
     uint32_t* counts = (uint32_t*)s.counts.p;
     uint32_t* offsets = (uint32_t*)(b ? s.offsets2 : s.offsets).p;
     uint32_t* cursor = (uint32_t*)s.cursor.p;
@@ -843,11 +869,11 @@ static int msm_sort_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, cons
     // grid-stride only when a narrow top window is aggregated per CTA (fewer, longer-lived CTAs flush less often)
     const uint32_t sort_grid = (pl.top_bins && nblk > (uint32_t)ctx.sm_count * 32) ? (uint32_t)ctx.sm_count * 32 : nblk;
     ctx.prof.mark(PROF_BEGIN, stream);
-    H2B_LAUNCH(msm_decompose_kernel, sort_grid, 256, 0, stream, (const uint4*)d_scalars, pl, (uint32_t*)s.digits.p, counts);
+    H2B_LAUNCH(msm_decompose_kernel, dim3(sort_grid, pl.ncols), 256, 0, stream, cols, pl, (uint32_t*)s.digits.p, counts);
     ctx.prof.mark(PROF_MSM_DECOMPOSE, stream);
     H2B_TRY(exclusive_scan(s, counts, pl.B, offsets, cursor, stream));
     ctx.prof.mark(PROF_MSM_SCAN, stream);
-    H2B_LAUNCH(msm_scatter_kernel, sort_grid, 256, 0, stream, pl, (const uint32_t*)s.digits.p, cursor, sorted);
+    H2B_LAUNCH(msm_scatter_kernel, dim3(sort_grid, pl.ncols), 256, 0, stream, cols, pl, (const uint32_t*)s.digits.p, cursor, sorted);
     H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_SCATTER, stream);
     return H2B_OK;
@@ -867,7 +893,7 @@ static int msm_accumulate_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl
     // of HBM (~18 G gathers/s; more resident warps, software prefetch and 64-byte fetch hints change nothing), where the XYZZ
     // accumulation hides ONE gather behind ten multiplications.  41.5 ms without, 48.0 / 48.8 / 50.1 ms with 1 / 2 / 3 levels.
     // H2B_MSM_PAIR_LEVELS=1..3 turns it on (tests run it on the emulator).  Entries must leave bit 30 free for PAIR_BIT.
-    const uint64_t upper = (uint64_t)pl.n * pl.W;
+    const uint64_t upper = (uint64_t)pl.n * pl.W * pl.ncols;
     uint32_t levels = 0;
     {
         static int env_levels = -2;
@@ -967,7 +993,11 @@ static int msm_run_chunks(DeviceCtx& ctx, MsmScratch& s, MsmPlan pl, const void*
         if (before_chunk) H2B_TRY((*before_chunk)(j));          // e.g. the staged upload of this chunk's scalars onto `stream`
         if (uploaded) H2B_CUDA(cudaStreamWaitEvent(ss, uploaded[j], 0));
         if (overlap && j >= 2) H2B_CUDA(cudaStreamWaitEvent(ss, s.ev_accumulated[b], 0));      // buffers b are free again
-        H2B_TRY(msm_sort_chunk(ctx, s, pl, (const char*)d_scalars + done * 32, b, ss));
+        MsmCols cols;
+        memset(&cols, 0, sizeof(cols));
+        cols.scalars[0] = (const uint4*)((const char*)d_scalars + done * 32);
+        cols.len[0] = (uint32_t)m;
+        H2B_TRY(msm_sort_chunk(ctx, s, pl, cols, b, ss));
         if (overlap) {
             H2B_CUDA(cudaEventRecord(s.ev_sorted[b], ss));
             H2B_CUDA(cudaStreamWaitEvent(stream, s.ev_sorted[b], 0));
@@ -984,15 +1014,16 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
     // 4 below that (each level is then a serial chain of 2m additions, and latency is all that matters)
     static int env_logm = -1;
     if (env_logm < 0) env_logm = env_int("H2B_MSM_REDUCE_LOGM", 0);
-    uint32_t logm = (uint64_t)pl.m * pl.Nb >= (1u << 21) ? 4u : 2u;
+    const uint32_t sets = pl.ncols * pl.m;      // bucket sets in flight (batched MSM: m per column)
+    uint32_t logm = (uint64_t)sets * pl.Nb >= (1u << 21) ? 4u : 2u;
     if (env_logm >= 1 && env_logm <= 6) logm = (uint32_t)env_logm;
     uint32_t N = pl.Nb;
     uint32_t J0 = (N + (1u << logm) - 1) >> logm;
     if (J0 < 1) J0 = 1;
-    H2B_TRY(s.redA.reserve((size_t)pl.m * J0 * 128));
-    H2B_TRY(s.redB.reserve((size_t)pl.m * J0 * 128));
-    H2B_TRY(s.redC.reserve((size_t)pl.m * J0 * 128));
-    H2B_TRY(s.redD.reserve((size_t)pl.m * J0 * 128));
+    H2B_TRY(s.redA.reserve((size_t)sets * J0 * 128));
+    H2B_TRY(s.redB.reserve((size_t)sets * J0 * 128));
+    H2B_TRY(s.redC.reserve((size_t)sets * J0 * 128));
+    H2B_TRY(s.redD.reserve((size_t)sets * J0 * 128));
     ctx.prof.mark(PROF_BEGIN, stream);
     const uint4* Bin = (const uint4*)s.bucket_acc.p;
     const uint4* Din = nullptr;
@@ -1003,14 +1034,14 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
     int pp = 0;
     while (N > REDUCE_TAIL_MAX) {
         uint32_t J = (N + (1u << logm) - 1) >> logm;
-        uint32_t threads = pl.m * J;
-        H2B_LAUNCH(msm_reduce_level_kernel, (threads + 127) / 128, 128, 0, stream, Bin, Din, offs, N, logm, pl.m, Bping[pp], Dping[pp]);
+        uint32_t threads = sets * J;
+        H2B_LAUNCH(msm_reduce_level_kernel, (threads + 127) / 128, 128, 0, stream, Bin, Din, offs, N, logm, sets, Bping[pp], Dping[pp]);
         Bin = Bping[pp];
         Din = Dping[pp];
         offs = nullptr;
         pp ^= 1;
         N = J;
-        if (env_logm < 1 && (uint64_t)pl.m * N < (1u << 21)) logm = 2;
+        if (env_logm < 1 && (uint64_t)sets * N < (1u << 21)) logm = 2;
     }
     {
         if (!ctx.msm_attr_set) {      // a per-device function attribute
@@ -1019,11 +1050,11 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
         }
         uint32_t tthreads = 32;
         while (tthreads < N) tthreads <<= 1;
-        H2B_LAUNCH(msm_reduce_tail_kernel, pl.m, tthreads, (size_t)tthreads * 128, stream, Bin, Din, offs, N, Dping[pp]);
+        H2B_LAUNCH(msm_reduce_tail_kernel, sets, tthreads, (size_t)tthreads * 128, stream, Bin, Din, offs, N, Dping[pp]);
         Din = Dping[pp];
     }
     ctx.prof.mark(PROF_MSM_REDUCE, stream);
-    H2B_LAUNCH(msm_final_kernel, 1, 32, 0, stream, Din, pl.m, pl.c, (uint4*)d_result, accumulate ? 1u : 0u);
+    H2B_LAUNCH(msm_final_kernel, pl.ncols, 32, 0, stream, Din, pl.m, pl.c, (uint4*)d_result, accumulate ? 1u : 0u);
     H2B_CUDA(cudaGetLastError());
     ctx.prof.mark(PROF_MSM_FINAL, stream);
     return H2B_OK;
@@ -1146,6 +1177,72 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
     return H2B_OK;
 }
 
+// ---- batched MSM: `count` independent scalar columns over the same points, one kernel sequence ----------------------------
+// d_cols[j]: lens[j] scalars on the device; every column uses rows [row0, row0 + lens[j]) of the point set.  d_out_blocks:
+// count x 224 bytes (Jacobian | XYZZ per column).  The window is chosen for the longest column.
+int msm_run_batch(DeviceCtx& ctx, const void* const* d_cols, const size_t* lens, uint32_t count, const MsmBases& bases, void* d_out_blocks, cudaStream_t stream) {
+    if (count == 0) return H2B_OK;
+    if (count > MSM_BATCH_MAX) { set_error("msm batch: at most %u columns per call", MSM_BATCH_MAX); return H2B_ERR_BAD_ARGUMENT; }
+    if (!ctx.msm) ctx.msm = new MsmScratch();
+    MsmScratch& s = *ctx.msm;
+    size_t n_max = 0;
+    for (uint32_t j = 0; j < count; ++j) n_max = lens[j] > n_max ? lens[j] : n_max;
+    H2B_TRY(s.result.reserve((size_t)MSM_BATCH_MAX * 224));
+    if (n_max == 0) {
+        uint32_t host[56];
+        memset(host, 0, sizeof(host));
+        for (int i = 0; i < 8; ++i) host[8 + i] = FpParams<FQ>::ONE(i);
+        for (uint32_t j = 0; j < count; ++j) H2B_CUDA(cudaMemcpyAsync((char*)d_out_blocks + 224 * (size_t)j, host, 224, cudaMemcpyHostToDevice, stream));
+        H2B_CUDA(cudaStreamSynchronize(stream));
+        return H2B_OK;
+    }
+    MsmCols cols;
+    memset(&cols, 0, sizeof(cols));
+    for (uint32_t j = 0; j < count; ++j) {
+        if (lens[j] && !d_cols[j]) { set_error("msm batch: column %u is null", j); return H2B_ERR_BAD_ARGUMENT; }
+        cols.scalars[j] = (const uint4*)d_cols[j];
+        cols.len[j] = (uint32_t)lens[j];
+    }
+    H2B_TRY(msm_check_args(d_cols, bases, n_max, d_out_blocks));
+    if (n_max > ((size_t)1 << 26)) { set_error("msm batch: columns of at most 2^26 scalars"); return H2B_ERR_BAD_ARGUMENT; }
+    MsmPlan pl;
+    H2B_TRY(msm_plan(ctx, s, bases, n_max, false, stream, pl, count));
+    const void* tables;
+    size_t row0;
+    chunk_points(bases, 0, &tables, &row0);
+    H2B_TRY(msm_size_chunk(ctx, s, pl, row0, (uint32_t)n_max, 0));
+    H2B_TRY(msm_sort_chunk(ctx, s, pl, cols, 0, stream));
+    H2B_TRY(msm_accumulate_chunk(ctx, s, pl, tables, 0, stream));
+    H2B_TRY(msm_finish(ctx, s, pl, s.result.p, false, stream));
+    H2B_CUDA(cudaMemcpyAsync(d_out_blocks, s.result.p, 224 * (size_t)count, cudaMemcpyDeviceToDevice, stream));
+    return H2B_OK;
+}
+
+// the same with the columns in host memory: uploads into d_staging (count x n_max x 32 bytes at least), synchronous,
+// h_out_blocks: count x 224 bytes
+int msm_run_host_batch(DeviceCtx& ctx, const void* const* h_cols, const size_t* lens, uint32_t count, void* d_staging, const MsmBases& bases, void* h_out_blocks) {
+    if (count == 0) return H2B_OK;
+    if (count > MSM_BATCH_MAX) { set_error("msm batch: at most %u columns per call", MSM_BATCH_MAX); return H2B_ERR_BAD_ARGUMENT; }
+    cudaStream_t stream = ctx.stream;
+    const void* d_cols[MSM_BATCH_MAX];
+    size_t off = 0;
+    for (uint32_t j = 0; j < count; ++j) {
+        d_cols[j] = (char*)d_staging + off;
+        if (lens[j]) {
+            if (!h_cols[j]) { set_error("msm batch: column %u is null", j); return H2B_ERR_BAD_ARGUMENT; }
+            H2B_TRY(host_upload(ctx, (char*)d_staging + off, h_cols[j], lens[j] * 32, stream, j == 0));
+        }
+        off += lens[j] * 32;
+    }
+    if (!ctx.msm) ctx.msm = new MsmScratch();
+    H2B_TRY(ctx.msm->batch_out.reserve((size_t)MSM_BATCH_MAX * 224));
+    H2B_TRY(msm_run_batch(ctx, d_cols, lens, count, bases, ctx.msm->batch_out.p, stream));
+    H2B_CUDA(cudaMemcpyAsync(h_out_blocks, ctx.msm->batch_out.p, 224 * (size_t)count, cudaMemcpyDeviceToHost, stream));
+    H2B_CUDA(cudaStreamSynchronize(stream));
+    return H2B_OK;
+}
+uint32_t msm_batch_max() { return MSM_BATCH_MAX; }
+
 // sum of `count` partial results (224-byte blocks: Jacobian | XYZZ) -> Jacobian.  Used to fold the per-device
 // partial sums of a point-range-sharded MSM.
 __global__ void msm_sum_partials_kernel(const uint4* __restrict__ blocks, uint32_t count, uint4* __restrict__ out_jac) {
@@ -1178,7 +1275,7 @@ void msm_release(DeviceCtx& ctx) {
     }
     DevBuf* all[] = {&s.digits, &s.counts, &s.offsets, &s.offsets2, &s.sorted2, &s.cursor, &s.block_sums, &s.sorted, &s.ctrl, &s.split_list, &s.heavy, &s.chunk_desc, &s.chunk_out,
                      &s.bucket_acc, &s.bucket_tmp, &s.head_partial, &s.redA, &s.redB, &s.redC, &s.redD, &s.result, &s.pair_pts, &s.pair_counts,
-                     &s.pair_offsets[0], &s.pair_offsets[1], &s.pair_offsets[2], &s.pair_sorted[0], &s.pair_sorted[1], &s.pair_sorted[2]};
+                     &s.pair_offsets[0], &s.pair_offsets[1], &s.pair_offsets[2], &s.pair_sorted[0], &s.pair_sorted[1], &s.pair_sorted[2], &s.batch_out};
     for (DevBuf* b : all) b->release();
     delete ctx.msm;
     ctx.msm = nullptr;

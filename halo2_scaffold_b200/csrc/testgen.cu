@@ -110,6 +110,58 @@ int gen_scalars_run(DeviceCtx& ctx, uint64_t seed, size_t n, int kind, void* d_o
     return H2B_OK;
 }
 
+// ---- O(n) checksum of an MSM over the synthetic points ----------------------------------------------------------------
+// For P_i = [z_i] G (gen_points, stream `seed`):  sum_i s_i P_i = [ sum_i s_i z_i mod r ] G.  The dot product is field
+// arithmetic only -- no group law, no buckets, no sorting -- so it checks a timed 2^24 .. 2^27-point MSM result against
+// something that shares no code with the MSM (bench.py `verified`, tests at the full benchmark sizes).
+__global__ void __launch_bounds__(256) checksum_partial_kernel(const uint4* __restrict__ scalars, uint64_t seed, uint64_t first, uint64_t n,
+                                                             uint4* __restrict__ partial) {
+    __shared__ uint4 sh[256 * 2];
+    Fr acc = fp_zero<FR>();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t z = splitmix64_at(seed, first + i);
+        Fr zf = fp_zero<FR>();
+        zf.l[0] = (uint32_t)z;
+        zf.l[1] = (uint32_t)(z >> 32);
+        // s is held in Montgomery form (s R) and z is canonical: their Montgomery product (s R) z / R = s z is canonical
+        acc = fp_add(acc, fp_mul(fp_load<FR>(scalars + 2 * i), zf));
+    }
+    fp_store<FR>(sh + 2 * threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            acc = fp_add(acc, fp_load<FR>(sh + 2 * (threadIdx.x + d)));
+            fp_store<FR>(sh + 2 * threadIdx.x, acc);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fp_store<FR>(partial + 2 * (size_t)blockIdx.x, acc);
+}
+__global__ void __launch_bounds__(256) checksum_final_kernel(const uint4* __restrict__ partial, uint32_t count, uint4* __restrict__ out) {
+    __shared__ uint4 sh[256 * 2];
+    Fr acc = fp_zero<FR>();
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc = fp_add(acc, fp_load<FR>(partial + 2 * (size_t)i));
+    fp_store<FR>(sh + 2 * threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if (threadIdx.x < d) {
+            acc = fp_add(acc, fp_load<FR>(sh + 2 * (threadIdx.x + d)));
+            fp_store<FR>(sh + 2 * threadIdx.x, acc);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fp_store<FR>(out, acc);
+}
+// d_out: one Fr (32 B), CANONICAL (not Montgomery) value of sum_i s_i z_i mod r, i over [0, n), z from stream `seed` at first + i
+int msm_checksum_run(DeviceCtx& ctx, const void* d_scalars, uint64_t seed, uint64_t first, size_t n, void* d_out, cudaStream_t stream) {
+    const uint32_t blocks = (uint32_t)ctx.sm_count * 8;
+    H2B_TRY(ctx.scan_scratch.reserve((size_t)blocks * 32));
+    H2B_LAUNCH(checksum_partial_kernel, blocks, 256, 0, stream, (const uint4*)d_scalars, seed, first, (uint64_t)n, (uint4*)ctx.scan_scratch.p);
+    H2B_LAUNCH(checksum_final_kernel, 1, 256, 0, stream, (const uint4*)ctx.scan_scratch.p, blocks, (uint4*)d_out);
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
 // ---- arithmetic self-tests -------------------------------------------------------------------------------
 // op: 0 add, 1 sub, 2 mul, 3 sqr(a), 4 inv(a), 5 from_mont(a), 6 to_mont(a)
 template <int F>

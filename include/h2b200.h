@@ -65,10 +65,18 @@ int h2b_is_emulator(void);
 
 /* ---- drop-in entry points (host pointers, synchronous) ------------------------------------------- */
 /* best_multiexp(coeffs, bases): out_jac = sum_i scalars[i] * bases[i].  n may be any value >= 0
- * (n == 0 gives the identity).  The bases array is uploaded once and cached on the device(s),
- * keyed by (pointer, sampled contents), because the only base arrays of the prover are the SRS
- * vectors `g` and `g_lagrange`.  With more than one device the point range is
- * split across devices and the partial sums are added on device 0. */
+ * (n == 0 gives the identity).  A pure function of its arguments, like upstream's:
+ *  - arrays of fewer than 4096 points, or whose length is not a multiple of 1024 points (verifier MSMs,
+ *    odd prefixes), are uploaded for the call and never cached;
+ *  - longer arrays -- in a prover only the SRS vectors `g` and `g_lagrange` -- are kept
+ *    resident (window tables from the second use on) and found again by CONTENT: a 128-bit digest of
+ *    every 64 KiB block is taken at upload time, and a resident copy is used for a call only if every block
+ *    of the caller's array still matches (host threads verify while the GPU runs the MSM; a mismatch discards
+ *    the result, re-uploads and recomputes).  In-place edits and address reuse can therefore not return stale
+ *    results, and the same vector re-loaded at another address (src/scaffold.rs:174) is recognised.
+ * With more than one device the resident copy is sharded by point range (device d holds rows
+ * [d n/D, (d+1) n/D)), every device runs a complete Pippenger on its slice and the partial sums are
+ * added on device 0.  H2B_IMPLICIT_CACHE=0 disables the cache. */
 int h2b_msm_bn254_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]);
 
 /* best_fft(a, omega, log_n) for G = Fr: in place, natural order in and out, no scaling;
@@ -81,6 +89,12 @@ int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n);
  * single shared bucket set.  ParamsKZG's `g` and `g_lagrange` ([UP] halo2_proofs/src/poly/kzg/commitment.rs) are
  * the two vectors a prover registers.  Implicitly cached arrays (h2b_msm_bn254_g1) get their tables on second use. */
 int h2b_register_bases(const uint64_t* bases, size_t n, uint64_t* handle);
+/* The same with the rows split over the devices of h2b_init: device d keeps rows [d n/D, (d+1) n/D) and their tables
+ * (1/D of the memory and of the registration time; table spacing chosen for n/D points).  MSMs over such a set are split
+ * by point range over the devices that hold the rows; with one device it equals
+ * h2b_register_bases. */
+int h2b_register_bases_sharded(const uint64_t* bases, size_t n, uint64_t* handle);
+/* Drops one reference; calls still running on the set finish on it (device memory is released afterwards). */
 int h2b_unregister_bases(uint64_t handle);
 /* MSM over bases[offset .. offset+n) of a registered set. */
 int h2b_msm_bn254_g1_registered(const uint64_t* scalars, uint64_t handle, size_t offset, size_t n, uint64_t out_jac[12]);
@@ -91,6 +105,9 @@ int h2b_msm_bn254_g1_registered(const uint64_t* scalars, uint64_t handle, size_t
  * once, each on a device that holds its own copy of the SRS tables.  Results are identical to `count` single calls. */
 int h2b_msm_bn254_g1_batch_registered(const uint64_t* const* scalars, const size_t* lens, size_t count, uint64_t handle,
                                       uint64_t* out_jac /* count x 12 */);
+/* Columns that land on the same device and are short enough to be latency bound (<= 2^21 scalars) share ONE
+ * decompose / sort / accumulate / reduce sequence (column id in the bucket index; up to 32 columns and 2^23 scalars per
+ * group): the examples the reference ships run k = 16..20, where a single MSM is dominated by dependent steps. */
 int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omega[4], uint32_t log_n);
 
 /* ---- device-resident entry points (device pointers on `device`, caller's CUDA stream) ------------- */
@@ -108,6 +125,10 @@ int h2b_msm_bn254_g1_dev(int device, const void* d_scalars, const void* d_bases,
 int h2b_msm_bn254_g1_dev_partial(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_block /* 224 B */, void* stream);
 /* same over rows [offset, offset + n) of a registered base set (uses its window tables); d_scalars on `device` */
 int h2b_msm_bn254_g1_dev_registered(int device, const void* d_scalars, uint64_t handle, size_t offset, size_t n, void* d_out_block /* 224 B */, void* stream);
+/* `count` device-resident columns (d_scalars: host array of device pointers, lens[j] scalars each) over rows [0, lens[j]) of a
+ * registered set in one batched kernel sequence; d_out_blocks: count x 224 B.  Asynchronous on `stream`. */
+int h2b_msm_bn254_g1_dev_batch_registered(int device, const void* const* d_scalars, const size_t* lens, size_t count, uint64_t handle,
+                                          void* d_out_blocks, void* stream);
 int h2b_msm_fold_partials(int device, const uint64_t* host_blocks /* count x 28 u64 */, size_t count, uint64_t out_jac[12]);
 /* same, blocks and result in device memory, asynchronous on `stream` */
 int h2b_msm_fold_partials_dev(int device, const void* d_blocks, size_t count, void* d_out_jac /* 96 B */, void* stream);
@@ -302,6 +323,10 @@ int h2b_dev_sync(int device);
 int h2b_gen_points_dev(int device, uint64_t seed, size_t n, void* d_out_affine, void* stream);
 /* kind 0: uniform in [0, r);  kind 1: witness-like (50% 0, 20% 1, 20% < 2^19, 10% r - small). */
 int h2b_gen_scalars_dev(int device, uint64_t seed, size_t n, int kind, void* d_out, void* stream);
+/* O(n) checksum of an MSM over the synthetic points: for P_i = [z_i] G (h2b_gen_points_dev, stream `seed`, indices first + i),
+ * sum_i s_i P_i = [sum_i s_i z_i mod r] G.  Writes the CANONICAL (non-Montgomery) value of sum_i s_i z_i mod r as 32 bytes at d_out;
+ * field arithmetic only, so it shares no code with the MSM it checks (bench.py `verified`). */
+int h2b_msm_checksum_dev(int device, const void* d_scalars /* n x 32 B Montgomery */, uint64_t seed, uint64_t first, size_t n, void* d_out, void* stream);
 /* element-wise field op on host arrays.  field: 0 Fr, 1 Fq.  op: 0 add, 1 sub, 2 mul, 3 sqr(a), 4 inv(a),
  * 5 from_mont(a), 6 to_mont(a) */
 int h2b_field_op(int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
@@ -324,8 +349,11 @@ int h2b_set_msm_window(int c);
 /* window-table policy for base sets registered from now on: -1 no tables, 0 automatic spacing, 2..24 forced
  * spacing (tuning / tests; the environment variable H2B_MSM_PRECOMP sets the initial value) */
 int h2b_set_msm_precomp(int spacing);
-/* tables, spacing (bits) and device bytes per device of a registered base set */
+/* tables, spacing (bits) and device bytes per device (the largest share) of a registered base set */
 int h2b_base_set_info(uint64_t handle, uint32_t* n_tables, uint32_t* spacing, uint64_t* device_bytes);
+/* implicit cache of h2b_msm_bn254_g1: out = {uploads, verified hits, stale copies discarded, uncached (direct) calls,
+ * resident implicit sets, of which with tables} -- diagnostics / tests */
+int h2b_implicit_cache_stats(uint64_t out[6]);
 
 #ifdef __cplusplus
 }

@@ -35,11 +35,12 @@ def emu():
 
 @pytest.fixture(scope="session")
 def gpu():
-    """The product library on cuda:0. Fails loudly (no skip, no fallback) if it cannot run."""
+    """The product library on EVERY visible B200 (host-pointer MSMs from 2^18 points on are split by point range across them,
+    columns go round-robin; the *_dev tests address device 0).  Fails loudly (no skip, no fallback) if it cannot run."""
     from halo2_scaffold_b200 import load
     L = load()
     assert not L.is_emulator
-    L.init_device(0)
+    L.init(0)
     return L
 
 

@@ -763,3 +763,153 @@ def check_evaluate_h_sharded(L, oc, ek=7, k=5, groups=2, seed=6, shards=((0, 40,
         raise AssertionError("a halo that is too small was accepted")
     except H2BError as e:
         assert "halo" in str(e)
+
+
+# ---- implicit SRS cache of h2b_msm_bn254_g1 (best_multiexp is a pure function) ---------------------------------------------------
+def check_implicit_cache_is_content_addressed(L, oc, n, block, seed=41):
+    """n: a multiple of the digest block, >= the cache threshold of this process.  Models create_proof followed by verify_proof
+    (/root/reference/src/scaffold.rs:191-230): the same SRS vector over and over, re-loaded at new addresses, edited in place,
+    prefixes of it, and small fresh arrays in between."""
+    s, P = oc.random_fr(seed, n), oc.gen_points(seed + 1, n)
+    want = affine_of(oc, oc.best_multiexp(s, P))
+    st0 = L.implicit_cache_stats()
+    for _ in range(3):      # 1st call: upload, 2nd: window tables are built, 3rd: tables reused
+        assert (affine_of(oc, L.msm(s, P)) == want).all()
+    st = L.implicit_cache_stats()
+    assert st["uploads"] == st0["uploads"] + 1 and st["hits"] == st0["hits"] + 2, (st0, st)
+    P2 = P.copy()           # the same vector at another address (scaffold.rs:174 re-reads the params file per proof): no new upload
+    assert (affine_of(oc, L.msm(s, P2)) == want).all()
+    assert L.implicit_cache_stats()["uploads"] == st["uploads"]
+    # in-place edits of single rows that no sparse sample would look at: the old device copy must not be used
+    for row in (1, 15, n // 2 + 3, n - 2):
+        P2[row] = oc.gen_points(1000 + row, 1)[0]
+        want2 = affine_of(oc, oc.best_multiexp(s, P2))
+        assert (affine_of(oc, L.msm(s, P2)) == want2).all(), row
+    st2 = L.implicit_cache_stats()
+    assert st2["stale"] + st2["uploads"] > st["stale"] + st["uploads"]
+    # only one limb of one coordinate changes (an invalid point, but the MSM of the OLD array must not come back)
+    want_p = affine_of(oc, oc.best_multiexp(s, P))
+    assert (affine_of(oc, L.msm(s, P)) == want_p).all()
+    # prefixes that are whole blocks reuse the resident copy; ragged ones are uploaded per call
+    up = L.implicit_cache_stats()["uploads"]
+    for m in (n // 2 - (n // 2) % block, n - block):
+        if m >= block and m * 1 >= 1:
+            assert (affine_of(oc, L.msm(s[:m], P[:m])) == affine_of(oc, oc.best_multiexp(s[:m], P[:m]))).all(), m
+    m = n - 3
+    d0 = L.implicit_cache_stats()["direct"]
+    assert (affine_of(oc, L.msm(s[:m], P[:m])) == affine_of(oc, oc.best_multiexp(s[:m], P[:m]))).all()
+    assert L.implicit_cache_stats()["direct"] == d0 + 1
+    # 17 points, only row 15 differs between two calls at the same address
+    s17, P17 = oc.random_fr(seed + 5, 17), oc.gen_points(seed + 6, 17)
+    a = affine_of(oc, L.msm(s17, P17))
+    P17[15] = oc.gen_points(seed + 7, 1)[0]
+    b = affine_of(oc, L.msm(s17, P17))
+    assert (a != b).any() and (b == affine_of(oc, oc.best_multiexp(s17, P17))).all()
+    return up
+
+
+def check_implicit_cache_under_threads(L, oc, n, threads=8, rounds=3, seed=51):
+    """8 host threads: distinct small base arrays (verifier-sized MSMs) interleaved with commits over one large vector.  The large
+    vector is uploaded once and never evicted; every result is the oracle's."""
+    import threading
+    s, P = oc.random_fr(seed, n), oc.gen_points(seed + 1, n)
+    want = affine_of(oc, oc.best_multiexp(s, P))
+    assert (affine_of(oc, L.msm(s, P)) == want).all()
+    up0 = L.implicit_cache_stats()["uploads"]
+    small = []
+    for t in range(threads):
+        m = 20 + 7 * t
+        ss, pp = oc.random_fr(seed + 10 + t, m), oc.gen_points(seed + 40 + t, m)
+        small.append((ss, pp, affine_of(oc, oc.best_multiexp(ss, pp))))
+    errors = []
+
+    def worker(t):
+        try:
+            ss, pp, w = small[t]
+            for r in range(rounds):
+                if not (affine_of(oc, L.msm(ss, pp)) == w).all():
+                    errors.append(("small", t, r))
+                if not (affine_of(oc, L.msm(s, P)) == want).all():
+                    errors.append(("large", t, r))
+        except Exception as e:      # noqa: BLE001
+            errors.append(("exception", t, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(threads)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errors, errors[:4]
+    st = L.implicit_cache_stats()
+    assert st["uploads"] == up0, st      # no re-registration of the large vector
+
+
+def check_sharded_base_set(L, oc, n, spacing=0, kind=0, seed=61):
+    """h2b_register_bases_sharded: rows split over the devices; whole-set, prefix and offset MSMs and batched columns."""
+    s, P = edge_msm_inputs(L, oc, n, kind, seed)
+    if spacing:
+        L.set_msm_precomp(spacing)
+    try:
+        h = L.register_bases_sharded(P)
+    finally:
+        L.set_msm_precomp(0)
+    try:
+        D = L.device_count()
+        info = L.base_set_info(h)
+        if D > 1 and info["n_tables"] >= 1:
+            assert info["device_bytes"] <= info["n_tables"] * ((n + D - 1) // D + 1) * 64
+        for off, m in ((0, n), (0, n // 3), (n // 5, n // 2), (n - 1, 1), (n // 2, 0)):
+            got = affine_of(oc, L.msm_registered(s[:m], h, off))
+            assert (got == affine_of(oc, oc.best_multiexp(s[:m], P[off:off + m]))).all(), (off, m)
+        cols = [oc.random_fr(seed + 20 + j, n - 11 * j) for j in range(3)]
+        got = L.msm_batch_registered(cols, h)
+        for j, c in enumerate(cols):
+            assert (affine_of(oc, got[j]) == affine_of(oc, oc.best_multiexp(c, P[:c.shape[0]]))).all(), j
+    finally:
+        L.unregister_bases(h)
+
+
+def check_batched_columns(L, oc, n, ncols, spacing=0, kinds=(0, 1), window=0, seed=71):
+    """h2b_msm_bn254_g1_batch_registered / _dev_batch_registered: columns of different lengths and distributions (uniform,
+    witness-like, all zero, one scalar everywhere) through ONE kernel sequence == single calls == the oracle."""
+    P = oc.gen_points(seed, n)
+    cols = []
+    for j in range(ncols):
+        m = n - (j * 37) % (n // 2 + 1)
+        c = L.gen_scalars(seed + 1 + j, m, kinds[j % len(kinds)]) if hasattr(L, "gen_scalars") else oc.random_fr(seed + 1 + j, m)
+        if j == 2:
+            c = np.zeros((m, 4), dtype=np.uint64)
+        if j == 3:
+            c = np.repeat(oc.fr_to_mont(np.array([[5, 0, 0, 0]], dtype=np.uint64)), m, axis=0)
+        cols.append(np.ascontiguousarray(c))
+    cols.append(np.zeros((0, 4), dtype=np.uint64))
+    want = [affine_of(oc, oc.best_multiexp(c, P[:c.shape[0]])) for c in cols]
+    if spacing:
+        L.set_msm_precomp(spacing)
+    try:
+        h = L.register_bases(P)
+    finally:
+        L.set_msm_precomp(0)
+    try:
+        L.L.h2b_set_msm_window(window)
+        got = L.msm_batch_registered(cols, h)
+        for j in range(len(cols)):
+            assert (affine_of(oc, got[j]) == want[j]).all(), ("host batch", j)
+            assert (affine_of(oc, L.msm_registered(cols[j], h, 0)) == want[j]).all(), ("single", j)
+        # device-resident columns
+        d_cols = []
+        for c in cols:
+            p = L.dev_alloc(0, max(c.nbytes, 32))
+            if c.nbytes:
+                L.h2d(0, p, c)
+            d_cols.append(p)
+        d_out = L.dev_alloc(0, 224 * len(cols))
+        L.msm_dev_batch_registered(0, d_cols, [c.shape[0] for c in cols], h, d_out)
+        L.dev_sync(0)
+        out = np.zeros((len(cols), 28), dtype=np.uint64)
+        L.d2h(0, out, d_out)
+        for j in range(len(cols)):
+            assert (affine_of(oc, out[j, :12]) == want[j]).all(), ("device batch", j)
+        for p in d_cols + [d_out]:
+            L.dev_free(0, p)
+    finally:
+        L.L.h2b_set_msm_window(0)
+        L.unregister_bases(h)

@@ -531,3 +531,48 @@ def test_lookup_compress_expressions(emu, oc):
     e0, e1, e2 = mul(fix[0], adv[0]), np.roll(adv[1], -1, axis=0), add(np.roll(adv[0], 1, axis=0), five)
     want = add(mul(add(mul(e0, th), e1), th), e2)
     assert (got == want).all()
+
+
+def _emu_subprocess(emu, body, env_extra, timeout=900):
+    import os, subprocess, sys
+    root = pc.__file__.rsplit('/tests/', 1)[0]
+    code = ("import sys; sys.path[:0]=[%r,%r,%r]\n"
+            "import numpy as np, oracle_c as oc, parity_cases as pc\n"
+            "from halo2_scaffold_b200._lib import Lib\n"
+            "L=Lib(%r, allow_emulator=True); L.init(0)\n" % (root, root + '/oracle', root + '/tests', emu.path)) + body + "\nprint('ok')\n"
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env_extra), capture_output=True, text=True, timeout=timeout)
+    assert out.returncode == 0 and "ok" in out.stdout, (out.stdout[-1000:], out.stderr[-3000:])
+
+
+def test_implicit_cache_is_content_addressed(emu):
+    # digest blocks of 16 points, arrays from 64 points on are cached: the logic of the 1024 / 4096 production values at CPU sizes
+    _emu_subprocess(emu, "pc.check_implicit_cache_is_content_addressed(L, oc, 320, 16)\n"
+                         "pc.check_implicit_cache_under_threads(L, oc, 256, threads=8, rounds=2)",
+                    dict(H2B_DIGEST_BLOCK_LOG="4", H2B_IMPLICIT_MIN_LOG="6"))
+
+
+def test_implicit_cache_can_be_disabled(emu):
+    _emu_subprocess(emu, "s, P = oc.random_fr(1, 256), oc.gen_points(2, 256)\n"
+                         "w = pc.affine_of(oc, oc.best_multiexp(s, P))\n"
+                         "assert all((pc.affine_of(oc, L.msm(s, P)) == w).all() for _ in range(2))\n"
+                         "st = L.implicit_cache_stats(); assert st['uploads'] == 0 and st['direct'] == 2, st",
+                    dict(H2B_DIGEST_BLOCK_LOG="4", H2B_IMPLICIT_MIN_LOG="6", H2B_IMPLICIT_CACHE="0"))
+
+
+@pytest.mark.parametrize("devices", ["2", "3"])
+def test_multi_device_host_logic_on_emulated_devices(emu, devices):
+    # H2B_EMU_DEVICES: the emulator reports several devices, so point-range sharding, sharded base sets (tables per slice),
+    # the table all-gather of replicated sets, round-robin + batched columns and the implicit cache's sharded copies all run here
+    _emu_subprocess(emu, "assert L.device_count() == %s\n"
+                         "pc.check_sharded_base_set(L, oc, 700, spacing=8)\n"
+                         "pc.check_sharded_base_set(L, oc, 333, spacing=0, kind=1)\n"
+                         "pc.check_msm_tables(L, oc, 600, 8, kind=0, ranges=[(0, 600), (100, 450)])\n"
+                         "pc.check_msm(L, oc, 500, kind=1)\n"
+                         "pc.check_implicit_cache_is_content_addressed(L, oc, 320, 16)\n"
+                         "pc.check_batched_columns(L, oc, 300, 7, spacing=8)" % devices,
+                    dict(H2B_EMU_DEVICES=devices, H2B_MULTI_DEVICE_MIN_LOG="7", H2B_DIGEST_BLOCK_LOG="4", H2B_IMPLICIT_MIN_LOG="6"))
+
+
+@pytest.mark.parametrize("n,ncols,spacing,window", [(600, 6, 8, 0), (600, 5, 8, 4), (257, 9, 0, 0), (1200, 4, 12, 6), (40, 33, 6, 0), (300, 4, -1, 0)])
+def test_batched_columns_one_kernel_sequence(emu, oc, n, ncols, spacing, window):
+    pc.check_batched_columns(emu, oc, n, ncols, spacing=spacing, window=window)

@@ -178,6 +178,9 @@ static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyPeer(void* d, int, const void* s, int, size_t n) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = 0) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
@@ -192,7 +195,9 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+// H2B_EMU_DEVICES=D makes the emulator report D devices (they share the host heap): the multi-device host logic -- point-range
+// sharding, sharded base sets, round-robin columns -- runs under the CPU suite
+static inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = getenv("H2B_EMU_DEVICES"); *n = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 1; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof(*p)); p->multiProcessorCount = 148; p->totalGlobalMem = (size_t)180 << 30; strcpy(p->name, "emu"); p->major = 10;
     p->sharedMemPerBlockOptin = 227 * 1024; return cudaSuccess;

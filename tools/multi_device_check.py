@@ -19,12 +19,20 @@ oc.build()
 L = Lib()
 L.init(0)                                  # every visible device
 nd = L.device_count()
-n = (1 << 20) + 333                        # >= 2^18: sharded across the devices
+n = 1 << 20                                # >= 2^18 and a whole number of digest blocks: cached, sharded across the devices
 s = L.gen_scalars(5, n, 0)
 P = L.gen_points(6, n)
 want = pc.affine_of(oc, oc.best_multiexp(s, P))
 for _ in range(3):                         # 1st call plain upload, 2nd builds the window tables on every device, 3rd reuses them
     assert (pc.affine_of(oc, L.msm(s, P)) == want).all()
+st = L.implicit_cache_stats()
+assert st["uploads"] == 1 and st["hits"] == 2 and st["sets_with_tables"] == 1, st
+hs = L.register_bases_sharded(P)           # explicit point-range residency: device d keeps rows [d n/D, (d+1) n/D) and their tables
+info = L.base_set_info(hs)
+assert info["device_bytes"] <= info["n_tables"] * ((n + nd - 1) // nd + 1) * 64, info
+assert (pc.affine_of(oc, L.msm_registered(s, hs)) == want).all()
+assert (pc.affine_of(oc, L.msm_registered(s[:300001], hs, 77)) == pc.affine_of(oc, oc.best_multiexp(s[:300001], P[77:300078]))).all()
+L.unregister_bases(hs)
 h = L.register_bases(P)
 assert (pc.affine_of(oc, L.msm_registered(s, h)) == want).all()
 off, m = 12345, 1 << 19

@@ -1,0 +1,108 @@
+#!/usr/bin/env python3
+"""The multi-GPU modes a single prover process uses (`h2b_init(D)`), measured and checked in ONE process:
+
+  parity : one host-pointer MSM split by point range over D devices (implicit cache -> sharded resident copy; sharded
+           registered set), batched columns round-robin over the devices, batched NTTs -- each against the CPU oracle
+           (2^18 .. 2^20 points, sizes the oracle finishes in seconds);
+  strong : ONE MSM of fixed total size 2^k over D devices through the host-pointer entry point with pageable scalars
+           (what a Rust Vec is): sharded registration time, end-to-end ms, and the O(n) checksum [sum s_i z_i] G of the result.
+
+Prints one JSON object.  usage: python tools/multi_gpu_inprocess.py D [k ...]        (bench.py runs it at N > 1, rank 0)
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import numpy as np
+
+from halo2_scaffold_b200._lib import Lib
+from halo2_scaffold_b200 import verify as V
+
+
+def main():
+    D = int(sys.argv[1])
+    ks = [int(a) for a in sys.argv[2:]]
+    L = Lib()
+    L.init(D)
+    assert L.device_count() == D
+    out = {"devices": D}
+
+    # ---- parity against the oracle ----------------------------------------------------------------------------------
+    import oracle_c as oc
+    import parity_cases as pc
+    oc.build()
+    t0 = time.perf_counter()
+    n = 1 << 19
+    s = L.gen_scalars(5, n, 0)
+    P = L.gen_points(6, n)
+    want = pc.affine_of(oc, oc.best_multiexp(s, P))
+    checks = {}
+    ok = all((pc.affine_of(oc, L.msm(s, P)) == want).all() for _ in range(3))      # upload (sharded), tables, reuse
+    st = L.implicit_cache_stats()
+    checks["implicit_sharded_msm"] = bool(ok and st["uploads"] == 1 and st["hits"] == 2)
+    hs = L.register_bases_sharded(P)
+    info = L.base_set_info(hs)
+    ok = (pc.affine_of(oc, L.msm_registered(s, hs)) == want).all()
+    m, off = 200001, 77
+    ok = ok and (pc.affine_of(oc, L.msm_registered(s[:m], hs, off)) == pc.affine_of(oc, oc.best_multiexp(s[:m], P[off:off + m]))).all()
+    checks["registered_sharded_msm"] = bool(ok and info["device_bytes"] <= info["n_tables"] * ((n + D - 1) // D + 1) * 64)
+    L.unregister_bases(hs)
+    h = L.register_bases(P)
+    cols = [L.gen_scalars(400 + j, (1 << 16) - 100 * j, j % 2) for j in range(2 * D + 1)]
+    got = L.msm_batch_registered(cols, h)
+    checks["batched_columns_round_robin"] = bool(all((pc.affine_of(oc, got[j]) == pc.affine_of(oc, oc.best_multiexp(c, P[:c.shape[0]]))).all()
+                                                     for j, c in enumerate(cols)))
+    L.unregister_bases(h)
+    polys = [oc.random_fr(500 + j, 1 << 16) for j in range(2 * D + 1)]
+    wantp = [oc.best_fft(a, pc.omega_words(oc, 16), 16) for a in polys]
+    L.ntt_batch(polys, pc.omega_words(oc, 16), 16)
+    checks["batched_ntts_round_robin"] = bool(all((a == w_).all() for a, w_ in zip(polys, wantp)))
+    out["parity_vs_oracle"] = checks
+    out["parity_ok"] = all(checks.values())
+    out["parity_s"] = round(time.perf_counter() - t0, 2)
+    del s, P, cols, polys
+
+    # ---- strong scaling of one MSM -------------------------------------------------------------------------------------
+    strong = []
+    for k in ks:
+        n = 1 << k
+        seed_s, seed_p = 0xB2000000 + k, 0xB2001000 + k
+        d_s = L.dev_alloc(0, n * 32)
+        d_c = L.dev_alloc(0, 32)
+        L.gen_scalars_dev(0, seed_s, n, 0, d_s)
+        L.msm_checksum_dev(0, d_s, seed_p, n, d_c)
+        L.dev_sync(0)
+        s = np.empty((n, 4), dtype=np.uint64)          # pageable
+        L.d2h(0, s, d_s)
+        c = np.zeros(4, dtype=np.uint64)
+        L.d2h(0, c, d_c)
+        L.dev_free(0, d_s)
+        L.dev_free(0, d_c)
+        P = L.gen_points(seed_p, n)
+        t0 = time.perf_counter()
+        h = L.register_bases_sharded(P)
+        reg_ms = (time.perf_counter() - t0) * 1e3
+        info = L.base_set_info(h)
+        del P
+        for _ in range(2):
+            r = L.msm_registered(s, h)
+        steps = 5 if k <= 24 else 3
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = L.msm_registered(s, h)
+        ms = (time.perf_counter() - t0) / steps * 1e3
+        L.unregister_bases(h)
+        verified = V.jacobian_words_to_affine(r) == V.scalar_mul_generator(V.words_to_int(c))
+        strong.append({"k": k, "devices": D, "msm_e2e_ms": round(ms, 3), "points_per_s": n / ms * 1e3, "sharded_registration_ms": round(reg_ms, 1),
+                       "tables": info["n_tables"], "spacing": info["spacing"], "device_bytes": info["device_bytes"], "verified": bool(verified),
+                       "scalars": "pageable host memory"})
+        del s
+    out["strong"] = strong
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
