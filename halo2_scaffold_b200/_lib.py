@@ -38,7 +38,7 @@ _EXPORTS = [
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
     "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_graph_shard_dev", "h2b_evaluate_h_permutation_shard_dev", "h2b_evaluate_h_lookup_shard_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
-    "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev",
+    "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev", "h2b_ntt_bn254_fr_dev_batch",
 ]
 
 
@@ -142,6 +142,7 @@ class Lib:
         L.h2b_msm_checksum_dev.argtypes = [i32, vp, u64, u64, sz, vp, vp]
         L.h2b_msm_bn254_g1_registered.argtypes = [vp, u64, sz, sz, vp]
         L.h2b_ntt_bn254_fr_dev.argtypes = [i32, vp, vp, u32, vp]
+        L.h2b_ntt_bn254_fr_dev_batch.argtypes = [i32, vp, sz, vp, u32, vp]
         L.h2b_msm_bn254_g1_dev.argtypes = [i32, vp, vp, sz, vp, vp]
         L.h2b_msm_bn254_g1_dev_partial.argtypes = [i32, vp, vp, sz, vp, vp]
         L.h2b_msm_bn254_g1_dev_registered.argtypes = [i32, vp, u64, sz, sz, vp, vp]
@@ -284,6 +285,12 @@ class Lib:
     def ntt_dev(self, device: int, d_a: int, omega: np.ndarray, log_n: int, stream: int = 0):
         omega = _u64(omega)
         self.check(self.L.h2b_ntt_bn254_fr_dev(device, d_a, omega.ctypes.data, log_n, stream))
+
+    def ntt_dev_batch(self, device: int, d_polys, omega: np.ndarray, log_n: int, stream: int = 0):
+        """d_polys: device pointers of equally sized polynomials, transformed in place by shared pass launches"""
+        omega = _u64(omega)
+        ptrs = (ctypes.c_void_p * len(d_polys))(*d_polys)
+        self.check(self.L.h2b_ntt_bn254_fr_dev_batch(device, ptrs, len(d_polys), omega.ctypes.data, log_n, stream))
 
     def msm_dev(self, device: int, d_scalars: int, d_bases: int, n: int, d_out: int, stream: int = 0):
         self.check(self.L.h2b_msm_bn254_g1_dev(device, d_scalars, d_bases, n, d_out, stream))

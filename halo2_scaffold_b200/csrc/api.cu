@@ -564,32 +564,6 @@ static void jac_identity(uint64_t out_jac[12]) {
     for (int i = 0; i < 4; ++i) out_jac[4 + i] = (uint64_t)FpParams<FQ>::ONE(2 * i) | ((uint64_t)FpParams<FQ>::ONE(2 * i + 1) << 32);
 }
 
-// ---- batched entry points: independent columns, round-robin over the devices ------------
-// One worker thread per device; worker d takes columns d, d + D, d + 2D, ... and hands them to `some_columns` in groups.
-template <class F>
-static int run_round_robin(size_t count, F one_column) {
-    const size_t nd = G.devs.size();
-    const size_t workers = count < nd ? count : nd;
-    if (workers <= 1) {
-        for (size_t j = 0; j < count; ++j) H2B_TRY(one_column(j, 0));
-        return H2B_OK;
-    }
-    std::vector<int> rcs(workers, 0);
-    std::vector<std::string> errs(workers);
-    std::vector<std::thread> th;
-    for (size_t d = 0; d < workers; ++d) {
-        th.emplace_back([&, d] {
-            for (size_t j = d; j < count && rcs[d] == 0; j += workers) {
-                rcs[d] = one_column(j, d);
-                if (rcs[d]) errs[d] = get_error();
-            }
-        });
-    }
-    for (auto& t : th) t.join();
-    for (size_t d = 0; d < workers; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
-    return H2B_OK;
-}
-
 }  // namespace h2b
 
 using namespace h2b;
@@ -867,15 +841,47 @@ int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omeg
     for (size_t j = 0; j < count; ++j) if (!a[j]) { set_error("polynomial %zu: null pointer", j); return H2B_ERR_BAD_ARGUMENT; }
     if (log_n == 0) return H2B_OK;
     const size_t bytes = (size_t)32 << log_n;
-    return run_round_robin(count, [&](size_t j, size_t d) -> int {
+    // polynomial j goes to device j mod D; what lands on one device is transformed in groups that share every pass launch
+    const size_t nd = G.devs.size();
+    size_t group = ntt_batch_max();
+    while (group > 1 && group * bytes > ((size_t)1 << 31)) group >>= 1;
+    auto run_device = [&](size_t d) -> int {
         DeviceCtx& c = *G.devs[d];
+        std::vector<size_t> mine;
+        for (size_t j = d; j < count; j += nd) mine.push_back(j);
         std::lock_guard<std::mutex> lk(c.mu);
         H2B_CUDA(cudaSetDevice(c.device));
-        H2B_TRY(c.ntt_io.reserve(bytes));
-        H2B_TRY(host_upload(c, c.ntt_io.p, a[j], bytes, c.stream));
-        H2B_TRY(ntt_run(c, c.ntt_io.p, omega, log_n, c.stream));
-        return host_download(c, a[j], c.ntt_io.p, bytes, c.stream);
-    });
+        for (size_t g0 = 0; g0 < mine.size(); g0 += group) {
+            const size_t m = mine.size() - g0 < group ? mine.size() - g0 : group;
+            H2B_TRY(c.ntt_io.reserve(bytes * m));
+            std::vector<void*> ptrs(m);
+            for (size_t i = 0; i < m; ++i) {
+                ptrs[i] = (char*)c.ntt_io.p + bytes * i;
+                H2B_TRY(host_upload(c, ptrs[i], a[mine[g0 + i]], bytes, c.stream, i == 0));
+            }
+            H2B_TRY(ntt_run_batch(c, ptrs.data(), m, omega, log_n, c.stream));
+            for (size_t i = 0; i < m; ++i) H2B_TRY(host_download(c, a[mine[g0 + i]], ptrs[i], bytes, c.stream));
+        }
+        return H2B_OK;
+    };
+    const size_t workers = count < nd ? count : nd;
+    if (workers <= 1) return run_device(0);
+    std::vector<int> rcs(workers, 0);
+    std::vector<std::string> errs(workers);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < workers; ++d) th.emplace_back([&, d] { rcs[d] = run_device(d); if (rcs[d]) errs[d] = get_error(); });
+    for (auto& t : th) t.join();
+    for (size_t d = 0; d < workers; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
+    return H2B_OK;
+}
+
+int h2b_ntt_bn254_fr_dev_batch(int device, void* const* d_polys, size_t count, const uint64_t omega[4], uint32_t log_n, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (count == 0) return H2B_OK;
+    if (!d_polys || !omega) { set_error("h2b_ntt_bn254_fr_dev_batch: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    return ntt_run_batch(*c, d_polys, count, omega, log_n, (cudaStream_t)stream);
 }
 
 int h2b_ntt_bn254_fr_dev(int device, void* d_a, const uint64_t omega[4], uint32_t log_n, void* stream) {

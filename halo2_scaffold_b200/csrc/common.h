@@ -145,6 +145,8 @@ void evaluate_graph_last_info(uint32_t* slots, uint32_t* micro_ops);
 void evaluate_release(DeviceCtx& ctx);
 // ---- ntt.cu ----
 int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
+int ntt_run_batch(DeviceCtx& ctx, void* const* d_polys, size_t count, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
+uint32_t ntt_batch_max();
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);
 void ntt_release(DeviceCtx& ctx);
 // ---- msm.cu ----

@@ -24,9 +24,10 @@ static const int NTT_DEFAULT_TILE_LOG = 11;  // measured best on B200 (profiles/
 static const int NTT_MAX_PASSES = 4;
 static const int NTT_SINGLE_CTA_LOG = 10;    // up to 2^10 elements one CTA does the whole transform (latency)
 
+static const uint32_t NTT_BATCH_MAX = 16;    // polynomials per launch (blockIdx.y): independent (i)NTTs of one proof phase share the passes
 struct NttPassParams {
-    const uint4* in;
-    uint4* out;
+    const uint4* ins[NTT_BATCH_MAX];
+    uint4* outs[NTT_BATCH_MAX];
     const uint4* tw_small;   // Omega^t, t < N/2, Omega = w^(n/N)
     const uint4* tw_lo;      // w^j,          j < 2^h
     const uint4* tw_hi;      // w^(j * 2^h),  j < 2^(log_n - h)
@@ -115,6 +116,8 @@ __device__ __forceinline__ void ntt_round(uint4* lo, uint4* hi, const uint4* tlo
 
 __global__ void __launch_bounds__(512, 1) ntt_pass_kernel(NttPassParams p) {
     H2B_DYN_SMEM(uint4, sm);
+    const uint4* __restrict__ p_in = p.ins[blockIdx.y];
+    uint4* __restrict__ p_out = p.outs[blockIdx.y];
     const uint32_t b = p.b, logT = p.logT;
     const uint32_t N = 1u << b, T = 1u << logT, E = N << logT;
     const uint32_t data_slots = sm_slot(E - 1) + 1, tw_slots = sm_slot((N >> 1) ? (N >> 1) - 1 : 0) + 1;
@@ -146,12 +149,12 @@ __global__ void __launch_bounds__(512, 1) ntt_pass_kernel(NttPassParams p) {
             const uint32_t base = (seg << p.logL) + (tau << logT);
             for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
                 uint32_t half = idx & 1, t = (idx >> 1) & (T - 1), q = idx >> (1 + logT);
-                copy16_async((half ? hi : lo) + sm_slot((q << logT) + t), p.in + 2 * (size_t)(base + q * M + t) + half);
+                copy16_async((half ? hi : lo) + sm_slot((q << logT) + t), p_in + 2 * (size_t)(base + q * M + t) + half);
             }
         } else {
             for (uint32_t idx = tid; idx < 2 * E; idx += nthr) {
                 uint32_t half = idx & 1, q = (idx >> 1) & (N - 1), t = idx >> (1 + b);
-                copy16_async((half ? hi : lo) + sm_slot((t << b) + q), p.in + 2 * (size_t)(((t * nseg + tile) << b) + q) + half);
+                copy16_async((half ? hi : lo) + sm_slot((t << b) + q), p_in + 2 * (size_t)(((t * nseg + tile) << b) + q) + half);
             }
         }
     }
@@ -206,9 +209,9 @@ __global__ void __launch_bounds__(512, 1) ntt_pass_kernel(NttPassParams p) {
                     }
                     v = fp_mul(v, w);
                 }
-                fp_store<FR>(p.out + 2 * (size_t)(base + q * M + t), v);
+                fp_store<FR>(p_out + 2 * (size_t)(base + q * M + t), v);
                 if (has_next) {
-                    const uint4* src = p.in + 2 * (size_t)(nbase + q * M + t);
+                    const uint4* src = p_in + 2 * (size_t)(nbase + q * M + t);
                     copy16_async(lo + sm_slot(i), src);
                     copy16_async(hi + sm_slot(i), src + 1);
                 }
@@ -221,9 +224,9 @@ __global__ void __launch_bounds__(512, 1) ntt_pass_kernel(NttPassParams p) {
                 Fr v = sm_get(lo, hi, e);
                 uint32_t pos = ((t * nseg + tile) << b) + q;
                 uint32_t oidx = __brev(pos) >> (32 - p.log_n);
-                fp_store<FR>(p.out + 2 * (size_t)oidx, v);
+                fp_store<FR>(p_out + 2 * (size_t)oidx, v);
                 if (has_next) {
-                    const uint4* src = p.in + 2 * (size_t)(((t * nseg + next) << b) + q);
+                    const uint4* src = p_in + 2 * (size_t)(((t * nseg + next) << b) + q);
                     copy16_async(lo + sm_slot(e), src);
                     copy16_async(hi + sm_slot(e), src + 1);
                 }
@@ -446,16 +449,14 @@ static int ntt_get_twiddles(DeviceCtx& ctx, const uint64_t omega[4], uint32_t lo
     return H2B_OK;
 }
 
-int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream) {
-    if (log_n > 28) { set_error("ntt: log_n = %u exceeds the two-adicity of Fr (28)", log_n); return H2B_ERR_BAD_ARGUMENT; }
-    if (log_n == 0) return H2B_OK;
-    if (!d_a) { set_error("ntt: null data pointer"); return H2B_ERR_BAD_ARGUMENT; }
+// `count` <= NTT_BATCH_MAX transforms of the same (omega, log_n) in one launch per pass (polynomial = blockIdx.y)
+static int ntt_run_group(DeviceCtx& ctx, void* const* d_polys, uint32_t count, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream) {
     NttTwiddles* tw = nullptr;
     ctx.prof.mark(PROF_BEGIN, stream);
     H2B_TRY(ntt_get_twiddles(ctx, omega, log_n, stream, &tw));
     ctx.prof.mark(PROF_NTT_TWIDDLE, stream);
     const size_t n = (size_t)1 << log_n;
-    if (tw->npass > 1) H2B_TRY(ctx.ntt_work.reserve(n * 32));
+    if (tw->npass > 1) H2B_TRY(ctx.ntt_work.reserve(n * 32 * count));
     auto kfn = ntt_pass_kernel;
     if (!ctx.ntt_attr_set) {
         H2B_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -465,10 +466,14 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
     const uint4* tbl = (const uint4*)tw->buf.p;
     for (uint32_t p = 0; p < tw->npass; ++p) {
         NttPassParams a;
+        memset(&a, 0, sizeof(a));
         const bool first = (p == 0), last = (p + 1 == tw->npass);
         // pass 1: a -> work, middle passes in place in work, last pass: work -> a (scatter)
-        a.in = (const uint4*)(first ? d_a : ctx.ntt_work.p);
-        a.out = (uint4*)(last ? d_a : ctx.ntt_work.p);
+        for (uint32_t j = 0; j < count; ++j) {
+            uint4* work = (uint4*)ctx.ntt_work.p + 2 * n * j;
+            a.ins[j] = first ? (const uint4*)d_polys[j] : work;
+            a.outs[j] = last ? (uint4*)d_polys[j] : work;
+        }
         a.tw_small = tbl + 2 * (size_t)tw->small_off[p];
         a.tw_lo = tbl + 2 * (size_t)tw->lo_off;
         a.tw_hi = tbl + 2 * (size_t)tw->hi_off;
@@ -500,12 +505,36 @@ int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, 
         if (grid_cap < 0) { const char* e = getenv("H2B_NTT_GRID"); grid_cap = e ? atoi(e) : 0; }
         if (grid_cap > 0 && grid > (uint32_t)grid_cap) grid = (uint32_t)grid_cap;
         if (grid > ntiles) grid = ntiles;
-        H2B_LAUNCH(kfn, grid, threads, smem, stream, a);
+        H2B_LAUNCH(kfn, dim3(grid, count), threads, smem, stream, a);
         H2B_CUDA(cudaGetLastError());
         ctx.prof.mark(PROF_NTT_PASS0 + (int)p, stream);
     }
     return H2B_OK;
 }
+
+int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream) {
+    if (log_n > 28) { set_error("ntt: log_n = %u exceeds the two-adicity of Fr (28)", log_n); return H2B_ERR_BAD_ARGUMENT; }
+    if (log_n == 0) return H2B_OK;
+    if (!d_a) { set_error("ntt: null data pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    void* one[1] = {d_a};
+    return ntt_run_group(ctx, one, 1, omega, log_n, stream);
+}
+
+// Independent transforms of equal size (the per-polynomial (i)NTTs of a proof phase): groups of up to NTT_BATCH_MAX polynomials
+// and 2^26 elements share every pass launch, so that 2^16-element transforms (32 tiles each) fill the 148 SMs together.
+int ntt_run_batch(DeviceCtx& ctx, void* const* d_polys, size_t count, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream) {
+    if (log_n > 28) { set_error("ntt: log_n = %u exceeds the two-adicity of Fr (28)", log_n); return H2B_ERR_BAD_ARGUMENT; }
+    if (log_n == 0 || count == 0) return H2B_OK;
+    for (size_t j = 0; j < count; ++j) if (!d_polys[j]) { set_error("ntt batch: polynomial %zu is null", j); return H2B_ERR_BAD_ARGUMENT; }
+    size_t group = NTT_BATCH_MAX;
+    while (group > 1 && (group << log_n) > ((size_t)1 << 26)) group >>= 1;
+    for (size_t j0 = 0; j0 < count; j0 += group) {
+        const size_t m = count - j0 < group ? count - j0 : group;
+        H2B_TRY(ntt_run_group(ctx, d_polys + j0, (uint32_t)m, omega, log_n, stream));
+    }
+    return H2B_OK;
+}
+uint32_t ntt_batch_max() { return NTT_BATCH_MAX; }
 
 // a[i] *= factors[i % count]   (count 1 / 3: the 1/n of lagrange_to_coeff / extended_to_coeff and the zeta-coset pattern
 // of coeff_to_extended; count 2^(extended_k - k) <= 8: the t_evaluations of divide_by_vanishing_poly --

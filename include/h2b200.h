@@ -118,6 +118,9 @@ int h2b_ntt_bn254_fr_batch(uint64_t* const* a, size_t count, const uint64_t omeg
  * stream (what a prover thread does), or order the streams with events.  Different devices are independent.  (The compiled
  * programs of evaluate_h are the exception: they rotate through a small ring guarded by events.) */
 int h2b_ntt_bn254_fr_dev(int device, void* d_a, const uint64_t omega[4], uint32_t log_n, void* stream);
+/* `count` device-resident polynomials of 2^log_n elements each (d_polys: host array of device pointers), same omega: groups of up
+ * to 16 polynomials share every pass launch (polynomial index in blockIdx.y) -- the per-column (i)NTTs of a proof phase. */
+int h2b_ntt_bn254_fr_dev_batch(int device, void* const* d_polys, size_t count, const uint64_t omega[4], uint32_t log_n, void* stream);
 int h2b_msm_bn254_g1_dev(int device, const void* d_scalars, const void* d_bases, size_t n, void* d_out_jac /* 96 B */, void* stream);
 /* Point-range sharding across processes (one process per GPU): each rank computes a partial
  * result block (224 B: Jacobian x|y|z followed by the XYZZ form) for its slice, the blocks are gathered by the

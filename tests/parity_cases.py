@@ -913,3 +913,26 @@ def check_batched_columns(L, oc, n, ncols, spacing=0, kinds=(0, 1), window=0, se
     finally:
         L.L.h2b_set_msm_window(0)
         L.unregister_bases(h)
+
+
+def check_batched_ntts(L, oc, k, count, seed=81):
+    """h2b_ntt_bn254_fr_batch / _dev_batch: `count` transforms sharing every pass launch == single calls == the oracle"""
+    for inverse in (False, True):
+        w = omega_words(oc, k, inverse)
+        polys = [oc.random_fr(seed + j, 1 << k) for j in range(count)]
+        want = [oc.best_fft(a, w, k) for a in polys]
+        host = [a.copy() for a in polys]
+        L.ntt_batch(host, w, k)
+        assert all((a == b).all() for a, b in zip(host, want)), ("host batch", k, inverse)
+        ptrs = []
+        for a in polys:
+            p = L.dev_alloc(0, a.nbytes)
+            L.h2d(0, p, a)
+            ptrs.append(p)
+        L.ntt_dev_batch(0, ptrs, w, k)
+        L.dev_sync(0)
+        for p, b in zip(ptrs, want):
+            got = np.zeros_like(b)
+            L.d2h(0, got, p)
+            assert (got == b).all(), ("device batch", k, inverse)
+            L.dev_free(0, p)

@@ -576,3 +576,8 @@ def test_multi_device_host_logic_on_emulated_devices(emu, devices):
 @pytest.mark.parametrize("n,ncols,spacing,window", [(600, 6, 8, 0), (600, 5, 8, 4), (257, 9, 0, 0), (1200, 4, 12, 6), (40, 33, 6, 0), (300, 4, -1, 0)])
 def test_batched_columns_one_kernel_sequence(emu, oc, n, ncols, spacing, window):
     pc.check_batched_columns(emu, oc, n, ncols, spacing=spacing, window=window)
+
+
+@pytest.mark.parametrize("k,count", [(3, 5), (9, 4), (11, 3), (12, 17), (13, 2)])
+def test_batched_ntts_share_pass_launches(emu, oc, k, count):
+    pc.check_batched_ntts(emu, oc, k, count)

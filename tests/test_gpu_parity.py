@@ -278,6 +278,11 @@ def test_batched_columns_match_single_calls(gpu, oc):
         assert (a == w).all()
 
 
+@pytest.mark.parametrize("k,count", [(10, 33), (16, 8), (20, 3)])
+def test_batched_ntts_share_pass_launches(gpu, oc, k, count):
+    pc.check_batched_ntts(gpu, oc, k, count)
+
+
 def test_in_process_multi_device_paths(gpu):
     """Point-range sharding of one MSM across every visible GPU + concurrent callers (fresh process: own library instance)."""
     import os, subprocess, sys
