@@ -533,7 +533,11 @@ class Lib:
         """-> dict(k, g, g_lagrange, g2_bytes, handle_g, handle_g_lagrange); see h2b_srs_read"""
         with open(path, "rb") as f:
             k0 = int.from_bytes(f.read(4), "little")
-        n = 1 << min(k0, 28)
+        # the header is untrusted: size the host arrays only after the file length agrees with it (the library checks again)
+        point = 32 if fmt == 0 else 64
+        if k0 > 28 or os.path.getsize(path) < 4 + 2 * (1 << k0) * point + 4 * point:
+            raise H2BError(-2, "h2b_srs_read: %s is shorter than its header (k = %d) promises" % (path, k0))
+        n = 1 << k0
         g = np.empty((n, 8), dtype=np.uint64) if want_host else None
         gl = np.empty((n, 8), dtype=np.uint64) if want_host else None
         g2 = np.zeros(256, dtype=np.uint8)

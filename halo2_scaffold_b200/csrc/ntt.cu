@@ -557,10 +557,26 @@ __global__ void __launch_bounds__(256) ntt_scale_kernel(uint4* a, size_t n, Scal
     fp_store<FR>(a + 2 * i, fp_mul(v, f));
 }
 
+// count > 8 (divide_by_vanishing_poly of a circuit with cs.degree() > 9: 2^(extended_k - k) t_evaluations): factors from a device table
+__global__ void __launch_bounds__(256) ntt_scale_table_kernel(uint4* a, size_t n, const uint4* __restrict__ factors, uint32_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr f = fp_load<FR>(factors + 2 * (size_t)(i % count));
+    fp_store<FR>(a + 2 * i, fp_mul(fp_load<FR>(a + 2 * i), f));
+}
+
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors, int count, cudaStream_t stream) {
-    (void)ctx;
-    if (count < 1 || count > 8) { set_error("scale: count must be in [1, 8]"); return H2B_ERR_BAD_ARGUMENT; }
+    if (count < 1 || count > 4096) { set_error("scale: count must be in [1, 4096]"); return H2B_ERR_BAD_ARGUMENT; }
     if (n == 0) return H2B_OK;
+    if (count > 8) {
+        // the table is staged through a small device buffer of its own (grow-only; the copy is ordered on `stream`)
+        H2B_TRY(ctx.scale_table.reserve((size_t)count * 32));
+        H2B_CUDA(cudaMemcpyAsync(ctx.scale_table.p, factors, (size_t)count * 32, cudaMemcpyHostToDevice, stream));
+        H2B_CUDA(cudaStreamSynchronize(stream));      // `factors` is the caller's (pageable) memory: do not outlive the call
+        H2B_LAUNCH(ntt_scale_table_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, (uint4*)d_a, n, (const uint4*)ctx.scale_table.p, (uint32_t)count);
+        H2B_CUDA(cudaGetLastError());
+        return H2B_OK;
+    }
     ScaleParams s;
     memset(&s, 0, sizeof(s));
     s.count = (uint32_t)count;
@@ -575,6 +591,7 @@ void ntt_release(DeviceCtx& ctx) {
     ctx.twiddles.clear();
     ctx.ntt_work.release();
     ctx.ntt_io.release();
+    ctx.scale_table.release();
 }
 
 }  // namespace h2b

@@ -246,12 +246,13 @@ int fr_kate_division_run(DeviceCtx& ctx, const void* d_a, size_t n, const uint64
 // with the denominators inverted in one batch.  On the device: one elementwise kernel for the denominators, the batch
 // inversion, one elementwise kernel for the numerators, the exclusive prefix product, and the scaling by `start`
 // (last_z of the previous set).  The blinding rows at the end of z are the caller's (they are random).
-static const uint32_t PERM_MAX_COLUMNS = 16;        // a set holds cs.degree() - 2 columns
+static const uint32_t PERM_MAX_COLUMNS = 16;        // columns per launch; a set holds cs.degree() - 2 columns and longer sets run in pieces
 
 struct PermProductParams {
     const uint4* values[PERM_MAX_COLUMNS];
     const uint4* sigma[PERM_MAX_COLUMNS];
     uint32_t m;
+    uint32_t j0;            // index of values[0] inside the set (pieces after the first multiply into `out`)
     Fr beta, gamma, delta, deltaomega, omega;
 };
 
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(128) perm_denominator_kernel(PermProductParams
         const Fr t = fp_add(fp_add(fp_mul(p.beta, fp_load<FR>(p.sigma[j] + 2 * i)), p.gamma), fp_load<FR>(p.values[j] + 2 * i));
         acc = j ? fp_mul(acc, t) : t;
     }
+    if (p.j0) acc = fp_mul(acc, fp_load<FR>(out + 2 * i));
     fp_store<FR>(out + 2 * i, acc);
 }
 
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(128) perm_numerator_kernel(PermProductParams p
     const uint32_t stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     Fr w = fp_mul(fp_mul(p.deltaomega, p.beta), fp_pow_u32<FR>(p.omega, t));      // deltaomega * beta * omega^i
+    if (p.j0) w = fp_mul(w, fp_pow_u32<FR>(p.delta, p.j0));                        // ... * delta^j0 for a later piece of the set
     const Fr step = fp_pow_u32<FR>(p.omega, stride);
     for (size_t i = t; i < n; i += stride) {
         Fr acc = fp_load<FR>(out + 2 * i);
@@ -298,23 +301,31 @@ int permutation_product_run(DeviceCtx& ctx, const void* const* d_values, const v
         set_error("permutation_product: null pointer");
         return H2B_ERR_BAD_ARGUMENT;
     }
-    if (m == 0 || m > PERM_MAX_COLUMNS) { set_error("permutation_product: 1 .. %u columns per set", PERM_MAX_COLUMNS); return H2B_ERR_BAD_ARGUMENT; }
+    if (m == 0) { set_error("permutation_product: a set has at least one column"); return H2B_ERR_BAD_ARGUMENT; }
     if (n == 0) return H2B_OK;
     if (n > ((size_t)1 << 31)) { set_error("permutation_product: at most 2^31 rows"); return H2B_ERR_BAD_ARGUMENT; }
-    PermProductParams p;
-    memset(&p, 0, sizeof(p));
-    p.m = m;
-    for (uint32_t j = 0; j < m; ++j) {
-        if (!d_values[j] || !d_sigma[j]) { set_error("permutation_product: null column"); return H2B_ERR_BAD_ARGUMENT; }
-        p.values[j] = (const uint4*)d_values[j];
-        p.sigma[j] = (const uint4*)d_sigma[j];
-    }
-    memcpy(p.beta.l, beta, 32); memcpy(p.gamma.l, gamma, 32); memcpy(p.delta.l, delta, 32);
-    memcpy(p.deltaomega.l, deltaomega, 32); memcpy(p.omega.l, omega, 32);
-    H2B_LAUNCH(perm_denominator_kernel, (unsigned)((n + 127) / 128), 128, 0, stream, p, n, (uint4*)d_z);
+    for (uint32_t j = 0; j < m; ++j) if (!d_values[j] || !d_sigma[j]) { set_error("permutation_product: null column"); return H2B_ERR_BAD_ARGUMENT; }
+    // sets of more than PERM_MAX_COLUMNS columns (cs.degree() > 18) run in pieces: denominators multiplied up piece by piece,
+    // one batch inversion, numerators piece by piece with delta^j carried on
+    auto piece = [&](uint32_t j0) {
+        PermProductParams p;
+        memset(&p, 0, sizeof(p));
+        p.m = m - j0 < PERM_MAX_COLUMNS ? m - j0 : PERM_MAX_COLUMNS;
+        p.j0 = j0;
+        for (uint32_t j = 0; j < p.m; ++j) {
+            p.values[j] = (const uint4*)d_values[j0 + j];
+            p.sigma[j] = (const uint4*)d_sigma[j0 + j];
+        }
+        memcpy(p.beta.l, beta, 32); memcpy(p.gamma.l, gamma, 32); memcpy(p.delta.l, delta, 32);
+        memcpy(p.deltaomega.l, deltaomega, 32); memcpy(p.omega.l, omega, 32);
+        return p;
+    };
+    for (uint32_t j0 = 0; j0 < m; j0 += PERM_MAX_COLUMNS)
+        H2B_LAUNCH(perm_denominator_kernel, (unsigned)((n + 127) / 128), 128, 0, stream, piece(j0), n, (uint4*)d_z);
     H2B_TRY(fr_batch_invert_run(ctx, d_z, n, stream));
     const size_t want = (n + 127) / 128, cap = (size_t)ctx.sm_count * 8;
-    H2B_LAUNCH(perm_numerator_kernel, (unsigned)(want < cap ? want : cap), 128, 0, stream, p, n, (uint4*)d_z);
+    for (uint32_t j0 = 0; j0 < m; j0 += PERM_MAX_COLUMNS)
+        H2B_LAUNCH(perm_numerator_kernel, (unsigned)(want < cap ? want : cap), 128, 0, stream, piece(j0), n, (uint4*)d_z);
     H2B_TRY(fr_prefix_product_run(ctx, d_z, d_z, n, stream));
     if (!is_montgomery_one(last_z)) H2B_TRY(ntt_scale_run(ctx, d_z, n, last_z, 1, stream));
     H2B_CUDA(cudaGetLastError());

@@ -209,7 +209,7 @@ class EvaluationDomain {
             t_evaluations_.push_back(fr::invert(fr::sub(cur, fr::one())));
             cur = fr::mul(cur, step);
         } while (!(cur == orig));
-        if (t_evaluations_.size() != ((size_t)1 << (extended_k_ - k_)) || t_evaluations_.size() > 8) throw Panic("EvaluationDomain::new: unexpected t_evaluations period");
+        if (t_evaluations_.size() != ((size_t)1 << (extended_k_ - k_))) throw Panic("EvaluationDomain::new: unexpected t_evaluations period");
     }
     uint32_t k() const { return k_; }
     uint32_t extended_k() const { return extended_k_; }

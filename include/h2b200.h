@@ -135,7 +135,7 @@ int h2b_msm_bn254_g1_dev_batch_registered(int device, const void* const* d_scala
 int h2b_msm_fold_partials(int device, const uint64_t* host_blocks /* count x 28 u64 */, size_t count, uint64_t out_jac[12]);
 /* same, blocks and result in device memory, asynchronous on `stream` */
 int h2b_msm_fold_partials_dev(int device, const void* d_blocks, size_t count, void* d_out_jac /* 96 B */, void* stream);
-/* a[i] *= factors[i % count], 1 <= count <= 8: the 1/n scaling of lagrange_to_coeff / extended_to_coeff (count 1), the
+/* a[i] *= factors[i % count], 1 <= count <= 4096 (more than 8 factors go through a device table and synchronise the stream once): the 1/n scaling of lagrange_to_coeff / extended_to_coeff (count 1), the
  * (1, zeta, zeta^2) coset pattern of coeff_to_extended (count 3) and EvaluationDomain::divide_by_vanishing_poly, whose
  * t_evaluations repeat with period 2^(extended_k - k) ([UP] halo2_proofs/src/poly/domain.rs). */
 int h2b_fr_scale_dev(int device, void* d_a, size_t n, const uint64_t* factors, int count, void* stream);
@@ -169,7 +169,7 @@ int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64
  * ([UP] plonk/lookup/prover.rs compress_expressions) */
 int h2b_fr_lincomb_dev(int device, const void* const* d_cols, const uint64_t* coeffs /* m x 4 */, uint32_t m, size_t n, void* d_out, void* stream);
 /* The grand products themselves, on device-resident Lagrange-basis columns of n = 2^k rows:
- *   [UP] plonk/permutation/prover.rs Argument::commit, one call per set (chunk of cs.degree() - 2 columns, at most 16):
+ *   [UP] plonk/permutation/prover.rs Argument::commit, one call per set (chunk of cs.degree() - 2 columns; any number, 16 per launch):
  *        z[0] = last_z,  z[i+1] = z[i] * prod_j (v_j[i] + deltaomega * delta^j * omega^i * beta + gamma)
  *                                      / prod_j (v_j[i] + beta * s_j[i] + gamma)
  *        d_values[j] / d_permutations[j]: the j-th column of the set and its permutation column s_j; deltaomega = delta^(index of

@@ -488,7 +488,7 @@ def check_grand_products(L, oc, sizes):
         sc = oc.random_fr(0x9000 + n, 3)
         beta, gamma, last_z = sc
         one = fr_to_words(1)
-        for m, first_col in ((1, 0), (3, 0), (2, 3), (16, 5)):
+        for m, first_col in ((1, 0), (3, 0), (2, 3), (16, 5), (17, 0), (37, 2)):      # more than 16 columns: several launches per set
             vals = [oc.random_fr(0x9100 + 17 * n + j, n) for j in range(m)]
             sig = [oc.random_fr(0x9200 + 17 * n + j, n) for j in range(m)]
             dw = fr_to_words(pow(DELTA, first_col, o.R_MOD))

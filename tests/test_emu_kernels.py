@@ -415,7 +415,7 @@ def test_srs_reader_keeps_decoded_files_resident(emu, oc, tmp_path):
 
 
 def test_divide_by_vanishing_poly(emu, oc):
-    pc.check_vanishing_division(emu, oc, [(3, 3), (4, 4), (5, 5), (9, 4)])
+    pc.check_vanishing_division(emu, oc, [(3, 3), (4, 4), (5, 5), (9, 4), (10, 3), (18, 2)])
 
 
 def test_permutation_and_lookup_grand_products(emu, oc):

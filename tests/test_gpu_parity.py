@@ -211,7 +211,7 @@ def test_linear_combination_of_columns(gpu, oc):
 
 
 def test_divide_by_vanishing_poly(gpu, oc):
-    pc.check_vanishing_division(gpu, oc, [(3, 5), (4, 8), (5, 9), (9, 6)])
+    pc.check_vanishing_division(gpu, oc, [(3, 5), (4, 8), (5, 9), (9, 6), (12, 5)])
 
 
 def test_g1_point_codec(gpu, oc):
