@@ -38,7 +38,7 @@ _EXPORTS = [
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
     "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_graph_shard_dev", "h2b_evaluate_h_permutation_shard_dev", "h2b_evaluate_h_lookup_shard_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
-    "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev", "h2b_ntt_bn254_fr_dev_batch",
+    "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev", "h2b_ntt_bn254_fr_dev_batch", "h2b_lagrange_to_coeff_dev_batch", "h2b_coeff_to_extended_dev_batch", "h2b_memcpy_d2d_async", "h2b_memset_zero_async",
 ]
 
 
@@ -160,6 +160,8 @@ class Lib:
         L.h2b_lagrange_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev.argtypes = [i32, vp, u32, u32, vp, vp, vp]
         L.h2b_extended_to_coeff_dev.argtypes = [i32, vp, u32, vp, vp, vp]
+        L.h2b_lagrange_to_coeff_dev_batch.argtypes = [i32, vp, sz, u32, vp, vp, vp]
+        L.h2b_coeff_to_extended_dev_batch.argtypes = [i32, vp, sz, u32, u32, vp, vp, vp]
         L.h2b_fr_lincomb_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp]
         L.h2b_permutation_product_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_lookup_product_dev.argtypes = [i32, vp, vp, vp, vp, sz, vp, vp, vp, vp]
@@ -181,6 +183,8 @@ class Lib:
         L.h2b_memcpy_h2d.argtypes = [i32, vp, vp, sz]
         L.h2b_memcpy_d2h.argtypes = [i32, vp, vp, sz]
         L.h2b_memcpy_h2d_async.argtypes = [i32, vp, vp, sz, vp]
+        L.h2b_memcpy_d2d_async.argtypes = [i32, vp, vp, sz, vp]
+        L.h2b_memset_zero_async.argtypes = [i32, vp, sz, vp]
         L.h2b_dev_sync.argtypes = [i32]
         L.h2b_gen_points_dev.argtypes = [i32, u64, sz, vp, vp]
         L.h2b_gen_scalars_dev.argtypes = [i32, u64, sz, i32, vp, vp]
@@ -339,6 +343,16 @@ class Lib:
     def coeff_to_extended_dev(self, device: int, d_a: int, k: int, extended_k: int, extended_omega: np.ndarray, zeta_powers: np.ndarray, stream: int = 0):
         extended_omega, zeta_powers = _u64(extended_omega), _u64(zeta_powers).reshape(3, 4)
         self.check(self.L.h2b_coeff_to_extended_dev(device, d_a, k, extended_k, extended_omega.ctypes.data, zeta_powers.ctypes.data, stream))
+
+    def lagrange_to_coeff_dev_batch(self, device: int, d_cols, k: int, omega_inv: np.ndarray, ifft_divisor: np.ndarray, stream: int = 0):
+        omega_inv, ifft_divisor = _u64(omega_inv), _u64(ifft_divisor)
+        ptrs = (ctypes.c_void_p * len(d_cols))(*d_cols)
+        self.check(self.L.h2b_lagrange_to_coeff_dev_batch(device, ptrs, len(d_cols), k, omega_inv.ctypes.data, ifft_divisor.ctypes.data, stream))
+
+    def coeff_to_extended_dev_batch(self, device: int, d_cols, k: int, extended_k: int, extended_omega: np.ndarray, zeta_powers: np.ndarray, stream: int = 0):
+        extended_omega, zeta_powers = _u64(extended_omega), _u64(zeta_powers).reshape(3, 4)
+        ptrs = (ctypes.c_void_p * len(d_cols))(*d_cols)
+        self.check(self.L.h2b_coeff_to_extended_dev_batch(device, ptrs, len(d_cols), k, extended_k, extended_omega.ctypes.data, zeta_powers.ctypes.data, stream))
 
     def extended_to_coeff_dev(self, device: int, d_a: int, extended_k: int, extended_omega_inv: np.ndarray, factors: np.ndarray, stream: int = 0):
         extended_omega_inv, factors = _u64(extended_omega_inv), _u64(factors).reshape(3, 4)

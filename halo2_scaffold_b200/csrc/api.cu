@@ -1028,6 +1028,34 @@ int h2b_coeff_to_extended_dev(int device, void* d_a, uint32_t k, uint32_t extend
     return ntt_run(*c, d_a, extended_omega, extended_k, (cudaStream_t)stream);
 }
 
+// The two conversions every witness / product column goes through, for `count` columns at once: the (i)NTT passes and the scaling
+// are launched once for the whole batch (polynomial index in blockIdx.y).  d_cols: host array of device pointers.
+int h2b_lagrange_to_coeff_dev_batch(int device, void* const* d_cols, size_t count, uint32_t k, const uint64_t omega_inv[4], const uint64_t ifft_divisor[4],
+                                    void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (count == 0) return H2B_OK;
+    if (!d_cols || !omega_inv || !ifft_divisor) { set_error("h2b_lagrange_to_coeff_dev_batch: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    H2B_TRY(ntt_run_batch(*c, d_cols, count, omega_inv, k, (cudaStream_t)stream));
+    return ntt_scale_batch_run(*c, d_cols, count, (size_t)1 << k, ifft_divisor, 1, (cudaStream_t)stream);
+}
+
+int h2b_coeff_to_extended_dev_batch(int device, void* const* d_cols, size_t count, uint32_t k, uint32_t extended_k, const uint64_t extended_omega[4],
+                                    const uint64_t zeta_powers[12], void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (count == 0) return H2B_OK;
+    if (!d_cols || !extended_omega || !zeta_powers) { set_error("h2b_coeff_to_extended_dev_batch: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (extended_k < k || extended_k > 28) { set_error("h2b_coeff_to_extended_dev_batch: need k <= extended_k <= 28"); return H2B_ERR_BAD_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t n = (size_t)1 << k, en = (size_t)1 << extended_k;
+    H2B_TRY(ntt_scale_batch_run(*c, d_cols, count, n, zeta_powers, 3, (cudaStream_t)stream));
+    if (en > n)
+        for (size_t j = 0; j < count; ++j) H2B_CUDA(cudaMemsetAsync((char*)d_cols[j] + n * 32, 0, (en - n) * 32, (cudaStream_t)stream));
+    return ntt_run_batch(*c, d_cols, count, extended_omega, extended_k, (cudaStream_t)stream);
+}
+
 int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const uint64_t extended_omega_inv[4], const uint64_t factors[12], void* stream) {
     DeviceCtx* c = nullptr;
     H2B_TRY(get_ctx(device, &c));
@@ -1427,6 +1455,20 @@ int h2b_memcpy_h2d_async(int device, void* d_dst, const void* h_src, size_t byte
     if (bytes && (!d_dst || !h_src)) { set_error("h2b_memcpy_h2d_async: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
     std::lock_guard<std::mutex> lk(c->mu);
     return host_upload(*c, d_dst, h_src, bytes, (cudaStream_t)stream, false);
+}
+int h2b_memcpy_d2d_async(int device, void* d_dst, const void* d_src, size_t bytes, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (bytes && (!d_dst || !d_src)) { set_error("h2b_memcpy_d2d_async: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    H2B_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return H2B_OK;
+}
+int h2b_memset_zero_async(int device, void* d_dst, size_t bytes, void* stream) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (bytes && !d_dst) { set_error("h2b_memset_zero_async: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    H2B_CUDA(cudaMemsetAsync(d_dst, 0, bytes, (cudaStream_t)stream));
+    return H2B_OK;
 }
 int h2b_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes) {
     DeviceCtx* c = nullptr;

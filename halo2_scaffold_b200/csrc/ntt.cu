@@ -565,6 +565,38 @@ __global__ void __launch_bounds__(256) ntt_scale_table_kernel(uint4* a, size_t n
     fp_store<FR>(a + 2 * i, fp_mul(fp_load<FR>(a + 2 * i), f));
 }
 
+// the same factor pattern on up to NTT_BATCH_MAX columns in one launch (column = blockIdx.y)
+struct ScaleBatch { uint4* a[NTT_BATCH_MAX]; };
+__global__ void __launch_bounds__(256) ntt_scale_batch_kernel(ScaleBatch cols, size_t n, ScaleParams s) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4* a = cols.a[blockIdx.y];
+    const uint32_t k = s.count == 1 ? 0u : (uint32_t)(i % s.count);
+    Fr f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f.l[j] = s.f[k][j];
+    Fr v = fp_load<FR>(a + 2 * i);
+    fp_store<FR>(a + 2 * i, fp_mul(v, f));
+}
+int ntt_scale_batch_run(DeviceCtx& ctx, void* const* d_cols, size_t ncols, size_t n, const uint64_t* factors, int count, cudaStream_t stream) {
+    (void)ctx;
+    if (count < 1 || count > 8) { set_error("batched scale: count must be in [1, 8]"); return H2B_ERR_BAD_ARGUMENT; }
+    if (n == 0) return H2B_OK;
+    ScaleParams s;
+    memset(&s, 0, sizeof(s));
+    s.count = (uint32_t)count;
+    memcpy(s.f, factors, (size_t)count * 32);
+    for (size_t j0 = 0; j0 < ncols; j0 += NTT_BATCH_MAX) {
+        const size_t m = ncols - j0 < NTT_BATCH_MAX ? ncols - j0 : NTT_BATCH_MAX;
+        ScaleBatch b;
+        memset(&b, 0, sizeof(b));
+        for (size_t j = 0; j < m; ++j) b.a[j] = (uint4*)d_cols[j0 + j];
+        H2B_LAUNCH(ntt_scale_batch_kernel, dim3((unsigned)((n + 255) / 256), (unsigned)m), 256, 0, stream, b, n, s);
+    }
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors, int count, cudaStream_t stream) {
     if (count < 1 || count > 4096) { set_error("scale: count must be in [1, 4096]"); return H2B_ERR_BAD_ARGUMENT; }
     if (n == 0) return H2B_OK;

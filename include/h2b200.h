@@ -151,6 +151,12 @@ int h2b_lagrange_to_coeff_dev(int device, void* d_a, uint32_t k, const uint64_t 
 int h2b_coeff_to_extended_dev(int device, void* d_a, uint32_t k, uint32_t extended_k, const uint64_t extended_omega[4], const uint64_t zeta_powers[12],
                               void* stream);
 int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const uint64_t extended_omega_inv[4], const uint64_t factors[12], void* stream);
+/* lagrange_to_coeff / coeff_to_extended for `count` columns at once (d_cols: host array of device pointers; every column as in the
+ * single-column call): the transform passes and the scalings are launched once per batch of up to 16 columns */
+int h2b_lagrange_to_coeff_dev_batch(int device, void* const* d_cols, size_t count, uint32_t k, const uint64_t omega_inv[4], const uint64_t ifft_divisor[4],
+                                    void* stream);
+int h2b_coeff_to_extended_dev_batch(int device, void* const* d_cols, size_t count, uint32_t k, uint32_t extended_k, const uint64_t extended_omega[4],
+                                    const uint64_t zeta_powers[12], void* stream);
 
 /* Grand-product building blocks on a device-resident Fr column ([UP] halo2_proofs
  * plonk/permutation/prover.rs, plonk/lookup/prover.rs): z(omega^i) is the exclusive running product of
@@ -319,6 +325,9 @@ int h2b_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes);
  * call sees the data.  Pageable sources are consumed before the call returns (pinned staging threads), pinned sources must
  * stay valid until the stream reaches the copy. */
 int h2b_memcpy_h2d_async(int device, void* d_dst, const void* h_src, size_t bytes, void* stream);
+/* column copies / zero padding on the caller's stream (the padding of coeff_to_extended, copies that keep the Lagrange form) */
+int h2b_memcpy_d2d_async(int device, void* d_dst, const void* d_src, size_t bytes, void* stream);
+int h2b_memset_zero_async(int device, void* d_dst, size_t bytes, void* stream);
 int h2b_dev_sync(int device);
 
 /* ---- synthetic workload + diagnostics ---------------------------------------------------------------- */

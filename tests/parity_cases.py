@@ -754,10 +754,23 @@ def check_evaluate_h_sharded(L, oc, ek=7, k=5, groups=2, seed=6, shards=((0, 40,
                                zeta=zeta, extended_omega=fr_to_words(o.omega_for(ek))),
               lookups=[dict(product_coset=oc.random_fr(seed * 1000 + 700, size), permuted_input_coset=oc.random_fr(seed * 1000 + 701, size),
                             permuted_table_coset=oc.random_fr(seed * 1000 + 702, size))], lib=L)
-    whole = E.evaluate_h(**kw)
+    # the reference result comes from the ORACLE's three sequential loops, not from an unsharded run of the same library
+    def tup(g):
+        a = g.arrays()
+        return (a.constants, a.rotations, a.calculations, a.parts, a.n_intermediates)
+    ch = np.zeros((0, 4), dtype=np.uint64)
+    perm = kw["permutation"]
+    lk0 = kw["lookups"][0]
+    by_type = {"advice": advice, "fixed": fixed, "instance": instance}
+    want = oc.evaluate_graph(tup(E.custom_gates), fixed, advice, instance, ch, beta, gamma, theta, y, np.zeros((size, 4), dtype=np.uint64), rot_scale)
+    want = oc.evaluate_h_permutation(want, rot_scale, perm["product_cosets"], [by_type[t][i] for t, i in perm_cols], perm["cosets"], 2, -6, l0, l_last,
+                                     l_active, beta, gamma, y, delta, zeta, perm["extended_omega"])
+    want = oc.evaluate_h_lookup(tup(E.lookups[0]), fixed, advice, instance, ch, beta, gamma, theta, y, want, rot_scale, lk0["product_coset"],
+                                lk0["permuted_input_coset"], lk0["permuted_table_coset"], l0, l_last, l_active)
     assert sum(r for _, r, _ in shards) == size
     parts = [E.evaluate_h(shard=sh, **kw) for sh in shards]
-    assert (np.concatenate(parts) == whole).all()
+    assert (np.concatenate(parts) == want).all(), "row-sharded evaluate_h differs from the oracle"
+    assert (E.evaluate_h(**kw) == want).all()
     try:
         E.evaluate_h(shard=(shards[0][0], shards[0][1], 6 * rot_scale - 1), **kw)          # last_rotation = -6 needs 6 * rot_scale rows of halo
         raise AssertionError("a halo that is too small was accepted")

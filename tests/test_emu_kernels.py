@@ -581,3 +581,12 @@ def test_batched_columns_one_kernel_sequence(emu, oc, n, ncols, spacing, window)
 @pytest.mark.parametrize("k,count", [(3, 5), (9, 4), (11, 3), (12, 17), (13, 2)])
 def test_batched_ntts_share_pass_launches(emu, oc, k, count):
     pc.check_batched_ntts(emu, oc, k, count)
+
+
+@pytest.mark.parametrize("shape,batched", [(dict(k=5, A=1, LK=0, d=3), True), (dict(k=6, A=2, LK=1, d=4), True), (dict(k=6, A=3, LK=2, d=4), False)])
+def test_device_resident_proof_pipeline_matches_oracle_pipeline(emu, oc, shape, batched):
+    # tools/proof_pipeline_core.py (every column resident on the device, batched phase calls) against the same flow recomputed with
+    # the CPU oracle: every commitment and every evaluation
+    import pipeline_oracle
+    counts = pipeline_oracle.check_pipeline(emu, oc, shape, batched=batched)
+    assert counts["msm"] >= 7 and counts["eval"] >= 10

@@ -283,6 +283,16 @@ def test_batched_ntts_share_pass_launches(gpu, oc, k, count):
     pc.check_batched_ntts(gpu, oc, k, count)
 
 
+@pytest.mark.parametrize("shape,batched", [(dict(k=8, A=1, LK=0, d=3), True), (dict(k=12, A=2, LK=1, d=4), True), (dict(k=11, A=6, LK=2, d=4), True),
+                                           (dict(k=10, A=3, LK=1, d=4), False)])
+def test_device_resident_proof_pipeline_matches_oracle_pipeline(gpu, oc, shape, batched):
+    """tools/proof_pipeline_core.py -- every prover step on device-resident columns, the independent calls of a phase batched --
+    against the same flow recomputed with the CPU oracle: every commitment and every evaluation."""
+    import pipeline_oracle
+    counts = pipeline_oracle.check_pipeline(gpu, oc, shape, batched=batched)
+    assert counts["msm"] >= 7 and counts["eval"] >= 10
+
+
 def test_in_process_multi_device_paths(gpu):
     """Point-range sharding of one MSM across every visible GPU + concurrent callers (fresh process: own library instance)."""
     import os, subprocess, sys

@@ -78,7 +78,17 @@ gathered = [torch.zeros(rows * 4, dtype=torch.int64) for _ in range(world)]
 dist.all_gather(gathered, torch.from_numpy(mine.view(np.int64).reshape(-1).copy()))
 if rank == 0:
     got = np.concatenate([g.numpy().view(np.uint64).reshape(-1, 4) for g in gathered])
-    assert (got == E.evaluate_h(**kw)).all()
+    # against the ORACLE's three sequential loops over the whole domain (not against an unsharded run of the same library)
+    tup = lambda g: (lambda a: (a.constants, a.rotations, a.calculations, a.parts, a.n_intermediates))(g.arrays())
+    ch, pm, lk = np.zeros((0, 4), dtype=np.uint64), kw['permutation'], kw['lookups'][0]
+    by_type = {'advice': kw['advice'], 'fixed': kw['fixed'], 'instance': kw['instance']}
+    want = oc.evaluate_graph(tup(E.custom_gates), kw['fixed'], kw['advice'], kw['instance'], ch, kw['beta'], kw['gamma'], kw['theta'], kw['y'],
+                             np.zeros((size, 4), dtype=np.uint64), rot_scale)
+    want = oc.evaluate_h_permutation(want, rot_scale, pm['product_cosets'], [by_type[t][i] for t, i in perm_cols], pm['cosets'], 2, -6, kw['l0'], kw['l_last'],
+                                     kw['l_active_row'], kw['beta'], kw['gamma'], kw['y'], pm['delta'], pm['zeta'], pm['extended_omega'])
+    want = oc.evaluate_h_lookup(tup(E.lookups[0]), kw['fixed'], kw['advice'], kw['instance'], ch, kw['beta'], kw['gamma'], kw['theta'], kw['y'], want, rot_scale,
+                                lk['product_coset'], lk['permuted_input_coset'], lk['permuted_table_coset'], kw['l0'], kw['l_last'], kw['l_active_row'])
+    assert (got == want).all()
     print('ROWS_OK')
 dist.barrier(); dist.destroy_process_group()
 """
@@ -86,7 +96,7 @@ dist.barrier(); dist.destroy_process_group()
 
 def test_row_sharded_evaluate_h_two_ranks(emu, tmp_path):
     # evaluate_h sharded by rows: two ranks, each with its slice + halo of every column; the gathered rows equal
-    # the unsharded evaluation
+    # the oracle's evaluation of the whole domain
     script = tmp_path / "worker_rows.py"
     script.write_text(WORKER_ROWS % {"root": ROOT, "emu": emu.path})
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29537", H2B_EMU_THREADS="2")
