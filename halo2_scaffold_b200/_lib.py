@@ -38,7 +38,7 @@ _EXPORTS = [
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
     "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_graph_shard_dev", "h2b_evaluate_h_permutation_shard_dev", "h2b_evaluate_h_lookup_shard_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
-    "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev", "h2b_ntt_bn254_fr_dev_batch", "h2b_lagrange_to_coeff_dev_batch", "h2b_coeff_to_extended_dev_batch", "h2b_memcpy_d2d_async", "h2b_memset_zero_async",
+    "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev", "h2b_ntt_bn254_fr_dev_batch", "h2b_lagrange_to_coeff_dev_batch", "h2b_coeff_to_extended_dev_batch", "h2b_memcpy_d2d_async", "h2b_memset_zero_async", "h2b_column_pipeline",
 ]
 
 
@@ -185,6 +185,7 @@ class Lib:
         L.h2b_memcpy_h2d_async.argtypes = [i32, vp, vp, sz, vp]
         L.h2b_memcpy_d2d_async.argtypes = [i32, vp, vp, sz, vp]
         L.h2b_memset_zero_async.argtypes = [i32, vp, sz, vp]
+        L.h2b_column_pipeline.argtypes = [i32, vp, u64, u32, u32, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]
         L.h2b_dev_sync.argtypes = [i32]
         L.h2b_gen_points_dev.argtypes = [i32, u64, sz, vp, vp]
         L.h2b_gen_scalars_dev.argtypes = [i32, u64, sz, i32, vp, vp]
@@ -353,6 +354,23 @@ class Lib:
         extended_omega, zeta_powers = _u64(extended_omega), _u64(zeta_powers).reshape(3, 4)
         ptrs = (ctypes.c_void_p * len(d_cols))(*d_cols)
         self.check(self.L.h2b_coeff_to_extended_dev_batch(device, ptrs, len(d_cols), k, extended_k, extended_omega.ctypes.data, zeta_powers.ctypes.data, stream))
+
+    def column_pipeline(self, lagrange: np.ndarray, handle_g_lagrange: int, k: int, extended_k: int, omega_inv, ifft_divisor, extended_omega, zeta_powers,
+                        want_coeff: bool = True, want_extended: bool = True, keep_on_device: bool = False, device: int = 0):
+        """commit_lagrange + lagrange_to_coeff + coeff_to_extended of one host column with a single upload
+        -> dict(commitment (12 words), coeff, extended, d_extended)"""
+        lagrange = _u64(lagrange).reshape(-1, 4)
+        assert lagrange.shape[0] == 1 << k
+        w = [_u64(v) for v in (omega_inv, ifft_divisor, extended_omega)]
+        zp = _u64(zeta_powers).reshape(3, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        coeff = np.empty((1 << k, 4), dtype=np.uint64) if want_coeff else None
+        ext = np.empty((1 << extended_k, 4), dtype=np.uint64) if want_extended else None
+        d_ext = ctypes.c_void_p(0)
+        self.check(self.L.h2b_column_pipeline(device, lagrange.ctypes.data, handle_g_lagrange, k, extended_k, w[0].ctypes.data, w[1].ctypes.data,
+                                              w[2].ctypes.data, zp.ctypes.data, out.ctypes.data, coeff.ctypes.data if want_coeff else None,
+                                              ext.ctypes.data if want_extended else None, ctypes.byref(d_ext) if keep_on_device else None))
+        return dict(commitment=out, coeff=coeff, extended=ext, d_extended=d_ext.value)
 
     def extended_to_coeff_dev(self, device: int, d_a: int, extended_k: int, extended_omega_inv: np.ndarray, factors: np.ndarray, stream: int = 0):
         extended_omega_inv, factors = _u64(extended_omega_inv), _u64(factors).reshape(3, 4)

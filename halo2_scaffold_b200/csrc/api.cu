@@ -610,6 +610,7 @@ void h2b_shutdown(void) {
         c->msm_scalars.release();
         c->msm_out.release();
         c->msm_bases.release();
+        c->col_ext.release();
         c->scan_scratch.release();
         evaluate_release(*c);
         c->srs_status.release();
@@ -1054,6 +1055,55 @@ int h2b_coeff_to_extended_dev_batch(int device, void* const* d_cols, size_t coun
     if (en > n)
         for (size_t j = 0; j < count; ++j) H2B_CUDA(cudaMemsetAsync((char*)d_cols[j] + n * 32, 0, (en - n) * 32, (cudaStream_t)stream));
     return ntt_run_batch(*c, d_cols, count, extended_omega, extended_k, (cudaStream_t)stream);
+}
+
+// One witness / product column through the three steps such a column takes in create_proof ([UP] plonk/prover.rs: commit_lagrange,
+// EvaluationDomain::lagrange_to_coeff, EvaluationDomain::coeff_to_extended) with ONE upload and no intermediate round trip
+// (the call a patched prover.rs makes per column instead of three host-pointer drop-ins).
+int h2b_column_pipeline(int device, const uint64_t* lagrange, uint64_t handle_g_lagrange, uint32_t k, uint32_t extended_k, const uint64_t omega_inv[4],
+                        const uint64_t ifft_divisor[4], const uint64_t extended_omega[4], const uint64_t zeta_powers[12], uint64_t out_commitment_jac[12],
+                        uint64_t* out_coeff, uint64_t* out_extended, void** d_extended) {
+    DeviceCtx* c = nullptr;
+    H2B_TRY(get_ctx(device, &c));
+    if (!lagrange || !omega_inv || !ifft_divisor || !extended_omega || !zeta_powers || !out_commitment_jac) { set_error("h2b_column_pipeline: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
+    if (k > 28 || extended_k < k || extended_k > 28) { set_error("h2b_column_pipeline: need k <= extended_k <= 28"); return H2B_ERR_BAD_ARGUMENT; }
+    const size_t n = (size_t)1 << k, en = (size_t)1 << extended_k;
+    SetRef bs;
+    H2B_TRY(registered_set("h2b_column_pipeline", handle_g_lagrange, 0, n, &bs));
+    const size_t d = (size_t)device;
+    if (bs->lo[d] != 0 || bs->rows[d] < n) { set_error("h2b_column_pipeline: device %d does not hold rows [0, %zu) of the set (use a replicated registration)", device, n); return H2B_ERR_BAD_ARGUMENT; }
+    const bool want_ext = out_extended || d_extended;
+    void* d_ext = nullptr;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = c->stream;
+    H2B_TRY(c->ntt_io.reserve(n * 32));
+    H2B_TRY(c->msm_out.reserve(256));
+    if (want_ext) {
+        if (d_extended) {
+            cudaError_t e = cudaMalloc(&d_ext, en * 32);
+            if (e != cudaSuccess) { cudaGetLastError(); set_error("h2b_column_pipeline: cudaMalloc(%zu): %s", en * 32, cudaGetErrorString(e)); return H2B_ERR_OOM; }
+        } else {
+            H2B_TRY(c->col_ext.reserve(en * 32));
+            d_ext = c->col_ext.p;
+        }
+    }
+    int rc = host_upload(*c, c->ntt_io.p, lagrange, n * 32, st);
+    if (!rc) rc = msm_run(*c, c->ntt_io.p, bases_of(*bs, d, 0), n, c->msm_out.p, false, st);
+    if (!rc && cudaMemcpyAsync(out_commitment_jac, c->msm_out.p, 96, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = H2B_ERR_CUDA;
+    if (!rc) rc = ntt_run(*c, c->ntt_io.p, omega_inv, k, st);
+    if (!rc) rc = ntt_scale_run(*c, c->ntt_io.p, n, ifft_divisor, 1, st);
+    if (!rc && want_ext) {
+        if (cudaMemcpyAsync(d_ext, c->ntt_io.p, n * 32, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = H2B_ERR_CUDA;
+        if (!rc) rc = ntt_scale_run(*c, d_ext, n, zeta_powers, 3, st);
+        if (!rc && en > n && cudaMemsetAsync((char*)d_ext + n * 32, 0, (en - n) * 32, st) != cudaSuccess) rc = H2B_ERR_CUDA;
+        if (!rc) rc = ntt_run(*c, d_ext, extended_omega, extended_k, st);
+    }
+    if (!rc && out_coeff) rc = host_download(*c, out_coeff, c->ntt_io.p, n * 32, st);
+    if (!rc && out_extended) rc = host_download(*c, out_extended, d_ext, en * 32, st);
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_error("h2b_column_pipeline: %s", cudaGetErrorString(cudaGetLastError())); rc = H2B_ERR_CUDA; }
+    if (rc) { if (d_extended && d_ext) cudaFree(d_ext); if (rc == H2B_ERR_CUDA && !*get_error()) set_error("h2b_column_pipeline: CUDA error"); return rc; }
+    if (d_extended) *d_extended = d_ext;
+    return H2B_OK;
 }
 
 int h2b_extended_to_coeff_dev(int device, void* d_a, uint32_t extended_k, const uint64_t extended_omega_inv[4], const uint64_t factors[12], void* stream) {

@@ -93,6 +93,7 @@ struct DeviceCtx {
     bool ntt_attr_set = false;
     bool msm_attr_set = false;
     DevBuf ntt_io;                     // staging for the host-pointer NTT entry point
+    DevBuf col_ext;                    // extended form of h2b_column_pipeline when the caller only wants it on the host
     DevBuf scale_table;                // factor table of h2b_fr_scale_dev with more than 8 factors
     DevBuf msm_scalars;                // staging for host-pointer MSM scalars
     DevBuf msm_out;                    // 96-byte result

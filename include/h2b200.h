@@ -158,6 +158,16 @@ int h2b_lagrange_to_coeff_dev_batch(int device, void* const* d_cols, size_t coun
 int h2b_coeff_to_extended_dev_batch(int device, void* const* d_cols, size_t count, uint32_t k, uint32_t extended_k, const uint64_t extended_omega[4],
                                     const uint64_t zeta_powers[12], void* stream);
 
+/* ONE column through commit_lagrange -> lagrange_to_coeff -> coeff_to_extended with a single upload ([UP]
+ * plonk/prover.rs commits every advice / permuted / product column in Lagrange form and then converts it twice): `lagrange` is the
+ * host column (2^k x 4 words), handle_g_lagrange a registered copy of ParamsKZG::g_lagrange resident on `device`.  Writes the
+ * commitment (Jacobian), and -- each optional, NULL to skip -- the coefficient form (host, 2^k x 4), the extended-coset form to the
+ * host (2^extended_k x 4) and/or leaves it on the device (*d_extended, to be released with h2b_dev_free) for h2b_evaluate_*_dev.
+ * Synchronous.  Against three host-pointer drop-in calls it saves two uploads and one download of the column. */
+int h2b_column_pipeline(int device, const uint64_t* lagrange, uint64_t handle_g_lagrange, uint32_t k, uint32_t extended_k, const uint64_t omega_inv[4],
+                        const uint64_t ifft_divisor[4], const uint64_t extended_omega[4], const uint64_t zeta_powers[12], uint64_t out_commitment_jac[12],
+                        uint64_t* out_coeff, uint64_t* out_extended, void** d_extended);
+
 /* Grand-product building blocks on a device-resident Fr column ([UP] halo2_proofs
  * plonk/permutation/prover.rs, plonk/lookup/prover.rs): z(omega^i) is the exclusive running product of
  * numerator[i] / denominator[i], the denominators inverted with ff::BatchInvert.

@@ -949,3 +949,37 @@ def check_batched_ntts(L, oc, k, count, seed=81):
             L.d2h(0, got, p)
             assert (got == b).all(), ("device batch", k, inverse)
             L.dev_free(0, p)
+
+
+def check_column_pipeline(L, oc, j, k, seed=91):
+    """h2b_column_pipeline (commit_lagrange -> lagrange_to_coeff -> coeff_to_extended, one upload) == the three separate steps of the oracle"""
+    import halo2_scaffold_b200 as h2
+    from halo2_scaffold_b200.domain import fr_to_words
+    dom, ref = h2.EvaluationDomain(j, k, lib=L), o.EvaluationDomain(j, k)
+    n, en = 1 << k, 1 << ref.extended_k
+    col = L.gen_scalars(seed, n, 1)
+    gl = oc.gen_points(seed + 1, n)
+    h = L.register_bases(gl)
+    try:
+        zs = np.stack([fr_to_words(1), fr_to_words(ref.g_coset), fr_to_words(ref.g_coset_inv)])
+        r = L.column_pipeline(col, h, k, ref.extended_k, fr_to_words(ref.omega_inv), fr_to_words(ref.ifft_divisor), fr_to_words(ref.extended_omega), zs,
+                              keep_on_device=True)
+        want_commit = affine_of(oc, oc.best_multiexp(col, gl))
+        assert (affine_of(oc, r["commitment"]) == want_commit).all()
+        want_coeff = oc.fr_scale(oc.best_fft(col, fr_to_words(ref.omega_inv), k), fr_to_words(ref.ifft_divisor))
+        assert (r["coeff"] == want_coeff).all()
+        e = np.zeros((en, 4), dtype=np.uint64)
+        e[:n] = oc.field_op("fr", "mul", want_coeff, np.ascontiguousarray(np.tile(zs, ((n + 2) // 3, 1))[:n]))
+        want_ext = oc.best_fft(e, fr_to_words(ref.extended_omega), ref.extended_k)
+        assert (r["extended"] == want_ext).all()
+        back = np.zeros((en, 4), dtype=np.uint64)
+        L.d2h(0, back, r["d_extended"])
+        L.dev_free(0, r["d_extended"])
+        assert (back == want_ext).all()
+        # the same answers as the mirrored three-call path
+        assert (dom.lagrange_to_coeff(col) == r["coeff"]).all() and (dom.coeff_to_extended(r["coeff"]) == r["extended"]).all()
+        r2 = L.column_pipeline(col, h, k, ref.extended_k, fr_to_words(ref.omega_inv), fr_to_words(ref.ifft_divisor), fr_to_words(ref.extended_omega), zs,
+                               want_coeff=False, want_extended=False)
+        assert (affine_of(oc, r2["commitment"]) == want_commit).all() and r2["coeff"] is None
+    finally:
+        L.unregister_bases(h)

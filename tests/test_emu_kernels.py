@@ -590,3 +590,8 @@ def test_device_resident_proof_pipeline_matches_oracle_pipeline(emu, oc, shape, 
     import pipeline_oracle
     counts = pipeline_oracle.check_pipeline(emu, oc, shape, batched=batched)
     assert counts["msm"] >= 7 and counts["eval"] >= 10
+
+
+@pytest.mark.parametrize("j,k", [(3, 5), (4, 9), (5, 7)])
+def test_column_pipeline_single_upload(emu, oc, j, k):
+    pc.check_column_pipeline(emu, oc, j, k)

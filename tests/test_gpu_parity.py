@@ -293,6 +293,11 @@ def test_device_resident_proof_pipeline_matches_oracle_pipeline(gpu, oc, shape, 
     assert counts["msm"] >= 7 and counts["eval"] >= 10
 
 
+@pytest.mark.parametrize("j,k", [(3, 10), (4, 16), (4, 20)])
+def test_column_pipeline_single_upload(gpu, oc, j, k):
+    pc.check_column_pipeline(gpu, oc, j, k)
+
+
 def test_in_process_multi_device_paths(gpu):
     """Point-range sharding of one MSM across every visible GPU + concurrent callers (fresh process: own library instance)."""
     import os, subprocess, sys
