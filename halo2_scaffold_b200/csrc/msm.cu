@@ -54,6 +54,7 @@ struct MsmPlan {
                          //      cursor atomics are aggregated per CTA in shared memory instead of hammering 2-4 counters
     uint32_t ncols;      // batched MSM: independent scalar columns over the same points (blockIdx.y of the sort kernels); column j owns
                          //      bucket sets [j * m, (j + 1) * m), so B = ncols * m * Nb and everything after the sort is unchanged
+    uint32_t pb;         // > 0: partitioned sort (section 2c): buckets are grouped into partitions of 2^pb, P = ceil(B / 2^pb) of them
 };
 
 // scalar columns of a batched MSM (one sort / accumulate / reduce sequence for all of them): the columns a proof phase commits
@@ -91,6 +92,339 @@ __device__ __forceinline__ uint32_t limb_bits(const Fr& s, uint32_t bit, uint32_
     return v & ((1u << c) - 1);
 }
 
+// scalar -> signed window digits.  Calls emit(w, set, d, sign) for every window (d == 0: no entry)
+template <class F>
+__device__ __forceinline__ void msm_recode(const uint4* __restrict__ scalars, uint32_t i, bool live, const MsmPlan& pl, F emit) {
+    const uint32_t c = pl.c, half = 1u << (c - 1);
+    Fr s = fp_zero<FR>();
+    uint32_t neg = 0;
+    if (live) {
+        s = fp_from_mont(fp_load<FR>(scalars + 2 * (size_t)i));
+        if (fr_gt_half(s)) {
+            Fr r;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r.l[k] = FpParams<FR>::P(k);
+            uint32_t borrow = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint64_t d = (uint64_t)r.l[k] - s.l[k] - borrow;
+                s.l[k] = (uint32_t)d;
+                borrow = (uint32_t)(d >> 63);
+            }
+            neg = SIGN_BIT;
+        }
+    }
+    uint32_t carry = 0, set = 0;
+    for (uint32_t w = 0; w < pl.W; ++w) {
+        uint32_t d = limb_bits(s, w * c, c) + carry;
+        uint32_t sign = neg;
+        if (d > half) { d = (1u << c) - d; carry = 1; sign ^= SIGN_BIT; }
+        else carry = 0;
+        emit(w, set, d, sign);
+        if (++set == pl.m) set = 0;
+    }
+}
+
+// ---- 2c. partitioned sort ------------------------------------------------------------------------------------------------
+// The one-pass counting sort (sections 1-2) issues one returning L2 atomic and one scattered 4-byte store per entry.  At 2^24
+// points that is 218 M of each: ncu shows the kernel waiting on them (long-scoreboard 226 cycles per issue, L2 45 %, DRAM write
+// amplification 2.7x because 2^19 half-written 128-byte lines do not stay in the L2), 4.1 ms + 1.2 ms for the histogram's
+// reductions.  Here the sort is done in two levels that keep every random access on chip:
+//   digits    (msm_decompose_kernel, pb > 0): digits as before, but only a histogram over P ~ 512 PARTITIONS of 2^pb buckets,
+//             taken in shared memory and flushed with P global reductions per CTA;
+//   partition (msm_partition_kernel): a CTA takes a tile of scalars, groups its entries by partition in shared memory and
+//             appends each group to the partition's region of an intermediate list as one contiguous run (8-byte entries
+//             bucket | row+sign): coalesced writes, P global atomics per tile instead of one per entry;
+//   place     (msm_place_kernel): one CTA per partition counts its buckets in shared memory, scans them -- this yields
+//             offsets[] -- and places every entry at its final position with shared-memory cursors; the partition's slice of
+//             the sorted list (a few MB) is written while it is L2-resident.
+static const uint32_t PART_MAX = 2048;            // partitions (shared-memory histogram of the first two kernels)
+static const uint32_t PART_TILE_ENTRIES = 12288;  // entries staged per tile: 96 KiB of shared memory
+static const uint32_t PART_W_MAX = 16;            // windows per scalar kept in registers by msm_partition_kernel
+static const uint32_t PLACE_MAX_LOG = 13;         // buckets per partition in the place kernels: 32 KiB of cursors
+
+__device__ __forceinline__ void msm_decompose_partitions(const MsmCols& cols, const MsmPlan& pl, uint32_t* __restrict__ part_counts) {
+    __shared__ uint32_t part_hist[PART_MAX];
+    const uint32_t col = blockIdx.y;
+    const uint4* __restrict__ scalars = cols.scalars[col];
+    const uint32_t col_len = cols.len[col];
+    const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
+    const uint32_t gbase = col * pl.m * pl.Nb;
+    for (uint32_t b = threadIdx.x; b < P; b += blockDim.x) part_hist[b] = 0;
+    __syncthreads();
+    const uint32_t rounds = (pl.n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t round = 0; round < rounds; ++round) {
+        const uint32_t i = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        if (i >= col_len) continue;
+        msm_recode(scalars, i, true, pl, [&](uint32_t, uint32_t set, uint32_t d, uint32_t) {
+            if (d) atomicAdd(&part_hist[(gbase + set * pl.Nb + d - 1) >> pl.pb], 1u);
+        });
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < P; b += blockDim.x)
+        if (part_hist[b]) atomicAdd(&part_counts[b], part_hist[b]);
+}
+
+// exclusive scans over the P partition totals: entries -> part_off[0..P] (+ a copy: the append cursors), and chunks of
+// 2^chunk_log entries -> chunk0[0..P] (the place kernels work on chunks, so that a partition holding far more than its share --
+// the narrow top window of uniform scalars, the ones and zeros of a witness column -- is spread over many CTAs)
+__global__ void __launch_bounds__(1024) msm_partition_scan_kernel(const uint32_t* __restrict__ part_counts, uint32_t P, uint32_t chunk_log,
+                                                                uint32_t* __restrict__ part_off, uint32_t* __restrict__ part_cursor, uint32_t* __restrict__ chunk0) {
+    __shared__ uint32_t sh[1024], sh2[1024];
+    __shared__ uint32_t carry_sh, carry2_sh;
+    if (threadIdx.x == 0) { carry_sh = 0; carry2_sh = 0; }
+    __syncthreads();
+    for (uint32_t start = 0; start < P; start += 1024) {
+        const uint32_t idx = start + threadIdx.x;
+        const uint32_t v = idx < P ? part_counts[idx] : 0;
+        const uint32_t v2 = (v + (1u << chunk_log) - 1) >> chunk_log;
+        sh[threadIdx.x] = v;
+        sh2[threadIdx.x] = v2;
+        __syncthreads();
+        for (uint32_t o = 1; o < 1024; o <<= 1) {
+            const uint32_t add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0, add2 = threadIdx.x >= o ? sh2[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            sh2[threadIdx.x] += add2;
+            __syncthreads();
+        }
+        const uint32_t incl = sh[threadIdx.x], carry = carry_sh, incl2 = sh2[threadIdx.x], carry2 = carry2_sh;
+        if (idx < P) { part_off[idx] = carry + incl - v; part_cursor[idx] = carry + incl - v; chunk0[idx] = carry2 + incl2 - v2; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry_sh = carry + incl; carry2_sh = carry2 + incl2; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part_off[P] = carry_sh; chunk0[P] = carry2_sh; }
+}
+
+// one thread per scalar of the tile (blockDim.x == tile): the W <= 16 digits are recoded once and stay in registers
+__global__ void __launch_bounds__(1024) msm_partition_kernel(MsmCols cols, MsmPlan pl, uint32_t* __restrict__ part_cursor, uint2* __restrict__ inter) {
+    H2B_DYN_SMEM(uint32_t, smem);
+    const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
+    uint32_t* cnt = smem;                    // entries of this tile per partition, then the fill cursor
+    uint32_t* start = smem + P;              // first staging slot of the partition
+    uint32_t* base = smem + 2 * P;           // first slot of this tile's run in the partition's region
+    uint2* staging = (uint2*)(smem + 3 * P + (P & 1));
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t col = blockIdx.y;
+    const uint4* __restrict__ scalars = cols.scalars[col];
+    const uint32_t col_len = cols.len[col];
+    const uint32_t gbase = col * pl.m * pl.Nb;
+    const uint32_t tile = blockDim.x;
+    const uint32_t ntiles = (pl.n + tile - 1) / tile;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint32_t i = t * tile + threadIdx.x;
+        const bool live = i < col_len;
+        for (uint32_t b = threadIdx.x; b < P; b += blockDim.x) cnt[b] = 0;
+        uint32_t dig[PART_W_MAX];            // bucket (global index + 1, 0 = no entry) with the sign in bit 31
+#pragma unroll
+        for (uint32_t w = 0; w < PART_W_MAX; ++w) dig[w] = 0;
+        if (live)
+            msm_recode(scalars, i, true, pl, [&](uint32_t w, uint32_t set, uint32_t d, uint32_t sign) {
+#pragma unroll
+                for (uint32_t k = 0; k < PART_W_MAX; ++k)
+                    if (k == w) dig[k] = d ? ((gbase + set * pl.Nb + d) | sign) : 0u;
+            });
+        __syncthreads();
+#pragma unroll
+        for (uint32_t w = 0; w < PART_W_MAX; ++w)
+            if (dig[w]) atomicAdd(&cnt[((dig[w] & ~SIGN_BIT) - 1) >> pl.pb], 1u);
+        __syncthreads();
+        // exclusive scan of cnt over the P partitions, reserve the runs, reset cnt as fill cursor
+        {
+            const uint32_t per = (P + blockDim.x - 1) / blockDim.x;
+            const uint32_t lo = threadIdx.x * per < P ? threadIdx.x * per : P, hi = lo + per < P ? lo + per : P;
+            uint32_t sum = 0;
+            for (uint32_t b = lo; b < hi; ++b) sum += cnt[b];
+            uint32_t incl = sum;
+            const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            if (lane == 31) warp_tot[wid] = incl;
+            __syncthreads();
+            uint32_t run = incl - sum;
+            for (uint32_t k = 0; k < wid; ++k) run += warp_tot[k];
+            for (uint32_t b = lo; b < hi; ++b) {
+                const uint32_t c = cnt[b];
+                start[b] = run;
+                base[b] = c ? atomicAdd(&part_cursor[b], c) : 0u;
+                cnt[b] = 0;
+                run += c;
+            }
+        }
+        __syncthreads();
+        // stage the entries grouped by partition: (global bucket, table row | sign)
+        {
+            uint32_t set = 0, row = pl.row0 + i;
+#pragma unroll
+            for (uint32_t w = 0; w < PART_W_MAX; ++w) {
+                if (w < pl.W) {
+                    if (dig[w]) {
+                        const uint32_t g = (dig[w] & ~SIGN_BIT) - 1;
+                        const uint32_t p = g >> pl.pb;
+                        staging[start[p] + atomicAdd(&cnt[p], 1u)] = make_uint2(g, row | (dig[w] & SIGN_BIT));
+                    }
+                    if (++set == pl.m) { set = 0; row += pl.stride; }
+                }
+            }
+        }
+        __syncthreads();
+        // write-out: every partition's group goes to its region of the intermediate list as one contiguous run
+        const uint32_t total = start[P - 1] + cnt[P - 1];
+        for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+            const uint2 ent = staging[j];
+            const uint32_t p = ent.x >> pl.pb;
+            inter[base[p] + (j - start[p])] = ent;
+        }
+        __syncthreads();
+    }
+}
+
+// chunk c -> (partition, entry range).  chunk0 is ascending; the partition is the last one whose first chunk is <= c.
+__device__ __forceinline__ bool msm_chunk_range(const uint32_t* __restrict__ chunk0, const uint32_t* __restrict__ part_off, uint32_t P, uint32_t chunk_log,
+                                                uint32_t c, uint32_t& p, uint32_t& e0, uint32_t& e1) {
+    if (c >= chunk0[P]) return false;
+    uint32_t lo = 0, hi = P;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (chunk0[mid] <= c) lo = mid; else hi = mid;
+    }
+    p = lo;           // chunk0[p] <= c < chunk0[p + 1]: partitions without entries (chunk0[p] == chunk0[p + 1]) are never selected
+    e0 = part_off[p] + ((c - chunk0[p]) << chunk_log);
+    e1 = e0 + (1u << chunk_log) < part_off[p + 1] ? e0 + (1u << chunk_log) : part_off[p + 1];
+    return true;
+}
+
+// per-chunk bucket histogram (shared memory) -> chunk_hist[c][0 .. 2^pb)
+__global__ void __launch_bounds__(1024) msm_place_count_kernel(MsmPlan pl, uint32_t chunk_log, const uint32_t* __restrict__ chunk0, const uint32_t* __restrict__ part_off,
+                                                             const uint2* __restrict__ inter, uint32_t* __restrict__ chunk_hist) {
+    H2B_DYN_SMEM(uint32_t, cur);
+    const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
+    const uint32_t NB = 1u << pl.pb;
+    for (uint32_t c = blockIdx.x;; c += gridDim.x) {
+        uint32_t p, e0, e1;
+        if (!msm_chunk_range(chunk0, part_off, P, chunk_log, c, p, e0, e1)) return;
+        const uint32_t g0 = p << pl.pb;
+        const bool hot = (uint64_t)(part_off[p + 1] - part_off[p]) * P > 8ull * part_off[P];
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) cur[b] = 0;
+        __syncthreads();
+        for (uint32_t base = e0; base < e1; base += 4 * blockDim.x) {
+            uint32_t bk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = base + u * blockDim.x + threadIdx.x;
+                bk[u] = j < e1 ? inter[j].x - g0 : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (hot) {
+                    const unsigned peers = __match_any_sync(0xffffffffu, bk[u]);
+                    if (bk[u] != 0xffffffffu && (threadIdx.x & 31) == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&cur[bk[u]], (uint32_t)__popc(peers));
+                } else if (bk[u] != 0xffffffffu) atomicAdd(&cur[bk[u]], 1u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) chunk_hist[(size_t)c * NB + b] = cur[b];
+        __syncthreads();
+    }
+}
+
+// one CTA per partition: bucket totals over the partition's chunks, exclusive scan -> offsets[], and every chunk's histogram
+// row is replaced by the positions at which that chunk starts writing each bucket
+__global__ void __launch_bounds__(1024) msm_place_scan_kernel(MsmPlan pl, const uint32_t* __restrict__ chunk0, const uint32_t* __restrict__ part_off,
+                                                            uint32_t* __restrict__ chunk_hist, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
+    const uint32_t NB = 1u << pl.pb;
+    const uint32_t per = (NB + blockDim.x - 1) / blockDim.x;          // <= 8
+    for (uint32_t p = blockIdx.x; p < P; p += gridDim.x) {
+        const uint32_t c0 = chunk0[p], c1 = chunk0[p + 1];
+        const uint32_t g0 = p << pl.pb;
+        const uint32_t nb = (pl.B - g0 < NB) ? pl.B - g0 : NB;
+        const uint32_t lo = threadIdx.x * per < NB ? threadIdx.x * per : NB, hi = lo + per < NB ? lo + per : NB;
+        uint32_t tot[8];
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            tot[k] = 0;
+            if (lo + k < hi) {
+                uint32_t t = 0;
+                for (uint32_t c = c0; c < c1; ++c) t += chunk_hist[(size_t)c * NB + lo + k];
+                tot[k] = t;
+                sum += t;
+            }
+        }
+        uint32_t incl = sum;
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        uint32_t run = part_off[p] + incl - sum;
+        for (uint32_t k = 0; k < wid; ++k) run += warp_tot[k];
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            if (lo + k < hi) {
+                const uint32_t b = lo + k;
+                if (b < nb) offsets[g0 + b] = run;
+                uint32_t r = run;
+                for (uint32_t c = c0; c < c1; ++c) {
+                    const uint32_t v = chunk_hist[(size_t)c * NB + b];
+                    chunk_hist[(size_t)c * NB + b] = r;
+                    r += v;
+                }
+                run += tot[k];
+            }
+        }
+        if (p == P - 1 && threadIdx.x == 0) offsets[pl.B] = part_off[P];
+        __syncthreads();
+    }
+}
+
+// per chunk: cursors from the scanned histogram row, every entry to its final position
+__global__ void __launch_bounds__(1024) msm_place_kernel(MsmPlan pl, uint32_t chunk_log, const uint32_t* __restrict__ chunk0, const uint32_t* __restrict__ part_off,
+                                                       const uint2* __restrict__ inter, const uint32_t* __restrict__ chunk_hist, uint32_t* __restrict__ sorted) {
+    H2B_DYN_SMEM(uint32_t, cur);
+    const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
+    const uint32_t NB = 1u << pl.pb;
+    for (uint32_t c = blockIdx.x;; c += gridDim.x) {
+        uint32_t p, e0, e1;
+        if (!msm_chunk_range(chunk0, part_off, P, chunk_log, c, p, e0, e1)) return;
+        const uint32_t g0 = p << pl.pb;
+        const bool hot = (uint64_t)(part_off[p + 1] - part_off[p]) * P > 8ull * part_off[P];
+        for (uint32_t b = threadIdx.x; b < NB; b += blockDim.x) cur[b] = chunk_hist[(size_t)c * NB + b];
+        __syncthreads();
+        for (uint32_t base = e0; base < e1; base += 4 * blockDim.x) {
+            uint2 ent[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = base + u * blockDim.x + threadIdx.x;
+                ent[u] = j < e1 ? inter[j] : make_uint2(0xffffffffu, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool live = ent[u].x != 0xffffffffu;
+                const uint32_t b = ent[u].x - g0;
+                if (hot) {
+                    const unsigned peers = __match_any_sync(0xffffffffu, live ? b : 0xffffffffu);
+                    const uint32_t lane = threadIdx.x & 31, leader = (uint32_t)(__ffs((int)peers) - 1);
+                    uint32_t first = 0;
+                    if (live && lane == leader) first = atomicAdd(&cur[b], (uint32_t)__popc(peers));
+                    first = __shfl_sync(0xffffffffu, first, (int)leader);
+                    if (live) sorted[first + (uint32_t)__popc(peers & ((1u << lane) - 1))] = ent[u].y;
+                } else if (live) {
+                    sorted[atomicAdd(&cur[b], 1u)] = ent[u].y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- 1. decompose + histogram ------------------------------------------------------------------
 // (grid-stride over blocks of 256 scalars so that the per-CTA aggregation of a narrow top window is flushed rarely)
 __global__ void __launch_bounds__(256) msm_decompose_kernel(MsmCols cols, MsmPlan pl,
@@ -99,6 +433,12 @@ __global__ void __launch_bounds__(256) msm_decompose_kernel(MsmCols cols, MsmPla
     const uint32_t col = blockIdx.y;
     const uint4* __restrict__ scalars = cols.scalars[col];
     const uint32_t col_len = cols.len[col];
+    if (pl.pb) {
+        // partitioned sort: only the P partition totals are needed here (the per-bucket counts are taken per partition, in shared
+        // memory, by msm_place_kernel): a per-CTA histogram, flushed with one global reduction per partition
+        msm_decompose_partitions(cols, pl, counts);
+        return;
+    }
     counts += (size_t)col * pl.m * pl.Nb;
     digits += (size_t)col * pl.W * pl.n;
     const uint32_t top_set = (pl.W - 1) % pl.m;
@@ -702,6 +1042,8 @@ struct MsmScratch {
     DevBuf digits, counts, offsets, offsets2, cursor, block_sums, sorted, sorted2, ctrl, split_list, heavy, chunk_desc, chunk_out, bucket_acc, bucket_tmp, head_partial, redA, redB, redC, redD, result;
     DevBuf pair_pts, pair_counts, pair_offsets[3], pair_sorted[3];      // pair pre-reduction (batched affine additions)
     DevBuf batch_out;                                                   // result blocks of a batched host-pointer call
+    DevBuf part_counts, part_off, part_cursor, chunk0, chunk_hist, inter; // partitioned sort (section 2c)
+    bool part_attr_set = false;
 };
 
 static int g_forced_c = 0;
@@ -821,6 +1163,12 @@ static int msm_plan(DeviceCtx& ctx, MsmScratch& s, const MsmBases& bases, size_t
     return H2B_OK;
 }
 
+static uint32_t msm_sort2_chunk_log() {
+    static int v = -1;
+    if (v < 0) { v = env_int("H2B_MSM_SORT2_CHUNK_LOG", 15); if (v < 5 || v > 20) v = 15; }
+    return (uint32_t)v;
+}
+
 // where chunk [done, done + m) of the call finds its points
 static void chunk_points(const MsmBases& bases, size_t done, const void** tables, size_t* row0) {
     *row0 = bases.row0 + done;
@@ -846,6 +1194,29 @@ static int msm_size_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan& pl, size_t row
     else if (upper >= resident * SLICE_MIN) pl.G = (uint32_t)resident;
     else pl.G = (uint32_t)((upper + SLICE_MIN - 1) / SLICE_MIN);
     if (pl.G == 0) pl.G = 1;
+    // partitioned sort for large lists (H2B_MSM_SORT2=0 keeps the one-pass counting sort; H2B_MSM_SORT2_MIN_LOG lowers the threshold: tests)
+    {
+        static int env_on = -1, env_min = -1;
+        if (env_on < 0) env_on = env_int("H2B_MSM_SORT2", 1);
+        if (env_min < 0) env_min = env_int("H2B_MSM_SORT2_MIN_LOG", 29);      // measured (profiles/r02_partitioned_sort.jsonl): equal at 2^24 points, ahead from 2^25 on
+        pl.pb = 0;
+        if (env_on && upper >= ((uint64_t)1 << env_min) && pl.W <= PART_W_MAX && pl.B <= (1u << 24) && pl.B >= 64) {
+            uint32_t lb = 0;
+            while ((1u << lb) < pl.B) ++lb;
+            uint32_t pb = lb > 9 ? lb - 9 : 1;            // about 512 partitions
+            if (pb > PLACE_MAX_LOG) pb = PLACE_MAX_LOG;
+            if (((pl.B + (1u << pb) - 1) >> pb) <= PART_MAX) pl.pb = pb;
+        }
+        if (pl.pb) {
+            const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
+            H2B_TRY(s.part_counts.reserve((size_t)P * 4));
+            H2B_TRY(s.part_off.reserve(((size_t)P + 1) * 4));
+            H2B_TRY(s.part_cursor.reserve((size_t)P * 4));
+            H2B_TRY(s.chunk0.reserve(((size_t)P + 1) * 4));
+            H2B_TRY(s.chunk_hist.reserve((((size_t)upper >> msm_sort2_chunk_log()) + P + 1) * ((size_t)4 << pl.pb)));
+            H2B_TRY(s.inter.reserve((size_t)upper * 8 + 8));
+        }
+    }
     H2B_TRY(s.digits.reserve((size_t)upper * 4));
     H2B_TRY((b ? s.sorted2 : s.sorted).reserve((size_t)upper * 4 + 4));
     H2B_TRY((b ? s.offsets2 : s.offsets).reserve(((size_t)pl.B + 1) * 4));
@@ -864,8 +1235,47 @@ static int msm_sort_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, cons
     uint32_t* offsets = (uint32_t*)(b ? s.offsets2 : s.offsets).p;
     uint32_t* cursor = (uint32_t*)s.cursor.p;
     uint32_t* sorted = (uint32_t*)(b ? s.sorted2 : s.sorted).p;
-    H2B_CUDA(cudaMemsetAsync(counts, 0, (size_t)pl.B * 4, stream));
     const uint32_t nblk = (pl.n + 255) / 256;
+    if (pl.pb) {
+        // partitioned sort (section 2c)
+        const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
+        uint32_t* part_counts = (uint32_t*)s.part_counts.p;
+        H2B_CUDA(cudaMemsetAsync(part_counts, 0, (size_t)P * 4, stream));
+        ctx.prof.mark(PROF_BEGIN, stream);
+        const uint32_t dgrid = nblk > (uint32_t)ctx.sm_count * 16 ? (uint32_t)ctx.sm_count * 16 : nblk;
+        const uint32_t chunk_log = msm_sort2_chunk_log();
+        H2B_LAUNCH(msm_decompose_kernel, dim3(dgrid, pl.ncols), 256, 0, stream, cols, pl, (uint32_t*)s.digits.p, part_counts);
+        ctx.prof.mark(PROF_MSM_DECOMPOSE, stream);
+        H2B_LAUNCH(msm_partition_scan_kernel, 1, 1024, 0, stream, (const uint32_t*)part_counts, P, chunk_log, (uint32_t*)s.part_off.p, (uint32_t*)s.part_cursor.p,
+                   (uint32_t*)s.chunk0.p);
+        ctx.prof.mark(PROF_MSM_SCAN, stream);
+        uint32_t tile = (PART_TILE_ENTRIES / pl.W) & ~31u;
+        if (tile > 1024) tile = 1024;
+        const size_t smem1 = ((size_t)3 * P + 1) * 4 + (size_t)tile * pl.W * 8;
+        const size_t smem2 = (size_t)4 << pl.pb;
+        if (!s.part_attr_set) {
+            H2B_CUDA(cudaFuncSetAttribute(msm_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)3 * PART_MAX + 1) * 4 + (size_t)PART_TILE_ENTRIES * 8)));
+            H2B_CUDA(cudaFuncSetAttribute(msm_place_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 << PLACE_MAX_LOG)));
+            H2B_CUDA(cudaFuncSetAttribute(msm_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 << PLACE_MAX_LOG)));
+            s.part_attr_set = true;
+        }
+        const uint32_t ntiles = (pl.n + tile - 1) / tile;
+        const uint32_t pgrid = ntiles > (uint32_t)ctx.sm_count * 8 ? (uint32_t)ctx.sm_count * 8 : ntiles;
+        H2B_LAUNCH(msm_partition_kernel, dim3(pgrid, pl.ncols), tile, smem1, stream, cols, pl, (uint32_t*)s.part_cursor.p, (uint2*)s.inter.p);
+        ctx.prof.mark(PROF_MSM_PLAN, stream);
+        const uint64_t upper = (uint64_t)pl.n * pl.W * pl.ncols;
+        const uint32_t max_chunks = (uint32_t)(upper >> chunk_log) + P + 1;
+        const uint32_t cgrid = max_chunks > (uint32_t)ctx.sm_count * 16 ? (uint32_t)ctx.sm_count * 16 : max_chunks;
+        H2B_LAUNCH(msm_place_count_kernel, cgrid, 1024, smem2, stream, pl, chunk_log, (const uint32_t*)s.chunk0.p, (const uint32_t*)s.part_off.p, (const uint2*)s.inter.p,
+                   (uint32_t*)s.chunk_hist.p);
+        H2B_LAUNCH(msm_place_scan_kernel, P, 1024, 0, stream, pl, (const uint32_t*)s.chunk0.p, (const uint32_t*)s.part_off.p, (uint32_t*)s.chunk_hist.p, offsets);
+        H2B_LAUNCH(msm_place_kernel, cgrid, 1024, smem2, stream, pl, chunk_log, (const uint32_t*)s.chunk0.p, (const uint32_t*)s.part_off.p, (const uint2*)s.inter.p,
+                   (const uint32_t*)s.chunk_hist.p, sorted);
+        H2B_CUDA(cudaGetLastError());
+        ctx.prof.mark(PROF_MSM_SCATTER, stream);
+        return H2B_OK;
+    }
+    H2B_CUDA(cudaMemsetAsync(counts, 0, (size_t)pl.B * 4, stream));
     // grid-stride only when a narrow top window is aggregated per CTA (fewer, longer-lived CTAs flush less often)
     const uint32_t sort_grid = (pl.top_bins && nblk > (uint32_t)ctx.sm_count * 32) ? (uint32_t)ctx.sm_count * 32 : nblk;
     ctx.prof.mark(PROF_BEGIN, stream);
@@ -1275,7 +1685,7 @@ void msm_release(DeviceCtx& ctx) {
     }
     DevBuf* all[] = {&s.digits, &s.counts, &s.offsets, &s.offsets2, &s.sorted2, &s.cursor, &s.block_sums, &s.sorted, &s.ctrl, &s.split_list, &s.heavy, &s.chunk_desc, &s.chunk_out,
                      &s.bucket_acc, &s.bucket_tmp, &s.head_partial, &s.redA, &s.redB, &s.redC, &s.redD, &s.result, &s.pair_pts, &s.pair_counts,
-                     &s.pair_offsets[0], &s.pair_offsets[1], &s.pair_offsets[2], &s.pair_sorted[0], &s.pair_sorted[1], &s.pair_sorted[2], &s.batch_out};
+                     &s.pair_offsets[0], &s.pair_offsets[1], &s.pair_offsets[2], &s.pair_sorted[0], &s.pair_sorted[1], &s.pair_sorted[2], &s.batch_out, &s.part_counts, &s.part_off, &s.part_cursor, &s.chunk0, &s.chunk_hist, &s.inter};
     for (DevBuf* b : all) b->release();
     delete ctx.msm;
     ctx.msm = nullptr;

@@ -595,3 +595,19 @@ def test_device_resident_proof_pipeline_matches_oracle_pipeline(emu, oc, shape, 
 @pytest.mark.parametrize("j,k", [(3, 5), (4, 9), (5, 7)])
 def test_column_pipeline_single_upload(emu, oc, j, k):
     pc.check_column_pipeline(emu, oc, j, k)
+
+
+def test_msm_partitioned_sort(emu):
+    # section 2c of msm.cu (two-level sort: partition histogram in shared memory, contiguous runs per partition, chunked placement
+    # with shared-memory cursors) forced at CPU sizes -- it needs W <= 16 windows, i.e. 16-bit windows or wider: uniform /
+    # witness-like / one-bucket columns (hot partitions), table and plain mode, ragged batches, chunked uploads, tiny chunks
+    _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 3000, 16, kind=0, windows=(16,), ranges=[(0, 3000), (100, 2500)])\n"
+                         "pc.check_msm_tables(L, oc, 2500, 16, kind=1, windows=(16,))\n"
+                         "pc.check_msm_tables(L, oc, 1500, 18, kind=0, windows=(18,))\n"
+                         "pc.check_msm_single_bucket(L, oc, 40000, scalar=1, tables=True)\n"
+                         "pc.check_batched_columns(L, oc, 700, 5, spacing=16, window=16)\n"
+                         "pc.check_msm(L, oc, 1200, kind=0, windows=(16,))\n"
+                         "st = L.L.h2b_launch_count()",
+                    dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_SORT2_CHUNK_LOG="7", H2B_MSM_PRECOMP="16"), timeout=2400)
+    _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 5000, 16, kind=0, windows=(16,), ranges=[(0, 5000)])\npc.check_msm_tables(L, oc, 4097, 16, kind=1, windows=(16,))",
+                    dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_UPLOAD_CHUNK_LOG="10"), timeout=2400)
