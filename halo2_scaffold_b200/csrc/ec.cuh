@@ -68,20 +68,35 @@ __device__ __forceinline__ XYZZ xyzz_double_affine(const Affine& p) {
     return r;
 }
 
+// One shared, NON-inlined copy of the Fq multiplier for the kernels that run a few warps through long chains of dependent group
+// additions (bucket reduction, combine of cut buckets, final Horner).  With every multiplication expanded in line an addition is
+// ~4000 straight-line instructions and those warps stall on instruction fetch as often as on the arithmetic itself (ncu of
+// msm_reduce_level_kernel: "no instruction" 3.1 and fixed-latency wait 3.2 cycles per issue, 0.19 IPC at 1.7 warps per scheduler).
+static __device__ __noinline__ Fq fq_mul_shared(Fq a, Fq b) { return fp_mul(a, b); }
+template <bool SHARED> __device__ __forceinline__ Fq fq_m(const Fq& a, const Fq& b) {
+    if (SHARED) return fq_mul_shared(a, b);
+    return fp_mul(a, b);
+}
+template <bool SHARED> __device__ __forceinline__ Fq fq_s(const Fq& a) {
+    if (SHARED) return fq_mul_shared(a, a);
+    return fp_sqr(a);
+}
+
 // 2 * P in XYZZ  (EFD dbl-2008-s-1, a = 0).  y = 0 never happens on this curve (odd order).
+template <bool SHARED = false>
 __device__ __forceinline__ XYZZ xyzz_double(const XYZZ& p) {
     if (xyzz_is_identity(p)) return p;
     XYZZ r;
     Fq u = fp_dbl(p.y);
-    Fq v = fp_sqr(u);
-    Fq w = fp_mul(u, v);
-    Fq s = fp_mul(p.x, v);
-    Fq xx = fp_sqr(p.x);
+    Fq v = fq_s<SHARED>(u);
+    Fq w = fq_m<SHARED>(u, v);
+    Fq s = fq_m<SHARED>(p.x, v);
+    Fq xx = fq_s<SHARED>(p.x);
     Fq m = fp_add(fp_dbl(xx), xx);
-    r.x = fp_sub(fp_sqr(m), fp_dbl(s));
-    r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
-    r.zz = fp_mul(v, p.zz);
-    r.zzz = fp_mul(w, p.zzz);
+    r.x = fp_sub(fq_s<SHARED>(m), fp_dbl(s));
+    r.y = fp_sub(fq_m<SHARED>(m, fp_sub(s, r.x)), fq_m<SHARED>(w, p.y));
+    r.zz = fq_m<SHARED>(v, p.zz);
+    r.zzz = fq_m<SHARED>(w, p.zzz);
     return r;
 }
 
@@ -123,137 +138,30 @@ __device__ __forceinline__ void xyzz_add_affine(XYZZ& acc, const Affine& q_in, b
 }
 
 // acc += b, both XYZZ  (EFD add-2008-s: 12M + 2S)
+template <bool SHARED = false>
 __device__ __forceinline__ void xyzz_add(XYZZ& acc, const XYZZ& b) {
     if (xyzz_is_identity(b)) return;
     if (xyzz_is_identity(acc)) { acc = b; return; }
-    Fq u1 = fp_mul(acc.x, b.zz);
-    Fq u2 = fp_mul(b.x, acc.zz);
-    Fq s1 = fp_mul(acc.y, b.zzz);
-    Fq s2 = fp_mul(b.y, acc.zzz);
+    Fq u1 = fq_m<SHARED>(acc.x, b.zz);
+    Fq u2 = fq_m<SHARED>(b.x, acc.zz);
+    Fq s1 = fq_m<SHARED>(acc.y, b.zzz);
+    Fq s2 = fq_m<SHARED>(b.y, acc.zzz);
     Fq p = fp_sub(u2, u1);
     Fq r = fp_sub(s2, s1);
     if (fp_is_zero(p)) {
-        if (fp_is_zero(r)) acc = xyzz_double(acc);
+        if (fp_is_zero(r)) acc = xyzz_double<SHARED>(acc);
         else acc = xyzz_identity();
         return;
     }
-    Fq pp = fp_sqr(p);
-    Fq ppp = fp_mul(p, pp);
-    Fq qq = fp_mul(u1, pp);
-    Fq x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-    Fq y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(s1, ppp));
+    Fq pp = fq_s<SHARED>(p);
+    Fq ppp = fq_m<SHARED>(p, pp);
+    Fq qq = fq_m<SHARED>(u1, pp);
+    Fq x3 = fp_sub(fp_sub(fq_s<SHARED>(r), ppp), fp_dbl(qq));
+    Fq y3 = fp_sub(fq_m<SHARED>(r, fp_sub(qq, x3)), fq_m<SHARED>(s1, ppp));
     acc.x = x3;
     acc.y = y3;
-    acc.zz = fp_mul(fp_mul(acc.zz, b.zz), pp);
-    acc.zzz = fp_mul(fp_mul(acc.zzz, b.zzz), ppp);
-}
-
-// ---- quad-cooperative group law (latency-bound kernels) ----------------------------------------------------------------
-// The bucket reduction, the combine of cut buckets and the final Horner are chains of DEPENDENT group additions run by a
-// handful of warps: a lone warp needs ~2300 clocks per field multiplication (every IMAD.WIDE.X waits for the carry of the one
-// before), so a 14-multiplication addition is ~15 us deep and a 2^16-point MSM spends 0.7 of its 0.95 ms there.  Here FOUR
-// consecutive lanes hold the same operands and each computes one of the (up to four) independent multiplications of a step;
-// the products are exchanged by quad-wide shuffles.  An XYZZ addition becomes 4 multiplication steps instead of 14, a
-// doubling 3 instead of 9.  Results are bit-identical (same field operations).  Every lane executes every shuffle: operands
-// that need no arithmetic (identity, P + (-P)) are resolved after the last exchange, and callers give idle quads identities.
-__device__ __forceinline__ unsigned quad_mask() { return 0xFu << (threadIdx.x & 28u); }
-#ifdef H2B_EMU
-// The kernel-logic emulator implements a shuffle as two warp-wide fiber barriers: the exchanges below would make the CPU suite
-// ~8x slower.  There every lane of a quad computes the whole operation itself unless H2B_EMU_QUAD=1 (one test exercises the
-// shuffled form); the index math of the callers (one quad per item, idle quads on identities) is the same either way.
-static inline bool emu_quad_exchange() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("H2B_EMU_QUAD"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-#endif
-
-// lane q of the quad multiplies x[q] * y[q]; all four products are returned to every lane
-__device__ __forceinline__ void quad_mul(uint32_t q, unsigned mask, const Fq (&x)[4], const Fq (&y)[4], Fq (&out)[4]) {
-    Fq a, b;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        a.l[i] = q == 0 ? x[0].l[i] : (q == 1 ? x[1].l[i] : (q == 2 ? x[2].l[i] : x[3].l[i]));
-        b.l[i] = q == 0 ? y[0].l[i] : (q == 1 ? y[1].l[i] : (q == 2 ? y[2].l[i] : y[3].l[i]));
-    }
-    const Fq m = fp_mul(a, b);
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) out[s].l[i] = __shfl_sync(mask, m.l[i], s, 4);
-}
-
-// acc += b, both XYZZ, computed by the quad (acc and b replicated in its four lanes)
-__device__ __forceinline__ void xyzz_add_quad(XYZZ& acc, const XYZZ& b, uint32_t q, unsigned mask) {
-#ifdef H2B_EMU
-    if (!emu_quad_exchange()) { xyzz_add(acc, b); return; }
-#endif
-    const bool b_id = xyzz_is_identity(b), a_id = xyzz_is_identity(acc);
-    Fq o[4];
-    {
-        const Fq x[4] = {acc.x, b.x, acc.y, b.y}, y[4] = {b.zz, acc.zz, b.zzz, acc.zzz};
-        quad_mul(q, mask, x, y, o);
-    }
-    const Fq u1 = o[0], s1 = o[2];
-    const Fq p = fp_sub(o[1], u1), r = fp_sub(o[3], s1);
-    {
-        const Fq x[4] = {p, r, acc.zz, acc.zzz}, y[4] = {p, r, b.zz, b.zzz};
-        quad_mul(q, mask, x, y, o);
-    }
-    const Fq pp = o[0], rr = o[1];
-    {
-        const Fq x[4] = {p, u1, o[2], o[3]}, y[4] = {pp, pp, pp, p};
-        quad_mul(q, mask, x, y, o);
-    }
-    const Fq ppp = o[0], qq = o[1], zz3 = o[2], w = o[3];
-    const Fq x3 = fp_sub(fp_sub(rr, ppp), fp_dbl(qq));
-    {
-        const Fq x[4] = {r, s1, w, w}, y[4] = {fp_sub(qq, x3), ppp, pp, pp};
-        quad_mul(q, mask, x, y, o);
-    }
-    if (b_id) return;
-    if (a_id) { acc = b; return; }
-    if (fp_is_zero(p)) {
-        if (fp_is_zero(r)) acc = xyzz_double(acc);      // P + P: the plain doubling, computed by every lane (rare)
-        else acc = xyzz_identity();
-        return;
-    }
-    acc.x = x3;
-    acc.y = fp_sub(o[0], o[1]);
-    acc.zz = zz3;
-    acc.zzz = o[2];
-}
-
-// 2 * P by the quad
-__device__ __forceinline__ XYZZ xyzz_double_quad(const XYZZ& p, uint32_t q, unsigned mask) {
-#ifdef H2B_EMU
-    if (!emu_quad_exchange()) return xyzz_double(p);
-#endif
-    Fq o[4];
-    const Fq u = fp_dbl(p.y);
-    {
-        const Fq x[4] = {u, p.x, u, p.x}, y[4] = {u, p.x, u, p.x};
-        quad_mul(q, mask, x, y, o);
-    }
-    const Fq v = o[0], xx = o[1];
-    const Fq m = fp_add(fp_dbl(xx), xx);
-    {
-        const Fq x[4] = {u, p.x, m, v}, y[4] = {v, v, m, p.zz};
-        quad_mul(q, mask, x, y, o);
-    }
-    const Fq w = o[0], s = o[1], zz3 = o[3];
-    const Fq x3 = fp_sub(o[2], fp_dbl(s));
-    {
-        const Fq x[4] = {m, w, w, w}, y[4] = {fp_sub(s, x3), p.y, p.zzz, p.zzz};
-        quad_mul(q, mask, x, y, o);
-    }
-    if (xyzz_is_identity(p)) return p;
-    XYZZ r;
-    r.x = x3;
-    r.y = fp_sub(o[0], o[1]);
-    r.zz = zz3;
-    r.zzz = o[2];
-    return r;
+    acc.zz = fq_m<SHARED>(fq_m<SHARED>(acc.zz, b.zz), pp);
+    acc.zzz = fq_m<SHARED>(fq_m<SHARED>(acc.zzz, b.zzz), ppp);
 }
 
 // XYZZ -> a Jacobian representative (X', Y', Z') of the same point without an inversion:

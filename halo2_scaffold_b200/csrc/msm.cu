@@ -787,43 +787,29 @@ __global__ void __launch_bounds__(128) msm_combine_light_kernel(MsmPlan pl, cons
                                                               const uint32_t* __restrict__ split_list, HeavyDesc* __restrict__ heavy,
                                                               uint2* __restrict__ chunk_desc, const uint4* __restrict__ head_partial,
                                                               uint4* __restrict__ bucket_acc) {
-    // one QUAD of lanes per cut bucket (quad-cooperative additions, ec.cuh): the pieces are a serial chain of additions
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t idx = gt >> 2, q = gt & 3;
-    const unsigned mask = quad_mask();
-    const bool live = idx < ctrl[0];
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ctrl[0]) return;
     const uint32_t S = slice_len(offsets[pl.B], pl.G);
-    uint32_t b = 0, first = 0, pieces = 0;
-    if (live) {
-        b = split_list[idx];
-        first = offsets[b] / S;
-        pieces = (offsets[b + 1] - 1) / S - first;
-        if (pieces > COMBINE_HEAVY) {
-            if (q == 0) {
-                HeavyDesc d;
-                d.bucket = b;
-                d.nchunks = (pieces + COMBINE_CHUNK - 1) / COMBINE_CHUNK;
-                d.chunk0 = atomicAdd(&ctrl[2], d.nchunks);
-                d.pad = 0;
-                const uint32_t h = atomicAdd(&ctrl[1], 1u);
-                heavy[h] = d;
-                for (uint32_t i = 0; i < d.nchunks; ++i) chunk_desc[d.chunk0 + i] = make_uint2(h, i);
-            }
-            pieces = 0;
-        }
+    const uint32_t b = split_list[idx];
+    const uint32_t first = offsets[b] / S, last = (offsets[b + 1] - 1) / S;
+    const uint32_t pieces = last - first;
+    if (pieces > COMBINE_HEAVY) {
+        HeavyDesc d;
+        d.bucket = b;
+        d.nchunks = (pieces + COMBINE_CHUNK - 1) / COMBINE_CHUNK;
+        d.chunk0 = atomicAdd(&ctrl[2], d.nchunks);
+        d.pad = 0;
+        const uint32_t h = atomicAdd(&ctrl[1], 1u);
+        heavy[h] = d;
+        for (uint32_t i = 0; i < d.nchunks; ++i) chunk_desc[d.chunk0 + i] = make_uint2(h, i);
+        return;
     }
-    // every lane of the warp runs the same number of steps (idle quads add identities)
-    uint32_t steps = pieces;
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t v = __shfl_xor_sync(0xffffffffu, steps, o);
-        steps = v > steps ? v : steps;
+    XYZZ acc = xyzz_load(bucket_acc + 8 * (size_t)b);
+    for (uint32_t t = first + 1; t <= last; ++t) {
+        XYZZ q = xyzz_load(head_partial + 8 * (size_t)t);
+        xyzz_add(acc, q);
     }
-    XYZZ acc = pieces ? xyzz_load(bucket_acc + 8 * (size_t)b) : xyzz_identity();
-    for (uint32_t k = 1; k <= steps; ++k) {
-        XYZZ piece = k <= pieces ? xyzz_load(head_partial + 8 * (size_t)(first + k)) : xyzz_identity();
-        xyzz_add_quad(acc, piece, q, mask);
-    }
-    if (pieces && q == 0) xyzz_store(bucket_acc + 8 * (size_t)b, acc);
+    xyzz_store(bucket_acc + 8 * (size_t)b, acc);
 }
 
 // sum of `acc` over the 256 threads of the CTA, valid in thread 0
@@ -906,91 +892,89 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(uint32_t B, const uint32
 // therefore never written.
 __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, const uint32_t* __restrict__ offsets,
                                                              uint32_t N, uint32_t logm, uint32_t W, uint4* __restrict__ Bout, uint4* __restrict__ Dout) {
-    // one QUAD of lanes per chunk of m buckets (quad-cooperative additions, ec.cuh)
-    const uint32_t m = 1u << logm;
-    const uint32_t J = (N + m - 1) >> logm;
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t t = gt >> 2, q = gt & 3;
-    const unsigned mask = quad_mask();
-    const bool live = t < W * J;
-    const uint32_t w = live ? t / J : 0, j = live ? t - w * J : 0;
+    uint32_t m = 1u << logm;
+    uint32_t J = (N + m - 1) >> logm;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * J) return;
+    uint32_t w = t / J, j = t - w * J;
     const uint4* Bw = Bin + 8 * (size_t)w * N;
     const uint4* Dw = Din ? Din + 8 * (size_t)w * N : nullptr;
     const uint32_t* Ow = offsets ? offsets + (size_t)w * N : nullptr;
-    const uint32_t lo = j << logm;
-    const uint32_t hi = lo + m > N ? N : lo + m;
+    uint32_t lo = j << logm, hi = lo + m;
+    if (hi > N) hi = N;
     XYZZ running = xyzz_identity(), acc = xyzz_identity();
-    for (uint32_t k = 0; k < m; ++k) {
-        const uint32_t u = lo + (m - 1 - k);
-        const bool in = live && u < hi;
-        XYZZ bu = xyzz_identity();
-        if (in && (!Ow || Ow[u + 1] != Ow[u])) bu = xyzz_load(Bw + 8 * (size_t)u);
-        xyzz_add_quad(running, bu, q, mask);
-        XYZZ r2 = in ? running : xyzz_identity();
-        xyzz_add_quad(acc, r2, q, mask);
+    for (uint32_t u = hi; u-- > lo;) {
+        if (!Ow || Ow[u + 1] != Ow[u]) {
+            XYZZ bu = xyzz_load(Bw + 8 * (size_t)u);
+            xyzz_add<true>(running, bu);
+        }
+        xyzz_add<true>(acc, running);
         if (Dw) {
-            XYZZ du = in ? xyzz_load(Dw + 8 * (size_t)u) : xyzz_identity();
-            xyzz_add_quad(acc, du, q, mask);
+            XYZZ du = xyzz_load(Dw + 8 * (size_t)u);
+            xyzz_add<true>(acc, du);
         }
     }
-    if (live && q == 0) xyzz_store(Dout + 8 * ((size_t)w * J + j), acc);
-    for (uint32_t k = 0; k < logm; ++k) running = xyzz_double_quad(running, q, mask);
-    if (live && q == 0) {
-        if (j >= 1) xyzz_store(Bout + 8 * ((size_t)w * J + j - 1), running);
-        else xyzz_store(Bout + 8 * ((size_t)w * J + J - 1), xyzz_identity());
+    xyzz_store(Dout + 8 * ((size_t)w * J + j), acc);
+    if (j >= 1) {
+        for (uint32_t k = 0; k < logm; ++k) running = xyzz_double<true>(running);
+        xyzz_store(Bout + 8 * ((size_t)w * J + j - 1), running);
+    } else {
+        xyzz_store(Bout + 8 * ((size_t)w * J + J - 1), xyzz_identity());
     }
 }
 
-// Tail of the reduction, one CTA per set, N <= 256 items, one quad of lanes per item: S_w = sum_u (u+1) * B[u] + sum_u D[u] as a
-// suffix scan (sum_u (u+1) B[u] = sum_u suffix_u) followed by a tree sum, both in shared memory.  2 log2(N) + 1 additions deep.
-static const uint32_t REDUCE_TAIL_MAX = 256;
-__global__ void __launch_bounds__(1024) msm_reduce_tail_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, const uint32_t* __restrict__ offsets,
-                                                             uint32_t N, uint4* __restrict__ out) {
+// Tail of the reduction, one CTA per set, N <= 512 items: S_w = sum_u (u+1) * B[u] + sum_u D[u] as a suffix scan
+// (sum_u (u+1) B[u] = sum_u suffix_u) followed by a tree sum, both in shared memory.  2 log2(N) + 1 additions deep
+// instead of the 2 m per level of the chunked running sums: small MSMs are pure latency.
+static const uint32_t REDUCE_TAIL_MAX = 512;
+__global__ void __launch_bounds__(512) msm_reduce_tail_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, const uint32_t* __restrict__ offsets,
+                                                            uint32_t N, uint4* __restrict__ out) {
     H2B_DYN_SMEM(uint4, sh);
-    const uint32_t w = blockIdx.x, e = threadIdx.x >> 2, q = threadIdx.x & 3, E = blockDim.x >> 2;
-    const unsigned mask = quad_mask();
+    const uint32_t w = blockIdx.x, tid = threadIdx.x;
     XYZZ x = xyzz_identity();
-    if (e < N && (!offsets || offsets[(size_t)w * N + e + 1] != offsets[(size_t)w * N + e])) x = xyzz_load(Bin + 8 * ((size_t)w * N + e));
+    if (tid < N && (!offsets || offsets[(size_t)w * N + tid + 1] != offsets[(size_t)w * N + tid])) x = xyzz_load(Bin + 8 * ((size_t)w * N + tid));
     for (uint32_t d = 1; d < N; d <<= 1) {
-        if (q == 0) xyzz_store(sh + 8 * e, x);
+        xyzz_store(sh + 8 * tid, x);
         __syncthreads();
-        XYZZ o = (e + d < N) ? xyzz_load(sh + 8 * (e + d)) : xyzz_identity();
-        xyzz_add_quad(x, o, q, mask);
+        if (tid + d < N) {
+            XYZZ o = xyzz_load(sh + 8 * (tid + d));
+            xyzz_add<true>(x, o);
+        }
         __syncthreads();
     }
-    {
-        XYZZ dd = (Din && e < N) ? xyzz_load(Din + 8 * ((size_t)w * N + e)) : xyzz_identity();
-        if (Din) xyzz_add_quad(x, dd, q, mask);
+    if (Din && tid < N) {
+        XYZZ dd = xyzz_load(Din + 8 * ((size_t)w * N + tid));
+        xyzz_add<true>(x, dd);
     }
-    if (q == 0) xyzz_store(sh + 8 * e, x);
+    xyzz_store(sh + 8 * tid, x);
     __syncthreads();
-    for (uint32_t d = E >> 1; d > 0; d >>= 1) {
-        XYZZ o = (e < d) ? xyzz_load(sh + 8 * (e + d)) : xyzz_identity();
-        xyzz_add_quad(x, o, q, mask);
-        if (e < d && q == 0) xyzz_store(sh + 8 * e, x);
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if (tid < d) {
+            XYZZ o = xyzz_load(sh + 8 * (tid + d));
+            xyzz_add<true>(x, o);
+            xyzz_store(sh + 8 * tid, x);
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) xyzz_store(out + 8 * (size_t)w, x);
+    if (tid == 0) xyzz_store(out + 8 * (size_t)w, x);
 }
 
-// Horner over the set sums (S[w] = Dfinal[w], weight 2^(c*w)) and conversion to a Jacobian triple; one block (one warp: every quad
-// computes the same chain, lane 0 stores) per column of a batched MSM (sets [col * W, (col + 1) * W), result block col)
+// Horner over the set sums (S[w] = Dfinal[w], weight 2^(c*w)) and conversion to a Jacobian triple; one block per column of a
+// batched MSM (sets [col * W, (col + 1) * W), result block col)
 __global__ void msm_final_kernel(const uint4* __restrict__ S, uint32_t W, uint32_t c, uint4* __restrict__ out_jac, uint32_t accumulate) {
-    const uint32_t q = threadIdx.x & 3;
-    const unsigned mask = quad_mask();
+    if (threadIdx.x != 0) return;
     S += 8 * (size_t)blockIdx.x * W;
     out_jac += 14 * (size_t)blockIdx.x;
     XYZZ acc = xyzz_load(S + 8 * (size_t)(W - 1));
     for (uint32_t w = W - 1; w-- > 0;) {
-        for (uint32_t k = 0; k < c; ++k) acc = xyzz_double_quad(acc, q, mask);
+        for (uint32_t k = 0; k < c; ++k) acc = xyzz_double<true>(acc);
         XYZZ sw = xyzz_load(S + 8 * (size_t)w);
-        xyzz_add_quad(acc, sw, q, mask);
+        xyzz_add<true>(acc, sw);
     }
     if (accumulate) {       // running total across sub-MSMs is kept in XYZZ right behind the Jacobian slot
         XYZZ prev = xyzz_load(out_jac + 6);
-        xyzz_add_quad(acc, prev, q, mask);
+        xyzz_add<true>(acc, prev);
     }
-    if (threadIdx.x != 0) return;
     xyzz_store(out_jac + 6, acc);
     Fq X, Y, Z;
     xyzz_to_jacobian(acc, X, Y, Z);
@@ -1363,7 +1347,7 @@ static int msm_accumulate_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl
     H2B_LAUNCH(msm_accumulate_kernel, (pl.G + 255) / 256, 256, 0, stream, pl, (const uint4*)tables, offsets, sorted, ctrl, (uint32_t*)s.split_list.p, target,
                (uint4*)s.head_partial.p, pair_pts);
     ctx.prof.mark(PROF_MSM_ACCUMULATE, stream);
-    H2B_LAUNCH(msm_combine_light_kernel, (4 * pl.G + 127) / 128, 128, 0, stream, pl, offsets, ctrl, (const uint32_t*)s.split_list.p,
+    H2B_LAUNCH(msm_combine_light_kernel, (pl.G + 127) / 128, 128, 0, stream, pl, offsets, ctrl, (const uint32_t*)s.split_list.p,
                (HeavyDesc*)s.heavy.p, (uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, target);
     H2B_LAUNCH(msm_combine_chunk_kernel, ctx.sm_count * 2, 256, 0, stream, pl, offsets, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p,
                (const uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, (uint4*)s.chunk_out.p);
@@ -1460,8 +1444,8 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
     int pp = 0;
     while (N > REDUCE_TAIL_MAX) {
         uint32_t J = (N + (1u << logm) - 1) >> logm;
-        const uint64_t threads = 4ull * sets * J;      // one quad of lanes per chunk
-        H2B_LAUNCH(msm_reduce_level_kernel, (unsigned)((threads + 127) / 128), 128, 0, stream, Bin, Din, offs, N, logm, sets, Bping[pp], Dping[pp]);
+        uint32_t threads = sets * J;
+        H2B_LAUNCH(msm_reduce_level_kernel, (threads + 127) / 128, 128, 0, stream, Bin, Din, offs, N, logm, sets, Bping[pp], Dping[pp]);
         Bin = Bping[pp];
         Din = Dping[pp];
         offs = nullptr;
@@ -1474,9 +1458,9 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
             H2B_CUDA(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REDUCE_TAIL_MAX * 128)));
             ctx.msm_attr_set = true;
         }
-        uint32_t titems = 8;
-        while (titems < N) titems <<= 1;
-        H2B_LAUNCH(msm_reduce_tail_kernel, sets, 4 * titems, (size_t)titems * 128, stream, Bin, Din, offs, N, Dping[pp]);
+        uint32_t tthreads = 32;
+        while (tthreads < N) tthreads <<= 1;
+        H2B_LAUNCH(msm_reduce_tail_kernel, sets, tthreads, (size_t)tthreads * 128, stream, Bin, Din, offs, N, Dping[pp]);
         Din = Dping[pp];
     }
     ctx.prof.mark(PROF_MSM_REDUCE, stream);
@@ -1676,7 +1660,7 @@ __global__ void msm_sum_partials_kernel(const uint4* __restrict__ blocks, uint32
     XYZZ acc = xyzz_identity();
     for (uint32_t i = 0; i < count; ++i) {
         XYZZ p = xyzz_load(blocks + 14 * (size_t)i + 6);
-        xyzz_add(acc, p);
+        xyzz_add<true>(acc, p);
     }
     Fq X, Y, Z;
     xyzz_to_jacobian(acc, X, Y, Z);

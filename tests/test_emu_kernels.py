@@ -611,14 +611,3 @@ def test_msm_partitioned_sort(emu):
                     dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_SORT2_CHUNK_LOG="7", H2B_MSM_PRECOMP="16"), timeout=2400)
     _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 5000, 16, kind=0, windows=(16,), ranges=[(0, 5000)])\npc.check_msm_tables(L, oc, 4097, 16, kind=1, windows=(16,))",
                     dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_UPLOAD_CHUNK_LOG="10"), timeout=2400)
-
-
-def test_quad_cooperative_group_law(emu):
-    # ec.cuh xyzz_add_quad / xyzz_double_quad with the real lane exchanges (the emulator default lets every lane compute the whole
-    # operation: shuffles are expensive on fibers): bucket reduction levels + tail + final Horner + combine of cut buckets, with
-    # identities, P + P and P + (-P) meeting in the chains (edge_msm_inputs, one-bucket column)
-    _emu_subprocess(emu, "pc.check_msm(L, oc, 300, kind=0, windows=(0, 4))\n"
-                         "pc.check_msm_tables(L, oc, 400, 8, kind=1, windows=(0, 4), ranges=[(0, 400), (11, 300)])\n"
-                         "pc.check_msm_single_bucket(L, oc, 3000, scalar=1, tables=True)\n"
-                         "pc.check_batched_columns(L, oc, 120, 3, spacing=6)",
-                    dict(H2B_EMU_QUAD="1"), timeout=2400)
