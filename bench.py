@@ -180,6 +180,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: this framework has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # N ranks share one host: give each rank its share of the cores for the pinned-staging and digest threads of the host-pointer
+        # drop-in instead of 8 + 8 threads per rank (the e2e leg is host-memory bound at N = 8: 8 x (1 GiB digest + 0.5 GiB staging) per step)
+        share = max(2, min(8, (os.cpu_count() or 16) // world))
+        os.environ.setdefault("H2B_STAGE_THREADS", str(share))
+        os.environ.setdefault("H2B_DIGEST_THREADS", str(share))
     L = h2.load()
     L.init_device(local_rank)
     if world > 1:
@@ -541,7 +547,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 96,
                     "call": "h2b_msm_bn254_g1(scalars, bases): pageable host arrays, implicit SRS cache (every call re-verifies the digest of "
                             "the caller's %d MiB bases array on host threads while the GPU runs)" % (n * 64 >> 20),
-                    "implicit_cache": cache_stats},
+                    "implicit_cache": cache_stats,
+                    "host": "%d host cores for %d ranks; per step every rank hashes its bases array (%d MiB) and stages its pageable scalars (%d MiB) "
+                            "through pinned slots: at N = 8 this leg is bound by the host's memory bandwidth, not by the GPUs (compare e2e_registered_pinned)"
+                            % (os.cpu_count() or 0, world, n * 64 >> 20, n * 32 >> 20)},
             "e2e_registered_pinned": {"value": e2e_pinned_value, "unit": "points/s", "call": "h2b_msm_bn254_g1_registered, pinned scalars"},
             "verified": bool(all(checks.values())), "checks": {kk: bool(v) for kk, v in checks.items()},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ntt": ntt,

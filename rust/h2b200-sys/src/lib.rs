@@ -105,6 +105,23 @@ extern "C" {
     pub fn h2b_memcpy_h2d_async(device: c_int, d_dst: *mut c_void, h_src: *const c_void, bytes: usize, stream: *mut c_void) -> c_int;
     pub fn h2b_memcpy_d2h(device: c_int, h_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
     pub fn h2b_dev_sync(device: c_int) -> c_int;
+    // round 2: sharded residency, batched columns / polynomials, one-upload column pipeline, column copies
+    pub fn h2b_register_bases_sharded(bases: *const u64, n: usize, handle: *mut u64) -> c_int;
+    pub fn h2b_msm_bn254_g1_batch_registered(scalars: *const *const u64, lens: *const usize, count: usize, handle: u64, out_jac: *mut u64) -> c_int;
+    pub fn h2b_ntt_bn254_fr_batch(a: *const *mut u64, count: usize, omega: *const u64, log_n: u32) -> c_int;
+    pub fn h2b_msm_bn254_g1_dev_batch_registered(device: c_int, d_scalars: *const *const c_void, lens: *const usize, count: usize, handle: u64,
+                                                 d_out_blocks: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_ntt_bn254_fr_dev_batch(device: c_int, d_polys: *const *mut c_void, count: usize, omega: *const u64, log_n: u32, stream: *mut c_void) -> c_int;
+    pub fn h2b_lagrange_to_coeff_dev_batch(device: c_int, d_cols: *const *mut c_void, count: usize, k: u32, omega_inv: *const u64, ifft_divisor: *const u64,
+                                           stream: *mut c_void) -> c_int;
+    pub fn h2b_coeff_to_extended_dev_batch(device: c_int, d_cols: *const *mut c_void, count: usize, k: u32, extended_k: u32, extended_omega: *const u64,
+                                           zeta_powers: *const u64, stream: *mut c_void) -> c_int;
+    pub fn h2b_column_pipeline(device: c_int, lagrange: *const u64, handle_g_lagrange: u64, k: u32, extended_k: u32, omega_inv: *const u64,
+                               ifft_divisor: *const u64, extended_omega: *const u64, zeta_powers: *const u64, out_commitment_jac: *mut u64,
+                               out_coeff: *mut u64, out_extended: *mut u64, d_extended: *mut *mut c_void) -> c_int;
+    pub fn h2b_memcpy_d2d_async(device: c_int, d_dst: *mut c_void, d_src: *const c_void, bytes: usize, stream: *mut c_void) -> c_int;
+    pub fn h2b_memset_zero_async(device: c_int, d_dst: *mut c_void, bytes: usize, stream: *mut c_void) -> c_int;
+    pub fn h2b_implicit_cache_stats(out: *mut u64) -> c_int;
 }
 
 fn last_error() -> String {
