@@ -42,6 +42,9 @@ static int stager_init(DeviceCtx& ctx) {
     Stager* s = new Stager();
     unsigned hw = std::thread::hardware_concurrency();
     int want = hw >= 16 ? 8 : (hw >= 8 ? 4 : 2);
+    // several devices of one process stage at the same time (point-range split, round-robin columns): share the cores
+    const int nd = h2b_device_count();
+    if (nd > 1 && hw) { int share = (int)hw / nd; if (share < 2) share = 2; if (want > share) want = share; }
     const char* e = getenv("H2B_STAGE_THREADS");
     if (e && atoi(e) >= 1 && atoi(e) <= STAGE_THREADS_MAX) want = atoi(e);
     s->nthreads = want;
