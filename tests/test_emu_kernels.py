@@ -604,10 +604,8 @@ def test_msm_partitioned_sort(emu):
     _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 3000, 16, kind=0, windows=(16,), ranges=[(0, 3000), (100, 2500)])\n"
                          "pc.check_msm_tables(L, oc, 2500, 16, kind=1, windows=(16,))\n"
                          "pc.check_msm_tables(L, oc, 1500, 18, kind=0, windows=(18,))\n"
-                         "pc.check_msm_single_bucket(L, oc, 40000, scalar=1, tables=True)\n"
-                         "pc.check_batched_columns(L, oc, 700, 5, spacing=16, window=16)\n"
-                         "pc.check_msm(L, oc, 1200, kind=0, windows=(16,))\n"
-                         "st = L.L.h2b_launch_count()",
+                         "pc.check_msm_single_bucket(L, oc, 20000, scalar=1, tables=True)\n"
+                         "pc.check_batched_columns(L, oc, 300, 3, spacing=16, window=16)",
                     dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_SORT2_CHUNK_LOG="7", H2B_MSM_PRECOMP="16"), timeout=2400)
-    _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 5000, 16, kind=0, windows=(16,), ranges=[(0, 5000)])\npc.check_msm_tables(L, oc, 4097, 16, kind=1, windows=(16,))",
+    _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 4097, 16, kind=1, windows=(16,), ranges=[(0, 4097)])",
                     dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_UPLOAD_CHUNK_LOG="10"), timeout=2400)
