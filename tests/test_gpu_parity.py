@@ -382,6 +382,54 @@ def test_msm_window_tables_full_size_checksum(gpu, oc, k, kind):
         assert (o.from_mont(got_w[0], o.P_MOD), o.from_mont(got_w[1], o.P_MOD)) == want
 
 
+def test_device_checksum_matches_host_dot_product(gpu, oc):
+    """h2b_msm_checksum_dev (what bench.py's `verified` flag rests on) against the dot product taken with the oracle's field ops."""
+    n, seed_p = (1 << 18) + 77, 0xB2009000
+    s = gpu.gen_scalars(0xB2008000, n, 1)
+    d_s, d_c = gpu.dev_alloc(0, n * 32), gpu.dev_alloc(0, 32)
+    try:
+        gpu.h2d(0, d_s, s)
+        gpu.msm_checksum_dev(0, d_s, seed_p, n, d_c)
+        gpu.dev_sync(0)
+        c = np.zeros(4, dtype=np.uint64)
+        gpu.d2h(0, c, d_c)
+    finally:
+        gpu.dev_free(0, d_s)
+        gpu.dev_free(0, d_c)
+    assert sum(int(c[i]) << (64 * i) for i in range(4)) == _dot_with_generator_scalars(oc, s, seed_p, n)
+
+
+@pytest.mark.parametrize("k,kind,env", [(25, 0, {}), (22, 0, {"H2B_MSM_SORT2_MIN_LOG": "20"}), (22, 1, {"H2B_MSM_SORT2_MIN_LOG": "20"}),
+                                        (20, 0, {"H2B_MSM_SORT2_MIN_LOG": "16", "H2B_MSM_PRECOMP": "22"})])
+def test_msm_partitioned_sort_full_size_checksum(gpu, k, kind, env):
+    """The two-level partitioned sort (msm.cu section 2c; default from 2^25 points on, forced lower here) at full sizes: uniform and
+    witness-like columns, 20- and 22-bit windows, device-resident and host-pointer entry points, against the O(n) checksum.  Fresh
+    process per case (the thresholds are read once)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from halo2_scaffold_b200._lib import Lib\n"
+        "from halo2_scaffold_b200 import verify as V\n"
+        "L = Lib(); L.init_device(0)\n"
+        "k, kind = %d, %d; n = 1 << k; seed_p = 0xB2001000 + k\n"
+        "h = L.register_bases(L.gen_points(seed_p, n))\n"
+        "d_s, d_o, d_c = L.dev_alloc(0, n * 32), L.dev_alloc(0, 224), L.dev_alloc(0, 32)\n"
+        "L.gen_scalars_dev(0, 0xB2000000 + k, n, kind, d_s)\n"
+        "L.msm_checksum_dev(0, d_s, seed_p, n, d_c)\n"
+        "L.msm_dev_registered(0, d_s, h, 0, n, d_o); L.dev_sync(0)\n"
+        "out, c = np.zeros(28, dtype=np.uint64), np.zeros(4, dtype=np.uint64)\n"
+        "L.d2h(0, out, d_o); L.d2h(0, c, d_c)\n"
+        "s = np.empty((n, 4), dtype=np.uint64); L.d2h(0, s, d_s)\n"
+        "want = V.scalar_mul_generator(V.words_to_int(c))\n"
+        "assert V.jacobian_words_to_affine(out) == want, 'device-resident'\n"
+        "assert V.jacobian_words_to_affine(L.msm_registered(s, h)) == want, 'host pointer (chunked upload)'\n"
+        "print('SORT2_OK')\n") % (root, k, kind)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "SORT2_OK" in out.stdout, (out.stdout[-500:], out.stderr[-2000:])
+
+
 def test_ntt_full_size_round_trip_and_spot_values(gpu, oc):
     """k = 24: iNTT(NTT(a)) == n * a, and a handful of output coefficients checked by direct evaluation
     out[i] = sum_j a[j] w^(ij) for a sparse input (so the sum is cheap)."""
