@@ -72,6 +72,9 @@ __device__ __forceinline__ XYZZ xyzz_double_affine(const Affine& p) {
 // additions (bucket reduction, combine of cut buckets, final Horner).  With every multiplication expanded in line an addition is
 // ~4000 straight-line instructions and those warps stall on instruction fetch as often as on the arithmetic itself (ncu of
 // msm_reduce_level_kernel: "no instruction" 3.1 and fixed-latency wait 3.2 cycles per issue, 0.19 IPC at 1.7 warps per scheduler).
+// (A product-scanning C version with 64 independent addend-free products -- 560 instructions instead of 216, no carry chain through
+// the products -- was tried here for its instruction-level parallelism: a lone warp issued it at 5.5 instead of 9 clocks per
+// instruction, but 2.6x as many: reduction 0.91 -> 1.41 ms.  profiles/r02_shared_multiplier_latency_kernels.jsonl.)
 static __device__ __noinline__ Fq fq_mul_shared(Fq a, Fq b) { return fp_mul(a, b); }
 template <bool SHARED> __device__ __forceinline__ Fq fq_m(const Fq& a, const Fq& b) {
     if (SHARED) return fq_mul_shared(a, b);
