@@ -218,6 +218,10 @@ class EvaluationDomain {
     const Fr& get_omega() const { return omega_; }
     const Fr& get_omega_inv() const { return omega_inv_; }
     const Fr& get_extended_omega() const { return extended_omega_; }
+    const Fr& get_ifft_divisor() const { return ifft_divisor_; }
+    const Fr& get_g_coset() const { return g_coset_; }
+    const Fr& get_g_coset_inv() const { return g_coset_inv_; }
+    int device() const { return device_; }
 
     // pub fn lagrange_to_coeff(&self, a: Polynomial<_, LagrangeCoeff>) -> Polynomial<_, Coeff>
     std::vector<Fr> lagrange_to_coeff(const std::vector<Fr>& a) const {
@@ -325,8 +329,41 @@ class ParamsKZG {
     G1 commit(const std::vector<Fr>& poly) const { return msm(poly, g_); }
     // fn commit_lagrange(&self, poly: &Polynomial<_, LagrangeCoeff>, _: Blind<_>) -> G1
     G1 commit_lagrange(const std::vector<Fr>& poly) const { return msm(poly, g_lagrange_); }
+    // The independent commitments of one prover phase ([UP] plonk/prover.rs commits the advice / permuted / product columns of a phase
+    // one after the other): ONE batched kernel sequence per device, columns dealt round-robin over the devices.  Same results as
+    // commit_lagrange / commit called column by column.
+    std::vector<G1> commit_lagrange_many(const std::vector<std::vector<Fr>>& polys) const { return msm_many(polys, g_lagrange_); }
+    std::vector<G1> commit_many(const std::vector<std::vector<Fr>>& polys) const { return msm_many(polys, g_); }
+
+    // One witness / product column through commit_lagrange -> lagrange_to_coeff -> coeff_to_extended with a single upload
+    // (h2b_column_pipeline).  `extended` receives the 2^extended_k coset evaluations when non-null.
+    struct CommittedColumn { G1 commitment; std::vector<Fr> coeff; std::vector<Fr> extended; };
+    CommittedColumn commit_lagrange_and_convert(const EvaluationDomain& dom, const std::vector<Fr>& lagrange, bool want_extended = true) const {
+        if (lagrange.size() != n_ || dom.k() != k_) throw Panic("assertion failed: a.len() == 1 << self.k");
+        CommittedColumn out;
+        out.coeff.resize(n_);
+        if (want_extended) out.extended.resize(dom.extended_len());
+        const Fr z[3] = {fr::one(), dom.get_g_coset(), dom.get_g_coset_inv()};
+        check(h2b_column_pipeline(dom.device(), reinterpret_cast<const uint64_t*>(lagrange.data()), g_lagrange_, k_, dom.extended_k(), dom.get_omega_inv().l,
+                                  dom.get_ifft_divisor().l, dom.get_extended_omega().l, z[0].l, reinterpret_cast<uint64_t*>(&out.commitment),
+                                  reinterpret_cast<uint64_t*>(out.coeff.data()), want_extended ? reinterpret_cast<uint64_t*>(out.extended.data()) : nullptr,
+                                  nullptr), "commit_lagrange_and_convert");
+        return out;
+    }
 
   private:
+    std::vector<G1> msm_many(const std::vector<std::vector<Fr>>& polys, uint64_t handle) const {
+        std::vector<const uint64_t*> ptrs;
+        std::vector<size_t> lens;
+        for (const auto& p : polys) {
+            if (p.size() > n_) throw Panic("assertion failed: bases.len() >= size");
+            ptrs.push_back(reinterpret_cast<const uint64_t*>(p.data()));
+            lens.push_back(p.size());
+        }
+        std::vector<G1> out(polys.size());
+        check(h2b_msm_bn254_g1_batch_registered(ptrs.data(), lens.data(), polys.size(), handle, reinterpret_cast<uint64_t*>(out.data())), "commit (batched)");
+        return out;
+    }
     G1 msm(const std::vector<Fr>& poly, uint64_t handle) const {
         if (poly.size() > n_) throw Panic("assertion failed: bases.len() >= size");
         G1 out;

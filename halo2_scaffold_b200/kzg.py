@@ -67,6 +67,21 @@ class ParamsKZG:
         assert poly.shape[0] <= self.n
         return self.lib.msm_registered(poly, self._g_lagrange, 0)
 
+    def commit_many(self, polys) -> np.ndarray:
+        """the independent commitments of one prover phase over `g`: one batched kernel sequence per device -> (len(polys), 12)"""
+        return self.lib.msm_batch_registered(polys, self._g)
+
+    def commit_lagrange_many(self, polys) -> np.ndarray:
+        return self.lib.msm_batch_registered(polys, self._g_lagrange)
+
+    def commit_lagrange_and_convert(self, domain, lagrange: np.ndarray, want_extended: bool = True, keep_on_device: bool = False):
+        """commit_lagrange + EvaluationDomain::lagrange_to_coeff + coeff_to_extended of one column with a single upload
+        (h2b_column_pipeline) -> dict(commitment, coeff, extended, d_extended)"""
+        from .domain import fr_to_words
+        zs = np.stack([fr_to_words(1), fr_to_words(domain.g_coset), fr_to_words(domain.g_coset_inv)])
+        return self.lib.column_pipeline(lagrange, self._g_lagrange, self.k, domain.extended_k, fr_to_words(domain.omega_inv), fr_to_words(domain.ifft_divisor),
+                                        fr_to_words(domain.extended_omega), zs, want_extended=want_extended, keep_on_device=keep_on_device)
+
     def close(self):
         for h in (self._g, self._g_lagrange):
             if h:

@@ -67,6 +67,14 @@ int main(int argc, char** argv) {
             poly::kzg::ParamsKZG params(k, bases, bases);
             G1 c[2] = {params.commit(scalars), params.commit_lagrange(std::vector<Fr>(scalars.begin(), scalars.begin() + scalars.size() / 2))};
             write_all(dir + "/commit.bin", c, 2);
+            // the same two commitments + a third column through ONE batched call, and a column through the one-upload pipeline
+            std::vector<std::vector<Fr>> cols = {scalars, std::vector<Fr>(scalars.begin(), scalars.begin() + scalars.size() / 2), lagrange};
+            std::vector<G1> many = params.commit_lagrange_many(cols);
+            write_all(dir + "/commit_many.bin", many.data(), many.size());
+            auto cc = params.commit_lagrange_and_convert(dom, lagrange);
+            write_all(dir + "/pipeline_commit.bin", &cc.commitment, 1);
+            write_all(dir + "/pipeline_coeff.bin", cc.coeff.data(), cc.coeff.size());
+            write_all(dir + "/pipeline_extended.bin", cc.extended.data(), cc.extended.size());
         }
         // ---- the widened rows: vanishing division, SRS file round trip, GraphEvaluator, grand products, lookup permutation
         auto divided = dom.divide_by_vanishing_poly(ext);

@@ -71,3 +71,10 @@ def run_host_mirror(oc, lib_path, tmp_path, k=6, j=4):
     assert (pc.affine_of(oc, c[0]) == pc.affine_of(oc, oc.best_multiexp(s, P))).all()
     h = n // 2
     assert (pc.affine_of(oc, c[1]) == pc.affine_of(oc, oc.best_multiexp(s[:h], P[:h]))).all()
+    # batched commitments and the one-upload column pipeline of the C++ mirror
+    many = rd("commit_many", 12)
+    for got, col in zip(many, (s, s[:h], lag)):
+        assert (pc.affine_of(oc, got) == pc.affine_of(oc, oc.best_multiexp(col, P[:col.shape[0]]))).all()
+    assert (pc.affine_of(oc, rd("pipeline_commit", 12)[0]) == pc.affine_of(oc, oc.best_multiexp(lag, P))).all()
+    assert (rd("pipeline_coeff", 4) == words(coeff)).all()
+    assert (rd("pipeline_extended", 4) == words(ext)).all()

@@ -166,8 +166,13 @@ def test_domain_and_kzg_mirrors(gpu, oc, golden):
     evals = oc.random_fr(77, n)
     c1 = pc.affine_of(oc, params.commit_lagrange(evals))
     c2 = pc.affine_of(oc, params.commit(dom.lagrange_to_coeff(evals)))
+    # the same identity through the batched commits and the one-upload column pipeline of the mirror
+    many = params.commit_lagrange_many([evals, evals[: n // 2]])
+    r = params.commit_lagrange_and_convert(dom, evals)
+    c3 = pc.affine_of(oc, params.commit_many([r["coeff"]])[0])
     params.close()
-    assert (c1 == c2).all()
+    assert (c1 == c2).all() and (pc.affine_of(oc, many[0]) == c1).all() and (pc.affine_of(oc, r["commitment"]) == c1).all() and (c3 == c1).all()
+    assert (r["coeff"] == dom.lagrange_to_coeff(evals)).all() and (r["extended"] == dom.coeff_to_extended(r["coeff"])).all()
 
 
 def test_cpp_host_mirror_over_the_c_abi(gpu, oc, tmp_path):
