@@ -1542,7 +1542,24 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
         for (size_t done = 0; done < n; done += (size_t)1 << env_chunk) bounds.push_back(done);
     } else if (env_chunk == 0 && n >= ((size_t)1 << env_int("H2B_MSM_UPLOAD_MIN_LOG", 22))) {
         const size_t u = n / 16;
-        bounds = {0, u, 6 * u, 11 * u};
+        // Pinned scalars: every DMA is queued up front and PCIe is 4x faster than the kernels consume scalars: a short first chunk
+        // (1/32: the only transfer nothing can hide), then 4 : 11 : 16.  Pageable scalars are copied by host threads (stage.cu) right
+        // before a chunk's kernels are queued, at only ~3x the rate the GPU consumes them: chunk j + 1 has to be copied within the
+        // GPU time of chunk j, so the chunks grow 1 : 3 : 7 : 5 sixteenths (with 1 : 5 : 5 : 5 the GPU idled ~2 ms waiting for chunk 1).
+        // Measured at 2^24 (profiles/r02_e2e_matrix.jsonl): pageable 46.1 -> 44.2 ms, pinned 42.9 -> 42.3 ms (41.4 device-resident).
+        if (host_is_pageable(h_scalars)) bounds = {0, u, 4 * u, 11 * u};
+        else bounds = {0, u / 2, 5 * (u / 2), 8 * u};
+        if (const char* sched = getenv("H2B_MSM_UPLOAD_SCHED")) {      // tuning: chunk weights, e.g. "1,3,12,16" (any sum)
+            std::vector<size_t> wts;
+            size_t total = 0;
+            for (const char* q = sched; *q;) { char* end; const unsigned long v = strtoul(q, &end, 10); if (end == q) break; wts.push_back(v); total += v; q = *end ? end + 1 : end; }
+            if (wts.size() >= 1 && wts.size() <= 16 && total > 0) {
+                bounds.clear();
+                size_t acc = 0;
+                for (size_t v : wts) { bounds.push_back((size_t)((unsigned __int128)n * acc / total)); acc += v; }
+                for (size_t j = 1; j < bounds.size(); ++j) if (bounds[j] <= bounds[j - 1]) { bounds = {0}; break; }
+            }
+        }
     } else {
         bounds.push_back(0);
     }
