@@ -141,8 +141,21 @@ __device__ __forceinline__ void xyzz_add_affine(XYZZ& acc, const Affine& q_in, b
 }
 
 // acc += b, both XYZZ  (EFD add-2008-s: 12M + 2S)
+template <bool SHARED> __device__ __forceinline__ void xyzz_add_body(XYZZ& acc, const XYZZ& b);
+// ONE copy of the general addition for the latency-bound kernels: with the addition inlined at every call site the loop of
+// msm_reduce_level_kernel (three additions + a doubling) is 34 KB of straight-line code, more than the 32 KB L1.5 instruction
+// cache, and a lone warp waits for instruction fetch on everything but the shared multiplier
+static __device__ __noinline__ XYZZ xyzz_add_shared(XYZZ acc, XYZZ b) {
+    xyzz_add_body<true>(acc, b);
+    return acc;
+}
 template <bool SHARED = false>
 __device__ __forceinline__ void xyzz_add(XYZZ& acc, const XYZZ& b) {
+    if (SHARED) acc = xyzz_add_shared(acc, b);
+    else xyzz_add_body<false>(acc, b);
+}
+template <bool SHARED>
+__device__ __forceinline__ void xyzz_add_body(XYZZ& acc, const XYZZ& b) {
     if (xyzz_is_identity(b)) return;
     if (xyzz_is_identity(acc)) { acc = b; return; }
     Fq u1 = fq_m<SHARED>(acc.x, b.zz);

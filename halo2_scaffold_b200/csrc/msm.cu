@@ -819,7 +819,7 @@ __device__ __forceinline__ void block_sum_xyzz(XYZZ& acc, uint4* sh) {
     for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
         if (threadIdx.x < d) {
             XYZZ o = xyzz_load(sh + 8 * (threadIdx.x + d));
-            xyzz_add(acc, o);
+            xyzz_add<true>(acc, o);
             xyzz_store(sh + 8 * threadIdx.x, acc);
         }
         __syncthreads();
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(256) msm_combine_chunk_kernel(MsmPlan pl, cons
         XYZZ acc = xyzz_identity();
         for (uint32_t t = lo + threadIdx.x; t < hi; t += blockDim.x) {
             XYZZ q = xyzz_load(head_partial + 8 * (size_t)t);
-            xyzz_add(acc, q);
+            xyzz_add<true>(acc, q);
         }
         block_sum_xyzz(acc, sh);
         if (threadIdx.x == 0) xyzz_store(chunk_out + 8 * (size_t)item, acc);
@@ -859,12 +859,12 @@ __global__ void __launch_bounds__(256) msm_combine_heavy_kernel(const uint32_t* 
         XYZZ acc = xyzz_identity();
         for (uint32_t i = threadIdx.x; i < d.nchunks; i += blockDim.x) {
             XYZZ q = xyzz_load(chunk_out + 8 * (size_t)(d.chunk0 + i));
-            xyzz_add(acc, q);
+            xyzz_add<true>(acc, q);
         }
         block_sum_xyzz(acc, sh);
         if (threadIdx.x == 0) {
             XYZZ cur = xyzz_load(bucket_acc + 8 * (size_t)d.bucket);
-            xyzz_add(cur, acc);
+            xyzz_add<true>(cur, acc);
             xyzz_store(bucket_acc + 8 * (size_t)d.bucket, cur);
         }
         __syncthreads();
@@ -923,40 +923,58 @@ __global__ void __launch_bounds__(128) msm_reduce_level_kernel(const uint4* __re
     }
 }
 
-// Tail of the reduction, one CTA per set, N <= 512 items: S_w = sum_u (u+1) * B[u] + sum_u D[u] as a suffix scan
-// (sum_u (u+1) B[u] = sum_u suffix_u) followed by a tree sum, both in shared memory.  2 log2(N) + 1 additions deep
-// instead of the 2 m per level of the chunked running sums: small MSMs are pure latency.
+// Block level of the reduction: a CTA of M = blockDim.x threads (a power of two, 32..512) owns M consecutive items of one set and
+// computes, 2 log2(M) + 1 additions deep,
+//     A_j = sum_i B[jM + i]   and   C_j = sum_i (i + 1) B[jM + i] + sum_i D[jM + i]
+// as a suffix scan (sum_i (i + 1) B_i = sum_i suffix_i; A_j = suffix_0) followed by a tree sum, both in shared memory.  With more
+// than one block per set the outputs feed the next level like those of msm_reduce_level_kernel (B'[j-1] = M * A_j, B'[J-1] = 0,
+// D'[j] = C_j): 2.1 additions per bit of the item index, where the chunked running sums of one thread need 5.6 (2m additions + log2 m
+// doublings per log2 m bits) -- and a lone warp takes ~10 us per addition whatever the GPU has idle.  The tree sum runs MIRRORED
+// (the result lands in the last thread) so that thread 0, in another warp, does the log2(M) doublings of A_j in its shadow, one per
+// tree step.  Work is M log M additions per block: only for levels that no longer fill the GPU (the host picks: section
+// "bucket reduction hierarchy").  One block per set (gridDim.x == 1) is the tail: out[w] = S_w.
 static const uint32_t REDUCE_TAIL_MAX = 512;
-__global__ void __launch_bounds__(512) msm_reduce_tail_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, const uint32_t* __restrict__ offsets,
-                                                            uint32_t N, uint4* __restrict__ out) {
+static const uint32_t REDUCE_BLOCK = 128;
+__global__ void __launch_bounds__(512) msm_reduce_block_kernel(const uint4* __restrict__ Bin, const uint4* __restrict__ Din, const uint32_t* __restrict__ offsets,
+                                                             uint32_t N, uint4* __restrict__ Bout, uint4* __restrict__ Dout) {
     H2B_DYN_SMEM(uint4, sh);
-    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    const uint32_t w = blockIdx.y, j = blockIdx.x, J = gridDim.x, tid = threadIdx.x, M = blockDim.x;
+    const uint32_t u = j * M + tid;
+    const bool live = u < N;
     XYZZ x = xyzz_identity();
-    if (tid < N && (!offsets || offsets[(size_t)w * N + tid + 1] != offsets[(size_t)w * N + tid])) x = xyzz_load(Bin + 8 * ((size_t)w * N + tid));
-    for (uint32_t d = 1; d < N; d <<= 1) {
+    if (live && (!offsets || offsets[(size_t)w * N + u + 1] != offsets[(size_t)w * N + u])) x = xyzz_load(Bin + 8 * ((size_t)w * N + u));
+    for (uint32_t d = 1; d < M; d <<= 1) {
         xyzz_store(sh + 8 * tid, x);
         __syncthreads();
-        if (tid + d < N) {
+        if (tid + d < M) {
             XYZZ o = xyzz_load(sh + 8 * (tid + d));
             xyzz_add<true>(x, o);
         }
         __syncthreads();
     }
-    if (Din && tid < N) {
-        XYZZ dd = xyzz_load(Din + 8 * ((size_t)w * N + tid));
+    XYZZ a = x;                                 // thread 0: A_j
+    if (Din && live) {
+        XYZZ dd = xyzz_load(Din + 8 * ((size_t)w * N + u));
         xyzz_add<true>(x, dd);
     }
     xyzz_store(sh + 8 * tid, x);
     __syncthreads();
-    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
-        if (tid < d) {
-            XYZZ o = xyzz_load(sh + 8 * (tid + d));
+    for (uint32_t d = M >> 1; d > 0; d >>= 1) {
+        if (tid >= M - d) {
+            XYZZ o = xyzz_load(sh + 8 * (tid - d));
             xyzz_add<true>(x, o);
             xyzz_store(sh + 8 * tid, x);
+        } else if (tid == 0 && J > 1 && M >= 64) {
+            a = xyzz_double<true>(a);           // log2(M) tree steps = log2(M) doublings
         }
         __syncthreads();
     }
-    if (tid == 0) xyzz_store(out + 8 * (size_t)w, x);
+    if (tid == M - 1) xyzz_store(Dout + 8 * ((size_t)w * J + j), x);
+    if (tid == 0 && J > 1) {
+        if (M < 64) for (uint32_t d = M >> 1; d > 0; d >>= 1) a = xyzz_double<true>(a);
+        if (j >= 1) xyzz_store(Bout + 8 * ((size_t)w * J + j - 1), a);
+        else xyzz_store(Bout + 8 * ((size_t)w * J + J - 1), xyzz_identity());
+    }
 }
 
 // Horner over the set sums (S[w] = Dfinal[w], weight 2^(c*w)) and conversion to a Jacobian triple; one block per column of a
@@ -1442,7 +1460,32 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
     uint4* Bping[2] = {(uint4*)s.redA.p, (uint4*)s.redB.p};
     uint4* Dping[2] = {(uint4*)s.redC.p, (uint4*)s.redD.p};
     int pp = 0;
-    while (N > REDUCE_TAIL_MAX) {
+    if (!ctx.msm_attr_set) {      // a per-device function attribute
+        H2B_CUDA(cudaFuncSetAttribute(msm_reduce_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REDUCE_TAIL_MAX * 128)));
+        ctx.msm_attr_set = true;
+    }
+    // Levels that fill the GPU: chunked running sums, one thread per 2^logm items (work-efficient: 2 additions per item).  From
+    // 2^14 items in flight down a level is pure latency: block levels (msm_reduce_block_kernel, 2.1 instead of 5.6 additions deep
+    // per bit).  Measured (profiles/r02_block_reduce.jsonl): reduction 0.52 -> 0.31 ms at 2^15 buckets (a 2^16-point MSM: 0.87 ->
+    // 0.66 ms), 0.96 -> 0.75 ms at 2^19; switching at 2^16 items is 0.05 ms slower, 128- and 64-item blocks are equal, 256 slower.
+    // H2B_MSM_REDUCE_BLOCK_MAX_LOG moves the switch (0 = chunked levels all the way down to the tail, as in round 1).
+    static int env_block_log = -1;
+    if (env_block_log < 0) { env_block_log = env_int("H2B_MSM_REDUCE_BLOCK_MAX_LOG", 14); if (env_block_log > 24) env_block_log = 24; }
+    static int env_block = -1, env_tail = -1;
+    if (env_block < 0) { env_block = env_int("H2B_MSM_REDUCE_BLOCK", (int)REDUCE_BLOCK); if (env_block != 64 && env_block != 128 && env_block != 256 && env_block != 512) env_block = (int)REDUCE_BLOCK; }
+    if (env_tail < 0) { env_tail = env_int("H2B_MSM_REDUCE_TAIL", (int)REDUCE_TAIL_MAX); if (env_tail != 64 && env_tail != 128 && env_tail != 256 && env_tail != 512) env_tail = (int)REDUCE_TAIL_MAX; }
+    const uint32_t block_m = (uint32_t)env_block, tail_max = (uint32_t)env_tail;
+    while (N > tail_max) {
+        if (env_block_log > 0 && (uint64_t)sets * N <= ((uint64_t)1 << env_block_log)) {
+            const uint32_t J = (N + block_m - 1) / block_m;
+            H2B_LAUNCH(msm_reduce_block_kernel, dim3(J, sets), block_m, (size_t)block_m * 128, stream, Bin, Din, offs, N, Bping[pp], Dping[pp]);
+            Bin = Bping[pp];
+            Din = Dping[pp];
+            offs = nullptr;
+            pp ^= 1;
+            N = J;
+            continue;
+        }
         uint32_t J = (N + (1u << logm) - 1) >> logm;
         uint32_t threads = sets * J;
         H2B_LAUNCH(msm_reduce_level_kernel, (threads + 127) / 128, 128, 0, stream, Bin, Din, offs, N, logm, sets, Bping[pp], Dping[pp]);
@@ -1454,13 +1497,9 @@ static int msm_finish(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, void* d_
         if (env_logm < 1 && (uint64_t)sets * N < (1u << 21)) logm = 2;
     }
     {
-        if (!ctx.msm_attr_set) {      // a per-device function attribute
-            H2B_CUDA(cudaFuncSetAttribute(msm_reduce_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(REDUCE_TAIL_MAX * 128)));
-            ctx.msm_attr_set = true;
-        }
         uint32_t tthreads = 32;
         while (tthreads < N) tthreads <<= 1;
-        H2B_LAUNCH(msm_reduce_tail_kernel, sets, tthreads, (size_t)tthreads * 128, stream, Bin, Din, offs, N, Dping[pp]);
+        H2B_LAUNCH(msm_reduce_block_kernel, dim3(1, sets), tthreads, (size_t)tthreads * 128, stream, Bin, Din, offs, N, (uint4*)nullptr, Dping[pp]);
         Din = Dping[pp];
     }
     ctx.prof.mark(PROF_MSM_REDUCE, stream);

@@ -64,7 +64,7 @@ def test_msm_matches_oracle(emu, oc, n):
 
 def test_msm_witness_like_scalars_split_buckets(emu, oc):
     # 50% zero / 20% one / small / small negatives: exercises bucket splitting + warp combine
-    pc.check_msm(emu, oc, 3000, kind=1, windows=(0, 5, 10))
+    pc.check_msm(emu, oc, 3000, kind=1, windows=(0, 5, 10, 12))
 
 
 def test_msm_golden(emu, oc, golden):
