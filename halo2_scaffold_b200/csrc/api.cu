@@ -728,11 +728,90 @@ int h2b_msm_bn254_g1_registered(const uint64_t* scalars, uint64_t handle, size_t
     return msm_host(scalars, *bs, offset, n, out_jac);
 }
 
+// ---- ONE NTT across the devices of the process ("one NTT across GPUs") ---------------------------------------
+// Four-step transform of the n = R x C matrix a[i1 * C + i2] (R = 2^(log_n / 2) rows):
+//   A. device d takes the columns i2 in [d C/D, (d+1) C/D) straight from the caller's array (one strided upload per device: D PCIe links
+//      in parallel), transposes them, runs the C/D column transforms of length R (root w^C) and multiplies by w^(i2 k1);
+//   B. the one exchange step: device e pulls, from every device, the k1 in [e R/D, (e+1) R/D) part of its rows (2-D peer copies over
+//      NVLink: n/D^2 elements per pair);
+//   C. device e transposes, runs its R/D row transforms of length C (root w^R), transposes back and writes a_hat[k1 + R k2] into the
+//      caller's array (one strided download per device).
+// Transposes are HBM-bound passes over n/D elements (tens of microseconds); the transforms are the single-device kernels in their
+// strided-batch mode.  No collective: the exchange is D (D - 1) independent copies.
+static bool ntt_multi_applicable(uint32_t log_n, uint32_t* log_d) {
+    const size_t nd = G.devs.size();
+    if (nd < 2 || (nd & (nd - 1))) return false;
+    static int on = -1, min_log = -1;
+    if (on < 0) on = env_int_or("H2B_NTT_MULTI", 1);
+    if (min_log < 0) min_log = env_int_or("H2B_NTT_MULTI_MIN_LOG", 22);
+    uint32_t ld = 0;
+    while (((size_t)1 << ld) < nd) ++ld;
+    if (!on || log_n < (uint32_t)min_log || log_n / 2 < ld || log_n < 2) return false;
+    *log_d = ld;
+    return true;
+}
+
+static int on_all_devices(size_t nd, const std::function<int(size_t)>& fn) {
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < nd; ++d) th.emplace_back([&, d] { rcs[d] = fn(d); if (rcs[d]) errs[d] = get_error(); });
+    for (auto& t : th) t.join();
+    for (size_t d = 0; d < nd; ++d) if (rcs[d]) { set_error("device %zu: %s", d, errs[d].c_str()); return rcs[d]; }
+    return H2B_OK;
+}
+
+static int ntt_multi_device(uint64_t* a, const uint64_t omega[4], uint32_t log_n, uint32_t log_d) {
+    const size_t D = (size_t)1 << log_d;
+    const uint32_t r1 = log_n / 2, r2 = log_n - r1;
+    const size_t R = (size_t)1 << r1, C = (size_t)1 << r2, Rd = R >> log_d, Cd = C >> log_d;
+    const size_t slice = (size_t)32 << (log_n - log_d);
+    std::vector<std::unique_lock<std::mutex>> locks;      // every device, in index order
+    for (size_t d = 0; d < D; ++d) locks.emplace_back(G.devs[d]->mu);
+    uint64_t roots[8];                                    // w^C (order R) | w^R (order C)
+    {
+        DeviceCtx& c0 = *G.devs[0];
+        H2B_CUDA(cudaSetDevice(c0.device));
+        H2B_TRY(c0.msm_out.reserve(256));
+        H2B_TRY(ntt_root_powers_run(c0, omega, r2, r1, c0.msm_out.p, c0.stream));
+        H2B_CUDA(cudaMemcpyAsync(roots, c0.msm_out.p, 64, cudaMemcpyDeviceToHost, c0.stream));
+        H2B_CUDA(cudaStreamSynchronize(c0.stream));
+    }
+    H2B_TRY(on_all_devices(D, [&](size_t d) -> int {
+        DeviceCtx& c = *G.devs[d];
+        H2B_CUDA(cudaSetDevice(c.device));
+        H2B_TRY(c.ntt_io.reserve(slice));
+        H2B_TRY(c.ntt_fs[0].reserve(slice));
+        H2B_TRY(c.ntt_fs[1].reserve(slice));
+        H2B_TRY(host_upload_2d(c, c.ntt_io.p, (const char*)a + d * Cd * 32, C * 32, Cd * 32, R, c.stream));          // R x Cd
+        H2B_TRY(fr_transpose_run(c, c.ntt_io.p, c.ntt_fs[0].p, (uint32_t)R, (uint32_t)Cd, c.stream));                 // Cd x R
+        H2B_TRY(ntt_run_strided(c, c.ntt_fs[0].p, Cd, R, roots, r1, c.stream));
+        H2B_TRY(ntt_fourstep_twiddle_run(c, c.ntt_fs[0].p, (uint32_t)Cd, r1, (uint32_t)(d * Cd), omega, c.stream));
+        H2B_CUDA(cudaStreamSynchronize(c.stream));
+        return H2B_OK;
+    }));
+    return on_all_devices(D, [&](size_t e) -> int {
+        DeviceCtx& c = *G.devs[e];
+        H2B_CUDA(cudaSetDevice(c.device));
+        for (size_t k = 0; k < D; ++k) {                  // C x Rd, rows [d Cd, (d+1) Cd) from device d; every device starts with its own block
+            const size_t d = (e + k) & (D - 1);
+            H2B_CUDA(cudaMemcpy2DAsync((char*)c.ntt_io.p + d * Cd * Rd * 32, Rd * 32, (const char*)G.devs[d]->ntt_fs[0].p + e * Rd * 32, R * 32, Rd * 32, Cd,
+                                       cudaMemcpyDefault, c.stream));
+        }
+        H2B_TRY(fr_transpose_run(c, c.ntt_io.p, c.ntt_fs[1].p, (uint32_t)C, (uint32_t)Rd, c.stream));                 // Rd x C
+        H2B_TRY(ntt_run_strided(c, c.ntt_fs[1].p, Rd, C, roots + 4, r2, c.stream));
+        H2B_TRY(fr_transpose_run(c, c.ntt_fs[1].p, c.ntt_io.p, (uint32_t)Rd, (uint32_t)C, c.stream));                 // C x Rd: [k2][k1]
+        return host_download_2d(c, (char*)a + e * Rd * 32, R * 32, c.ntt_io.p, Rd * 32, C, c.stream);
+    });
+}
+
 int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n) {
     H2B_TRY(require_init());
     if (!a || !omega) { set_error("h2b_ntt_bn254_fr: null pointer"); return H2B_ERR_BAD_ARGUMENT; }
     if (log_n > 28) { set_error("h2b_ntt_bn254_fr: log_n = %u exceeds the two-adicity of Fr (28)", log_n); return H2B_ERR_BAD_ARGUMENT; }
     if (log_n == 0) return H2B_OK;
+    uint32_t log_d = 0;
+    if (ntt_multi_applicable(log_n, &log_d)) return ntt_multi_device(a, omega, log_n, log_d);
     std::unique_lock<std::mutex> lk;
     DeviceCtx* c = pick_device(lk);
     H2B_CUDA(cudaSetDevice(c->device));

@@ -93,6 +93,7 @@ struct DeviceCtx {
     bool ntt_attr_set = false;
     bool msm_attr_set = false;
     DevBuf ntt_io;                     // staging for the host-pointer NTT entry point
+    DevBuf ntt_fs[2];                  // the two other matrices of the multi-device four-step NTT (api.cu: ntt_multi_device)
     DevBuf col_ext;                    // extended form of h2b_column_pipeline when the caller only wants it on the host
     DevBuf scale_table;                // factor table of h2b_fr_scale_dev with more than 8 factors
     DevBuf msm_scalars;                // staging for host-pointer MSM scalars
@@ -113,6 +114,9 @@ struct DeviceCtx {
 // ---- stage.cu ----
 int host_upload(DeviceCtx& ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t consumer, bool order_after_consumer = true);
 int host_download(DeviceCtx& ctx, void* h_dst, const void* d_src, size_t bytes, cudaStream_t producer);
+// `height` rows of `width` bytes: host rows are `h_pitch` bytes apart, the device side is packed
+int host_upload_2d(DeviceCtx& ctx, void* d_dst, const void* h_src, size_t h_pitch, size_t width, size_t height, cudaStream_t consumer);
+int host_download_2d(DeviceCtx& ctx, void* h_dst, size_t h_pitch, const void* d_src, size_t width, size_t height, cudaStream_t producer);
 void stager_release(DeviceCtx& ctx);
 bool host_is_pageable(const void* p);
 // ---- scan.cu ----
@@ -149,6 +153,10 @@ void evaluate_release(DeviceCtx& ctx);
 int ntt_run(DeviceCtx& ctx, void* d_a, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
 int ntt_run_batch(DeviceCtx& ctx, void* const* d_polys, size_t count, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
 uint32_t ntt_batch_max();
+int ntt_run_strided(DeviceCtx& ctx, void* d_base, size_t count, size_t stride_elems, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream);
+int fr_transpose_run(DeviceCtx& ctx, const void* d_in, void* d_out, uint32_t rows, uint32_t cols, cudaStream_t stream);
+int ntt_fourstep_twiddle_run(DeviceCtx& ctx, void* d_y, uint32_t rows, uint32_t log_len, uint32_t row0, const uint64_t omega[4], cudaStream_t stream);
+int ntt_root_powers_run(DeviceCtx& ctx, const uint64_t omega[4], uint32_t e0, uint32_t e1, void* d_out, cudaStream_t stream);
 int ntt_scale_run(DeviceCtx& ctx, void* d_a, size_t n, const uint64_t* factors /*host, count x 4*/, int count, cudaStream_t stream);
 int ntt_scale_batch_run(DeviceCtx& ctx, void* const* d_cols, size_t ncols, size_t n, const uint64_t* factors, int count, cudaStream_t stream);
 void ntt_release(DeviceCtx& ctx);

@@ -28,6 +28,8 @@ static const uint32_t NTT_BATCH_MAX = 16;    // polynomials per launch (blockIdx
 struct NttPassParams {
     const uint4* ins[NTT_BATCH_MAX];
     uint4* outs[NTT_BATCH_MAX];
+    size_t in_stride, out_stride;   // != 0: polynomial y is ins[0] + y * in_stride / outs[0] + y * out_stride (uint4 units): any number of equally
+                                    // spaced transforms in one launch (the row / column transforms of the multi-device four-step NTT)
     const uint4* tw_small;   // Omega^t, t < N/2, Omega = w^(n/N)
     const uint4* tw_lo;      // w^j,          j < 2^h
     const uint4* tw_hi;      // w^(j * 2^h),  j < 2^(log_n - h)
@@ -116,8 +118,8 @@ __device__ __forceinline__ void ntt_round(uint4* lo, uint4* hi, const uint4* tlo
 
 __global__ void __launch_bounds__(512, 1) ntt_pass_kernel(NttPassParams p) {
     H2B_DYN_SMEM(uint4, sm);
-    const uint4* __restrict__ p_in = p.ins[blockIdx.y];
-    uint4* __restrict__ p_out = p.outs[blockIdx.y];
+    const uint4* __restrict__ p_in = p.out_stride ? p.ins[0] + p.in_stride * blockIdx.y : p.ins[blockIdx.y];
+    uint4* __restrict__ p_out = p.out_stride ? p.outs[0] + p.out_stride * blockIdx.y : p.outs[blockIdx.y];
     const uint32_t b = p.b, logT = p.logT;
     const uint32_t N = 1u << b, T = 1u << logT, E = N << logT;
     const uint32_t data_slots = sm_slot(E - 1) + 1, tw_slots = sm_slot((N >> 1) ? (N >> 1) - 1 : 0) + 1;
@@ -450,7 +452,7 @@ static int ntt_get_twiddles(DeviceCtx& ctx, const uint64_t omega[4], uint32_t lo
 }
 
 // `count` <= NTT_BATCH_MAX transforms of the same (omega, log_n) in one launch per pass (polynomial = blockIdx.y)
-static int ntt_run_group(DeviceCtx& ctx, void* const* d_polys, uint32_t count, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream) {
+static int ntt_run_group(DeviceCtx& ctx, void* const* d_polys, uint32_t count, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream, size_t stride_elems = 0) {
     NttTwiddles* tw = nullptr;
     ctx.prof.mark(PROF_BEGIN, stream);
     H2B_TRY(ntt_get_twiddles(ctx, omega, log_n, stream, &tw));
@@ -469,10 +471,18 @@ static int ntt_run_group(DeviceCtx& ctx, void* const* d_polys, uint32_t count, c
         memset(&a, 0, sizeof(a));
         const bool first = (p == 0), last = (p + 1 == tw->npass);
         // pass 1: a -> work, middle passes in place in work, last pass: work -> a (scatter)
-        for (uint32_t j = 0; j < count; ++j) {
-            uint4* work = (uint4*)ctx.ntt_work.p + 2 * n * j;
-            a.ins[j] = first ? (const uint4*)d_polys[j] : work;
-            a.outs[j] = last ? (uint4*)d_polys[j] : work;
+        if (stride_elems) {      // `count` transforms spaced stride_elems apart, starting at d_polys[0]
+            uint4* work = (uint4*)ctx.ntt_work.p;
+            a.ins[0] = first ? (const uint4*)d_polys[0] : work;
+            a.outs[0] = last ? (uint4*)d_polys[0] : work;
+            a.in_stride = first ? 2 * stride_elems : 2 * n;
+            a.out_stride = last ? 2 * stride_elems : 2 * n;
+        } else {
+            for (uint32_t j = 0; j < count; ++j) {
+                uint4* work = (uint4*)ctx.ntt_work.p + 2 * n * j;
+                a.ins[j] = first ? (const uint4*)d_polys[j] : work;
+                a.outs[j] = last ? (uint4*)d_polys[j] : work;
+            }
         }
         a.tw_small = tbl + 2 * (size_t)tw->small_off[p];
         a.tw_lo = tbl + 2 * (size_t)tw->lo_off;
@@ -535,6 +545,107 @@ int ntt_run_batch(DeviceCtx& ctx, void* const* d_polys, size_t count, const uint
     return H2B_OK;
 }
 uint32_t ntt_batch_max() { return NTT_BATCH_MAX; }
+
+// `count` in-place transforms of 2^log_n elements each, spaced stride_elems >= 2^log_n elements apart from d_base on: the rows of a matrix
+int ntt_run_strided(DeviceCtx& ctx, void* d_base, size_t count, size_t stride_elems, const uint64_t omega[4], uint32_t log_n, cudaStream_t stream) {
+    if (log_n > 28 || log_n == 0) { set_error("strided ntt: log_n = %u out of range", log_n); return H2B_ERR_BAD_ARGUMENT; }
+    if (count == 0) return H2B_OK;
+    if (!d_base || stride_elems < ((size_t)1 << log_n)) { set_error("strided ntt: bad base or stride"); return H2B_ERR_BAD_ARGUMENT; }
+    size_t group = 32768;                                        // gridDim.y
+    while (group > 1 && (group << log_n) > ((size_t)1 << 27)) group >>= 1;      // work buffer: at most 4 GiB
+    for (size_t j0 = 0; j0 < count; j0 += group) {
+        const size_t m = count - j0 < group ? count - j0 : group;
+        void* one[1] = {(char*)d_base + j0 * stride_elems * 32};
+        H2B_TRY(ntt_run_group(ctx, one, (uint32_t)m, omega, log_n, stream, stride_elems));
+    }
+    return H2B_OK;
+}
+
+// ---- pieces of the four-step NTT across the devices of one process (api.cu: ntt_multi_device) ------------------------------------
+// out[c * rows + r] = in[r * cols + c] for a rows x cols matrix of Fr elements (32-byte tiles through shared memory: both sides coalesced)
+__global__ void __launch_bounds__(256) fr_transpose_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t rows, uint32_t cols) {
+    __shared__ uint4 tile[2][32][33];
+    const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const uint32_t r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            tile[0][dy][threadIdx.x] = in[2 * ((size_t)r * cols + c)];
+            tile[1][dy][threadIdx.x] = in[2 * ((size_t)r * cols + c) + 1];
+        }
+    }
+    __syncthreads();
+    for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const uint32_t c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            out[2 * ((size_t)c * rows + r)] = tile[0][threadIdx.x][dy];
+            out[2 * ((size_t)c * rows + r) + 1] = tile[1][threadIdx.x][dy];
+        }
+    }
+}
+int fr_transpose_run(DeviceCtx& ctx, const void* d_in, void* d_out, uint32_t rows, uint32_t cols, cudaStream_t stream) {
+    (void)ctx;
+    if (rows == 0 || cols == 0) return H2B_OK;
+    const uint32_t gy = (rows + 31) / 32;
+    if (gy > 65535) { set_error("transpose: too many rows"); return H2B_ERR_BAD_ARGUMENT; }
+    H2B_LAUNCH(fr_transpose_kernel, dim3((cols + 31) / 32, gy), dim3(32, 8), 0, stream, (const uint4*)d_in, (uint4*)d_out, rows, cols);
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
+// y[row][k] *= w^((row0 + row) * k) for a rows x 2^log_len matrix (row-major): the twiddle step between the column and the row transforms.
+// A thread owns FS_RUN consecutive k of one row: g = w^(row0 + row), start g^(k0) by square-and-multiply, then one multiplication per step.
+static const uint32_t FS_RUN = 64;
+struct FsOmega { uint32_t w[8]; };
+__global__ void __launch_bounds__(128) ntt_fourstep_twiddle_kernel(uint4* __restrict__ y, uint32_t rows, uint32_t log_len, uint32_t row0, FsOmega om) {
+    const uint32_t len = 1u << log_len;
+    const uint32_t run = len < FS_RUN ? len : FS_RUN;
+    const uint32_t runs_per_row = len / run;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)rows * runs_per_row) return;
+    const uint32_t row = (uint32_t)(t / runs_per_row), k0 = (uint32_t)(t % runs_per_row) * run;
+    Fr w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w.l[i] = om.w[i];
+    const Fr g = fp_pow_u32(w, row0 + row);
+    Fr cur = fp_pow_u32(g, k0);
+    uint4* p = y + 2 * ((size_t)row * len + k0);
+    for (uint32_t k = 0; k < run; ++k) {
+        fp_store<FR>(p + 2 * k, fp_mul(fp_load<FR>(p + 2 * k), cur));
+        cur = fp_mul(cur, g);
+    }
+}
+int ntt_fourstep_twiddle_run(DeviceCtx& ctx, void* d_y, uint32_t rows, uint32_t log_len, uint32_t row0, const uint64_t omega[4], cudaStream_t stream) {
+    (void)ctx;
+    if (rows == 0) return H2B_OK;
+    FsOmega om;
+    memcpy(om.w, omega, 32);
+    const uint32_t len = 1u << log_len, run = len < FS_RUN ? len : FS_RUN;
+    const size_t threads = (size_t)rows * (len / run);
+    H2B_LAUNCH(ntt_fourstep_twiddle_kernel, (unsigned)((threads + 127) / 128), 128, 0, stream, (uint4*)d_y, rows, log_len, row0, om);
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
+
+// out[0] = w^(2^e0), out[1] = w^(2^e1): the roots of the column and row transforms (no field arithmetic on the host)
+__global__ void ntt_root_powers_kernel(FsOmega om, uint32_t e0, uint32_t e1, uint4* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fr w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w.l[i] = om.w[i];
+    Fr a = w, b = w;
+    for (uint32_t i = 0; i < e0; ++i) a = fp_sqr(a);
+    for (uint32_t i = 0; i < e1; ++i) b = fp_sqr(b);
+    fp_store<FR>(out, a);
+    fp_store<FR>(out + 2, b);
+}
+int ntt_root_powers_run(DeviceCtx& ctx, const uint64_t omega[4], uint32_t e0, uint32_t e1, void* d_out /*64 B*/, cudaStream_t stream) {
+    (void)ctx;
+    FsOmega om;
+    memcpy(om.w, omega, 32);
+    H2B_LAUNCH(ntt_root_powers_kernel, 1, 32, 0, stream, om, e0, e1, (uint4*)d_out);
+    H2B_CUDA(cudaGetLastError());
+    return H2B_OK;
+}
 
 // a[i] *= factors[i % count]   (count 1 / 3: the 1/n of lagrange_to_coeff / extended_to_coeff and the zeta-coset pattern
 // of coeff_to_extended; count 2^(extended_k - k) <= 8: the t_evaluations of divide_by_vanishing_poly --
@@ -623,6 +734,8 @@ void ntt_release(DeviceCtx& ctx) {
     ctx.twiddles.clear();
     ctx.ntt_work.release();
     ctx.ntt_io.release();
+    ctx.ntt_fs[0].release();
+    ctx.ntt_fs[1].release();
     ctx.scale_table.release();
 }
 

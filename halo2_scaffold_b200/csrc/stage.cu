@@ -177,4 +177,100 @@ int host_download(DeviceCtx& ctx, void* h_dst, const void* d_src, size_t bytes, 
     return H2B_OK;
 }
 
+// ---- strided host arrays (the row / column blocks of the multi-device NTT) ------------------------------------------------------
+// `height` rows of `width` bytes, `h_pitch` bytes apart in host memory, packed on the device.  Pinned host memory: one 2-D DMA.
+// Pageable: the staging threads gather whole rows into their pinned slots (a piece = as many rows as fit one slot) and DMA them.
+int host_upload_2d(DeviceCtx& ctx, void* d_dst, const void* h_src, size_t h_pitch, size_t width, size_t height, cudaStream_t consumer) {
+    if (width == 0 || height == 0) return H2B_OK;
+    if (h_pitch == width) return host_upload(ctx, d_dst, h_src, width * height, consumer);
+    if (!host_is_pageable(h_src) || width > STAGE_PIECE || width * height < STAGE_MIN_BYTES) {
+        H2B_CUDA(cudaMemcpy2DAsync(d_dst, width, h_src, h_pitch, width, height, cudaMemcpyHostToDevice, consumer));
+        return H2B_OK;
+    }
+    H2B_TRY(stager_init(ctx));
+    Stager& s = *ctx.stager;
+    H2B_CUDA(cudaEventRecord(s.ready, consumer));
+    const size_t rows_per_piece = STAGE_PIECE / width;
+    const size_t pieces = (height + rows_per_piece - 1) / rows_per_piece;
+    const int T = (int)(pieces < (size_t)s.nthreads ? pieces : (size_t)s.nthreads);
+    std::vector<cudaError_t> errs(T, cudaSuccess);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) {
+        th.emplace_back([&, t] {
+            cudaError_t e = cudaSetDevice(ctx.device);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s.stream[t], s.ready, 0);
+            size_t k = 0;
+            for (size_t p = t; p < pieces && e == cudaSuccess; p += T, ++k) {
+                const int sl = (int)(k % STAGE_SLOTS);
+                const size_t r0 = p * rows_per_piece, r1 = r0 + rows_per_piece < height ? r0 + rows_per_piece : height;
+                e = cudaEventSynchronize(s.slot_free[t][sl]);
+                if (e != cudaSuccess) break;
+                for (size_t r = r0; r < r1; ++r) memcpy((char*)s.slot[t][sl] + (r - r0) * width, (const char*)h_src + r * h_pitch, width);
+                e = cudaMemcpyAsync((char*)d_dst + r0 * width, s.slot[t][sl], (r1 - r0) * width, cudaMemcpyHostToDevice, s.stream[t]);
+                if (e == cudaSuccess) e = cudaEventRecord(s.slot_free[t][sl], s.stream[t]);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(s.done[t], s.stream[t]);
+            errs[t] = e;
+        });
+    }
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; ++t) H2B_CUDA(errs[t]);
+    for (int t = 0; t < T; ++t) H2B_CUDA(cudaStreamWaitEvent(consumer, s.done[t], 0));
+    return H2B_OK;
+}
+
+// Synchronous, like host_download.
+int host_download_2d(DeviceCtx& ctx, void* h_dst, size_t h_pitch, const void* d_src, size_t width, size_t height, cudaStream_t producer) {
+    if (width == 0 || height == 0) return H2B_OK;
+    if (h_pitch == width) return host_download(ctx, h_dst, d_src, width * height, producer);
+    if (!host_is_pageable(h_dst) || width > STAGE_PIECE || width * height < STAGE_MIN_BYTES) {
+        H2B_CUDA(cudaMemcpy2DAsync(h_dst, h_pitch, d_src, width, width, height, cudaMemcpyDeviceToHost, producer));
+        H2B_CUDA(cudaStreamSynchronize(producer));
+        return H2B_OK;
+    }
+    H2B_TRY(stager_init(ctx));
+    Stager& s = *ctx.stager;
+    H2B_CUDA(cudaEventRecord(s.ready, producer));
+    const size_t rows_per_piece = STAGE_PIECE / width;
+    const size_t pieces = (height + rows_per_piece - 1) / rows_per_piece;
+    const int T = (int)(pieces < (size_t)s.nthreads ? pieces : (size_t)s.nthreads);
+    std::vector<cudaError_t> errs(T, cudaSuccess);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) {
+        th.emplace_back([&, t] {
+            cudaError_t e = cudaSetDevice(ctx.device);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s.stream[t], s.ready, 0);
+            auto rows_of = [&](size_t k, size_t& r0, size_t& r1) {
+                const size_t p = t + k * (size_t)T;
+                r0 = p * rows_per_piece;
+                r1 = r0 + rows_per_piece < height ? r0 + rows_per_piece : height;
+            };
+            auto issue = [&](size_t k) -> cudaError_t {
+                size_t r0, r1;
+                rows_of(k, r0, r1);
+                const int sl = (int)(k % STAGE_SLOTS);
+                cudaError_t r = cudaMemcpyAsync(s.slot[t][sl], (const char*)d_src + r0 * width, (r1 - r0) * width, cudaMemcpyDeviceToHost, s.stream[t]);
+                if (r == cudaSuccess) r = cudaEventRecord(s.slot_free[t][sl], s.stream[t]);
+                return r;
+            };
+            const size_t mine = (pieces > (size_t)t) ? (pieces - t + T - 1) / T : 0;
+            if (e == cudaSuccess && mine > 0) e = issue(0);
+            for (size_t k = 0; k < mine && e == cudaSuccess; ++k) {
+                if (k + 1 < mine) e = issue(k + 1);
+                if (e != cudaSuccess) break;
+                size_t r0, r1;
+                rows_of(k, r0, r1);
+                const int sl = (int)(k % STAGE_SLOTS);
+                e = cudaEventSynchronize(s.slot_free[t][sl]);
+                if (e == cudaSuccess)
+                    for (size_t r = r0; r < r1; ++r) memcpy((char*)h_dst + r * h_pitch, (const char*)s.slot[t][sl] + (r - r0) * width, width);
+            }
+            errs[t] = e;
+        });
+    }
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; ++t) H2B_CUDA(errs[t]);
+    return H2B_OK;
+}
+
 }  // namespace h2b

@@ -80,7 +80,12 @@ int h2b_is_emulator(void);
 int h2b_msm_bn254_g1(const uint64_t* scalars, const uint64_t* bases, size_t n, uint64_t out_jac[12]);
 
 /* best_fft(a, omega, log_n) for G = Fr: in place, natural order in and out, no scaling;
- * a has 2^log_n elements, log_n <= 28. */
+ * a has 2^log_n elements, log_n <= 28.
+ * With D = 2^j > 1 devices and log_n >= 22 (H2B_NTT_MULTI_MIN_LOG; H2B_NTT_MULTI=0 turns it off) the ONE transform is split over
+ * the devices as a four-step NTT (SURVEY.md 8e "one NTT across GPUs"): device d uploads the column block [d C/D, (d+1) C/D) of the
+ * R x C matrix straight from `a` (D PCIe links in parallel), runs its column transforms and the twiddle step, the devices exchange
+ * n/D^2-element blocks by 2-D peer copies over NVLink (the only exchange; no collective), and every device runs its row transforms
+ * and writes its part of the result into `a`. */
 int h2b_ntt_bn254_fr(uint64_t* a, const uint64_t omega[4], uint32_t log_n);
 
 /* Explicit device residency for an SRS vector (copied; the host array may be freed afterwards).  Registration

@@ -573,6 +573,17 @@ def test_multi_device_host_logic_on_emulated_devices(emu, devices):
                     dict(H2B_EMU_DEVICES=devices, H2B_MULTI_DEVICE_MIN_LOG="7", H2B_DIGEST_BLOCK_LOG="4", H2B_IMPLICIT_MIN_LOG="6"))
 
 
+@pytest.mark.parametrize("devices", ["2", "4"])
+def test_one_ntt_across_emulated_devices(emu, devices):
+    # SURVEY.md 8e "one NTT across GPUs": the four-step split of h2b_ntt_bn254_fr (strided uploads of column blocks, transposes,
+    # strided-batch transforms, twiddles, 2-D peer copies, strided downloads) against best_fft, both directions, odd and even log_n,
+    # pageable host arrays through the staging threads with 1 KiB pieces (several rows per piece, several pieces per thread)
+    _emu_subprocess(emu, "assert L.device_count() == %s\n"
+                         "for k in (4, 5, 8, 11, 12, 13):\n"
+                         "    pc.check_ntt(L, oc, k)\n" % devices,
+                    dict(H2B_EMU_DEVICES=devices, H2B_NTT_MULTI_MIN_LOG="4", H2B_STAGE_PIECE_LOG="10", H2B_STAGE_THREADS="3"))
+
+
 @pytest.mark.parametrize("n,ncols,spacing,window", [(600, 6, 8, 0), (600, 5, 8, 4), (257, 9, 0, 0), (1200, 4, 12, 6), (40, 33, 6, 0), (300, 4, -1, 0)])
 def test_batched_columns_one_kernel_sequence(emu, oc, n, ncols, spacing, window):
     pc.check_batched_columns(emu, oc, n, ncols, spacing=spacing, window=window)

@@ -177,6 +177,10 @@ static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cud
 static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t = 0) {
+    for (size_t r = 0; r < height; ++r) memcpy((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemcpyPeer(void* d, int, const void* s, int, size_t n) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = 0) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }

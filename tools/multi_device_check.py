@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """In-process multi-GPU paths of libh2b200, checked against the oracle on every visible B200:
   * one host-pointer MSM split by point range across the devices (partials folded on device 0),
+  * one host-pointer NTT split over the devices (four-step: column blocks, one exchange of 2-D peer copies, row blocks),
   * independent NTTs / MSMs issued from concurrent host threads, spread round-robin over the devices.
 Prints MULTI_DEVICE_OK <n_devices>."""
 import os
@@ -48,6 +49,14 @@ wantp = [oc.best_fft(a, pc.omega_words(oc, 16), 16) for a in polys]
 L.ntt_batch(polys, pc.omega_words(oc, 16), 16)
 for a, w_ in zip(polys, wantp):
     assert (a == w_).all()
+
+# ONE NTT across the devices (four-step split of h2b_ntt_bn254_fr; a power-of-two device count): forward, inverse, odd log_n
+if nd >= 2 and nd & (nd - 1) == 0:
+    for k in (22, 23):
+        a = oc.random_fr(700 + k, 1 << k)
+        for inverse in (False, True):
+            w = pc.omega_words(oc, k, inverse)
+            assert (L.ntt(a.copy(), w, k) == oc.best_fft(a, w, k)).all(), ("one NTT across devices", k, inverse)
 
 # concurrent callers: 2 * nd threads, each an NTT round trip and a small MSM
 errs = []

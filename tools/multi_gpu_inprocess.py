@@ -2,7 +2,8 @@
 """The multi-GPU modes a single prover process uses (`h2b_init(D)`), measured and checked in ONE process:
 
   parity : one host-pointer MSM split by point range over D devices (implicit cache -> sharded resident copy; sharded
-           registered set), batched columns round-robin over the devices, batched NTTs -- each against the CPU oracle
+           registered set), batched columns round-robin over the devices, batched NTTs, ONE NTT split over the devices -- each
+           against the CPU oracle
            (2^18 .. 2^20 points, sizes the oracle finishes in seconds);
   strong : ONE MSM of fixed total size 2^k over D devices through the host-pointer entry point with pageable scalars
            (what a Rust Vec is): sharded registration time, end-to-end ms, and the O(n) checksum [sum s_i z_i] G of the result.
@@ -60,6 +61,15 @@ def main():
     wantp = [oc.best_fft(a, pc.omega_words(oc, 16), 16) for a in polys]
     L.ntt_batch(polys, pc.omega_words(oc, 16), 16)
     checks["batched_ntts_round_robin"] = bool(all((a == w_).all() for a, w_ in zip(polys, wantp)))
+    # one NTT split over the D devices (four-step: column blocks, one exchange, row blocks), forward and inverse, pageable array
+    if D & (D - 1) == 0:
+        a = oc.random_fr(900, 1 << 22)
+        ok = True
+        for inverse in (False, True):
+            w = pc.omega_words(oc, 22, inverse)
+            ok = ok and bool((L.ntt(a.copy(), w, 22) == oc.best_fft(a, w, 22)).all())
+        checks["one_ntt_across_devices"] = ok
+        del a
     out["parity_vs_oracle"] = checks
     out["parity_ok"] = all(checks.values())
     out["parity_s"] = round(time.perf_counter() - t0, 2)
@@ -117,6 +127,36 @@ def main():
                        "scalars": "pageable host memory (msm_e2e_ms) and pinned host memory (msm_e2e_ms_pinned_scalars)"})
         del s
     out["strong"] = strong
+
+    # ---- one NTT across the devices: end to end through h2b_ntt_bn254_fr, pageable and pinned host arrays ----------------------------
+    ntt = []
+    if D & (D - 1) == 0:
+        for k in ks:
+            n = 1 << k
+            w = pc.omega_words(oc, k)
+            a = L.gen_scalars(0xB2000000 + k, n, 0)         # pageable
+            row = {"k": k, "devices": D}
+            for name in ("pageable", "pinned"):
+                arr = a
+                if name == "pinned":
+                    try:
+                        import torch
+                        tp = torch.empty(n * 4, dtype=torch.int64).pin_memory()
+                        arr = tp.numpy().view(np.uint64).reshape(n, 4)
+                        arr[:] = a
+                    except Exception:       # noqa: BLE001
+                        continue
+                L.ntt(arr, w, k)
+                steps = 5 if k <= 24 else 3
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    L.ntt(arr, w, k)
+                ms = (time.perf_counter() - t0) / steps * 1e3
+                row["ntt_e2e_ms_" + name] = round(ms, 3)
+                row["elements_per_s_" + name] = n / ms * 1e3
+            ntt.append(row)
+            del a
+    out["one_ntt_across_devices"] = ntt
     print(json.dumps(out), flush=True)
 
 
