@@ -1579,7 +1579,9 @@ int msm_run_host(DeviceCtx& ctx, const void* h_scalars, void* d_staging, const M
     std::vector<size_t> bounds;
     if (env_chunk >= 10 && env_chunk <= 26 && n >= ((size_t)2 << env_chunk)) {
         for (size_t done = 0; done < n; done += (size_t)1 << env_chunk) bounds.push_back(done);
-    } else if (env_chunk == 0 && n >= ((size_t)1 << env_int("H2B_MSM_UPLOAD_MIN_LOG", 22))) {
+    } else if (env_chunk == 0 && n >= ((size_t)1 << env_int("H2B_MSM_UPLOAD_MIN_LOG", host_is_pageable(h_scalars) ? 20 : 21))) {
+        // (measured, profiles/r02_e2e_matrix.jsonl: chunking pays from 2^21 points with pinned scalars -- 7.20 -> 6.96 ms; 2^20: 4.10 -> 4.29 ms --
+        // and from 2^20 with pageable ones -- 5.81 -> 5.10 ms, 2^21: 8.48 -> 8.23 ms: the per-device share of a point-range split is that small)
         const size_t u = n / 16;
         // Pinned scalars: every DMA is queued up front and PCIe is 4x faster than the kernels consume scalars: a short first chunk
         // (1/32: the only transfer nothing can hide), then 4 : 11 : 16.  Pageable scalars are copied by host threads (stage.cu) right
