@@ -143,9 +143,10 @@ static const uint32_t PART_TILE_ENTRIES = 12288;  // entries staged per tile: 96
 static const uint32_t PART_W_MAX = 16;            // windows per scalar kept in registers by msm_partition_kernel
 static const uint32_t PLACE_MAX_LOG = 13;         // buckets per partition in the place kernels: 32 KiB of cursors
 
-__device__ __forceinline__ void msm_decompose_partitions(const MsmCols& cols, const MsmPlan& pl, uint32_t* __restrict__ part_counts) {
+__device__ __forceinline__ void msm_decompose_partitions(const MsmCols& cols, const MsmPlan& pl, uint32_t* __restrict__ digits, uint32_t* __restrict__ part_counts) {
     __shared__ uint32_t part_hist[PART_MAX];
     const uint32_t col = blockIdx.y;
+    digits += (size_t)col * pl.W * pl.n;
     const uint4* __restrict__ scalars = cols.scalars[col];
     const uint32_t col_len = cols.len[col];
     const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
@@ -156,8 +157,11 @@ __device__ __forceinline__ void msm_decompose_partitions(const MsmCols& cols, co
     for (uint32_t round = 0; round < rounds; ++round) {
         const uint32_t i = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
         if (i >= col_len) continue;
-        msm_recode(scalars, i, true, pl, [&](uint32_t, uint32_t set, uint32_t d, uint32_t) {
+        // the digits are kept (window-major, like the one-pass sort's): msm_partition_kernel reads them back instead of recoding the
+        // scalar -- the recoding (one Montgomery multiplication + 13 extractions) made both kernels instruction bound
+        msm_recode(scalars, i, true, pl, [&](uint32_t w, uint32_t set, uint32_t d, uint32_t sign) {
             if (d) atomicAdd(&part_hist[(gbase + set * pl.Nb + d - 1) >> pl.pb], 1u);
+            digits[(size_t)w * pl.n + i] = d ? (d | sign) : 0u;
         });
     }
     __syncthreads();
@@ -198,7 +202,8 @@ __global__ void __launch_bounds__(1024) msm_partition_scan_kernel(const uint32_t
 }
 
 // one thread per scalar of the tile (blockDim.x == tile): the W <= 16 digits are recoded once and stay in registers
-__global__ void __launch_bounds__(1024) msm_partition_kernel(MsmCols cols, MsmPlan pl, uint32_t* __restrict__ part_cursor, uint2* __restrict__ inter) {
+__global__ void __launch_bounds__(1024) msm_partition_kernel(MsmCols cols, MsmPlan pl, const uint32_t* __restrict__ digits, uint32_t* __restrict__ part_cursor,
+                                                           uint2* __restrict__ inter) {
     H2B_DYN_SMEM(uint32_t, smem);
     const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
     uint32_t* cnt = smem;                    // entries of this tile per partition, then the fill cursor
@@ -207,11 +212,11 @@ __global__ void __launch_bounds__(1024) msm_partition_kernel(MsmCols cols, MsmPl
     uint2* staging = (uint2*)(smem + 3 * P + (P & 1));
     __shared__ uint32_t warp_tot[32];
     const uint32_t col = blockIdx.y;
-    const uint4* __restrict__ scalars = cols.scalars[col];
     const uint32_t col_len = cols.len[col];
     const uint32_t gbase = col * pl.m * pl.Nb;
     const uint32_t tile = blockDim.x;
     const uint32_t ntiles = (pl.n + tile - 1) / tile;
+    digits += (size_t)col * pl.W * pl.n;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const uint32_t i = t * tile + threadIdx.x;
         const bool live = i < col_len;
@@ -219,12 +224,17 @@ __global__ void __launch_bounds__(1024) msm_partition_kernel(MsmCols cols, MsmPl
         uint32_t dig[PART_W_MAX];            // bucket (global index + 1, 0 = no entry) with the sign in bit 31
 #pragma unroll
         for (uint32_t w = 0; w < PART_W_MAX; ++w) dig[w] = 0;
-        if (live)
-            msm_recode(scalars, i, true, pl, [&](uint32_t w, uint32_t set, uint32_t d, uint32_t sign) {
+        if (live) {
+            uint32_t set = 0;
 #pragma unroll
-                for (uint32_t k = 0; k < PART_W_MAX; ++k)
-                    if (k == w) dig[k] = d ? ((gbase + set * pl.Nb + d) | sign) : 0u;
-            });
+            for (uint32_t w = 0; w < PART_W_MAX; ++w) {
+                if (w < pl.W) {
+                    const uint32_t e = digits[(size_t)w * pl.n + i];
+                    if (e) dig[w] = (gbase + set * pl.Nb + (e & ~SIGN_BIT)) | (e & SIGN_BIT);
+                    if (++set == pl.m) set = 0;
+                }
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (uint32_t w = 0; w < PART_W_MAX; ++w)
@@ -436,7 +446,7 @@ __global__ void __launch_bounds__(256) msm_decompose_kernel(MsmCols cols, MsmPla
     if (pl.pb) {
         // partitioned sort: only the P partition totals are needed here (the per-bucket counts are taken per partition, in shared
         // memory, by msm_place_kernel): a per-CTA histogram, flushed with one global reduction per partition
-        msm_decompose_partitions(cols, pl, counts);
+        msm_decompose_partitions(cols, pl, digits, counts);
         return;
     }
     counts += (size_t)col * pl.m * pl.Nb;
@@ -1279,7 +1289,7 @@ static int msm_sort_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, cons
         }
         const uint32_t ntiles = (pl.n + tile - 1) / tile;
         const uint32_t pgrid = ntiles > (uint32_t)ctx.sm_count * 8 ? (uint32_t)ctx.sm_count * 8 : ntiles;
-        H2B_LAUNCH(msm_partition_kernel, dim3(pgrid, pl.ncols), tile, smem1, stream, cols, pl, (uint32_t*)s.part_cursor.p, (uint2*)s.inter.p);
+        H2B_LAUNCH(msm_partition_kernel, dim3(pgrid, pl.ncols), tile, smem1, stream, cols, pl, (const uint32_t*)s.digits.p, (uint32_t*)s.part_cursor.p, (uint2*)s.inter.p);
         ctx.prof.mark(PROF_MSM_PLAN, stream);
         const uint64_t upper = (uint64_t)pl.n * pl.W * pl.ncols;
         const uint32_t max_chunks = (uint32_t)(upper >> chunk_log) + P + 1;
