@@ -582,6 +582,10 @@ def test_one_ntt_across_emulated_devices(emu, devices):
                          "for k in (4, 5, 8, 11, 12, 13):\n"
                          "    pc.check_ntt(L, oc, k)\n" % devices,
                     dict(H2B_EMU_DEVICES=devices, H2B_NTT_MULTI_MIN_LOG="4", H2B_STAGE_PIECE_LOG="10", H2B_STAGE_THREADS="3"))
+    # the strided-batch mode of the multi-pass plans (2, 3 and 4 passes per row / column transform; several tiles per CTA)
+    _emu_subprocess(emu, "for k in (12, 14, 15):\n"
+                         "    pc.check_ntt(L, oc, k)\n",
+                    dict(H2B_EMU_DEVICES=devices, H2B_NTT_MULTI_MIN_LOG="4", H2B_NTT_BMAX="2", H2B_NTT_GRID="3"))
 
 
 @pytest.mark.parametrize("n,ncols,spacing,window", [(600, 6, 8, 0), (600, 5, 8, 4), (257, 9, 0, 0), (1200, 4, 12, 6), (40, 33, 6, 0), (300, 4, -1, 0)])
