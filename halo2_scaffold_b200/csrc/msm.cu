@@ -1121,7 +1121,10 @@ uint32_t msm_pick_table_spacing(size_t n, uint32_t max_tables) {
     // measured on B200 (profiles/r01_msm_spacing.jsonl, r01_sweep.jsonl): small sets are latency bound and want few
     // buckets (8-bit windows, whose 5-bit top window is harmless), the mid range 16 bits, large sets 20 bits; 10/12/14/18
     // bits leave a 1-3 bit top window whose hot buckets cost more than they save
-    const uint32_t preferred = n < ((size_t)1 << 15) ? 8u : (n < ((size_t)1 << 20) ? 16u : 20u);
+    // from 2^25 points on 22 bits (12 tables): the accumulation saves 1/13 of its additions, and the costs that come with 2^21 buckets
+    // -- the partitioned sort, a throughput-bound first reduction level -- no longer grow with n (2^26: 163.5 -> 157.1 ms uniform,
+    // 15.7 -> 15.4 ms witness-like; 2^24: 41.1 against 41.3 ms uniform but +1 ms on every witness-like column, so 20 bits there)
+    const uint32_t preferred = n < ((size_t)1 << 15) ? 8u : (n < ((size_t)1 << 20) ? 16u : (n < ((size_t)1 << 25) ? 20u : 22u));
     if (windows_for(preferred) <= max_tables) return preferred;
     uint32_t best = 0;
     double best_cost = 1e300;
@@ -1226,7 +1229,7 @@ static int msm_size_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan& pl, size_t row
     {
         static int env_on = -1, env_min = -1;
         if (env_on < 0) env_on = env_int("H2B_MSM_SORT2", 1);
-        if (env_min < 0) env_min = env_int("H2B_MSM_SORT2_MIN_LOG", 29);      // measured (profiles/r02_partitioned_sort.jsonl): equal at 2^24 points, ahead from 2^25 on
+        if (env_min < 0) env_min = env_int("H2B_MSM_SORT2_MIN_LOG", 28);      // sorted entries, log2: 2^25 points x 12 windows and up (profiles/r02_partitioned_sort.jsonl: equal at 2^24 points on uniform scalars, behind on witness-like ones; ahead from 2^25 on)
         pl.pb = 0;
         if (env_on && upper >= ((uint64_t)1 << env_min) && pl.W <= PART_W_MAX && pl.B <= (1u << 24) && pl.B >= 64) {
             uint32_t lb = 0;
