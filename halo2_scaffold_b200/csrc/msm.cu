@@ -346,49 +346,51 @@ __global__ void __launch_bounds__(1024) msm_place_count_kernel(MsmPlan pl, uint3
 __global__ void __launch_bounds__(1024) msm_place_scan_kernel(MsmPlan pl, const uint32_t* __restrict__ chunk0, const uint32_t* __restrict__ part_off,
                                                             uint32_t* __restrict__ chunk_hist, uint32_t* __restrict__ offsets) {
     __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t base_sh;
     const uint32_t P = (pl.B + (1u << pl.pb) - 1) >> pl.pb;
     const uint32_t NB = 1u << pl.pb;
-    const uint32_t per = (NB + blockDim.x - 1) / blockDim.x;          // <= 8
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
     for (uint32_t p = blockIdx.x; p < P; p += gridDim.x) {
         const uint32_t c0 = chunk0[p], c1 = chunk0[p + 1];
         const uint32_t g0 = p << pl.pb;
         const uint32_t nb = (pl.B - g0 < NB) ? pl.B - g0 : NB;
-        const uint32_t lo = threadIdx.x * per < NB ? threadIdx.x * per : NB, hi = lo + per < NB ? lo + per : NB;
-        uint32_t tot[8];
-        uint32_t sum = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-            tot[k] = 0;
-            if (lo + k < hi) {
-                uint32_t t = 0;
-                for (uint32_t c = c0; c < c1; ++c) t += chunk_hist[(size_t)c * NB + lo + k];
-                tot[k] = t;
-                sum += t;
-            }
-        }
-        uint32_t incl = sum;
-        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (uint32_t)o) incl += v;
-        }
-        if (lane == 31) warp_tot[wid] = incl;
+        if (threadIdx.x == 0) base_sh = part_off[p];
         __syncthreads();
-        uint32_t run = part_off[p] + incl - sum;
-        for (uint32_t k = 0; k < wid; ++k) run += warp_tot[k];
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-            if (lo + k < hi) {
-                const uint32_t b = lo + k;
-                if (b < nb) offsets[g0 + b] = run;
+        // blockDim.x buckets at a time, bucket = q + threadIdx.x: every walk over the chunk rows is coalesced (with a thread owning
+        // `per` CONSECUTIVE buckets a 4096-bucket partition took 0.93 ms here at 2^24 points, 30x the 1024-bucket case)
+        for (uint32_t q = 0; q < NB; q += blockDim.x) {
+            const uint32_t bkt = q + threadIdx.x;
+            uint32_t tot = 0;
+            if (bkt < NB) {
+#pragma unroll 4
+                for (uint32_t c = c0; c < c1; ++c) tot += chunk_hist[(size_t)c * NB + bkt];
+            }
+            uint32_t incl = tot;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            if (lane == 31) warp_tot[wid] = incl;
+            __syncthreads();
+            const uint32_t base = base_sh;
+            uint32_t run = base + incl - tot;
+            for (uint32_t k = 0; k < wid; ++k) run += warp_tot[k];
+            if (bkt < NB) {
+                if (bkt < nb) offsets[g0 + bkt] = run;
                 uint32_t r = run;
                 for (uint32_t c = c0; c < c1; ++c) {
-                    const uint32_t v = chunk_hist[(size_t)c * NB + b];
-                    chunk_hist[(size_t)c * NB + b] = r;
+                    const uint32_t v = chunk_hist[(size_t)c * NB + bkt];
+                    chunk_hist[(size_t)c * NB + bkt] = r;
                     r += v;
                 }
-                run += tot[k];
             }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t t = base;
+                for (uint32_t k = 0; k < nwarps; ++k) t += warp_tot[k];
+                base_sh = t;
+            }
+            __syncthreads();
         }
         if (p == P - 1 && threadIdx.x == 0) offsets[pl.B] = part_off[P];
         __syncthreads();
@@ -789,6 +791,9 @@ __global__ void __launch_bounds__(256) msm_accumulate_kernel(MsmPlan pl, const u
 // chunks of COMBINE_CHUNK pieces by one CTA each, then one CTA per bucket over the chunk sums.
 static const uint32_t COMBINE_HEAVY = 24;      // more pieces than this: tree
 static const uint32_t COMBINE_CHUNK = 1024;    // pieces per CTA in the first tree level
+static const uint32_t COMBINE_THREADS = 256;   // CTAs of the two tree levels; two per SM (capped at 128 registers).  64-thread CTAs over 256-piece chunks were tried for the
+                                               // ~1500 moderately heavy buckets of a narrow top window (22-bit tables: combine 0.63 -> 0.41 ms) but cost a witness-like column, whose
+                                               // one bucket is cut into 13 000 pieces, 0.11 ms
 
 struct HeavyDesc { uint32_t bucket, chunk0, nchunks, pad; };
 
@@ -822,7 +827,7 @@ __global__ void __launch_bounds__(128) msm_combine_light_kernel(MsmPlan pl, cons
     xyzz_store(bucket_acc + 8 * (size_t)b, acc);
 }
 
-// sum of `acc` over the 256 threads of the CTA, valid in thread 0
+// sum of `acc` over the threads of the CTA, valid in thread 0
 __device__ __forceinline__ void block_sum_xyzz(XYZZ& acc, uint4* sh) {
     xyzz_store(sh + 8 * threadIdx.x, acc);
     __syncthreads();
@@ -836,10 +841,10 @@ __device__ __forceinline__ void block_sum_xyzz(XYZZ& acc, uint4* sh) {
     }
 }
 
-__global__ void __launch_bounds__(256) msm_combine_chunk_kernel(MsmPlan pl, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ctrl,
+__global__ void __launch_bounds__(COMBINE_THREADS, 2) msm_combine_chunk_kernel(MsmPlan pl, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ctrl,
                                                               const HeavyDesc* __restrict__ heavy, const uint2* __restrict__ chunk_desc,
                                                               const uint4* __restrict__ head_partial, uint4* __restrict__ chunk_out) {
-    __shared__ uint4 sh[256 * 8];
+    __shared__ uint4 sh[COMBINE_THREADS * 8];
     const uint32_t S = slice_len(offsets[pl.B], pl.G);
     const uint32_t nchunks = ctrl[2];
     for (uint32_t item = blockIdx.x; item < nchunks; item += gridDim.x) {
@@ -860,9 +865,9 @@ __global__ void __launch_bounds__(256) msm_combine_chunk_kernel(MsmPlan pl, cons
     }
 }
 
-__global__ void __launch_bounds__(256) msm_combine_heavy_kernel(const uint32_t* __restrict__ ctrl, const HeavyDesc* __restrict__ heavy,
+__global__ void __launch_bounds__(COMBINE_THREADS, 2) msm_combine_heavy_kernel(const uint32_t* __restrict__ ctrl, const HeavyDesc* __restrict__ heavy,
                                                               const uint4* __restrict__ chunk_out, uint4* __restrict__ bucket_acc) {
-    __shared__ uint4 sh[256 * 8];
+    __shared__ uint4 sh[COMBINE_THREADS * 8];
     const uint32_t nheavy = ctrl[1];
     for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
         const HeavyDesc d = heavy[h];
@@ -1299,7 +1304,9 @@ static int msm_sort_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl, cons
         const uint32_t cgrid = max_chunks > (uint32_t)ctx.sm_count * 16 ? (uint32_t)ctx.sm_count * 16 : max_chunks;
         H2B_LAUNCH(msm_place_count_kernel, cgrid, 1024, smem2, stream, pl, chunk_log, (const uint32_t*)s.chunk0.p, (const uint32_t*)s.part_off.p, (const uint2*)s.inter.p,
                    (uint32_t*)s.chunk_hist.p);
-        H2B_LAUNCH(msm_place_scan_kernel, P, 1024, 0, stream, pl, (const uint32_t*)s.chunk0.p, (const uint32_t*)s.part_off.p, (uint32_t*)s.chunk_hist.p, offsets);
+        static int scan_threads = -1;      // tests: fewer threads than buckets per partition (several passes per partition)
+        if (scan_threads < 0) { scan_threads = env_int("H2B_MSM_PLACE_SCAN_THREADS", 1024); if (scan_threads < 32 || scan_threads > 1024 || (scan_threads & 31)) scan_threads = 1024; }
+        H2B_LAUNCH(msm_place_scan_kernel, P, (unsigned)scan_threads, 0, stream, pl, (const uint32_t*)s.chunk0.p, (const uint32_t*)s.part_off.p, (uint32_t*)s.chunk_hist.p, offsets);
         H2B_LAUNCH(msm_place_kernel, cgrid, 1024, smem2, stream, pl, chunk_log, (const uint32_t*)s.chunk0.p, (const uint32_t*)s.part_off.p, (const uint2*)s.inter.p,
                    (const uint32_t*)s.chunk_hist.p, sorted);
         H2B_CUDA(cudaGetLastError());
@@ -1380,9 +1387,9 @@ static int msm_accumulate_chunk(DeviceCtx& ctx, MsmScratch& s, const MsmPlan& pl
     ctx.prof.mark(PROF_MSM_ACCUMULATE, stream);
     H2B_LAUNCH(msm_combine_light_kernel, (pl.G + 127) / 128, 128, 0, stream, pl, offsets, ctrl, (const uint32_t*)s.split_list.p,
                (HeavyDesc*)s.heavy.p, (uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, target);
-    H2B_LAUNCH(msm_combine_chunk_kernel, ctx.sm_count * 2, 256, 0, stream, pl, offsets, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p,
+    H2B_LAUNCH(msm_combine_chunk_kernel, ctx.sm_count * 2, COMBINE_THREADS, 0, stream, pl, offsets, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p,
                (const uint2*)s.chunk_desc.p, (const uint4*)s.head_partial.p, (uint4*)s.chunk_out.p);
-    H2B_LAUNCH(msm_combine_heavy_kernel, ctx.sm_count, 256, 0, stream, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p, (const uint4*)s.chunk_out.p,
+    H2B_LAUNCH(msm_combine_heavy_kernel, ctx.sm_count * 2, COMBINE_THREADS, 0, stream, (const uint32_t*)ctrl, (const HeavyDesc*)s.heavy.p, (const uint4*)s.chunk_out.p,
                target);
     if (pl.add_into)
         H2B_LAUNCH(msm_merge_kernel, (pl.B + 127) / 128, 128, 0, stream, pl.B, offsets, (const uint4*)target, (uint4*)s.bucket_acc.p);

@@ -624,3 +624,7 @@ def test_msm_partitioned_sort(emu):
                     dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_SORT2_CHUNK_LOG="7", H2B_MSM_PRECOMP="16"), timeout=2400)
     _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 4097, 16, kind=1, windows=(16,), ranges=[(0, 4097)])",
                     dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_UPLOAD_CHUNK_LOG="10"), timeout=2400)
+    # the bucket scan of a partition in several passes of blockDim buckets (the 4096-bucket partitions of 22-bit tables)
+    _emu_subprocess(emu, "pc.check_msm_tables(L, oc, 3000, 16, kind=0, windows=(16,), ranges=[(0, 3000), (100, 2500)])\n"
+                         "pc.check_msm_tables(L, oc, 2500, 18, kind=1, windows=(18,))",
+                    dict(H2B_MSM_SORT2_MIN_LOG="8", H2B_MSM_SORT2_CHUNK_LOG="7", H2B_MSM_PLACE_SCAN_THREADS="32"), timeout=2400)
