@@ -1236,7 +1236,10 @@ static int msm_size_chunk(DeviceCtx& ctx, MsmScratch& s, MsmPlan& pl, size_t row
         if (env_on < 0) env_on = env_int("H2B_MSM_SORT2", 1);
         if (env_min < 0) env_min = env_int("H2B_MSM_SORT2_MIN_LOG", 28);      // sorted entries, log2: 2^25 points x 12 windows and up (profiles/r02_partitioned_sort.jsonl: equal at 2^24 points on uniform scalars, behind on witness-like ones; ahead from 2^25 on)
         pl.pb = 0;
-        if (env_on && upper >= ((uint64_t)1 << env_min) && pl.W <= PART_W_MAX && pl.B <= (1u << 24) && pl.B >= 64) {
+        // with 2^21 buckets and more (22-bit tables) the one-pass scatter loses its L2 residency: the partitioned sort also takes the shorter lists of
+        // the upload chunks of a host-pointer call (2^25 points end to end: 87.5 ms with one-pass sorted chunks)
+        const uint64_t min_entries = (pl.B >= (1u << 21) && env_min > 24) ? ((uint64_t)1 << 24) : ((uint64_t)1 << env_min);
+        if (env_on && upper >= min_entries && pl.W <= PART_W_MAX && pl.B <= (1u << 24) && pl.B >= 64) {
             uint32_t lb = 0;
             while ((1u << lb) < pl.B) ++lb;
             uint32_t pb = lb > 9 ? lb - 9 : 1;            // about 512 partitions
