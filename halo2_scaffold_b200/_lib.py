@@ -36,7 +36,7 @@ _EXPORTS = [
     "h2b_set_msm_precomp", "h2b_base_set_info", "h2b_msm_bn254_g1_batch_registered", "h2b_ntt_bn254_fr_batch",
     "h2b_lagrange_to_coeff_dev", "h2b_coeff_to_extended_dev", "h2b_extended_to_coeff_dev",
     "h2b_fr_batch_invert_dev", "h2b_fr_prefix_product_dev", "h2b_fr_eval_polynomial_dev", "h2b_fr_kate_division_dev",
-    "h2b_fr_lincomb_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
+    "h2b_fr_lincomb_dev", "h2b_fr_transpose_dev", "h2b_permutation_product_dev", "h2b_lookup_product_dev", "h2b_lookup_permute_dev", "h2b_lookup_permute_async_dev", "h2b_g1_decode_dev", "h2b_g1_encode_dev", "h2b_srs_read", "h2b_srs_write", "h2b_srs_cache_clear",
     "h2b_evaluate_graph_dev", "h2b_evaluate_graph_shard_dev", "h2b_evaluate_h_permutation_shard_dev", "h2b_evaluate_h_lookup_shard_dev", "h2b_evaluate_h_permutation_dev", "h2b_evaluate_h_lookup_dev", "h2b_evaluate_graph_info",
     "h2b_register_bases_sharded", "h2b_msm_bn254_g1_dev_batch_registered", "h2b_implicit_cache_stats", "h2b_msm_checksum_dev", "h2b_ntt_bn254_fr_dev_batch", "h2b_lagrange_to_coeff_dev_batch", "h2b_coeff_to_extended_dev_batch", "h2b_memcpy_d2d_async", "h2b_memset_zero_async", "h2b_column_pipeline",
 ]
@@ -163,6 +163,7 @@ class Lib:
         L.h2b_lagrange_to_coeff_dev_batch.argtypes = [i32, vp, sz, u32, vp, vp, vp]
         L.h2b_coeff_to_extended_dev_batch.argtypes = [i32, vp, sz, u32, u32, vp, vp, vp]
         L.h2b_fr_lincomb_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp]
+        L.h2b_fr_transpose_dev.argtypes = [i32, vp, vp, u32, u32, vp]
         L.h2b_permutation_product_dev.argtypes = [i32, vp, vp, u32, sz, vp, vp, vp, vp, vp, vp, vp, vp]
         L.h2b_lookup_product_dev.argtypes = [i32, vp, vp, vp, vp, sz, vp, vp, vp, vp]
         L.h2b_lookup_permute_dev.argtypes = [i32, vp, vp, u32, vp, vp, vp]
@@ -459,6 +460,24 @@ class Lib:
         c = _u64(coeffs).reshape(-1, 4)
         assert c.shape[0] == p.shape[0]
         self.check(self.L.h2b_fr_lincomb_dev(device, p.ctypes.data if p.size else None, c.ctypes.data if c.size else None, p.shape[0], n, d_out, stream))
+
+    def fr_transpose(self, a: np.ndarray, device: int = 0) -> np.ndarray:
+        """(rows, cols, 4) uint64 matrix of Fr elements -> its transpose (cols, rows, 4), through the device"""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        rows, cols = a.shape[0], a.shape[1]
+        out = np.empty((cols, rows, 4), dtype=np.uint64)
+        if rows == 0 or cols == 0:
+            return out
+        d_in, d_out = self.dev_alloc(device, a.nbytes), self.dev_alloc(device, a.nbytes)
+        try:
+            self.h2d(device, d_in, a)
+            self.check(self.L.h2b_fr_transpose_dev(device, d_in, d_out, rows, cols, None))
+            self.dev_sync(device)
+            self.d2h(device, out, d_out)
+        finally:
+            self.dev_free(device, d_in)
+            self.dev_free(device, d_out)
+        return out
 
     def fr_lincomb(self, cols, coeffs, device: int = 0) -> np.ndarray:
         """sum_j coeffs[j] * cols[j], host arrays in and out"""

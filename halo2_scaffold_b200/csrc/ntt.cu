@@ -582,11 +582,66 @@ __global__ void __launch_bounds__(256) fr_transpose_kernel(const uint4* __restri
         }
     }
 }
+#ifndef H2B_EMU
+// The same transpose with the tile brought in by the TMA unit: one thread arms an mbarrier with the tile's byte count and issues 32
+// bulk copies (cp.async.bulk.shared::cluster.global, 1 KiB = one tile row each; UBLKCP in SASS) into rows padded by 16 bytes, every
+// thread waits on the barrier's phase and the transposed reads are conflict-free (row stride 260 words: lanes 4 banks apart).  No
+// thread touches the incoming data before it sits in shared memory and no register or LSU slot is spent on it.  Whole tiles only
+// (rows and cols multiples of 32); other shapes take fr_transpose_kernel.
+static const uint32_t TR_ROW_BYTES = 32 * 32 + 16;
+__global__ void __launch_bounds__(256) fr_transpose_bulk_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t rows, uint32_t cols) {
+    __shared__ __align__(128) unsigned char tile[32 * TR_ROW_BYTES];
+    __shared__ __align__(8) unsigned long long mbar;
+    const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const uint32_t tid = threadIdx.y * 32 + threadIdx.x;
+    const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(&mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(32u * 1024u) : "memory");
+        for (uint32_t r = 0; r < 32; ++r) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + r * TR_ROW_BYTES);
+            const uint4* src = in + 2 * ((size_t)(r0 + r) * cols + c0);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(1024u), "r"(mbar_s)
+                         : "memory");
+        }
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TR_DONE;\n"
+        "bra TR_WAIT;\n"
+        "TR_DONE:\n"
+        "}" ::"r"(mbar_s), "r"(0u)
+        : "memory");
+    for (uint32_t dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const uint4* e = reinterpret_cast<const uint4*>(tile + threadIdx.x * TR_ROW_BYTES + dy * 32);
+        const size_t o = 2 * ((size_t)(c0 + dy) * rows + r0 + threadIdx.x);
+        out[o] = e[0];
+        out[o + 1] = e[1];
+    }
+}
+#endif
+
 int fr_transpose_run(DeviceCtx& ctx, const void* d_in, void* d_out, uint32_t rows, uint32_t cols, cudaStream_t stream) {
     (void)ctx;
     if (rows == 0 || cols == 0) return H2B_OK;
     const uint32_t gy = (rows + 31) / 32;
     if (gy > 65535) { set_error("transpose: too many rows"); return H2B_ERR_BAD_ARGUMENT; }
+#ifndef H2B_EMU
+    static int bulk = -1;
+    if (bulk < 0) { const char* e = getenv("H2B_TRANSPOSE_BULK"); bulk = e ? atoi(e) : 1; }
+    if (bulk && rows % 32 == 0 && cols % 32 == 0 && ((uintptr_t)d_in & 15) == 0) {
+        H2B_LAUNCH(fr_transpose_bulk_kernel, dim3(cols / 32, gy), dim3(32, 8), 0, stream, (const uint4*)d_in, (uint4*)d_out, rows, cols);
+        H2B_CUDA(cudaGetLastError());
+        return H2B_OK;
+    }
+#endif
     H2B_LAUNCH(fr_transpose_kernel, dim3((cols + 31) / 32, gy), dim3(32, 8), 0, stream, (const uint4*)d_in, (uint4*)d_out, rows, cols);
     H2B_CUDA(cudaGetLastError());
     return H2B_OK;

@@ -189,6 +189,10 @@ int h2b_fr_kate_division_dev(int device, const void* d_a, size_t n, const uint64
  * the multi-open argument ([UP] poly/kzg/multiopen/shplonk/prover.rs) and the theta-compression of lookup expressions
  * ([UP] plonk/lookup/prover.rs compress_expressions) */
 int h2b_fr_lincomb_dev(int device, const void* const* d_cols, const uint64_t* coeffs /* m x 4 */, uint32_t m, size_t n, void* d_out, void* stream);
+/* out[c * rows + r] = in[r * cols + c] for a rows x cols matrix of Fr elements (out must not alias in): the re-layout step of the
+ * four-step NTT that splits one transform over several devices (h2b_ntt_bn254_fr), usable on its own for row / column blocks of
+ * device-resident columns.  Whole 32 x 32 tiles are moved by the TMA unit (cp.async.bulk + mbarrier). */
+int h2b_fr_transpose_dev(int device, const void* d_in, void* d_out, uint32_t rows, uint32_t cols, void* stream);
 /* The grand products themselves, on device-resident Lagrange-basis columns of n = 2^k rows:
  *   [UP] plonk/permutation/prover.rs Argument::commit, one call per set (chunk of cs.degree() - 2 columns; any number, 16 per launch):
  *        z[0] = last_z,  z[i+1] = z[i] * prod_j (v_j[i] + deltaomega * delta^j * omega^i * beta + gamma)

@@ -60,6 +60,7 @@ extern "C" {
     pub fn h2b_fr_prefix_product_dev(device: c_int, d_in: *const c_void, d_out: *mut c_void, n: usize, stream: *mut c_void) -> c_int;
     pub fn h2b_fr_eval_polynomial_dev(device: c_int, d_coeffs: *const c_void, n: usize, x: *const u64, d_out: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn h2b_fr_kate_division_dev(device: c_int, d_a: *const c_void, n: usize, b: *const u64, d_q: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn h2b_fr_transpose_dev(device: c_int, d_in: *const c_void, d_out: *mut c_void, rows: u32, cols: u32, stream: *mut c_void) -> c_int;
     pub fn h2b_fr_lincomb_dev(device: c_int, d_cols: *const *const c_void, coeffs: *const u64, m: u32, n: usize, d_out: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn h2b_permutation_product_dev(device: c_int, d_values: *const *const c_void, d_permutations: *const *const c_void, n_columns: u32, n: usize,
                                        beta: *const u64, gamma: *const u64, delta: *const u64, deltaomega: *const u64, omega: *const u64,

@@ -63,6 +63,14 @@ def check_ntt(L, oc, k, seed=0):
         assert (got == want).all(), "NTT mismatch at k=%d inverse=%s" % (k, inverse)
 
 
+def check_fr_transpose(L, oc, shapes=((32, 32), (64, 96), (256, 32), (1, 5), (33, 70), (96, 1), (1024, 512))):
+    """h2b_fr_transpose_dev against numpy: whole 32 x 32 tiles (the TMA bulk-copy kernel on the GPU) and ragged shapes"""
+    for rows, cols in shapes:
+        a = oc.random_fr(0x7A00 + rows * 131 + cols, rows * cols).reshape(rows, cols, 4)
+        got = L.fr_transpose(a)
+        assert got.shape == (cols, rows, 4) and (got == a.transpose(1, 0, 2)).all(), "transpose mismatch %dx%d" % (rows, cols)
+
+
 def edge_msm_inputs(L, oc, n, kind, seed):
     s = L.gen_scalars(seed, n, kind)
     P = oc.gen_points(seed + 1, n) if n <= (1 << 16) else L.gen_points(seed + 1, n)

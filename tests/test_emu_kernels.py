@@ -573,6 +573,10 @@ def test_multi_device_host_logic_on_emulated_devices(emu, devices):
                     dict(H2B_EMU_DEVICES=devices, H2B_MULTI_DEVICE_MIN_LOG="7", H2B_DIGEST_BLOCK_LOG="4", H2B_IMPLICIT_MIN_LOG="6"))
 
 
+def test_fr_transpose(emu, oc):
+    pc.check_fr_transpose(emu, oc, shapes=((32, 32), (64, 96), (1, 5), (33, 70), (96, 1)))
+
+
 @pytest.mark.parametrize("devices", ["2", "4"])
 def test_one_ntt_across_emulated_devices(emu, devices):
     # SURVEY.md 8e "one NTT across GPUs": the four-step split of h2b_ntt_bn254_fr (strided uploads of column blocks, transposes,

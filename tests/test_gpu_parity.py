@@ -303,6 +303,12 @@ def test_column_pipeline_single_upload(gpu, oc, j, k):
     pc.check_column_pipeline(gpu, oc, j, k)
 
 
+def test_fr_transpose_tma_and_ragged(gpu, oc):
+    # the re-layout step of the split NTT: whole tiles go through cp.async.bulk + mbarrier (UBLKCP), ragged shapes through the LSU kernel
+    pc.check_fr_transpose(gpu, oc)
+    pc.check_fr_transpose(gpu, oc, shapes=((2048, 4096),))
+
+
 def test_in_process_multi_device_paths(gpu):
     """Point-range sharding of one MSM across every visible GPU + concurrent callers (fresh process: own library instance)."""
     import os, subprocess, sys
