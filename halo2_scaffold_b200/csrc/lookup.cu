@@ -87,6 +87,27 @@ __global__ void __launch_bounds__(256) bitonic_global2_kernel(uint4* __restrict_
     key_store(keys, i00, a); key_store(keys, i01, b); key_store(keys, i10, c); key_store(keys, i11, d);
 }
 
+// three consecutive passes (distances j, j / 2, j / 4, all >= SORT_TILE) in one sweep: a thread owns the eight keys of a three-level
+// butterfly (64 registers of keys).  The sort is bound by its sweeps over HBM: 2^22 rows need 30 + 13 of them instead of 42 + 13
+__global__ void __launch_bounds__(256) bitonic_global3_kernel(uint4* __restrict__ keys, uint32_t eighth, uint32_t j, uint32_t k) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= eighth) return;
+    const uint32_t h = j >> 1, q = j >> 2;
+    const uint32_t i0 = ((t & ~(q - 1)) << 3) | (t & (q - 1));
+    const bool up = (i0 & k) == 0;
+    Key v[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) v[x] = key_load(keys, i0 | ((x & 4) ? j : 0u) | ((x & 2) ? h : 0u) | ((x & 1) ? q : 0u));
+#pragma unroll
+    for (int x = 0; x < 4; ++x) key_cmpx(v[x], v[x + 4], up);                          // distance j
+#pragma unroll
+    for (int x = 0; x < 8; ++x) if (!(x & 2)) key_cmpx(v[x], v[x + 2], up);            // distance j / 2
+#pragma unroll
+    for (int x = 0; x < 8; x += 2) key_cmpx(v[x], v[x + 1], up);                       // distance j / 4
+#pragma unroll
+    for (int x = 0; x < 8; ++x) key_store(keys, i0 | ((x & 4) ? j : 0u) | ((x & 2) ? h : 0u) | ((x & 1) ? q : 0u), v[x]);
+}
+
 // all passes with distance < SORT_TILE of one tile in shared memory.  k_lo == 0: the whole network up to runs of SORT_TILE
 // (the first phase); otherwise the tail j = min(k_lo, SORT_TILE) / 2 ... 1 of the stage with run length k_lo.
 __global__ void __launch_bounds__(512) bitonic_shared_kernel(uint4* __restrict__ keys, uint32_t count, uint32_t k_lo) {
@@ -137,6 +158,10 @@ static int bitonic_sort(uint4* keys, uint32_t padded, cudaStream_t stream) {    
     H2B_LAUNCH(bitonic_shared_kernel, tiles, 512, 0, stream, keys, padded, 0u);
     for (uint32_t k = SORT_TILE << 1; k != 0 && k <= padded; k <<= 1) {
         uint32_t j = k >> 1;
+        static int three = -1;
+        if (three < 0) { const char* e = getenv("H2B_SORT_THREE"); three = e ? atoi(e) : 1; }
+        for (; three && j >= 4 * SORT_TILE; j >>= 3)    // three distances per sweep while all are >= SORT_TILE
+            H2B_LAUNCH(bitonic_global3_kernel, (padded / 8 + 255) / 256, 256, 0, stream, keys, padded / 8, j, k);
         for (; j >= 2 * SORT_TILE; j >>= 2)             // two distances per sweep while both are >= SORT_TILE
             H2B_LAUNCH(bitonic_global2_kernel, (padded / 4 + 255) / 256, 256, 0, stream, keys, padded / 4, j, k);
         if (j >= SORT_TILE) H2B_LAUNCH(bitonic_global_kernel, (padded / 2 + 255) / 256, 256, 0, stream, keys, padded / 2, j, k);
